@@ -1,0 +1,147 @@
+"""Pin the CPU oracle (oracle/) against vectors produced by the unmodified
+reference modules (oracle/gen_golden.py -> tests/golden/*.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from audio_depth_estimation_b200 import synthetic
+from oracle import feature_oracle as fo
+from oracle import loss_oracle as lo
+from oracle import unet_oracle as uo
+
+
+def rel_to_max(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def feat(golden_dir):
+    return np.load(os.path.join(golden_dir, "feature.npz"))
+
+
+def test_stft_small_512(feat):
+    w = synthetic.waveform(1, 1000, seed=13)[0]
+    got = fo.stft_mag(w, 512, 64, 16)
+    assert got.shape == feat["small_spec_512"].shape
+    assert rel_to_max(got, feat["small_spec_512"]) <= 1e-5
+
+
+def test_stft_small_400(feat):
+    w = synthetic.waveform(1, 2000, seed=14)[0]
+    got = fo.stft_mag(w, 400, 200, 100)
+    assert got.shape == feat["small_spec_400"].shape
+    assert rel_to_max(got, feat["small_spec_400"]) <= 1e-5
+
+
+@pytest.mark.parametrize("name,echo", [("v2", False), ("v2echo", True)])
+def test_feature_v2(feat, name, echo):
+    w = synthetic.waveform(1, 8000, seed=11, echo=echo)[0]
+    spec = fo.stft_mag(w[:, :fo.cut_length(30.0)], 512, 64, 16)
+    assert spec.shape == (2, 257, 487)
+    assert rel_to_max(spec[:, :, ::37], feat[name + "_spec_slice"]) <= 1e-5
+    got = fo.feature_v2(w, 30.0, 256)
+    # After log + min-max the values are in [0,1].  The reference's own fp32 FFT
+    # is only accurate to ~7e-4 *element-relative* on near-zero bins (SURVEY.md
+    # section 7), the log turns that into an absolute error and the per-channel
+    # min (taken at exactly such a bin) shifts the whole plane, so the feature
+    # is compared with an absolute bound of 5e-4 (2e-3 for the echo variant,
+    # whose dynamic range is far wider); the spectrogram itself is held to 1e-5
+    # of its max above.
+    assert np.abs(got - feat[name + "_feat"]).max() <= (2e-3 if echo else 5e-4)
+
+
+def test_feature_v1(feat):
+    w = synthetic.waveform(1, synthetic.V1_LEN, seed=12)[0]
+    spec = fo.stft_mag(w, 512, 64, 16)
+    assert spec.shape == (2, 257, 201)
+    assert rel_to_max(spec[:, :, ::13], feat["v1_spec_slice"]) <= 1e-5
+    assert rel_to_max(fo.feature_v1(w), feat["v1_feat"]) <= 1e-5
+
+
+def test_resize(feat):
+    rng = np.random.default_rng(15)
+    plane = rng.uniform(0, 1, size=(2, 257, 101)).astype(np.float32)
+    assert np.abs(fo.resize(plane, 64) - feat["resize_257x101_to_64"]).max() <= 1e-6
+
+
+def test_loss(golden_dir):
+    g = np.load(os.path.join(golden_dir, "loss.npz"))
+    for i, (shape, dn, md) in enumerate([((2, 1, 64, 64), False, 30.0), ((3, 1, 32, 32), True, 12.0)]):
+        gt = synthetic.gt_depth(shape[0], shape[2], md, seed=710 + i, normalised=dn)
+        pred = g["case%d_pred" % i]
+        loss, l1, si, grad = lo.depth_loss_and_grad(pred, gt, scale=md if dn else 1.0)
+        ref = g["case%d_loss" % i]
+        assert abs(loss - ref[0]) <= 1e-5 * abs(ref[0])
+        assert abs(l1 - ref[1]) <= 1e-5 * abs(ref[1])
+        assert abs(si - ref[2]) <= 1e-5 * abs(ref[2])
+        rg = g["case%d_grad" % i]
+        assert np.abs(grad - rg).max() <= 1e-5 * np.abs(rg).max()
+        # the torch restatement used for the U-Net step agrees too
+        tl = uo.depth_loss(torch.from_numpy(pred), torch.from_numpy(gt), depth_norm=dn, max_depth=md)
+        assert abs(tl.item() - ref[0]) <= 1e-5 * abs(ref[0])
+
+
+UNET_CASES = {
+    "u128_ngf16_b3_sigmoid": ("unet_128", 16, 3, 128, True, 12.0, 200, True, False),
+    "u128_ngf64_b2_relu": ("unet_128", 64, 2, 128, False, 30.0, 300, True, False),
+    "u128_ngf16_b2_eval": ("unet_128", 16, 2, 128, False, 30.0, 400, False, True),
+    "u256_ngf64_b2_relu": ("unet_256", 64, 2, 256, False, 30.0, 100, True, False),
+    "u256_ngf64_b1_eval": ("unet_256", 64, 1, 256, True, 12.0, 500, False, True),
+}
+
+
+def build_case(case):
+    netG, ngf, batch, size, dn, md, seed, train, warm = case
+    nd = 8 if netG == "unet_256" else 7
+    sd = uo.make_state_dict(ngf, nd, seed=seed)
+    if warm:
+        rng = np.random.default_rng(seed + 1)
+        for k in sd:
+            if k.endswith("running_mean"):
+                sd[k] = torch.from_numpy(rng.normal(0, 0.05, sd[k].shape).astype(np.float32))
+            if k.endswith("running_var"):
+                sd[k] = torch.from_numpy(rng.uniform(0.5, 1.5, sd[k].shape).astype(np.float32))
+    x = torch.from_numpy(synthetic.feature_like(batch, size, seed=seed + 2))
+    gt = torch.from_numpy(synthetic.gt_depth(batch, size, md, seed=seed + 3, normalised=dn))
+    return nd, sd, x, gt
+
+
+@pytest.mark.parametrize("name", list(UNET_CASES))
+def test_unet_oracle(golden_dir, name):
+    case = UNET_CASES[name]
+    netG, ngf, batch, size, dn, md, seed, train, warm = case
+    g = np.load(os.path.join(golden_dir, "unet_%s.npz" % name))
+    nd, sd, x, gt = build_case(case)
+    torch.set_num_threads(8)
+    if not train:
+        with torch.no_grad():
+            y = uo.unet_forward(x, sd, nd, dn, training=False)
+        assert rel_to_max(y.numpy(), g["y"]) <= 1e-5
+        return
+    names = [str(n) for n in g["param_names"]]
+    for n in names:
+        sd["model." + n if not n.startswith("model.") else n].requires_grad_(True)
+    y = uo.unet_forward(x, sd, nd, dn, training=True)
+    y.retain_grad()
+    loss = uo.depth_loss(y, gt, depth_norm=dn, max_depth=md)
+    loss.backward()
+    assert rel_to_max(y.detach().numpy(), g["y"]) <= 1e-4
+    assert abs(loss.item() - g["loss"][0]) <= 1e-4 * abs(g["loss"][0])
+    assert rel_to_max(y.grad.numpy(), g["dy"]) <= 1e-4
+    gn = np.array([sd[n].grad.double().norm().item() for n in names])
+    assert np.all(np.abs(gn - g["grad_norms"]) <= 2e-3 * g["grad_norms"].max())
+    stats = [str(s) for s in g["stat_names"]]
+    got = np.stack([sd[s][:8].numpy() for s in stats])
+    assert np.abs(got - g["stat_head"]).max() <= 1e-4
+    # optimiser restatement
+    params = [sd[n].detach() for n in names]
+    grads = [sd[n].grad for n in names]
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+    tn = uo.clip_adamw_step(params, grads, m, v, 1, 0.002)
+    assert abs(tn.item() - g["total_norm"][0]) <= 1e-3 * g["total_norm"][0]
+    head = np.stack([p.reshape(-1)[:16].numpy() if p.numel() >= 16 else
+                     np.pad(p.reshape(-1).numpy(), (0, 16 - p.numel())) for p in params])
+    assert np.abs(head - g["param_head_after"]).max() <= 2e-4
