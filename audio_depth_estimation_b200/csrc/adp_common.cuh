@@ -1,0 +1,194 @@
+// Shared helpers for libadp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/adp_b200.h"
+
+void adp_set_error(const char* fmt, ...);
+
+#define ADP_CHECK_ARG(cond, ...)                         \
+  do {                                                   \
+    if (!(cond)) {                                       \
+      adp_set_error(__VA_ARGS__);                        \
+      return ADP_ERR_ARG;                                \
+    }                                                    \
+  } while (0)
+
+#define ADP_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      adp_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return ADP_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+void adp_count_launch();
+
+#define ADP_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    adp_count_launch();                                                             \
+    cudaError_t e_ = cudaGetLastError();                                            \
+    if (e_ != cudaSuccess) {                                                        \
+      adp_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      return ADP_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define ADP_TRY(call)            \
+  do {                           \
+    int r_ = (call);             \
+    if (r_ != ADP_OK) return r_; \
+  } while (0)
+
+static inline int adp_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t adp_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+typedef __nv_bfloat16 bf16;
+
+// ---- 4-wide typed loads / stores (fp32: 16 B, bf16: 8 B) -------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&a);
+}
+
+__device__ __forceinline__ float lrelu(float z, float slope) { return z > 0.f ? z : z * slope; }
+__device__ __forceinline__ float lrelu_grad(float z, float slope) { return z > 0.f ? 1.f : slope; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ordered-int encoding of floats for atomicMin/atomicMax
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) {
+  return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+
+// ---- internal cross-file entry points (host) -------------------------------
+namespace adp {
+
+int sm_count();
+
+// Optional per-family device timing (CUDA events on the launching stream), read by bench.py.
+enum ProfKind { PROF_GATHER = 0, PROF_PARITY, PROF_WGRAD, PROF_THIN, PROF_ELEM, PROF_KINDS };
+struct ProfScope {
+  int slot;
+  cudaStream_t stream;
+  ProfScope(int kind, cudaStream_t s, double work);
+  ~ProfScope();
+};
+
+// elementwise / BN (adp_elem.cu).  All tensors are [rows, C] (NHWC flattened), C % 4 == 0.
+// sums[0:C] += sum x, sums[C:2C] += sum x^2
+int bn_stats(int dtype, const void* x, long long rows, int C, double* sums, cudaStream_t s);
+// training: batch statistics from sums (+ running-stat update); eval: running statistics.
+int bn_finalize(const double* sums, long long rows, int C, const float* gamma, const float* beta,
+                float* running_mean, float* running_var, int training, float eps, float momentum,
+                float* scale, float* shift, float* mean, float* invstd, cudaStream_t s);
+// z = x*scale+shift (scale==NULL: z = x); out0 = lrelu(z, slope0); out1 (optional) = lrelu(z, slope1)
+int affine_act(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift,
+               float slope0, void* out0, float slope1, void* out1, cudaStream_t s);
+// gz = gA*act0'(z) + gB*act1'(z) (either may be NULL); z = x*scale+shift (scale NULL: z = x).
+// sums[0:C] += sum gz, sums[C:2C] += sum gz*xhat,  xhat = (x-mean)*invstd
+int act_bn_bwd_reduce(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, const void* gA, float slope0,
+                      const void* gB, float slope1, double* sums, cudaStream_t s);
+// mode 0: dx = gz (no BN); 1: dx = gz*scale (eval BN); 2: dx = scale*(gz - s1/M - xhat*s2/M) (batch stats)
+int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift,
+                     const float* mean, const float* invstd, const void* gA, float slope0,
+                     const void* gB, float slope1, const double* sums, int mode, void* dx, cudaStream_t s);
+// dgamma[c] = sums[C+c], dbeta[c] = sums[c]
+int bn_param_grads(const double* sums, int C, float* dgamma, float* dbeta, cudaStream_t s);
+// final head: y = act(u + bias); du = dy*act'(y) ; dbias[0] += sum du   (out_ch == 1)
+int head_bwd(const float* y, const float* dy, long long n, int final_sigmoid, float* du, float* dbias,
+             cudaStream_t s);
+int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t s);
+// src [R][16][C] fp32 -> dst [C][16][R] bf16
+int cast_transpose_taps(const float* src, void* dst, int R, int C, cudaStream_t s);
+
+// SIMT implicit-GEMM convolutions (adp_conv_simt.cu); T selected by dtype, fp32 accumulate,
+// weights always fp32 in the master layouts.
+// F1: y[b,oy,ox,n] = sum_{kh,kw,c} x[b,2oy-1+kh,2ox-1+kw,c] * w[n][kh*4+kw][c]; output split (y0: n<N0 | y1: rest)
+int simt_gather_conv(int dtype, const void* x, const float* w, void* y0, int N0, void* y1, int N1,
+                     int B, int Hi, int Wi, int C, cudaStream_t s);
+// F2: y[b,2i+a,2j+bb,n] = sum_{2x2 taps,c} x[b,i+a-1+th,j+bb-1+tw,c] * w[c][kh*4+kw][n]; input concat (x0:C0 | x1:C1)
+int simt_parity_convT(int dtype, const void* x0, int C0, const void* x1, int C1, const float* w, void* y,
+                      int B, int Hi, int Wi, int N, cudaStream_t s);
+// F3: dw[m][tap][n] += sum_{b,i,j} S[b,i,j,m] * G[b,2i-1+kh,2j-1+kw,n]; S = (s0:M0 | s1:M1) [B,Hs,Ws,*], G [B,2Hs,2Ws,N]
+int simt_wgrad(int dtype, const void* s0, int M0, const void* s1, int M1, const void* g, int N,
+               float* dw, int B, int Hs, int Ws, cudaStream_t s);
+// first conv (tiny Cin): x NCHW fp32 [B,Cin,H,W], w [N][16][Cin] -> NHWC [B,H/2,W/2,N]:
+// out0 = lrelu(conv, slope0), out1 (optional) = lrelu(conv, slope1)
+int first_conv_fprop(int dtype, const float* x, const float* w, float slope0, void* out0, float slope1,
+                     void* out1, int B, int H, int W, int Cin, int N, cudaStream_t s);
+int first_conv_wgrad(int dtype, const float* x, const void* dy, float* dw, int B, int H, int W, int Cin, int N,
+                     cudaStream_t s);
+// last convT (Cout = 1): inputs (x0 | x1) NHWC [B,Hi,Wi,C0+C1], w [C][16] fp32.
+// u = convT + bias; y = final act(u)  -> y fp32 [B,1,2Hi,2Wi]
+int last_convT_fprop(int dtype, const void* x0, int C0, const void* x1, int C1, const float* w,
+                     const float* bias, int final_sigmoid, float* y, int B, int Hi, int Wi, cudaStream_t s);
+// du fp32 [B,1,2Hi,2Wi] -> g0 [B,Hi,Wi,C0], g1 [B,Hi,Wi,C1]
+int last_convT_dgrad(int dtype, const float* du, const float* w, void* g0, int C0, void* g1, int C1,
+                     int B, int Hi, int Wi, cudaStream_t s);
+int last_convT_wgrad(int dtype, const void* x0, int C0, const void* x1, int C1, const float* du,
+                     float* dw, int B, int Hi, int Wi, cudaStream_t s);
+
+// tcgen05 paths (adp_conv_tc.cu), bf16 operands, fp32 accumulate in TMEM.
+// w_nk: bf16 [N][16][C] (K-major B operand)
+int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, int N1,
+                   int B, int Hi, int Wi, int C, cudaStream_t s);
+int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* w_nk, void* y,
+                    int B, int Hi, int Wi, int N, cudaStream_t s);
+int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int N,
+             float* dw, int B, int Hs, int Ws, cudaStream_t s);
+bool tc_supported_gather(int B, int Hi, int Wi, int C, int N0, int N1);
+bool tc_supported_parity(int B, int Hi, int Wi, int C0, int C1, int N);
+bool tc_supported_wgrad(int B, int Hs, int Ws, int M0, int M1, int N);
+// 0 = SIMT only, 1 = tcgen05 where supported (default).  Read from ADP_TC env once, or set explicitly.
+int tc_enabled();
+
+}  // namespace adp

@@ -1,0 +1,367 @@
+// Bandwidth-bound elementwise / reduction kernels of the U-Net: BatchNorm statistics and
+// normalise+activation, their backward, the output head, weight casts.
+//
+// Replaces, for models/unetbaseline_model.py:187-229: nn.BatchNorm2d (:190,:192,:219),
+// nn.LeakyReLU(0.2, inplace) (:189), nn.ReLU(inplace) (:191), torch.cat (:235, eliminated:
+// the decoder reads the two halves of the concat as two tensors) and nn.Sigmoid/ReLU head
+// (:201-206).  All activation tensors are NHWC, viewed as [rows = B*H*W, C].
+#include "adp_common.cuh"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+// ------------------------------------------------------------------ BN statistics
+// block (32, 8): threadIdx.x owns 4 consecutive channels, rows strided over threadIdx.y / blockIdx.y
+template <class T>
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const T* __restrict__ x, long long rows, int C, double* __restrict__ sums) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (c < C) {
+    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
+      float4 v = ld4(x + r * C + c);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]);
+      q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+    }
+  }
+  __shared__ float red[8][32][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red[threadIdx.y][threadIdx.x][i] = s[i];
+    red[threadIdx.y][threadIdx.x][4 + i] = q[i];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double a = 0.0, b = 0.0;
+      for (int y = 0; y < 8; ++y) {
+        a += (double)red[y][threadIdx.x][i];
+        b += (double)red[y][threadIdx.x][4 + i];
+      }
+      atomicAdd(&sums[c + i], a);
+      atomicAdd(&sums[C + c + i], b);
+    }
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long rows, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ rm, float* __restrict__ rv, int training, float eps,
+                                   float momentum, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_o, float* __restrict__ invstd_o) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, invstd;
+  if (training) {
+    double m = sums[c] / (double)rows;
+    double var = sums[C + c] / (double)rows - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (rm) {
+      double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+      rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
+      rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean = rm[c];
+    invstd = rsqrtf(rv[c] + eps);
+  }
+  float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  mean_o[c] = mean;
+  invstd_o[c] = invstd;
+}
+
+// ------------------------------------------------------------------ normalise + activation
+template <class T>
+__global__ void __launch_bounds__(EW_THREADS)
+affine_act_kernel(const T* __restrict__ x, long long n4, int C, const float* __restrict__ scale,
+                  const float* __restrict__ shift, float slope0, T* __restrict__ out0, float slope1,
+                  T* __restrict__ out1) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = ld4(x + 4 * i);
+    if (scale) {
+      int c = (int)((4 * i) % C);
+      float4 sc = ld4(scale + c), sh = ld4(shift + c);
+      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+      v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    }
+    st4(out0 + 4 * i, make_float4(lrelu(v.x, slope0), lrelu(v.y, slope0), lrelu(v.z, slope0), lrelu(v.w, slope0)));
+    if (out1)
+      st4(out1 + 4 * i, make_float4(lrelu(v.x, slope1), lrelu(v.y, slope1), lrelu(v.z, slope1), lrelu(v.w, slope1)));
+  }
+}
+
+// ------------------------------------------------------------------ backward: activation (+BN)
+template <class T>
+__device__ __forceinline__ float4 load_gz(const T* x, long long off, int c, const float* scale, const float* shift,
+                                          const T* gA, float slope0, const T* gB, float slope1, float4& xv) {
+  xv = ld4(x + off);
+  float4 z = xv;
+  if (scale) {
+    float4 sc = ld4(scale + c), sh = ld4(shift + c);
+    z.x = fmaf(z.x, sc.x, sh.x); z.y = fmaf(z.y, sc.y, sh.y);
+    z.z = fmaf(z.z, sc.z, sh.z); z.w = fmaf(z.w, sc.w, sh.w);
+  }
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (gA) {
+    float4 a = ld4(gA + off);
+    g.x = a.x * lrelu_grad(z.x, slope0); g.y = a.y * lrelu_grad(z.y, slope0);
+    g.z = a.z * lrelu_grad(z.z, slope0); g.w = a.w * lrelu_grad(z.w, slope0);
+  }
+  if (gB) {
+    float4 b = ld4(gB + off);
+    g.x = fmaf(b.x, lrelu_grad(z.x, slope1), g.x); g.y = fmaf(b.y, lrelu_grad(z.y, slope1), g.y);
+    g.z = fmaf(b.z, lrelu_grad(z.z, slope1), g.z); g.w = fmaf(b.w, lrelu_grad(z.w, slope1), g.w);
+  }
+  return g;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+act_bn_bwd_reduce_kernel(const T* __restrict__ x, long long rows, int C, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const T* __restrict__ gA, float slope0,
+                         const T* __restrict__ gB, float slope1, double* __restrict__ sums) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (c < C) {
+    float4 mu = ld4(mean + c), is = ld4(invstd + c);
+    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
+      float4 xv;
+      float4 g = load_gz(x, r * C + c, c, scale, shift, gA, slope0, gB, slope1, xv);
+      s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
+      q[0] = fmaf(g.x, (xv.x - mu.x) * is.x, q[0]); q[1] = fmaf(g.y, (xv.y - mu.y) * is.y, q[1]);
+      q[2] = fmaf(g.z, (xv.z - mu.z) * is.z, q[2]); q[3] = fmaf(g.w, (xv.w - mu.w) * is.w, q[3]);
+    }
+  }
+  __shared__ float red[8][32][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red[threadIdx.y][threadIdx.x][i] = s[i];
+    red[threadIdx.y][threadIdx.x][4 + i] = q[i];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double a = 0.0, b = 0.0;
+      for (int y = 0; y < 8; ++y) {
+        a += (double)red[y][threadIdx.x][i];
+        b += (double)red[y][threadIdx.x][4 + i];
+      }
+      atomicAdd(&sums[c + i], a);
+      atomicAdd(&sums[C + c + i], b);
+    }
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(EW_THREADS)
+act_bn_bwd_apply_kernel(const T* __restrict__ x, long long n4, long long rows, int C,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const T* __restrict__ gA, float slope0, const T* __restrict__ gB, float slope1,
+                        const double* __restrict__ sums, int mode, T* __restrict__ dx) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float inv_m = 1.f / (float)rows;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int c = (int)((4 * i) % C);
+    float4 xv;
+    float4 g = load_gz(x, 4 * i, c, scale, shift, gA, slope0, gB, slope1, xv);
+    if (mode == 1) {
+      float4 sc = ld4(scale + c);
+      g.x *= sc.x; g.y *= sc.y; g.z *= sc.z; g.w *= sc.w;
+    } else if (mode == 2) {
+      float4 sc = ld4(scale + c), mu = ld4(mean + c), is = ld4(invstd + c);
+      float s1[4], s2[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s1[k] = (float)sums[c + k] * inv_m;
+        s2[k] = (float)sums[C + c + k] * inv_m;
+      }
+      g.x = sc.x * (g.x - s1[0] - (xv.x - mu.x) * is.x * s2[0]);
+      g.y = sc.y * (g.y - s1[1] - (xv.y - mu.y) * is.y * s2[1]);
+      g.z = sc.z * (g.z - s1[2] - (xv.z - mu.z) * is.z * s2[2]);
+      g.w = sc.w * (g.w - s1[3] - (xv.w - mu.w) * is.w * s2[3]);
+    }
+    st4(dx + 4 * i, g);
+  }
+}
+
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    dbeta[c] = (float)sums[c];
+    dgamma[c] = (float)sums[C + c];
+  }
+}
+
+// ------------------------------------------------------------------ output head backward
+__global__ void __launch_bounds__(EW_THREADS)
+head_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, long long n, int final_sigmoid,
+                float* __restrict__ du, float* __restrict__ dbias) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float yv = y[i], g = dy[i];
+    float d = final_sigmoid ? g * yv * (1.f - yv) : (yv > 0.f ? g : 0.f);
+    du[i] = d;
+    acc += d;
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[EW_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < EW_THREADS / 32; ++w) t += red[w];
+    atomicAdd(dbias, t);
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+    st4(dst + 4 * i, ld4(src + 4 * i));
+}
+
+// src [R][16][C] fp32 -> dst [C][16][R] bf16, 32x32 tiles per tap through shared memory
+__global__ void __launch_bounds__(256)
+cast_transpose_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int R, int C) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int r = r0 + y, c = c0 + threadIdx.x;
+    tile[y][threadIdx.x] = (r < R && c < C) ? src[((size_t)r * 16 + tap) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int c = c0 + y, r = r0 + threadIdx.x;
+    if (c < C && r < R) dst[((size_t)c * 16 + tap) * R + r] = __float2bfloat16_rn(tile[threadIdx.x][y]);
+  }
+}
+
+int ew_grid(long long n4) {
+  long long blocks = (n4 + EW_THREADS - 1) / EW_THREADS;
+  long long cap = (long long)adp::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+dim3 col_grid(long long rows, int C) {
+  int gx = adp_cdiv(C, 128);
+  long long gy = (rows + 63) / 64;  // >= 8 rows per thread
+  long long cap = (long long)adp::sm_count() * 4 / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  return dim3(gx, (unsigned)gy);
+}
+
+}  // namespace
+
+namespace adp {
+
+#define ADP_DISPATCH_T(dtype, ...)                          \
+  if ((dtype) == ADP_F32) {                                 \
+    using T = float;                                        \
+    __VA_ARGS__                                             \
+  } else if ((dtype) == ADP_BF16) {                         \
+    using T = bf16;                                         \
+    __VA_ARGS__                                             \
+  } else {                                                  \
+    adp_set_error("unknown dtype %d", (int)(dtype));        \
+    return ADP_ERR_ARG;                                     \
+  }
+
+int bn_stats(int dtype, const void* x, long long rows, int C, double* sums, cudaStream_t s) {
+  ADP_CHECK_ARG(C % 4 == 0, "bn_stats: C %% 4 != 0");
+  ADP_DISPATCH_T(dtype, bn_stats_kernel<T><<<col_grid(rows, C), dim3(32, 8), 0, s>>>((const T*)x, rows, C, sums);)
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int bn_finalize(const double* sums, long long rows, int C, const float* gamma, const float* beta,
+                float* running_mean, float* running_var, int training, float eps, float momentum,
+                float* scale, float* shift, float* mean, float* invstd, cudaStream_t s) {
+  bn_finalize_kernel<<<adp_cdiv(C, 128), 128, 0, s>>>(sums, rows, C, gamma, beta, running_mean, running_var,
+                                                      training, eps, momentum, scale, shift, mean, invstd);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int affine_act(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift,
+               float slope0, void* out0, float slope1, void* out1, cudaStream_t s) {
+  ADP_CHECK_ARG(C % 4 == 0, "affine_act: C %% 4 != 0");
+  long long n4 = rows * C / 4;
+  ADP_DISPATCH_T(dtype, affine_act_kernel<T><<<ew_grid(n4), EW_THREADS, 0, s>>>(
+                            (const T*)x, n4, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1);)
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int act_bn_bwd_reduce(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, const void* gA, float slope0, const void* gB,
+                      float slope1, double* sums, cudaStream_t s) {
+  ADP_CHECK_ARG(C % 4 == 0, "act_bn_bwd_reduce: C %% 4 != 0");
+  ADP_DISPATCH_T(dtype, act_bn_bwd_reduce_kernel<T><<<col_grid(rows, C), dim3(32, 8), 0, s>>>(
+                            (const T*)x, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
+                            (const T*)gB, slope1, sums);)
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift,
+                     const float* mean, const float* invstd, const void* gA, float slope0, const void* gB,
+                     float slope1, const double* sums, int mode, void* dx, cudaStream_t s) {
+  ADP_CHECK_ARG(C % 4 == 0, "act_bn_bwd_apply: C %% 4 != 0");
+  long long n4 = rows * C / 4;
+  ADP_DISPATCH_T(dtype, act_bn_bwd_apply_kernel<T><<<ew_grid(n4), EW_THREADS, 0, s>>>(
+                            (const T*)x, n4, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
+                            (const T*)gB, slope1, sums, mode, (T*)dx);)
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int bn_param_grads(const double* sums, int C, float* dgamma, float* dbeta, cudaStream_t s) {
+  bn_param_grads_kernel<<<adp_cdiv(C, 128), 128, 0, s>>>(sums, C, dgamma, dbeta);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int head_bwd(const float* y, const float* dy, long long n, int final_sigmoid, float* du, float* dbias,
+             cudaStream_t s) {
+  long long blocks = (n + EW_THREADS * 8 - 1) / (EW_THREADS * 8);
+  long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  head_bwd_kernel<<<(int)blocks, EW_THREADS, 0, s>>>(y, dy, n, final_sigmoid, du, dbias);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t s) {
+  ADP_CHECK_ARG(n % 4 == 0, "cast: n %% 4 != 0");
+  cast_kernel<<<ew_grid(n / 4), EW_THREADS, 0, s>>>(src, (bf16*)dst, n / 4);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int cast_transpose_taps(const float* src, void* dst, int R, int C, cudaStream_t s) {
+  dim3 grid(adp_cdiv(C, 32), adp_cdiv(R, 32), 16);
+  cast_transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(src, (bf16*)dst, R, C);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+}  // namespace adp

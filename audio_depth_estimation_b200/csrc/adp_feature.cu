@@ -1,0 +1,252 @@
+// Waveform -> |STFT| -> (log, per-channel min-max) -> antialiased bilinear resize.
+//
+// Replaces the library ops reached by the reference at
+//   dataloader/BatvisionV2_Dataset.py:96-135, :177-185   (T.Spectrogram, log, min-max, Resize)
+//   dataloader/BatvisionV1_Dataset.py:70-78,  :86-95     (T.Spectrogram, Resize)
+//   dataloader/utils_dataset.py:18-20                    (transforms.Resize((S,S)))
+//
+// T.Spectrogram(n_fft, win_length, hop, power=1) == torch.stft(center=True, reflect pad,
+// periodic Hann of win_length zero-padded (centred) to n_fft, onesided) + abs.  Because the
+// window has only win_length non-zero taps, frame t touches x[t*hop + n - win/2], n < win, and
+//   S[k,t] = | sum_n hann[n] * xr[t*hop + n - win/2] * exp(-2*pi*i*k*n/n_fft) |
+// (the centring offset is a unit phase factor).  This file evaluates that pruned DFT directly:
+// one thread owns one bin k and FRAMES_PER_THREAD frames, the windowed twiddle w[n]*W^(kn) is
+// read once per tap and reused over the frames, samples are staged in shared memory and read
+// as broadcast float4.
+#include "adp_common.cuh"
+
+namespace {
+
+constexpr int STFT_THREADS = 256;
+constexpr int FRAMES_PER_THREAD = 16;
+constexpr int FRAME_GROUPS = 4;
+constexpr int FRAMES_PER_BLOCK = FRAMES_PER_THREAD * FRAME_GROUPS;  // 64
+
+// grid: (ceil(T / 64), rows).  smem: twiddle[n_fft] float2 | window[win] | samples[(64-1)*hop + win]
+__global__ void __launch_bounds__(STFT_THREADS)
+stft_mag_kernel(const float* __restrict__ wave, int L, int pitch, int n_fft, int win, int hop, int T,
+                float* __restrict__ spec, int log_mode, int* __restrict__ minmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tw = reinterpret_cast<float2*>(smem_raw);
+  float* wnd = reinterpret_cast<float*>(tw + n_fft);
+  float* xs = wnd + win;  // 16-byte aligned: n_fft*8 + win*4 with win % 4 == 0
+
+  const int row = blockIdx.y;
+  const int t0 = blockIdx.x * FRAMES_PER_BLOCK;
+  const int nsamp = (FRAMES_PER_BLOCK - 1) * hop + win;
+  const int F = n_fft / 2 + 1;
+  const float* x = wave + (size_t)row * pitch;
+
+  for (int i = threadIdx.x; i < n_fft; i += STFT_THREADS) {
+    float s, c;
+    sincospif(2.0f * (float)i / (float)n_fft, &s, &c);
+    tw[i] = make_float2(c, -s);
+  }
+  for (int i = threadIdx.x; i < win; i += STFT_THREADS)
+    wnd[i] = 0.5f - 0.5f * cospif(2.0f * (float)i / (float)win);
+  for (int i = threadIdx.x; i < nsamp; i += STFT_THREADS) {
+    int j = t0 * hop + i - win / 2;
+    if (j < 0) j = -j;
+    if (j >= L) j = 2 * (L - 1) - j;
+    j = min(max(j, 0), L - 1);
+    xs[i] = x[j];
+  }
+  __syncthreads();
+
+  float vmin = INFINITY, vmax = -INFINITY;
+  const int items = F * FRAME_GROUPS;
+  for (int item = threadIdx.x; item < items; item += STFT_THREADS) {
+    const int g = item / F;  // frame group; consecutive lanes -> consecutive k
+    const int k = item - g * F;
+    const int tb = g * FRAMES_PER_THREAD;
+    if (t0 + tb >= T) continue;
+    float re[FRAMES_PER_THREAD], im[FRAMES_PER_THREAD];
+#pragma unroll
+    for (int f = 0; f < FRAMES_PER_THREAD; ++f) re[f] = im[f] = 0.f;
+    const float* xb = xs + tb * hop;
+    int idx = 0;  // (k * n) mod n_fft
+    for (int n = 0; n < win; n += 4) {
+      float2 w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 t = tw[idx];
+        float wn = wnd[n + q];
+        w[q] = make_float2(t.x * wn, t.y * wn);
+        idx += k;
+        if (idx >= n_fft) idx -= n_fft;
+      }
+#pragma unroll
+      for (int f = 0; f < FRAMES_PER_THREAD; ++f) {
+        float4 v = *reinterpret_cast<const float4*>(xb + f * hop + n);
+        re[f] = fmaf(v.x, w[0].x, re[f]);
+        im[f] = fmaf(v.x, w[0].y, im[f]);
+        re[f] = fmaf(v.y, w[1].x, re[f]);
+        im[f] = fmaf(v.y, w[1].y, im[f]);
+        re[f] = fmaf(v.z, w[2].x, re[f]);
+        im[f] = fmaf(v.z, w[2].y, im[f]);
+        re[f] = fmaf(v.w, w[3].x, re[f]);
+        im[f] = fmaf(v.w, w[3].y, im[f]);
+      }
+    }
+    float* out = spec + ((size_t)row * F + k) * T + t0 + tb;
+#pragma unroll
+    for (int f = 0; f < FRAMES_PER_THREAD; ++f) {
+      if (t0 + tb + f < T) {
+        float m = sqrtf(re[f] * re[f] + im[f] * im[f]);
+        if (log_mode) {
+          m = logf(m + 1e-8f);
+          vmin = fminf(vmin, m);
+          vmax = fmaxf(vmax, m);
+        }
+        out[f] = m;
+      }
+    }
+  }
+  if (log_mode) {
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0 && vmin <= vmax) {
+      atomicMin(&minmax[2 * row], float_to_ordered(vmin));
+      atomicMax(&minmax[2 * row + 1], float_to_ordered(vmax));
+    }
+  }
+}
+
+__global__ void init_minmax_kernel(int* mm, int rows) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) {
+    mm[2 * i] = float_to_ordered(INFINITY);
+    mm[2 * i + 1] = float_to_ordered(-INFINITY);
+  }
+}
+
+// aten::_upsample_bilinear2d_aa index/weight rule for one axis (align_corners = False)
+struct AxisTaps {
+  int lo, size;
+  float center, invscale, total;
+};
+__device__ __forceinline__ float aa_w(const AxisTaps& a, int j) {
+  float t = fabsf(((float)(j + a.lo) - a.center + 0.5f) * a.invscale);
+  return t < 1.f ? 1.f - t : 0.f;
+}
+__device__ __forceinline__ AxisTaps aa_axis(int i, int n_in, int n_out) {
+  AxisTaps a;
+  float scale = (float)n_in / (float)n_out;
+  float support = scale >= 1.f ? scale : 1.f;
+  a.invscale = scale >= 1.f ? 1.f / scale : 1.f;
+  a.center = scale * ((float)i + 0.5f);
+  a.lo = max((int)(a.center - support + 0.5f), 0);
+  a.size = min((int)(a.center + support + 0.5f), n_in) - a.lo;
+  float tot = 0.f;
+  for (int j = 0; j < a.size; ++j) tot += aa_w(a, j);
+  a.total = tot;
+  return a;
+}
+
+// in [rows,H,W] -> out [rows,S,S]; optional (x - min)/(max - min) per row applied on load.
+__global__ void __launch_bounds__(256)
+resize_aa_kernel(const float* __restrict__ in, int H, int W, int S, float* __restrict__ out,
+                 const int* __restrict__ minmax) {
+  const int row = blockIdx.z;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if (o >= S) return;
+  float mn = 0.f, den = 1.f;
+  bool zero = false;
+  if (minmax) {
+    mn = ordered_to_float(minmax[2 * row]);
+    float mx = ordered_to_float(minmax[2 * row + 1]);
+    zero = !(mx > mn);
+    den = mx - mn;
+  }
+  AxisTaps ah = aa_axis(p, H, S);
+  AxisTaps aw = aa_axis(o, W, S);
+  const float* src = in + (size_t)row * H * W;
+  float acc = 0.f;
+  for (int jh = 0; jh < ah.size; ++jh) {
+    const float* line = src + (size_t)(ah.lo + jh) * W + aw.lo;
+    float hacc = 0.f;
+    for (int jw = 0; jw < aw.size; ++jw) {
+      float v = line[jw];
+      if (minmax) v = (v - mn) / den;
+      hacc += v * (aw.total != 0.f ? aa_w(aw, jw) / aw.total : aa_w(aw, jw));
+    }
+    acc += hacc * (ah.total != 0.f ? aa_w(ah, jh) / ah.total : aa_w(ah, jh));
+  }
+  if (zero) acc = 0.f;
+  out[((size_t)row * S + p) * S + o] = acc;
+}
+
+int check_stft_args(int rows, int L, int pitch, int n_fft, int win, int hop) {
+  ADP_CHECK_ARG(rows > 0 && L > 0 && pitch >= L, "stft: bad rows/L/pitch (%d,%d,%d)", rows, L, pitch);
+  ADP_CHECK_ARG(n_fft >= 8 && n_fft <= 4096 && n_fft % 2 == 0, "stft: n_fft %d unsupported", n_fft);
+  ADP_CHECK_ARG(win > 0 && win <= n_fft && win % 4 == 0, "stft: win_length %d must be a multiple of 4 and <= n_fft", win);
+  ADP_CHECK_ARG(hop > 0 && hop % 4 == 0, "stft: hop %d must be a positive multiple of 4", hop);
+  ADP_CHECK_ARG(n_fft / 2 < L, "stft: reflect padding needs n_fft/2 < L");
+  return ADP_OK;
+}
+
+size_t stft_smem(int n_fft, int win, int hop) {
+  return (size_t)n_fft * 8 + (size_t)win * 4 + (size_t)((FRAMES_PER_BLOCK - 1) * hop + win) * 4;
+}
+
+int launch_stft(const float* wave, int rows, int L, int pitch, int n_fft, int win, int hop, float* spec,
+                int log_mode, int* minmax, cudaStream_t s) {
+  const int T = 1 + L / hop;
+  size_t smem = stft_smem(n_fft, win, hop);
+  ADP_CHECK_ARG(smem <= 200 * 1024, "stft: shared memory %zu too large", smem);
+  if (smem > 48 * 1024)
+    ADP_CUDA(cudaFuncSetAttribute(stft_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(adp_cdiv(T, FRAMES_PER_BLOCK), rows);
+  stft_mag_kernel<<<grid, STFT_THREADS, smem, s>>>(wave, L, pitch, n_fft, win, hop, T, spec, log_mode, minmax);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+}  // namespace
+
+extern "C" int adp_stft_mag(const float* wave, int rows, int L, int wave_pitch, int n_fft, int win_length,
+                            int hop, float* spec, void* stream) {
+  ADP_TRY(check_stft_args(rows, L, wave_pitch, n_fft, win_length, hop));
+  ADP_CHECK_ARG(wave && spec, "stft: null pointer");
+  return launch_stft(wave, rows, L, wave_pitch, n_fft, win_length, hop, spec, 0, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" size_t adp_feature_workspace_bytes(int rows, int L, int n_fft, int hop) {
+  if (rows <= 0 || L <= 0 || n_fft <= 0 || hop <= 0) return 0;
+  size_t T = 1 + (size_t)L / hop, F = (size_t)n_fft / 2 + 1;
+  return adp_align_up((size_t)rows * F * T * 4, 256) + adp_align_up((size_t)rows * 8, 256);
+}
+
+extern "C" int adp_resize_aa(const float* in, int rows, int H, int W, int out_size, float* out, void* stream) {
+  ADP_CHECK_ARG(in && out && rows > 0 && H > 0 && W > 0 && out_size > 0, "resize: bad arguments");
+  ADP_CHECK_ARG(rows <= 65535 && out_size <= 65535, "resize: rows/out_size too large for one launch");
+  dim3 grid(adp_cdiv(out_size, 256), out_size, rows);
+  resize_aa_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, H, W, out_size, out, nullptr);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+extern "C" int adp_feature_forward(const float* wave, int rows, int L, int wave_pitch, int n_fft, int win_length,
+                                   int hop, int log_minmax, int out_size, float* out, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ADP_TRY(check_stft_args(rows, L, wave_pitch, n_fft, win_length, hop));
+  ADP_CHECK_ARG(wave && out && workspace, "feature: null pointer");
+  ADP_CHECK_ARG(out_size > 0 && out_size <= 65535 && rows <= 65535, "feature: bad out_size/rows");
+  ADP_CHECK_ARG(workspace_bytes >= adp_feature_workspace_bytes(rows, L, n_fft, hop),
+                "feature: workspace too small (%zu)", workspace_bytes);
+  const int T = 1 + L / hop, F = n_fft / 2 + 1;
+  float* spec = reinterpret_cast<float*>(workspace);
+  int* minmax = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) +
+                                       adp_align_up((size_t)rows * F * T * 4, 256));
+  if (log_minmax) {
+    init_minmax_kernel<<<adp_cdiv(rows, 256), 256, 0, s>>>(minmax, rows);
+    ADP_LAUNCH_CHECK();
+  }
+  ADP_TRY(launch_stft(wave, rows, L, wave_pitch, n_fft, win_length, hop, spec, log_minmax ? 1 : 0, minmax, s));
+  dim3 grid(adp_cdiv(out_size, 256), out_size, rows);
+  resize_aa_kernel<<<grid, 256, 0, s>>>(spec, F, T, out_size, out, log_minmax ? minmax : nullptr);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}

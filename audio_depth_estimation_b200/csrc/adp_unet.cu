@@ -1,0 +1,356 @@
+// U-Net orchestration: the whole UnetGenerator forward and backward as one stream of kernel
+// launches (no host synchronisation, CUDA-graph capturable), plus the per-layer C ABI.
+//
+// Dataflow of models/unetbaseline_model.py:123-235, level l = 0 outermost:
+//   e[0] = Conv(x);  a[l] = LeakyReLU_0.2(bn(e[l]));  r[l] = ReLU(bn(e[l]))   (the in-place
+//   LeakyReLU followed by the parent's in-place ReLU makes the skip ReLU(e), App. D-1)
+//   e[l] = Conv(a[l-1]) (+BatchNorm for 0 < l < D-1)
+//   t[l-1] = ConvT(r[l] | q[l])  (l = D-1: r only);  q[l-1] = ReLU(BatchNorm(t[l-1]))
+//   y = act(ConvT(r[0] | q[0]) + bias)
+// torch.cat never materialises: the transposed convolutions read the two halves as two tensors.
+#include <string.h>
+#include "adp_common.cuh"
+
+namespace {
+
+using namespace adp;
+
+struct LevelPlan {
+  int cin, cout, hin, hout;      // encoder conv of this level
+  int t_c1, t_cout;              // decoder convT: inputs (r: cout | q: t_c1), output channels t_cout
+  bool bn_down, bn_up;
+  size_t e, a, r, t, q;          // activations (level-l shaped: [B,hout,hout,cout])
+  size_t g_a, g_r, g_q, g_e, g_t;
+  size_t bn_down_f, bn_up_f;     // float[4*C]: scale, shift, mean, invstd
+  size_t sums_down, sums_up;     // double[2C] forward statistics
+  size_t bsums_down, bsums_up;   // double[2C] backward reductions
+  size_t wb_conv_nk, wb_conv_t, wb_convT_nk, wb_convT_t;
+};
+
+struct Plan {
+  int D, B, esz;
+  LevelPlan lv[ADP_MAX_LEVELS];
+  size_t du;                     // float [B,1,S,S]
+  size_t sums_begin, sums_end;   // forward BN sums region (zeroed every forward)
+  size_t bsums_begin, bsums_end; // backward sums region
+  size_t total;
+};
+
+int make_plan(const adp_unet_desc* d, Plan* p) {
+  ADP_CHECK_ARG(d, "unet: null descriptor");
+  ADP_CHECK_ARG(d->num_downs >= 2 && d->num_downs <= ADP_MAX_LEVELS, "unet: num_downs %d unsupported", d->num_downs);
+  ADP_CHECK_ARG(d->batch > 0 && d->ngf > 0 && d->ngf % 4 == 0, "unet: bad batch/ngf");
+  ADP_CHECK_ARG(d->out_ch == 1, "unet: output_nc must be 1 (define_G call sites: train.py:381, test.py:120)");
+  ADP_CHECK_ARG(d->in_ch >= 1 && d->in_ch <= 16, "unet: input_nc %d unsupported", d->in_ch);
+  ADP_CHECK_ARG(d->size > 0 && d->size % (1 << d->num_downs) == 0, "unet: size %d not divisible by 2^num_downs", d->size);
+  ADP_CHECK_ARG(d->dtype == ADP_F32 || d->dtype == ADP_BF16, "unet: bad dtype");
+  const int D = d->num_downs;
+  p->D = D; p->B = d->batch; p->esz = d->dtype == ADP_F32 ? 4 : 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += adp_align_up(bytes, 256); return o; };
+  int ch[ADP_MAX_LEVELS];
+  for (int l = 0; l < D; ++l) ch[l] = d->ngf * (l < 3 ? (1 << l) : 8);
+  for (int l = 0; l < D; ++l) {
+    LevelPlan& L = p->lv[l];
+    L.cin = l == 0 ? d->in_ch : ch[l - 1];
+    L.cout = ch[l];
+    L.hin = d->size >> l;
+    L.hout = L.hin / 2;
+    L.t_c1 = l == D - 1 ? 0 : ch[l];
+    L.t_cout = l == 0 ? d->out_ch : ch[l - 1];
+    L.bn_down = l > 0 && l < D - 1;
+    L.bn_up = l > 0;
+  }
+  p->sums_begin = off;
+  for (int l = 0; l < D; ++l) {
+    LevelPlan& L = p->lv[l];
+    L.sums_down = take(sizeof(double) * 2 * L.cout);
+    L.sums_up = take(sizeof(double) * 2 * (L.t_cout > 4 ? L.t_cout : 4));
+  }
+  p->sums_end = off;
+  p->bsums_begin = off;
+  for (int l = 0; l < D; ++l) {
+    LevelPlan& L = p->lv[l];
+    L.bsums_down = take(sizeof(double) * 2 * L.cout);
+    L.bsums_up = take(sizeof(double) * 2 * (L.t_cout > 4 ? L.t_cout : 4));
+  }
+  p->bsums_end = off;
+  for (int l = 0; l < D; ++l) {
+    LevelPlan& L = p->lv[l];
+    const size_t act = (size_t)d->batch * L.hout * L.hout * L.cout * p->esz;
+    L.bn_down_f = take(sizeof(float) * 4 * L.cout);
+    L.bn_up_f = take(sizeof(float) * 4 * (L.t_cout > 4 ? L.t_cout : 4));
+    L.e = take(act); L.a = take(act); L.r = take(act);
+    L.g_a = take(act); L.g_r = take(act); L.g_e = take(act);
+    if (l < D - 1) { L.t = take(act); L.q = take(act); L.g_q = take(act); L.g_t = take(act); }
+    else { L.t = L.q = L.g_q = L.g_t = 0; }
+    const size_t wc = (size_t)L.cout * 16 * L.cin * 2, wt = (size_t)(L.cout + L.t_c1) * 16 * L.t_cout * 2;
+    L.wb_conv_nk = take(wc); L.wb_conv_t = take(wc);
+    L.wb_convT_nk = take(wt); L.wb_convT_t = take(wt);
+  }
+  p->du = take((size_t)d->batch * d->size * d->size * sizeof(float));
+  p->total = off;
+  return ADP_OK;
+}
+
+inline char* at(void* ws, size_t off) { return reinterpret_cast<char*>(ws) + off; }
+
+struct BnBuf { float *scale, *shift, *mean, *invstd; };
+inline BnBuf bnbuf(void* ws, size_t off, int C) {
+  float* f = reinterpret_cast<float*>(at(ws, off));
+  return BnBuf{f, f + C, f + 2 * C, f + 3 * C};
+}
+
+bool use_tc(int dtype) { return dtype == ADP_BF16 && tc_enabled(); }
+
+// ---- family dispatch: tensor cores when the operands are bf16 and the shape is supported
+int conv_gather(int dtype, const void* x, const float* w, const void* wb, void* y0, int N0, void* y1, int N1,
+                int B, int Hi, int Wi, int C, cudaStream_t s) {
+  ProfScope prof(PROF_GATHER, s, 2.0 * B * (Hi / 2) * (Wi / 2) * (double)(N0 + N1) * 16.0 * C);
+  if (use_tc(dtype) && wb && tc_supported_gather(B, Hi, Wi, C, N0, N1))
+    return tc_gather_conv(x, wb, y0, N0, y1, N1, B, Hi, Wi, C, s);
+  return simt_gather_conv(dtype, x, w, y0, N0, y1, N1, B, Hi, Wi, C, s);
+}
+int conv_parity(int dtype, const void* x0, int C0, const void* x1, int C1, const float* w, const void* wb, void* y,
+                int B, int Hi, int Wi, int N, cudaStream_t s) {
+  ProfScope prof(PROF_PARITY, s, 2.0 * B * Hi * Wi * 4.0 * (double)N * 4.0 * (C0 + C1));
+  if (use_tc(dtype) && wb && tc_supported_parity(B, Hi, Wi, C0, C1, N))
+    return tc_parity_convT(x0, C0, x1, C1, wb, y, B, Hi, Wi, N, s);
+  return simt_parity_convT(dtype, x0, C0, x1, C1, w, y, B, Hi, Wi, N, s);
+}
+int conv_wgrad(int dtype, const void* s0, int M0, const void* s1, int M1, const void* g, int N, float* dw,
+               int B, int Hs, int Ws, cudaStream_t s) {
+  ProfScope prof(PROF_WGRAD, s, 2.0 * B * Hs * Ws * 16.0 * (double)N * (M0 + M1));
+  if (use_tc(dtype) && tc_supported_wgrad(B, Hs, Ws, M0, M1, N))
+    return tc_wgrad(s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s);
+  return simt_wgrad(dtype, s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s);
+}
+
+int check_params(const adp_unet_desc* d, const Plan& p, const adp_unet_level* params) {
+  ADP_CHECK_ARG(params, "unet: null params");
+  for (int l = 0; l < p.D; ++l) {
+    const LevelPlan& L = p.lv[l];
+    ADP_CHECK_ARG(params[l].conv_w && params[l].convT_w, "unet: level %d missing conv weights", l);
+    if (L.bn_down)
+      ADP_CHECK_ARG(params[l].bn_down_w && params[l].bn_down_b && params[l].bn_down_rm && params[l].bn_down_rv,
+                    "unet: level %d missing down-norm tensors", l);
+    if (L.bn_up)
+      ADP_CHECK_ARG(params[l].bn_up_w && params[l].bn_up_b && params[l].bn_up_rm && params[l].bn_up_rv,
+                    "unet: level %d missing up-norm tensors", l);
+  }
+  (void)d;
+  return ADP_OK;
+}
+
+}  // namespace
+
+extern "C" size_t adp_unet_workspace_bytes(const adp_unet_desc* d) {
+  Plan p;
+  if (make_plan(d, &p) != ADP_OK) return 0;
+  return p.total;
+}
+
+extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const adp_unet_level* params,
+                                void* ws, size_t ws_bytes, float* y, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  Plan p;
+  ADP_TRY(make_plan(d, &p));
+  ADP_TRY(check_params(d, p, params));
+  ADP_CHECK_ARG(x && y && ws && ws_bytes >= p.total, "unet_forward: null pointer or workspace too small (%zu < %zu)",
+                ws_bytes, p.total);
+  const int D = p.D, B = p.B, dt = d->dtype;
+  const bool tc = use_tc(dt);
+
+  if (tc && !d->reuse_weight_cache) {
+    for (int l = 0; l < D; ++l) {
+      const LevelPlan& L = p.lv[l];
+      if (l > 0) {
+        ADP_TRY(cast_f32_to_bf16(params[l].conv_w, at(ws, L.wb_conv_nk), (long long)L.cout * 16 * L.cin, s));
+        ADP_TRY(cast_transpose_taps(params[l].conv_w, at(ws, L.wb_conv_t), L.cout, L.cin, s));
+        ADP_TRY(cast_f32_to_bf16(params[l].convT_w, at(ws, L.wb_convT_nk), (long long)(L.cout + L.t_c1) * 16 * L.t_cout, s));
+        ADP_TRY(cast_transpose_taps(params[l].convT_w, at(ws, L.wb_convT_t), L.cout + L.t_c1, L.t_cout, s));
+      }
+    }
+  }
+  if (d->training)
+    ADP_CUDA(cudaMemsetAsync(at(ws, p.sums_begin), 0, p.sums_end - p.sums_begin, s));
+
+  // ---- encoder
+  {
+    const LevelPlan& L = p.lv[0];
+    ADP_TRY(first_conv_fprop(dt, x, params[0].conv_w, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), B, L.hin, L.hin, L.cin,
+                             L.cout, s));
+  }
+  for (int l = 1; l < D; ++l) {
+    const LevelPlan& L = p.lv[l];
+    const long long rows = (long long)B * L.hout * L.hout;
+    ADP_TRY(conv_gather(dt, at(ws, p.lv[l - 1].a), params[l].conv_w, tc ? at(ws, L.wb_conv_nk) : nullptr,
+                        at(ws, L.e), L.cout, nullptr, 0, B, L.hin, L.hin, L.cin, s));
+    if (L.bn_down) {
+      BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
+      double* sums = reinterpret_cast<double*>(at(ws, L.sums_down));
+      if (d->training) ADP_TRY(bn_stats(dt, at(ws, L.e), rows, L.cout, sums, s));
+      ADP_TRY(bn_finalize(sums, rows, L.cout, params[l].bn_down_w, params[l].bn_down_b, params[l].bn_down_rm,
+                          params[l].bn_down_rv, d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean,
+                          bn.invstd, s));
+      ADP_TRY(affine_act(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), s));
+    } else {
+      ADP_TRY(affine_act(dt, at(ws, L.e), rows, L.cout, nullptr, nullptr, 0.f, at(ws, L.r), 0.f, nullptr, s));
+    }
+  }
+  // ---- decoder
+  for (int l = D - 1; l >= 1; --l) {
+    const LevelPlan& L = p.lv[l];
+    const LevelPlan& O = p.lv[l - 1];  // output lives at level l-1's resolution
+    const long long rows = (long long)B * O.hout * O.hout;
+    ADP_TRY(conv_parity(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, params[l].convT_w,
+                        tc ? at(ws, L.wb_convT_t) : nullptr, at(ws, O.t), B, L.hout, L.hout, L.t_cout, s));
+    BnBuf bn = bnbuf(ws, L.bn_up_f, L.t_cout);
+    double* sums = reinterpret_cast<double*>(at(ws, L.sums_up));
+    if (d->training) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));
+    ADP_TRY(bn_finalize(sums, rows, L.t_cout, params[l].bn_up_w, params[l].bn_up_b, params[l].bn_up_rm,
+                        params[l].bn_up_rv, d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean,
+                        bn.invstd, s));
+    ADP_TRY(affine_act(dt, at(ws, O.t), rows, L.t_cout, bn.scale, bn.shift, 0.f, at(ws, O.q), 0.f, nullptr, s));
+  }
+  {
+    const LevelPlan& L = p.lv[0];
+    ADP_TRY(last_convT_fprop(dt, at(ws, L.r), L.cout, at(ws, L.q), L.t_c1, params[0].convT_w, params[0].convT_bias,
+                             d->final_sigmoid, y, B, L.hout, L.hout, s));
+  }
+  return ADP_OK;
+}
+
+extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, const float* y, const float* dy,
+                                        const adp_unet_level* params, const adp_unet_level* grads, void* ws,
+                                        size_t ws_bytes, int stage_begin, int stage_end, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  Plan p;
+  ADP_TRY(make_plan(d, &p));
+  ADP_TRY(check_params(d, p, params));
+  ADP_CHECK_ARG(x && y && dy && grads && ws && ws_bytes >= p.total, "unet_backward: null pointer or workspace too small");
+  const int D = p.D, B = p.B, dt = d->dtype;
+  ADP_CHECK_ARG(stage_begin >= 0 && stage_end <= 2 * D && stage_begin <= stage_end, "unet_backward: bad stage range");
+  const bool tc = use_tc(dt);
+  const int bn_mode = d->training ? 2 : 1;
+
+  // BatchNorm + ReLU backward of q[l] (up-norm of level l+1): g_q[l] -> g_t[l]
+  auto up_norm_bwd = [&](int l) -> int {
+    const LevelPlan& L = p.lv[l];
+    const LevelPlan& U = p.lv[l + 1];
+    const long long rows = (long long)B * L.hout * L.hout;
+    const int C = U.t_cout;
+    BnBuf bn = bnbuf(ws, U.bn_up_f, C);
+    double* bs = reinterpret_cast<double*>(at(ws, U.bsums_up));
+    ADP_TRY(act_bn_bwd_reduce(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f,
+                              nullptr, 0.f, bs, s));
+    ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f,
+                             nullptr, 0.f, bs, bn_mode, at(ws, L.g_t), s));
+    ADP_TRY(bn_param_grads(bs, C, grads[l + 1].bn_up_w, grads[l + 1].bn_up_b, s));
+    return ADP_OK;
+  };
+
+  for (int st = stage_begin; st < stage_end; ++st) {
+    if (st == 0) {
+      const LevelPlan& L = p.lv[0];
+      const int Ct = L.cout + L.t_c1;
+      ADP_CUDA(cudaMemsetAsync(at(ws, p.bsums_begin), 0, p.bsums_end - p.bsums_begin, s));
+      float* du = reinterpret_cast<float*>(at(ws, p.du));
+      ADP_CHECK_ARG(grads[0].convT_bias, "unet_backward: level 0 convT bias gradient missing");
+      ADP_CUDA(cudaMemsetAsync(grads[0].convT_bias, 0, sizeof(float), s));
+      ADP_TRY(head_bwd(y, dy, (long long)B * d->size * d->size, d->final_sigmoid, du, grads[0].convT_bias, s));
+      ADP_CUDA(cudaMemsetAsync(grads[0].convT_w, 0, sizeof(float) * 16 * Ct, s));
+      ADP_TRY(last_convT_wgrad(dt, at(ws, L.r), L.cout, at(ws, L.q), L.t_c1, du, grads[0].convT_w, B, L.hout, L.hout, s));
+      ADP_TRY(last_convT_dgrad(dt, du, params[0].convT_w, at(ws, L.g_r), L.cout, at(ws, L.g_q), L.t_c1, B, L.hout,
+                               L.hout, s));
+      ADP_TRY(up_norm_bwd(0));
+    } else if (st < D) {
+      const int l = st;
+      const LevelPlan& L = p.lv[l];
+      const LevelPlan& O = p.lv[l - 1];
+      const int Ct = L.cout + L.t_c1;
+      ADP_CUDA(cudaMemsetAsync(grads[l].convT_w, 0, sizeof(float) * 16 * (size_t)Ct * L.t_cout, s));
+      ADP_TRY(conv_wgrad(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, at(ws, O.g_t), L.t_cout,
+                         grads[l].convT_w, B, L.hout, L.hout, s));
+      ADP_TRY(conv_gather(dt, at(ws, O.g_t), params[l].convT_w, tc ? at(ws, L.wb_convT_nk) : nullptr, at(ws, L.g_r),
+                          L.cout, L.t_c1 ? at(ws, L.g_q) : nullptr, L.t_c1, B, O.hout, O.hout, L.t_cout, s));
+      if (l < D - 1) ADP_TRY(up_norm_bwd(l));
+    } else {
+      const int l = 2 * D - 1 - st;
+      const LevelPlan& L = p.lv[l];
+      const long long rows = (long long)B * L.hout * L.hout;
+      if (l == D - 1) {
+        ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.e), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_r), 0.f,
+                                 nullptr, 0.f, nullptr, 0, at(ws, L.g_e), s));
+      } else if (L.bn_down) {
+        BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
+        double* bs = reinterpret_cast<double*>(at(ws, L.bsums_down));
+        ADP_TRY(act_bn_bwd_reduce(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd,
+                                  at(ws, L.g_a), 0.2f, at(ws, L.g_r), 0.f, bs, s));
+        ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_a),
+                                 0.2f, at(ws, L.g_r), 0.f, bs, bn_mode, at(ws, L.g_e), s));
+        ADP_TRY(bn_param_grads(bs, L.cout, grads[l].bn_down_w, grads[l].bn_down_b, s));
+      } else {  // level 0: no norm; sign(e) == sign(a)
+        ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.a), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_a), 0.2f,
+                                 at(ws, L.g_r), 0.f, nullptr, 0, at(ws, L.g_e), s));
+      }
+      ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, s));
+      if (l == 0) {
+        ADP_TRY(first_conv_wgrad(dt, x, at(ws, L.g_e), grads[0].conv_w, B, L.hin, L.hin, L.cin, L.cout, s));
+      } else {
+        const LevelPlan& I = p.lv[l - 1];
+        ADP_TRY(conv_wgrad(dt, at(ws, L.g_e), L.cout, nullptr, 0, at(ws, I.a), L.cin, grads[l].conv_w, B, L.hout,
+                           L.hout, s));
+        ADP_TRY(conv_parity(dt, at(ws, L.g_e), L.cout, nullptr, 0, params[l].conv_w, tc ? at(ws, L.wb_conv_t) : nullptr,
+                            at(ws, I.g_a), B, L.hout, L.hout, L.cin, s));
+      }
+    }
+  }
+  return ADP_OK;
+}
+
+extern "C" int adp_unet_backward(const adp_unet_desc* d, const float* x, const float* y, const float* dy,
+                                 const adp_unet_level* params, const adp_unet_level* grads, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (!d) { adp_set_error("unet_backward: null descriptor"); return ADP_ERR_ARG; }
+  return adp_unet_backward_stages(d, x, y, dy, params, grads, workspace, workspace_bytes, 0, 2 * d->num_downs, stream);
+}
+
+// ------------------------------------------------------------------ per-layer C ABI
+extern "C" int adp_weight_operand(const float* w, int R, int C, int transpose, void* out, void* stream) {
+  ADP_CHECK_ARG(w && out && R > 0 && C > 0, "weight_operand: bad arguments");
+  if (transpose) return cast_transpose_taps(w, out, R, C, (cudaStream_t)stream);
+  ADP_CHECK_ARG(((long long)R * 16 * C) % 4 == 0, "weight_operand: size must be a multiple of 4");
+  return cast_f32_to_bf16(w, out, (long long)R * 16 * C, (cudaStream_t)stream);
+}
+
+extern "C" int adp_conv2d_k4s2_fprop(int dtype, const void* x, const float* w, const void* w_op, void* y, int B,
+                                     int Hin, int Win, int Cin, int Cout, void* stream) {
+  ADP_CHECK_ARG(x && w && y, "conv2d_fprop: null pointer");
+  return conv_gather(dtype, x, w, w_op, y, Cout, nullptr, 0, B, Hin, Win, Cin, (cudaStream_t)stream);
+}
+extern "C" int adp_conv2d_k4s2_dgrad(int dtype, const void* dy, const float* w, const void* w_op, void* dx, int B,
+                                     int Hin, int Win, int Cin, int Cout, void* stream) {
+  ADP_CHECK_ARG(dy && w && dx, "conv2d_dgrad: null pointer");
+  return conv_parity(dtype, dy, Cout, nullptr, 0, w, w_op, dx, B, Hin / 2, Win / 2, Cin, (cudaStream_t)stream);
+}
+extern "C" int adp_conv2d_k4s2_wgrad(int dtype, const void* x, const void* dy, float* dw, int B, int Hin, int Win,
+                                     int Cin, int Cout, void* stream) {
+  ADP_CHECK_ARG(x && dy && dw, "conv2d_wgrad: null pointer");
+  return conv_wgrad(dtype, dy, Cout, nullptr, 0, x, Cin, dw, B, Hin / 2, Win / 2, (cudaStream_t)stream);
+}
+extern "C" int adp_convT2d_k4s2_fprop(int dtype, const void* x0, int c0, const void* x1, int c1, const float* w,
+                                      const void* w_op, void* y, int B, int Hin, int Win, int Cout, void* stream) {
+  ADP_CHECK_ARG(x0 && w && y && (c1 == 0 || x1), "convT2d_fprop: null pointer");
+  return conv_parity(dtype, x0, c0, x1, c1, w, w_op, y, B, Hin, Win, Cout, (cudaStream_t)stream);
+}
+extern "C" int adp_convT2d_k4s2_dgrad(int dtype, const void* dy, const float* w, const void* w_op, void* dx0, int c0,
+                                      void* dx1, int c1, int B, int Hin, int Win, int Cout, void* stream) {
+  ADP_CHECK_ARG(dy && w && dx0 && (c1 == 0 || dx1), "convT2d_dgrad: null pointer");
+  return conv_gather(dtype, dy, w, w_op, dx0, c0, dx1, c1, B, 2 * Hin, 2 * Win, Cout, (cudaStream_t)stream);
+}
+extern "C" int adp_convT2d_k4s2_wgrad(int dtype, const void* x0, int c0, const void* x1, int c1, const void* dy,
+                                      float* dw, int B, int Hin, int Win, int Cout, void* stream) {
+  ADP_CHECK_ARG(x0 && dy && dw && (c1 == 0 || x1), "convT2d_wgrad: null pointer");
+  return conv_wgrad(dtype, x0, c0, x1, c1, dy, Cout, dw, B, Hin, Win, (cudaStream_t)stream);
+}

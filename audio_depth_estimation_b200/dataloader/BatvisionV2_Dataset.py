@@ -1,0 +1,87 @@
+"""Mirror of dataloader/BatvisionV2_Dataset.py (reference :12-197) for the audio hot path.
+
+Same constructor, `instances` DataFrame, `__getitem__ -> (input[2,S,S], gt_depth[1,S,S])` and
+`_get_spectrogram` signature.  The spectrogram / log / min-max / Resize chain (:96-135) runs on
+the GPU through libadp_b200; depth files and audio are read on the host exactly as the reference
+does (:65-78, :142-175).  `audio_format='waveform'` returns the cut waveform so that the batched
+transform (feature.SpectrogramTransform.for_cfg(cfg)) can run once per collated batch.
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import torch
+from torch.utils.data import Dataset
+
+from .. import feature
+from ._common import load_audio, nearest_resize
+from .utils_dataset import get_transform  # noqa: F401  (re-exported like the reference module)
+
+
+class BatvisionV2Dataset(Dataset):
+    def __init__(self, cfg, annotation_file, location_blacklist=None, use_image=False):
+        self.cfg = cfg
+        self.root_dir = cfg.dataset.dataset_dir
+        self.audio_format = cfg.dataset.audio_format
+        self.use_image = use_image
+        self.device = torch.device("cuda") if torch.cuda.is_available() else None
+        if use_image:
+            raise NotImplementedError("use_image=True (camera branch, reference :199-210) is outside the audio hot path")
+        locations = sorted(d for d in os.listdir(self.root_dir)
+                           if os.path.isdir(os.path.join(self.root_dir, d))
+                           and not d.startswith((".", "__")) and not d.endswith("_unzipped"))
+        if location_blacklist:
+            locations = [d for d in locations if d not in location_blacklist]
+        frames = []
+        for loc in locations:
+            csv = os.path.join(self.root_dir, loc, annotation_file)
+            if os.path.exists(csv):
+                frames.append(pd.read_csv(csv))
+            else:
+                print("Warning: %s not found, skipping location %s" % (csv, loc))
+        if not frames:
+            raise ValueError("No valid locations found with %s in %s" % (annotation_file, self.root_dir))
+        self.instances = pd.concat(frames)
+
+    def __len__(self):
+        return len(self.instances)
+
+    def _depth(self, inst):
+        d = np.load(os.path.join(self.root_dir, inst["depth path"], inst["depth file name"])).astype(np.float32)
+        d = d / 1000.0
+        if self.cfg.dataset.max_depth:
+            d[d > self.cfg.dataset.max_depth] = self.cfg.dataset.max_depth
+        d[d < 0] = 0
+        d = nearest_resize(d, self.cfg.dataset.images_size)
+        return torch.from_numpy(np.ascontiguousarray(d)).unsqueeze(0)
+
+    def __getitem__(self, idx):
+        inst = self.instances.iloc[idx]
+        gt_depth = self._depth(inst)
+        waveform, sr = load_audio(os.path.join(self.root_dir, inst["audio path"], inst["audio file name"]))
+        n_fft, win_length, hop_length = 400, 200, 100
+        if self.cfg.dataset.max_depth:
+            waveform = waveform[:, :feature.cut_length(self.cfg.dataset.max_depth, sr)]
+            n_fft, win_length, hop_length = feature.stft_params(self.cfg.dataset.max_depth)
+        if "spectrogram" in self.audio_format:
+            if "mel" in self.audio_format:
+                raise NotImplementedError("mel_spectrogram (reference :187-197) is not on the B200 hot path yet; "
+                                          "use audio_format='spectrogram' or 'waveform'")
+            if "resize" not in str(self.cfg.dataset.preprocess):
+                raise NotImplementedError("the fused feature kernel always resizes (cfg.dataset.preprocess='resize')")
+            # STFT + log + per-channel min-max + Resize (reference :117-135) as one fused library call
+            fused = feature.SpectrogramTransform(self.cfg.dataset.images_size, self.cfg.dataset.max_depth,
+                                                 log_minmax=True, cut=False, stft=(n_fft, win_length, hop_length))
+            return fused(self._to_device(waveform)), gt_depth
+        if "waveform" in self.audio_format:
+            return waveform, gt_depth
+        raise ValueError("unknown audio_format %r" % (self.audio_format,))
+
+    def _to_device(self, waveform):
+        if self.device is None:
+            raise RuntimeError("BatvisionV2Dataset needs a CUDA device for the spectrogram transform "
+                               "(no CPU fallback); use audio_format='waveform' in CPU worker processes")
+        return waveform.to(self.device, dtype=torch.float32)
+
+    def _get_spectrogram(self, waveform, n_fft=400, power=1.0, win_length=400, hop_length=100):
+        return feature.spectrogram(waveform, n_fft=n_fft, power=power, win_length=win_length, hop_length=hop_length)

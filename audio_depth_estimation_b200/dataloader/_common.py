@@ -1,0 +1,40 @@
+"""Host-side pieces shared by the two BatVision dataset mirrors (file I/O stays on the host)."""
+import os
+import wave as _wave
+
+import numpy as np
+import torch
+
+
+def nearest_resize(depth, size):
+    """cv2.resize(..., interpolation=cv2.INTER_NEAREST) index rule: src = min(floor(dst*src/dst_n), src_n-1)."""
+    h, w = depth.shape
+    iy = np.minimum(np.floor(np.arange(size) * (h / size)).astype(np.int64), h - 1)
+    ix = np.minimum(np.floor(np.arange(size) * (w / size)).astype(np.int64), w - 1)
+    return depth[iy][:, ix]
+
+
+def load_audio(path):
+    """Returns (waveform [C,L] float32 tensor, sample_rate).  .npy and PCM .wav are read directly."""
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".npy":
+        arr = np.load(path).astype(np.float32)
+        if arr.ndim == 1:
+            arr = arr[None]
+        return torch.from_numpy(arr), 44100
+    if ext == ".wav":
+        with _wave.open(path, "rb") as f:
+            sr, ch, width, n = f.getframerate(), f.getnchannels(), f.getsampwidth(), f.getnframes()
+            raw = f.readframes(n)
+        if width == 2:
+            data = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+        elif width == 4:
+            data = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+        elif width == 1:
+            data = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+        else:
+            raise ValueError("unsupported wav sample width %d in %s" % (width, path))
+        return torch.from_numpy(data.reshape(-1, ch).T.copy()), sr
+    import torchaudio
+    wav, sr = torchaudio.load(path)
+    return wav, sr

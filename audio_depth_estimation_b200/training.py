@@ -1,0 +1,101 @@
+"""The training / inference step of the reference loop on one GPU or on N data-parallel ranks.
+
+`TrainStep` is the body of train.py:633-693 -- (GPU feature transform ->) model forward -> masked
+criterion -> backward -> clip_grad_norm_(1.0) -> AdamW step -- with every numerical stage in
+libadp_b200 and no host synchronisation inside the step.
+
+Data parallelism replaces the reference's single-process nn.DataParallel
+(models/unetbaseline_model.py:52-55: scatter, replicate 54 M parameters every forward, gather on
+GPU 0) by one process per GPU over torch.distributed/NCCL:
+  * batch-sharded inputs, replicated model, per-replica BatchNorm statistics (as DataParallel);
+  * the four loss statistics {N, sum|p-g|, sum d, sum d^2} are all-reduced before the loss value and
+    its gradient are formed, so the loss is the GLOBAL-batch loss the reference computes on the
+    gathered predictions (train.py:642-669) -- not a mean of per-rank losses;
+  * gradients are SUM-all-reduced per group of backward stages, launched while the later stages
+    of backward are still running (NCCL's stream overlaps the compute stream);
+  * the clip norm is computed after the all-reduce, hence identical on every rank.
+"""
+import torch
+import torch.distributed as dist
+
+from .feature import SpectrogramTransform
+from .optim import FusedClipAdamW
+from .utils_loss import DepthCriterion
+
+
+def default_stage_groups(num_downs, stages_per_group=2):
+    n = 2 * num_downs
+    return [(b, min(b + stages_per_group, n)) for b in range(0, n, stages_per_group)]
+
+
+class GradientReducer:
+    """Bucketed gradient all-reduce driven by UnetGenerator's backward stage groups."""
+
+    def __init__(self, model, process_group=None, stages_per_group=2):
+        self.model = model
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.pending = []
+        model.stage_groups = default_stage_groups(model.num_downs, stages_per_group)
+        model.grad_ready_hook = self._on_group_done if self.world > 1 else None
+
+    def _on_group_done(self, gi):
+        _, flat_g, slices = self.model.flat_buffers()
+        b, e = self.model.stage_groups[gi]
+        lo, hi = slices[b][0], slices[e - 1][1]
+        if hi > lo:
+            self.pending.append(dist.all_reduce(flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def reduce_loss_sums(self, sums):
+        if self.world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+
+    def wait(self):
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+
+    def broadcast_parameters(self, src=0):
+        """Make every replica start from rank `src`'s weights and BatchNorm buffers."""
+        if self.world <= 1:
+            return
+        flat_p, _, _ = self.model.flat_buffers()
+        dist.broadcast(flat_p, src=src, group=self.group)
+        for buf in self.model.buffers():
+            dist.broadcast(buf, src=src, group=self.group)
+        self.model.mark_weights_dirty()
+
+
+class TrainStep:
+    def __init__(self, cfg, model, lr=None, max_norm=1.0, process_group=None, stages_per_group=2,
+                 waveform_input=True):
+        self.cfg = cfg
+        self.model = model
+        self.transform = SpectrogramTransform.for_cfg(cfg) if waveform_input else None
+        self.reducer = GradientReducer(model, process_group, stages_per_group)
+        self.criterion = DepthCriterion.from_cfg(cfg, reduce_fn=self.reducer.reduce_loss_sums
+                                                 if self.reducer.world > 1 else None)
+        lr = lr if lr is not None else getattr(cfg.mode, "learning_rate", 1e-3)
+        self.optimizer = FusedClipAdamW(model, lr=lr, max_norm=max_norm)
+
+    def features(self, batch):
+        return self.transform(batch) if self.transform is not None else batch
+
+    def __call__(self, batch, gtdepth):
+        """batch: waveform [B,2,L] (or features [B,2,S,S] when waveform_input=False), gtdepth [B,1,S,S];
+        CUDA fp32.  Returns the loss as a 0-dim device tensor (no synchronisation)."""
+        self.model.train()
+        x = self.features(batch)
+        pred = self.model(x)
+        loss = self.criterion(pred, gtdepth)
+        loss.backward()
+        self.reducer.wait()
+        self.optimizer.step()
+        return loss.detach()
+
+    @torch.no_grad()
+    def evaluate(self, batch, gtdepth):
+        """test.py:231-241: eval-mode forward + masked criterion."""
+        self.model.eval()
+        pred = self.model(self.features(batch))
+        return pred, self.criterion(pred, gtdepth)

@@ -1,0 +1,195 @@
+/*
+ * adp_b200.h -- C ABI of libadp_b200.so: the B200 (sm_100a) implementation of the
+ * audio-depth hot path  waveform -> STFT log-magnitude feature -> UNetBaseline ->
+ * masked depth loss (forward and backward) -> clip + AdamW.
+ *
+ * The reference (Kang-ChangWoo/audio-depth-estimation) has no FFI layer: its
+ * boundary is the Python API of dataloader/, models/unetbaseline_model.py and
+ * utils_loss.py, all of which dispatch into torch/torchaudio/torchvision ops.
+ * Each entry point below names the reference call site (file:line, relative to
+ * the reference root) whose library op it replaces.
+ *
+ * Conventions
+ *  - plain C symbols, raw DEVICE pointers and sizes, caller-owned memory, no
+ *    allocation inside; workspaces are sized with the *_workspace_bytes calls;
+ *  - every call enqueues on `stream` (a cudaStream_t passed as void*) and
+ *    returns without synchronising;
+ *  - return value 0 = ok, negative = error; adp_last_error() gives the text
+ *    (thread-local);
+ *  - activations are NHWC; Conv2d weights are [Cout][kh][kw][Cin] and
+ *    ConvTranspose2d weights [Cin][kh][kw][Cout] -- i.e. the reference's
+ *    [Cout,Cin,4,4] / [Cin,Cout,4,4] tensors held in torch.channels_last memory
+ *    format, so state_dict shapes are unchanged;
+ *  - re-entrant per (device, stream).
+ */
+#ifndef ADP_B200_H
+#define ADP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADP_OK 0
+#define ADP_ERR_ARG (-1)
+#define ADP_ERR_CUDA (-2)
+#define ADP_ERR_UNSUPPORTED (-3)
+
+#define ADP_F32 0
+#define ADP_BF16 1
+
+#define ADP_MAX_LEVELS 10
+
+const char* adp_last_error(void);
+int adp_version(void);
+/* 1 when the running device is sm_100 (B200); the tcgen05 path refuses others. */
+int adp_device_is_sm100(void);
+
+/* ------------------------------------------------------------------ feature
+ * _get_spectrogram: dataloader/BatvisionV2_Dataset.py:177-185,
+ * dataloader/BatvisionV1_Dataset.py:86-95  (T.Spectrogram(n_fft, win_length,
+ * power=1, hop_length) -> torch.stft + abs).
+ * wave: [rows, L] fp32 with row pitch `wave_pitch` elements (so the V2 cut of
+ * BatvisionV2_Dataset.py:102-104 is just L < pitch); spec: [rows, n_fft/2+1, T],
+ * T = 1 + L/hop. */
+int adp_stft_mag(const float* wave, int rows, int L, int wave_pitch,
+                 int n_fft, int win_length, int hop, float* spec, void* stream);
+
+/* Whole audio branch of __getitem__ on a batch:
+ * BatvisionV2_Dataset.py:96-135 (log_minmax = 1: log(x+1e-8), per-channel
+ * min-max) / BatvisionV1_Dataset.py:70-78 (log_minmax = 0), then
+ * utils_dataset.py:18-20 Resize((S,S)) (antialiased bilinear).
+ * wave [B*C rows, L] -> out [B*C, S, S] fp32.  workspace: adp_feature_workspace_bytes. */
+size_t adp_feature_workspace_bytes(int rows, int L, int n_fft, int hop);
+int adp_feature_forward(const float* wave, int rows, int L, int wave_pitch,
+                        int n_fft, int win_length, int hop, int log_minmax,
+                        int out_size, float* out, void* workspace, size_t workspace_bytes,
+                        void* stream);
+/* utils_dataset.py:18-20 alone: [rows, H, W] -> [rows, S, S]. */
+int adp_resize_aa(const float* in, int rows, int H, int W, int out_size, float* out, void* stream);
+
+/* --------------------------------------------------------------------- loss
+ * train.py:646-669 + utils_loss.py:29-49.  Three phases so that data-parallel
+ * ranks can all-reduce the four sufficient statistics in between
+ * (sums = {N_valid, sum|p-g|, sum d, sum d^2}, doubles, ACCUMULATED into).
+ * use_mask = 1: only pixels with gt != 0 count (train.py:646); 0: every element counts
+ * (SIlogLoss / L1Loss called on already-masked vectors, utils_loss.py:29). */
+int adp_depth_loss_sums(const float* pred, const float* gt, int64_t n, float scale, float eps,
+                        int use_mask, double* sums, void* stream);
+/* loss_out[3] = {loss, l1, silog};  loss = l1_w*l1 + silog_w*silog */
+int adp_depth_loss_value(const double* sums, float l1_w, float silog_w, float lam,
+                         float* loss_out, void* stream);
+/* dpred = grad_scale * d loss / d pred  (grad_scale: device scalar or NULL = 1) */
+int adp_depth_loss_backward(const float* pred, const float* gt, int64_t n, float scale, float eps,
+                            int use_mask, const double* sums, float l1_w, float silog_w, float lam,
+                            const float* grad_scale, float* dpred, void* stream);
+
+/* --------------------------------------------------------------------- convs
+ * nn.Conv2d(k4,s2,p1,bias=False)  models/unetbaseline_model.py:187 and
+ * nn.ConvTranspose2d(k4,s2,p1)    models/unetbaseline_model.py:196,209,218,
+ * forward (cudnnConvolutionForward), dgrad (BackwardData) and wgrad (BackwardFilter).
+ * dtype = ADP_F32 (fp32 storage, SIMT fp32 kernels) or ADP_BF16 (bf16 storage; tcgen05/TMEM
+ * implicit GEMM with fp32 accumulation when `w_op` is given and the shape qualifies,
+ * otherwise the SIMT kernel on bf16 storage).  All activations NHWC.
+ *   w     : fp32 master weight in the layout stated at the top of this file;
+ *   w_op  : optional bf16 tensor-core operand made by adp_weight_operand (NULL = none);
+ *   x1/c1 : second half of a channel concat (decoder skip), NULL/0 if none;
+ *   dw    : fp32, same layout as w, ACCUMULATED into (zero it first). */
+
+/* w [R][16][C] fp32 -> bf16 [R][16][C] (transpose = 0) or [C][16][R] (transpose = 1).
+ * Operands: conv fprop  <- conv  weight, transpose 0;  conv dgrad  <- conv  weight, transpose 1;
+ *           convT fprop <- convT weight, transpose 1;  convT dgrad <- convT weight, transpose 0. */
+int adp_weight_operand(const float* w, int R, int C, int transpose, void* out, void* stream);
+
+int adp_conv2d_k4s2_fprop(int dtype, const void* x, const float* w, const void* w_op, void* y,
+                          int B, int Hin, int Win, int Cin, int Cout, void* stream);
+int adp_conv2d_k4s2_dgrad(int dtype, const void* dy, const float* w, const void* w_op, void* dx,
+                          int B, int Hin, int Win, int Cin, int Cout, void* stream);
+int adp_conv2d_k4s2_wgrad(int dtype, const void* x, const void* dy, float* dw,
+                          int B, int Hin, int Win, int Cin, int Cout, void* stream);
+/* Hin/Win: spatial size of the transposed conv's INPUT (output is 2Hin x 2Win). */
+int adp_convT2d_k4s2_fprop(int dtype, const void* x0, int c0, const void* x1, int c1,
+                           const float* w, const void* w_op, void* y, int B, int Hin, int Win,
+                           int Cout, void* stream);
+int adp_convT2d_k4s2_dgrad(int dtype, const void* dy, const float* w, const void* w_op,
+                           void* dx0, int c0, void* dx1, int c1, int B, int Hin, int Win, int Cout,
+                           void* stream);
+int adp_convT2d_k4s2_wgrad(int dtype, const void* x0, int c0, const void* x1, int c1,
+                           const void* dy, float* dw, int B, int Hin, int Win, int Cout, void* stream);
+/* 1 = use tcgen05 kernels for bf16 tensors where supported (default), 0 = SIMT only.
+ * Returns the previous setting.  (Also: environment ADP_TC=0.) */
+int adp_set_tensor_core(int on);
+
+/* --------------------------------------------------------------------- U-Net
+ * UnetGenerator / UnetSkipConnectionBlock, models/unetbaseline_model.py:123-235. */
+typedef struct adp_unet_desc {
+  int batch;        /* B */
+  int in_ch;        /* input_nc (2) */
+  int out_ch;       /* output_nc (1) */
+  int ngf;          /* 64 */
+  int num_downs;    /* 8 = unet_256, 7 = unet_128 */
+  int size;         /* input H = W, a multiple of 2^num_downs */
+  int dtype;        /* ADP_F32 | ADP_BF16 : storage + conv arithmetic of the hidden layers */
+  int final_sigmoid;/* cfg.dataset.depth_norm: Sigmoid head (1) or ReLU head (0), :201-206 */
+  int training;     /* BatchNorm uses batch statistics and updates running stats */
+  float bn_eps;     /* 1e-5 */
+  float bn_momentum;/* 0.1 */
+  int reuse_weight_cache; /* 1: the bf16 weight operands in the workspace are still valid (inference) */
+} adp_unet_desc;
+
+typedef struct adp_unet_level {      /* level 0 = outermost block */
+  float* conv_w;       /* [Cout][4][4][Cin] */
+  float* convT_w;      /* [CinT][4][4][CoutT] */
+  float* convT_bias;   /* [out_ch] (outermost only) or NULL */
+  float* bn_down_w; float* bn_down_b; float* bn_down_rm; float* bn_down_rv;  /* NULL where the block has no down-norm */
+  float* bn_up_w;   float* bn_up_b;   float* bn_up_rm;   float* bn_up_rv;
+} adp_unet_level;
+
+size_t adp_unet_workspace_bytes(const adp_unet_desc* d);
+/* x [B,in_ch,S,S] fp32 NCHW -> y [B,out_ch,S,S] fp32.  `params` has num_downs
+ * entries.  The workspace keeps what backward needs. */
+int adp_unet_forward(const adp_unet_desc* d, const float* x, const adp_unet_level* params,
+                     void* workspace, size_t workspace_bytes, float* y, void* stream);
+/* dy [B,out_ch,S,S] fp32 -> gradients of every parameter (same layouts, fp32,
+ * OVERWRITTEN).  `grads` mirrors `params` (running-stat slots ignored). */
+int adp_unet_backward(const adp_unet_desc* d, const float* x, const float* y, const float* dy,
+                      const adp_unet_level* params, const adp_unet_level* grads,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* The same backward in 2*num_downs stages so that a data-parallel caller can start the
+ * all-reduce of finished gradients while later stages run.  Stage s < num_downs: decoder
+ * level s (its ConvTranspose2d weight/bias and the up-norm of level s+1 become final);
+ * stage num_downs + k: encoder level num_downs-1-k (its Conv2d weight and down-norm).
+ * Runs stages [stage_begin, stage_end); stages must be run in order. */
+int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, const float* y, const float* dy,
+                             const adp_unet_level* params, const adp_unet_level* grads,
+                             void* workspace, size_t workspace_bytes, int stage_begin, int stage_end,
+                             void* stream);
+
+/* ----------------------------------------------------------------- optimiser
+ * clip_grad_norm_(max_norm) + AdamW.step  train.py:471-476, :689-691.
+ * Multi-tensor: n tensors described by device-visible pointer tables. */
+typedef struct adp_tensor_ref { float* p; float* g; float* m; float* v; int64_t n; } adp_tensor_ref;
+/* sumsq[0] += sum g^2 over all tensors (double, device) */
+int adp_grad_sumsq(const adp_tensor_ref* refs_host, int n_tensors, double* sumsq, void* stream);
+/* p,m,v updated in place; clip coefficient min(1, max_norm/(sqrt(sumsq)+1e-6)) taken
+ * from the device scalar; norm_out (device float, may be NULL) receives the total norm. */
+int adp_clip_adamw_step(const adp_tensor_ref* refs_host, int n_tensors, const double* sumsq,
+                        float max_norm, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, int step, float* norm_out, void* stream);
+
+/* ------------------------------------------------------------------ measurement
+ * Kernel launches issued by this library since load (bench.py's gpu_launches). */
+long long adp_launch_count(void);
+/* CUDA-event timing of the convolution kernel families on their launching stream.
+ * adp_profile_enable(1) clears and starts, (0) stops; adp_profile_read (after the stream is
+ * synchronised) fills 5-entry arrays {gather conv, parity convT, wgrad, thin first/last layers,
+ * elementwise}: total ms, total algorithmic FLOP, timed calls. */
+int adp_profile_enable(int on);
+int adp_profile_read(double* ms, double* work, long long* calls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADP_B200_H */

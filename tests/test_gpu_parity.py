@@ -1,0 +1,413 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every check calls the CUDA path through
+the C ABI (ctypes) and compares with the CPU oracle (oracle/, pinned to the reference by
+tests/test_oracle_golden.py) and with the committed reference-generated golden vectors.
+
+Tolerances (BASELINE.json north_star): spectrogram <= 1e-4 of the tensor max in fp32; depth map and
+loss <= 1e-3 relative in fp32 mode, <= 2e-2 in bf16 mode; masking / indexing bit-exact.
+"""
+import ctypes
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from audio_depth_estimation_b200 import _lib, feature, synthetic
+from oracle import feature_oracle as fo
+from oracle import loss_oracle as lo
+from oracle import unet_oracle as uo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_to_max(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def feat(golden_dir):
+    return np.load(os.path.join(golden_dir, "feature.npz"))
+
+
+# ----------------------------------------------------------------------------- feature
+def test_device_is_b200_and_library_loaded():
+    lib = _lib.load()
+    assert torch.cuda.is_available()
+    assert lib.adp_device_is_sm100() == 1
+
+
+@pytest.mark.parametrize("key,L,seed,p", [("small_spec_512", 1000, 13, (512, 64, 16)),
+                                           ("small_spec_400", 2000, 14, (400, 200, 100))])
+def test_stft_golden(feat, key, L, seed, p):
+    w = cuda(synthetic.waveform(1, L, seed=seed)[0])
+    got = feature.spectrogram(w, n_fft=p[0], power=1.0, win_length=p[1], hop_length=p[2]).cpu().numpy()
+    assert got.shape == feat[key].shape
+    assert rel_to_max(got, feat[key]) <= 1e-4
+
+
+def test_stft_v2_v1_shapes_and_oracle(feat):
+    w = synthetic.waveform(3, 8000, seed=21)
+    got = feature.spectrogram(cuda(w), 512, 1.0, 64, 16, length=fo.cut_length(30.0)).cpu().numpy()
+    assert got.shape == (3, 2, 257, 487)
+    ref = fo.stft_mag(w[:, :, :fo.cut_length(30.0)], 512, 64, 16)
+    assert rel_to_max(got, ref) <= 1e-4
+    w1 = synthetic.waveform(1, synthetic.V1_LEN, seed=12)[0]
+    got1 = feature.spectrogram(cuda(w1), 512, 1.0, 64, 16).cpu().numpy()
+    assert got1.shape == (2, 257, 201)
+    assert rel_to_max(got1[:, :, ::13], feat["v1_spec_slice"]) <= 1e-4
+
+
+@pytest.mark.parametrize("name,echo", [("v2", False), ("v2echo", True)])
+def test_feature_v2_golden(feat, name, echo):
+    w = cuda(synthetic.waveform(1, 8000, seed=11, echo=echo)[0])
+    tr = feature.SpectrogramTransform(256, 30.0, log_minmax=True, cut=True)
+    got = tr(w).cpu().numpy()
+    assert got.shape == (2, 256, 256)
+    # same bound as the oracle-vs-reference pin (see tests/test_oracle_golden.py for why it is absolute)
+    assert np.abs(got - feat[name + "_feat"]).max() <= (2e-3 if echo else 5e-4)
+    assert got.min() >= -1e-6 and got.max() <= 1.0 + 1e-6
+
+
+def test_feature_v1_golden(feat):
+    w = cuda(synthetic.waveform(1, synthetic.V1_LEN, seed=12)[0])
+    tr = feature.SpectrogramTransform(256, 12.0, log_minmax=False, cut=False, stft=(512, 64, 16))
+    assert rel_to_max(tr(w).cpu().numpy(), feat["v1_feat"]) <= 1e-4
+
+
+def test_feature_batched_vs_oracle():
+    w = synthetic.waveform(5, 8000, seed=31)
+    tr = feature.SpectrogramTransform(256, 30.0, log_minmax=True, cut=True)
+    got = tr(cuda(w)).cpu().numpy()
+    assert got.shape == (5, 2, 256, 256)
+    for b in range(5):
+        assert np.abs(got[b] - fo.feature_v2(w[b], 30.0, 256)).max() <= 5e-4
+
+
+def test_feature_constant_channel_gives_zeros():
+    # max == min -> zeros (BatvisionV2_Dataset.py:130-132)
+    w = np.zeros((1, 2, 8000), dtype=np.float32)
+    w[0, 1] = synthetic.waveform(1, 8000, seed=5)[0, 0]
+    got = feature.SpectrogramTransform(256, 30.0)(cuda(w)).cpu().numpy()
+    assert np.all(got[0, 0] == 0.0)
+    assert got[0, 1].max() > 0.5
+
+
+def test_resize_golden(feat):
+    rng = np.random.default_rng(15)
+    plane = rng.uniform(0, 1, size=(2, 257, 101)).astype(np.float32)
+    got = feature.resize(cuda(plane), 64).cpu().numpy()
+    assert np.abs(got - feat["resize_257x101_to_64"]).max() <= 2e-6
+
+
+# ----------------------------------------------------------------------------- loss
+def test_loss_golden_and_grad(golden_dir):
+    from audio_depth_estimation_b200.utils_loss import DepthCriterion
+    g = np.load(os.path.join(golden_dir, "loss.npz"))
+    for i, (shape, dn, md) in enumerate([((2, 1, 64, 64), False, 30.0), ((3, 1, 32, 32), True, 12.0)]):
+        gt = synthetic.gt_depth(shape[0], shape[2], md, seed=710 + i, normalised=dn)
+        pred = cuda(g["case%d_pred" % i]).requires_grad_(True)
+        crit = DepthCriterion("Combined", 0.237, 0.637, 0.869, depth_norm=dn, max_depth=md)
+        loss = crit(pred, cuda(gt))
+        loss.backward()
+        ref = g["case%d_loss" % i]
+        parts = crit.last_parts.cpu().numpy()
+        assert np.all(np.abs(parts - ref) <= 1e-5 * np.abs(ref))
+        rg = g["case%d_grad" % i]
+        got = pred.grad.cpu().numpy()
+        assert np.abs(got - rg).max() <= 1e-4 * np.abs(rg).max()
+        # masking is bit-exact: zero gradient exactly where gt == 0, and nowhere else by construction
+        assert np.array_equal(got[gt == 0.0], np.zeros_like(got[gt == 0.0]))
+        assert np.array_equal(got == 0.0, rg == 0.0)
+
+
+def test_loss_large_vs_oracle_and_criteria():
+    from audio_depth_estimation_b200.utils_loss import DepthCriterion, SIlogLoss
+    gt = synthetic.gt_depth(4, 256, 30.0, seed=77)
+    rng = np.random.default_rng(78)
+    pred = np.maximum(gt + rng.normal(0, 3.0, gt.shape), 0).astype(np.float32)
+    for crit_name, l1w, siw in (("L1", 1.0, 0.0), ("SIlog", 0.0, 1.0), ("Combined", 0.237, 0.637)):
+        p = cuda(pred).requires_grad_(True)
+        crit = DepthCriterion(crit_name, 0.237, 0.637, 0.869)
+        loss = crit(p, cuda(gt))
+        loss.backward()
+        rl, _, _, rgrad = lo.depth_loss_and_grad(pred, gt, l1w, siw, 0.869)
+        assert abs(loss.item() - rl) <= 1e-5 * abs(rl)
+        assert np.abs(p.grad.cpu().numpy() - rgrad).max() <= 1e-4 * np.abs(rgrad).max()
+    # SIlogLoss keeps the reference signature: already-masked vectors, no mask inside
+    m = gt != 0
+    pv, gv = pred[m], gt[m]
+    got = SIlogLoss(lambda_scale=0.869)(cuda(pv), cuda(gv)).item()
+    n, _, sd, sd2 = lo.loss_sums(pv, gv)
+    ref = np.sqrt(max(sd2 / n - 0.869 * (sd / n) ** 2, 0.0))
+    assert abs(got - ref) <= 1e-5 * ref
+
+
+# ----------------------------------------------------------------------------- convolutions (per-layer C ABI)
+def nhwc(t, dtype):
+    return t.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def from_nhwc(t):
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def op_weights(lib, w_master, R, C, transpose):
+    out = torch.empty(R * 16 * C, device=DEV, dtype=torch.bfloat16)
+    _lib.check(lib.adp_weight_operand(w_master.data_ptr(), R, C, transpose, out.data_ptr(), None))
+    return out
+
+
+CONV_SHAPES = [  # B, H, Cin, Cout
+    (2, 16, 16, 32), (3, 8, 32, 16), (1, 32, 64, 128), (2, 4, 128, 128), (4, 2, 64, 64), (2, 64, 64, 64),
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16_simt", "bf16_tc"])
+@pytest.mark.parametrize("B,H,Cin,Cout", CONV_SHAPES)
+def test_conv2d_k4s2_all_passes(mode, B, H, Cin, Cout):
+    lib = _lib.load()
+    lib.adp_set_tensor_core(0 if mode == "bf16_simt" else 1)
+    dt, tdt = (_lib.ADP_F32, torch.float32) if mode == "fp32" else (_lib.ADP_BF16, torch.bfloat16)
+    tol = 1e-4 if mode == "fp32" else 1.5e-2
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + Cin)
+    x = torch.randn(B, Cin, H, H, generator=g).to(DEV)
+    w = (torch.randn(Cout, Cin, 4, 4, generator=g) * 0.05).to(DEV)
+    dy = torch.randn(B, Cout, H // 2, H // 2, generator=g).to(DEV)
+    xr = nhwc(x, tdt)
+    dyr = nhwc(dy, tdt)
+    xq, dyq = from_nhwc(xr), from_nhwc(dyr)          # what the kernel actually sees
+    wm = w.permute(0, 2, 3, 1).contiguous()          # [Cout][4][4][Cin]
+    wq = wm if mode == "fp32" else wm.to(torch.bfloat16).float()
+    wq_nchw = wq.permute(0, 3, 1, 2).contiguous()
+    w_f = op_weights(lib, wm, Cout, Cin, 0) if mode == "bf16_tc" else None
+    w_t = op_weights(lib, wm, Cout, Cin, 1) if mode == "bf16_tc" else None
+    wref = wq_nchw if mode == "bf16_tc" else w
+    # fprop
+    y = torch.empty(B, H // 2, H // 2, Cout, device=DEV, dtype=tdt)
+    _lib.check(lib.adp_conv2d_k4s2_fprop(dt, xr.data_ptr(), wm.data_ptr(), w_f.data_ptr() if w_f is not None else None,
+                                         y.data_ptr(), B, H, H, Cin, Cout, None))
+    ref = F.conv2d(xq, wref, stride=2, padding=1)
+    assert rel_to_max(from_nhwc(y).cpu(), ref.cpu()) <= tol
+    # dgrad
+    dx = torch.empty(B, H, H, Cin, device=DEV, dtype=tdt)
+    _lib.check(lib.adp_conv2d_k4s2_dgrad(dt, dyr.data_ptr(), wm.data_ptr(), w_t.data_ptr() if w_t is not None else None,
+                                         dx.data_ptr(), B, H, H, Cin, Cout, None))
+    ref = F.conv_transpose2d(dyq, wref, stride=2, padding=1)
+    assert rel_to_max(from_nhwc(dx).cpu(), ref.cpu()) <= tol
+    # wgrad (fp32 output, accumulated into)
+    dw = torch.zeros(Cout, 4, 4, Cin, device=DEV)
+    _lib.check(lib.adp_conv2d_k4s2_wgrad(dt, xr.data_ptr(), dyr.data_ptr(), dw.data_ptr(), B, H, H, Cin, Cout, None))
+    xg = xq.clone().requires_grad_(True)
+    wg = w.clone().requires_grad_(True)
+    F.conv2d(xg, wg, stride=2, padding=1).backward(dyq)
+    assert rel_to_max(dw.permute(0, 3, 1, 2).cpu(), wg.grad.cpu()) <= (1e-4 if mode == "fp32" else 2e-3)
+    lib.adp_set_tensor_core(1)
+
+
+CONVT_SHAPES = [  # B, Hin, C0, C1, Cout
+    (2, 8, 32, 32, 16), (3, 4, 64, 0, 64), (1, 16, 64, 64, 32), (2, 2, 128, 128, 128), (2, 1, 64, 0, 64),
+    (2, 32, 64, 64, 64),
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16_simt", "bf16_tc"])
+@pytest.mark.parametrize("B,H,C0,C1,Cout", CONVT_SHAPES)
+def test_convT2d_k4s2_all_passes(mode, B, H, C0, C1, Cout):
+    lib = _lib.load()
+    lib.adp_set_tensor_core(0 if mode == "bf16_simt" else 1)
+    dt, tdt = (_lib.ADP_F32, torch.float32) if mode == "fp32" else (_lib.ADP_BF16, torch.bfloat16)
+    tol = 1e-4 if mode == "fp32" else 1.5e-2
+    Cin = C0 + C1
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + Cin)
+    x = torch.randn(B, Cin, H, H, generator=g).to(DEV)
+    w = (torch.randn(Cin, Cout, 4, 4, generator=g) * 0.05).to(DEV)
+    dy = torch.randn(B, Cout, 2 * H, 2 * H, generator=g).to(DEV)
+    x0r = nhwc(x[:, :C0], tdt)
+    x1r = nhwc(x[:, C0:], tdt) if C1 else None
+    dyr = nhwc(dy, tdt)
+    xq = torch.cat([from_nhwc(x0r)] + ([from_nhwc(x1r)] if C1 else []), 1)
+    dyq = from_nhwc(dyr)
+    wm = w.permute(0, 2, 3, 1).contiguous()          # [Cin][4][4][Cout]
+    wq = wm if mode == "fp32" else wm.to(torch.bfloat16).float()
+    wq_nchw = wq.permute(0, 3, 1, 2).contiguous()
+    w_f = op_weights(lib, wm, Cin, Cout, 1) if mode == "bf16_tc" else None   # fprop operand [Cout][16][Cin]
+    w_d = op_weights(lib, wm, Cin, Cout, 0) if mode == "bf16_tc" else None   # dgrad operand [Cin][16][Cout]
+    wref = wq_nchw if mode == "bf16_tc" else w
+    p = lambda t: t.data_ptr() if t is not None else None
+    y = torch.empty(B, 2 * H, 2 * H, Cout, device=DEV, dtype=tdt)
+    _lib.check(lib.adp_convT2d_k4s2_fprop(dt, p(x0r), C0, p(x1r), C1, wm.data_ptr(), p(w_f), y.data_ptr(),
+                                          B, H, H, Cout, None))
+    ref = F.conv_transpose2d(xq, wref, stride=2, padding=1)
+    assert rel_to_max(from_nhwc(y).cpu(), ref.cpu()) <= tol
+    dx0 = torch.empty(B, H, H, C0, device=DEV, dtype=tdt)
+    dx1 = torch.empty(B, H, H, C1, device=DEV, dtype=tdt) if C1 else None
+    _lib.check(lib.adp_convT2d_k4s2_dgrad(dt, dyr.data_ptr(), wm.data_ptr(), p(w_d), dx0.data_ptr(), C0, p(dx1), C1,
+                                          B, H, H, Cout, None))
+    ref = F.conv2d(dyq, wref, stride=2, padding=1)
+    got = torch.cat([from_nhwc(dx0)] + ([from_nhwc(dx1)] if C1 else []), 1)
+    assert rel_to_max(got.cpu(), ref.cpu()) <= tol
+    dw = torch.zeros(Cin, 4, 4, Cout, device=DEV)
+    _lib.check(lib.adp_convT2d_k4s2_wgrad(dt, p(x0r), C0, p(x1r), C1, dyr.data_ptr(), dw.data_ptr(), B, H, H, Cout, None))
+    wg = w.clone().requires_grad_(True)
+    F.conv_transpose2d(xq, wg, stride=2, padding=1).backward(dyq)
+    assert rel_to_max(dw.permute(0, 3, 1, 2).cpu(), wg.grad.cpu()) <= (1e-4 if mode == "fp32" else 2e-3)
+    lib.adp_set_tensor_core(1)
+
+
+# ----------------------------------------------------------------------------- U-Net + step vs golden
+UNET_CASES = {
+    "u128_ngf16_b3_sigmoid": ("unet_128", 16, 3, 128, True, 12.0, 200, True, False),
+    "u128_ngf64_b2_relu": ("unet_128", 64, 2, 128, False, 30.0, 300, True, False),
+    "u128_ngf16_b2_eval": ("unet_128", 16, 2, 128, False, 30.0, 400, False, True),
+    "u256_ngf64_b2_relu": ("unet_256", 64, 2, 256, False, 30.0, 100, True, False),
+    "u256_ngf64_b1_eval": ("unet_256", 64, 1, 256, True, 12.0, 500, False, True),
+}
+
+
+def make_cfg(dn, md, size, precision):
+    return SimpleNamespace(dataset=SimpleNamespace(depth_norm=dn, max_depth=md, images_size=size, preprocess="resize",
+                                                   name="batvisionv2"),
+                           mode=SimpleNamespace(criterion="Combined", l1_weight=0.237, silog_weight=0.637,
+                                                silog_lambda=0.869, learning_rate=0.002),
+                           model=SimpleNamespace(precision=precision))
+
+
+def build_case(case, precision):
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    netG, ngf, batch, size, dn, md, seed, train, warm = case
+    nd = 8 if netG == "unet_256" else 7
+    sd = uo.make_state_dict(ngf, nd, seed=seed)
+    if warm:
+        rng = np.random.default_rng(seed + 1)
+        for k in sd:
+            if k.endswith("running_mean"):
+                sd[k] = torch.from_numpy(rng.normal(0, 0.05, sd[k].shape).astype(np.float32))
+            if k.endswith("running_var"):
+                sd[k] = torch.from_numpy(rng.uniform(0.5, 1.5, sd[k].shape).astype(np.float32))
+    cfg = make_cfg(dn, md, size, precision)
+    net = define_G(cfg, 2, 1, ngf, netG, "batch", False, gpu_ids=[0])
+    net.load_state_dict(uo.ordered_state_dict(sd, nd), strict=True)
+    x = cuda(synthetic.feature_like(batch, size, seed=seed + 2))
+    gt = cuda(synthetic.gt_depth(batch, size, md, seed=seed + 3, normalised=dn))
+    return cfg, net, x, gt
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(UNET_CASES))
+def test_unet_step_vs_reference_golden(golden_dir, name, precision):
+    from audio_depth_estimation_b200.optim import FusedClipAdamW
+    from audio_depth_estimation_b200.utils_loss import DepthCriterion
+    case = UNET_CASES[name]
+    netG, ngf, batch, size, dn, md, seed, train, warm = case
+    g = np.load(os.path.join(golden_dir, "unet_%s.npz" % name))
+    cfg, net, x, gt = build_case(case, precision)
+    fp32 = precision == "fp32"
+    if not train:
+        net.eval()
+        with torch.no_grad():
+            y = net(x)
+            y2 = net(x)        # second call reuses the cached bf16 weight operands
+        assert rel_to_max(y.cpu().numpy(), g["y"]) <= (1e-3 if fp32 else 2e-2)
+        assert torch.equal(y, y2)
+        return
+    net.train()
+    crit = DepthCriterion.from_cfg(cfg)
+    y = net(x)
+    loss = crit(y, gt)
+    y.retain_grad()
+    loss.backward()
+    assert rel_to_max(y.detach().cpu().numpy(), g["y"]) <= (1e-3 if fp32 else 2e-2)
+    assert abs(loss.item() - g["loss"][0]) <= (1e-3 if fp32 else 2e-2) * abs(g["loss"][0])
+    # masking bit-exact: dL/dy is exactly zero where gt == 0
+    dyv = y.grad.cpu().numpy()
+    assert np.all(dyv[gt.cpu().numpy() == 0.0] == 0.0)
+    if fp32:
+        assert rel_to_max(dyv, g["dy"]) <= 1e-3
+    names = [str(n) for n in g["param_names"]]
+    params = dict(net.named_parameters())
+    assert list(params) == names
+    gn = np.array([params[n].grad.double().norm().item() for n in names])
+    gtol = 2e-3 if fp32 else 6e-2
+    assert np.all(np.abs(gn - g["grad_norms"]) <= gtol * np.maximum(g["grad_norms"], 0.05 * g["grad_norms"].max())), \
+        list(zip(names, gn, g["grad_norms"]))
+    head = np.stack([params[n].grad.reshape(-1)[:16].cpu().numpy() if params[n].numel() >= 16 else
+                     np.pad(params[n].grad.reshape(-1).cpu().numpy(), (0, 16 - params[n].numel())) for n in names])
+    scale = np.abs(g["grad_head"]).max(axis=1, keepdims=True) + 1e-12
+    assert np.abs((head - g["grad_head"]) / scale).max() <= (5e-3 if fp32 else 0.25)
+    sdo = net.state_dict()
+    stats = [str(s) for s in g["stat_names"]]
+    got = np.stack([sdo[s][:8].cpu().numpy() for s in stats])
+    assert np.abs(got - g["stat_head"]).max() <= (1e-4 if fp32 else 5e-3)
+    for k in sdo:
+        if k.endswith("num_batches_tracked"):
+            assert int(sdo[k]) == 1
+    # fused clip + AdamW against torch's clip_grad_norm_ + AdamW(lr=0.002)
+    opt = FusedClipAdamW(net, lr=0.002, max_norm=1.0)
+    tn = opt.step()
+    assert abs(tn.item() - g["total_norm"][0]) <= (1e-3 if fp32 else 3e-2) * g["total_norm"][0]
+    after = np.stack([params[n].detach().reshape(-1)[:16].cpu().numpy() if params[n].numel() >= 16 else
+                      np.pad(params[n].detach().reshape(-1).cpu().numpy(), (0, 16 - params[n].numel()))
+                      for n in names])
+    if fp32:
+        assert np.abs(after - g["param_head_after"]).max() <= 2e-4
+    else:
+        # first AdamW step moves every weight by ~lr*sign(g): bounded by 2*lr whatever the precision
+        assert np.abs(after - g["param_head_after"]).max() <= 2 * 0.002 + 1e-4
+
+
+def test_unet_bf16_matches_fp32_path_at_b200_shapes():
+    """Full-size check without an oracle run: the tensor-core bf16 path against this library's own
+    fp32 SIMT path (itself pinned to the reference above) on a larger batch."""
+    case = ("unet_256", 64, 4, 256, False, 30.0, 900, True, False)
+    _, net32, x, gt = build_case(case, "fp32")
+    _, net16, _, _ = build_case(case, "bf16")
+    net32.train(); net16.train()
+    with torch.no_grad():
+        y32, y16 = net32(x), net16(x)
+    assert rel_to_max(y16.cpu().numpy(), y32.cpu().numpy()) <= 2e-2
+
+
+def test_optimizer_vs_oracle_multi_step():
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    from audio_depth_estimation_b200.optim import FusedClipAdamW
+    cfg = make_cfg(False, 30.0, 128, "fp32")
+    net = define_G(cfg, 2, 1, 16, "unet_128", "batch", False, gpu_ids=[0])
+    net.train()
+    net(torch.rand(1, 2, 128, 128, device=DEV))      # flattens the parameters
+    flat_p, flat_g, _ = net.flat_buffers()
+    rng = np.random.default_rng(3)
+    p0 = rng.normal(0, 0.05, flat_p.numel()).astype(np.float32)
+    flat_p.copy_(cuda(p0))
+    ref_p = [torch.from_numpy(p0.copy())]
+    m, v = [torch.zeros_like(ref_p[0])], [torch.zeros_like(ref_p[0])]
+    opt = FusedClipAdamW(net, lr=0.002, max_norm=1.0)
+    for step in range(1, 4):
+        gnp = rng.normal(0, 0.01 * step, flat_p.numel()).astype(np.float32)
+        flat_g.copy_(cuda(gnp))
+        tn = opt.step()
+        rn = uo.clip_adamw_step(ref_p, [torch.from_numpy(gnp)], m, v, step, 0.002)
+        assert abs(tn.item() - rn.item()) <= 1e-5 * rn.item()
+        assert np.abs(flat_p.cpu().numpy() - ref_p[0].numpy()).max() <= 1e-6
+
+
+def test_train_step_end_to_end_loss_decreases():
+    """waveform -> feature -> U-Net -> loss -> backward -> clip+AdamW, a few steps on one batch."""
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    from audio_depth_estimation_b200.training import TrainStep
+    cfg = make_cfg(False, 30.0, 256, "bf16")
+    torch.manual_seed(0)
+    net = define_G(cfg, 2, 1, 64, "unet_256", "batch", False, gpu_ids=[0])
+    step = TrainStep(cfg, net, lr=0.002)
+    wave = cuda(synthetic.waveform(4, synthetic.V2_LEN, seed=1))
+    gt = cuda(synthetic.gt_depth(4, 256, 30.0, seed=2))
+    losses = [step(wave, gt).item() for _ in range(6)]
+    assert all(np.isfinite(losses))
+    assert losses[-1] < losses[0]
