@@ -67,6 +67,7 @@ SIGNATURES = {
     "adp_unet_backward_stages": (_i, [C.POINTER(UnetDesc), _vp, _vp, _vp, C.POINTER(UnetLevel),
                                       C.POINTER(UnetLevel), _vp, _sz, _i, _i, _vp]),
     "adp_launch_count": (C.c_longlong, []),
+    "adp_tc_launch_count": (C.c_longlong, []),
     "adp_profile_enable": (_i, [_i]),
     "adp_profile_read": (_i, [_vp, _vp, _vp]),
     "adp_grad_sumsq": (_i, [C.POINTER(TensorRef), _i, _vp, _vp]),

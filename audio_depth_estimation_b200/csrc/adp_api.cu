@@ -28,6 +28,9 @@ extern "C" int adp_device_is_sm100(void) {
 static long long g_launches = 0;
 void adp_count_launch() { ++g_launches; }
 extern "C" long long adp_launch_count(void) { return g_launches; }
+static long long g_tc_launches = 0;
+void adp_count_tc_launch() { ++g_tc_launches; }
+extern "C" long long adp_tc_launch_count(void) { return g_tc_launches; }
 
 namespace adp {
 

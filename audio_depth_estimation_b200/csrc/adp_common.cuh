@@ -26,6 +26,7 @@ void adp_set_error(const char* fmt, ...);
   } while (0)
 
 void adp_count_launch();
+void adp_count_tc_launch();
 
 #define ADP_LAUNCH_CHECK()                                                          \
   do {                                                                              \
@@ -185,6 +186,8 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
                     int B, int Hi, int Wi, int N, cudaStream_t s);
 int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int N,
              float* dw, int B, int Hs, int Ws, cudaStream_t s);
+// fp32 scratch used to split the K range of deep, small-M layers across CTAs (NULL: never split)
+void tc_set_scratch(void* ptr, size_t bytes);
 bool tc_supported_gather(int B, int Hi, int Wi, int C, int N0, int N1);
 bool tc_supported_parity(int B, int Hi, int Wi, int C0, int C1, int N);
 bool tc_supported_wgrad(int B, int Hs, int Ws, int M0, int M1, int N);

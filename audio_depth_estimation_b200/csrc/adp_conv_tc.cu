@@ -1,13 +1,395 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolutions (placeholder until the kernels land).
-#include "adp_common.cuh"
+// tcgen05 / TMEM / TMA implicit-GEMM convolutions for the U-Net hidden layers (bf16 operands, fp32
+// accumulation in tensor memory).  Replaces cuDNN's kernels behind nn.Conv2d(k4,s2,p1) and
+// nn.ConvTranspose2d(k4,s2,p1) (models/unetbaseline_model.py:187,:196,:209,:218).
+//
+// Kernel 1 (tc_igemm_kernel) serves the "gather" (F1) and "parity" (F2) families of
+// adp_conv_simt.cu as   D[128 pixels x BLOCK_N channels] = sum_kblocks A[128 x 64] * W[BLOCK_N x 64]^T :
+//   * A tiles are fetched by TMA straight from the NHWC activation tensor.  No im2col, no padded or
+//     space-to-depth copy: the stride-2 4x4 window is expressed through a 5-D view of the tensor
+//     (2C | W/2 | row parity | H/2 | B) whose boxes, shifted by one per tap, cover exactly the
+//     128 output pixels of the tile; out-of-bounds box elements (the conv padding, and the batch
+//     tail) are zero-filled by the TMA unit.  The transposed conv's parity classes use a 4-D view.
+//     The decoder's skip concat is two tensor maps: the K loop switches map at C0.
+//   * W tiles come from the bf16 weight operand [N][16][C] (K-major), 2-D map.
+//   * one elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) on SWIZZLE_128B smem
+//     descriptors; completion is signalled to the TMA producer / epilogue through tcgen05.commit
+//     on mbarriers; a STAGES-deep smem ring overlaps TMA with MMA.
+//   * the epilogue (4 warps = 128 TMEM lanes) reads the accumulator with tcgen05.ld and writes bf16
+//     NHWC rows (strided by parity for F2, split into two tensors for a concat gradient), or
+//     accumulates fp32 partial sums when the K range is split across CTAs (deep, small-M layers).
+#include "adp_tc.cuh"
+
 namespace adp {
-bool tc_supported_gather(int, int, int, int, int, int) { return false; }
-bool tc_supported_parity(int, int, int, int, int, int) { return false; }
-bool tc_supported_wgrad(int, int, int, int, int, int) { return false; }
-int tc_gather_conv(const void*, const void*, void*, int, void*, int, int, int, int, int, cudaStream_t) {
-  adp_set_error("tc_gather_conv: not built"); return ADP_ERR_UNSUPPORTED; }
-int tc_parity_convT(const void*, int, const void*, int, const void*, void*, int, int, int, int, cudaStream_t) {
-  adp_set_error("tc_parity_convT: not built"); return ADP_ERR_UNSUPPORTED; }
-int tc_wgrad(const void*, int, const void*, int, const void*, int, float*, int, int, int, cudaStream_t) {
-  adp_set_error("tc_wgrad: not built"); return ADP_ERR_UNSUPPORTED; }
+namespace tc {
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
 }
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    adp_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return ADP_ERR_CUDA;
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    adp_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu,%llu] box [%u,%u,%u,%u,%u]", (int)r, rank,
+                  (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0), (unsigned long long)(rank > 2 ? gd[2] : 0),
+                  (unsigned long long)(rank > 3 ? gd[3] : 0), (unsigned long long)(rank > 4 ? gd[4] : 0), bx[0],
+                  rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0);
+    return ADP_ERR_CUDA;
+  }
+  return ADP_OK;
+}
+
+}  // namespace tc
+
+namespace {
+
+using namespace tc;
+
+constexpr int TILE_M = 128;
+constexpr int TILE_K = 64;            // bf16 elements = one 128-byte swizzled row
+constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;
+constexpr int IGEMM_THREADS = 192;    // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+struct IgemmParams {
+  CUtensorMap tmA0, tmA1, tmW;
+  // tile geometry over the "small" pixel grid (conv outputs for F1, convT inputs for F2)
+  int Wt, Ht, Bt, tiles_w, tiles_h;
+  int B, Hs, Ws;                      // small grid extent
+  int mode;                           // 0 = gather (F1), 1 = parity (F2)
+  int C0, C1, Ct;                     // input channels (concat halves)
+  int N, N0, N1;                      // output channels and split
+  int kblocks, splits, kb_per_split;
+  bf16* y0; bf16* y1;
+  float* partial;                     // fp32 [out pixels][N] when splits > 1
+};
+
+template <int BLOCK_N>
+struct IgemmSmem {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * TILE_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = BLOCK_N <= 64 ? 6 : (BLOCK_N <= 128 ? 5 : 4);
+  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid_constant__ IgemmParams p) {
+  using S = IgemmSmem<BLOCK_N>;
+  constexpr int STAGES = S::STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  const int tm = blockIdx.x;
+  const int tw_i = tm % p.tiles_w, th_i = (tm / p.tiles_w) % p.tiles_h, tb_i = tm / (p.tiles_w * p.tiles_h);
+  const int x0 = tw_i * p.Wt, y0c = th_i * p.Ht, b0 = tb_i * p.Bt;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int zpar = p.mode == 1 ? (int)(blockIdx.z & 3) : 0;
+  const int split = p.mode == 1 ? (int)(blockIdx.z >> 2) : (int)blockIdx.z;
+  const int pa = zpar >> 1, pb = zpar & 1;
+  const int kb_begin = split * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.kblocks);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tmA0);
+    if (p.C1 > 0) prefetch_tmap(&p.tmA1);
+    prefetch_tmap(&p.tmW);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N < 32 ? 32 : BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const int nchunk = p.Ct / TILE_K;
+      for (int it = 0; it < nkb; ++it) {
+        const int kb = kb_begin + it;
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* a_dst = smem + s * S::STAGE_BYTES;
+        unsigned char* b_dst = a_dst + A_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        const int tap = kb / nchunk;
+        const int c = (kb - tap * nchunk) * TILE_K;
+        if (p.mode == 0) {
+          // 4x4 stride-2 window: tap row kh -> (row offset, row parity) = kh:0 (-1,1) 1 (0,0) 2 (0,1) 3 (+1,0)
+          const int kh = tap >> 2, kw = tap & 3;
+          const int di = (kh + 1) / 2 - 1, ra = (kh + 1) & 1;
+          const int dj = (kw + 1) / 2 - 1, rb = (kw + 1) & 1;
+          tma_load_5d(a_dst, &p.tmA0, &full_bar[s], rb * p.Ct + c, x0 + dj, ra, y0c + di, b0);
+          tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + c, n0);
+        } else {
+          const int th = tap >> 1, tw = tap & 1;
+          const int cx = x0 + pb - 1 + tw, cy = y0c + pa - 1 + th;
+          if (c < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], c, cx, cy, b0);
+          else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], c - p.C0, cx, cy, b0);
+          const int wtap = (3 - pa - 2 * th) * 4 + (3 - pb - 2 * tw);
+          tma_load_2d(b_dst, &p.tmW, &full_bar[s], wtap * p.Ct + c, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < TILE_K / 16; ++k) {
+          const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
+          const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                  // accumulator row = pixel within the tile
+    const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
+    const int b = b0 + bt, py = y0c + ht, px = x0 + wt;
+    const bool valid = b < p.B && nkb > 0;
+    size_t opix;
+    if (p.mode == 0) opix = ((size_t)b * p.Hs + py) * p.Ws + px;
+    else opix = ((size_t)b * 2 * p.Hs + 2 * py + pa) * (2 * p.Ws) + 2 * px + pb;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < BLOCK_N; cc += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+      if (!valid) continue;
+      const int n = n0 + cc;
+      if (p.splits > 1) {
+        float* dst = p.partial + opix * p.N + n;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
+      } else {
+        bf16* dst = n < p.N0 ? p.y0 + opix * p.N0 + n : p.y1 + opix * p.N1 + (n - p.N0);
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(v[i + 0], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
+          u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+          *reinterpret_cast<uint4*>(dst + i) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BLOCK_N < 32 ? 32 : BLOCK_N);
+  }
+}
+
+// fp32 partial sums [pixels][N] -> bf16 outputs (split at N0)
+__global__ void __launch_bounds__(256)
+finish_partial_kernel(const float* __restrict__ partial, long long pixels, int N, int N0, int N1, bf16* __restrict__ y0,
+                      bf16* __restrict__ y1) {
+  const long long n4 = pixels * N / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = 4 * i;
+    const long long pix = e / N;
+    const int n = (int)(e - pix * N);
+    float4 v = ld4(partial + e);
+    if (n < N0) st4(y0 + pix * N0 + n, v);
+    else st4(y1 + pix * N1 + (n - N0), v);
+  }
+}
+
+bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int pick_block_n(int N, int N0, int N1) {
+  const int cands[3] = {128, 64, 32};
+  for (int c : cands)
+    if (N % c == 0 && (N1 == 0 || N0 % c == 0)) return c;
+  return 0;
+}
+
+bool tile_geometry(int B, int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
+  if (!pow2(Hs) || !pow2(Ws)) return false;
+  *Wt = Ws < TILE_M ? Ws : TILE_M;
+  int rest = TILE_M / *Wt;
+  *Ht = Hs < rest ? Hs : rest;
+  *Bt = rest / *Ht;
+  (void)B;
+  return *Bt <= 256;
+}
+
+template <int BLOCK_N>
+int launch_igemm(const IgemmParams& p, dim3 grid, cudaStream_t s) {
+  using S = IgemmSmem<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADP_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    attr_set = true;
+  }
+  tc_igemm_kernel<BLOCK_N><<<grid, IGEMM_THREADS, S::BYTES, s>>>(p);
+  adp_count_tc_launch();
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes, cudaStream_t s) {
+  const int m_tiles = p.tiles_w * p.tiles_h * adp_cdiv(p.B, p.Bt);
+  const int n_tiles = p.N / block_n;
+  const int par = p.mode == 1 ? 4 : 1;
+  const long long out_pixels = (long long)p.B * p.Hs * p.Ws * par;
+  // split the K range when the tile count cannot fill the machine (deep layers: small M, huge K)
+  int splits = 1;
+  const long long ctas = (long long)m_tiles * n_tiles * par;
+  if (scratch && ctas < sm_count()) {
+    splits = (int)((sm_count() + ctas - 1) / ctas);
+    const int max_by_k = p.kblocks / 4 > 0 ? p.kblocks / 4 : 1;
+    if (splits > max_by_k) splits = max_by_k;
+    if (splits > 32) splits = 32;
+    if ((size_t)out_pixels * p.N * sizeof(float) > scratch_bytes) splits = 1;
+  }
+  p.kb_per_split = adp_cdiv(p.kblocks, splits);
+  splits = adp_cdiv(p.kblocks, p.kb_per_split);
+  p.splits = splits;
+  p.partial = splits > 1 ? scratch : nullptr;
+  if (splits > 1) ADP_CUDA(cudaMemsetAsync(scratch, 0, (size_t)out_pixels * p.N * sizeof(float), s));
+  dim3 grid(m_tiles, n_tiles, par * splits);
+  switch (block_n) {
+    case 128: ADP_TRY(launch_igemm<128>(p, grid, s)); break;
+    case 64: ADP_TRY(launch_igemm<64>(p, grid, s)); break;
+    case 32: ADP_TRY(launch_igemm<32>(p, grid, s)); break;
+    default: adp_set_error("tc igemm: bad BLOCK_N %d", block_n); return ADP_ERR_ARG;
+  }
+  if (splits > 1) {
+    long long n4 = out_pixels * p.N / 4;
+    int blocks = (int)((n4 + 255) / 256 < (long long)sm_count() * 8 ? (n4 + 255) / 256 : (long long)sm_count() * 8);
+    finish_partial_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, s>>>(scratch, out_pixels, p.N, p.N0, p.N1, p.y0, p.y1);
+    ADP_LAUNCH_CHECK();
+  }
+  return ADP_OK;
+}
+
+float* g_scratch = nullptr;
+size_t g_scratch_bytes = 0;
+
+}  // namespace
+
+void tc_set_scratch(void* ptr, size_t bytes) {
+  g_scratch = reinterpret_cast<float*>(ptr);
+  g_scratch_bytes = bytes;
+}
+
+bool tc_supported_gather(int B, int Hi, int Wi, int C, int N0, int N1) {
+  int Wt, Ht, Bt;
+  if (!adp_device_is_sm100() || !encode_tiled_fn()) return false;
+  if (Hi % 2 || Wi % 2 || C % TILE_K || B < 1) return false;
+  if (!tile_geometry(B, Hi / 2, Wi / 2, &Wt, &Ht, &Bt)) return false;
+  return pick_block_n(N0 + N1, N0, N1) != 0;
+}
+
+bool tc_supported_parity(int B, int Hi, int Wi, int C0, int C1, int N) {
+  int Wt, Ht, Bt;
+  if (!adp_device_is_sm100() || !encode_tiled_fn()) return false;
+  if (C0 % TILE_K || C1 % TILE_K || C0 <= 0 || B < 1) return false;
+  if (!tile_geometry(B, Hi, Wi, &Wt, &Ht, &Bt)) return false;
+  return pick_block_n(N, N, 0) != 0;
+}
+
+int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, int N1, int B, int Hi, int Wi, int C,
+                   cudaStream_t s) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int Ho = Hi / 2, Wo = Wi / 2, N = N0 + N1;
+  ADP_CHECK_ARG(tile_geometry(B, Ho, Wo, &p.Wt, &p.Ht, &p.Bt), "tc_gather_conv: unsupported spatial size %dx%d", Hi, Wi);
+  const int bn = pick_block_n(N, N0, N1);
+  ADP_CHECK_ARG(bn != 0 && C % TILE_K == 0, "tc_gather_conv: unsupported channels C=%d N0=%d N1=%d", C, N0, N1);
+  p.tiles_w = Wo / p.Wt; p.tiles_h = Ho / p.Ht;
+  p.B = B; p.Hs = Ho; p.Ws = Wo; p.mode = 0; p.C0 = C; p.C1 = 0; p.Ct = C; p.N = N; p.N0 = N0; p.N1 = N1;
+  p.kblocks = 16 * (C / TILE_K);
+  p.y0 = (bf16*)y0; p.y1 = (bf16*)y1;
+  {  // x viewed as (2C | Wi/2 | 2 | Hi/2 | B)
+    uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)Wo, 2, (uint64_t)Ho, (uint64_t)B};
+    uint64_t str[4] = {(uint64_t)2 * C * 2, (uint64_t)Wi * C * 2, (uint64_t)2 * Wi * C * 2, (uint64_t)Hi * Wi * C * 2};
+    uint32_t box[5] = {TILE_K, (uint32_t)p.Wt, 1, (uint32_t)p.Ht, (uint32_t)p.Bt};
+    ADP_TRY(make_tmap_bf16(&p.tmA0, x, 5, dims, str, box));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)16 * C, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)16 * C * 2};
+    uint32_t box[2] = {TILE_K, (uint32_t)bn};
+    ADP_TRY(make_tmap_bf16(&p.tmW, w_nk, 2, dims, str, box));
+  }
+  return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
+}
+
+int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* w_nk, void* y, int B, int Hi, int Wi, int N,
+                    cudaStream_t s) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  ADP_CHECK_ARG(tile_geometry(B, Hi, Wi, &p.Wt, &p.Ht, &p.Bt), "tc_parity_convT: unsupported spatial size %dx%d", Hi, Wi);
+  const int bn = pick_block_n(N, N, 0);
+  ADP_CHECK_ARG(bn != 0 && C0 % TILE_K == 0 && C1 % TILE_K == 0, "tc_parity_convT: unsupported channels");
+  const int Ct = C0 + C1;
+  p.tiles_w = Wi / p.Wt; p.tiles_h = Hi / p.Ht;
+  p.B = B; p.Hs = Hi; p.Ws = Wi; p.mode = 1; p.C0 = C0; p.C1 = C1; p.Ct = Ct; p.N = N; p.N0 = N; p.N1 = 0;
+  p.kblocks = 4 * (Ct / TILE_K);
+  p.y0 = (bf16*)y; p.y1 = nullptr;
+  for (int h = 0; h < 2; ++h) {
+    const int C = h == 0 ? C0 : C1;
+    if (C == 0) continue;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)Wi * C * 2, (uint64_t)Hi * Wi * C * 2};
+    uint32_t box[4] = {TILE_K, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
+    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, box));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)16 * Ct, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)16 * Ct * 2};
+    uint32_t box[2] = {TILE_K, (uint32_t)bn};
+    ADP_TRY(make_tmap_bf16(&p.tmW, w_nk, 2, dims, str, box));
+  }
+  return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
+}
+
+// wgrad on tensor cores: see adp_wgrad_tc.cu
+}  // namespace adp

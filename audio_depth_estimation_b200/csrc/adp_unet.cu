@@ -31,6 +31,7 @@ struct Plan {
   int D, B, esz;
   LevelPlan lv[ADP_MAX_LEVELS];
   size_t du;                     // float [B,1,S,S]
+  size_t tc_scratch, tc_scratch_bytes;  // fp32 split-K partial sums of the tensor-core convolutions
   size_t sums_begin, sums_end;   // forward BN sums region (zeroed every forward)
   size_t bsums_begin, bsums_end; // backward sums region
   size_t total;
@@ -89,6 +90,9 @@ int make_plan(const adp_unet_desc* d, Plan* p) {
     L.wb_convT_nk = take(wt); L.wb_convT_t = take(wt);
   }
   p->du = take((size_t)d->batch * d->size * d->size * sizeof(float));
+  // a layer only splits K when it has fewer tiles than SMs, i.e. fewer than ~148*128*128 outputs
+  p->tc_scratch_bytes = d->dtype == ADP_BF16 ? (size_t)16 << 20 : 0;
+  p->tc_scratch = take(p->tc_scratch_bytes);
   p->total = off;
   return ADP_OK;
 }
@@ -160,6 +164,7 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
                 ws_bytes, p.total);
   const int D = p.D, B = p.B, dt = d->dtype;
   const bool tc = use_tc(dt);
+  tc_set_scratch(p.tc_scratch_bytes ? at(ws, p.tc_scratch) : nullptr, p.tc_scratch_bytes);
 
   if (tc && !d->reuse_weight_cache) {
     for (int l = 0; l < D; ++l) {
@@ -233,6 +238,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
   ADP_CHECK_ARG(stage_begin >= 0 && stage_end <= 2 * D && stage_begin <= stage_end, "unet_backward: bad stage range");
   const bool tc = use_tc(dt);
   const int bn_mode = d->training ? 2 : 1;
+  tc_set_scratch(p.tc_scratch_bytes ? at(ws, p.tc_scratch) : nullptr, p.tc_scratch_bytes);
 
   // BatchNorm + ReLU backward of q[l] (up-norm of level l+1): g_q[l] -> g_t[l]
   auto up_norm_bwd = [&](int l) -> int {
@@ -317,6 +323,7 @@ extern "C" int adp_unet_backward(const adp_unet_desc* d, const float* x, const f
 }
 
 // ------------------------------------------------------------------ per-layer C ABI
+// (no workspace argument: the tensor-core kernels run without K-splitting here)
 extern "C" int adp_weight_operand(const float* w, int R, int C, int transpose, void* out, void* stream) {
   ADP_CHECK_ARG(w && out && R > 0 && C > 0, "weight_operand: bad arguments");
   if (transpose) return cast_transpose_taps(w, out, R, C, (cudaStream_t)stream);
@@ -327,11 +334,13 @@ extern "C" int adp_weight_operand(const float* w, int R, int C, int transpose, v
 extern "C" int adp_conv2d_k4s2_fprop(int dtype, const void* x, const float* w, const void* w_op, void* y, int B,
                                      int Hin, int Win, int Cin, int Cout, void* stream) {
   ADP_CHECK_ARG(x && w && y, "conv2d_fprop: null pointer");
+  tc_set_scratch(nullptr, 0);
   return conv_gather(dtype, x, w, w_op, y, Cout, nullptr, 0, B, Hin, Win, Cin, (cudaStream_t)stream);
 }
 extern "C" int adp_conv2d_k4s2_dgrad(int dtype, const void* dy, const float* w, const void* w_op, void* dx, int B,
                                      int Hin, int Win, int Cin, int Cout, void* stream) {
   ADP_CHECK_ARG(dy && w && dx, "conv2d_dgrad: null pointer");
+  tc_set_scratch(nullptr, 0);
   return conv_parity(dtype, dy, Cout, nullptr, 0, w, w_op, dx, B, Hin / 2, Win / 2, Cin, (cudaStream_t)stream);
 }
 extern "C" int adp_conv2d_k4s2_wgrad(int dtype, const void* x, const void* dy, float* dw, int B, int Hin, int Win,
@@ -342,11 +351,13 @@ extern "C" int adp_conv2d_k4s2_wgrad(int dtype, const void* x, const void* dy, f
 extern "C" int adp_convT2d_k4s2_fprop(int dtype, const void* x0, int c0, const void* x1, int c1, const float* w,
                                       const void* w_op, void* y, int B, int Hin, int Win, int Cout, void* stream) {
   ADP_CHECK_ARG(x0 && w && y && (c1 == 0 || x1), "convT2d_fprop: null pointer");
+  tc_set_scratch(nullptr, 0);
   return conv_parity(dtype, x0, c0, x1, c1, w, w_op, y, B, Hin, Win, Cout, (cudaStream_t)stream);
 }
 extern "C" int adp_convT2d_k4s2_dgrad(int dtype, const void* dy, const float* w, const void* w_op, void* dx0, int c0,
                                       void* dx1, int c1, int B, int Hin, int Win, int Cout, void* stream) {
   ADP_CHECK_ARG(dy && w && dx0 && (c1 == 0 || dx1), "convT2d_dgrad: null pointer");
+  tc_set_scratch(nullptr, 0);
   return conv_gather(dtype, dy, w, w_op, dx0, c0, dx1, c1, B, 2 * Hin, 2 * Win, Cout, (cudaStream_t)stream);
 }
 extern "C" int adp_convT2d_k4s2_wgrad(int dtype, const void* x0, int c0, const void* x1, int c1, const void* dy,

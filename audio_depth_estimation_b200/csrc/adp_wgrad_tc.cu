@@ -1,0 +1,233 @@
+// Weight gradients of the k4-s2-p1 convolutions on tcgen05 tensor cores (family F3):
+//   dw[m][kh,kw][n] += sum_{b,i,j} S[b,i,j,m] * G[b,2i-1+kh,2j-1+kw,n]
+// (Conv2d: S = dL/dy, G = layer input;  ConvTranspose2d: S = layer input (r|q concat), G = dL/dy.)
+// Replaces cudnnConvolutionBackwardFilter behind models/unetbaseline_model.py:187,:196,:209,:218.
+//
+// Per filter tap this is a GEMM whose reduction index is the PIXEL, while both NHWC operands are
+// contiguous in their channel index -- i.e. both operands are "MN-major".  tcgen05 reads such
+// operands directly through MN-major SWIZZLE_128B shared-memory descriptors, so there is no
+// transpose pass: TMA drops [64 pixels x 64 channels] boxes of S and of the tap-shifted view of G
+// (same 5-D stride-2 view and zero-filled halo as the forward conv) into smem, and one CTA
+// accumulates a [128 x NT] weight tile for FOUR taps at once in tensor memory (4*NT <= 512
+// columns), re-using the S tile across the taps.  The pixel range is split across CTAs until
+// the grid fills the GPU; partial tiles are reduced with fp32 red.global.add.
+#include "adp_tc.cuh"
+
+namespace adp {
+namespace {
+
+using namespace tc;
+
+constexpr int WG_M = 128;            // weight-tile rows (channels of S)
+constexpr int WG_P = 64;             // pixels per k-block
+constexpr int WG_TAPS = 4;           // taps accumulated per CTA (one kernel row kh)
+constexpr int WG_THREADS = 192;
+constexpr int WG_BOX_BYTES = WG_P * 128;   // one [64 pixels x 64 channels] bf16 box
+
+struct WgradParams {
+  CUtensorMap tmS0, tmS1, tmG;
+  int Wt, Ht, Bt, tiles_w, tiles_h, tiles_b;
+  int M0, M1, N;
+  int kblocks, kb_per_split;
+  float* dw;
+};
+
+template <int NT>
+struct WgradSmem {
+  static constexpr int A_BYTES = 2 * WG_BOX_BYTES;
+  static constexpr int B_TAP_BYTES = (NT / 64) * WG_BOX_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + WG_TAPS * B_TAP_BYTES;
+  static constexpr int STAGES = NT == 128 ? 2 : 4;
+  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = WG_TAPS * NT;   // 512 or 256
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using S = WgradSmem<NT>;
+  constexpr int STAGES = S::STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * WG_M;
+  const int n0 = blockIdx.y * NT;
+  const int kh = blockIdx.z & 3;                 // tap group = kernel row
+  const int split = blockIdx.z >> 2;
+  const int kb_begin = split * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.kblocks);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tmS0);
+    if (p.M1 > 0) prefetch_tmap(&p.tmS1);
+    prefetch_tmap(&p.tmG);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const bool second = m0 >= p.M0;
+      const CUtensorMap* tmS = second ? &p.tmS1 : &p.tmS0;
+      const int mc = second ? m0 - p.M0 : m0;
+      const int di = (kh + 1) / 2 - 1, ra = (kh + 1) & 1;
+      for (int it = 0; it < nkb; ++it) {
+        const int kb = kb_begin + it;
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
+        const int tw_i = kb % p.tiles_w, th_i = (kb / p.tiles_w) % p.tiles_h, tb_i = kb / (p.tiles_w * p.tiles_h);
+        const int x0 = tw_i * p.Wt, y0 = th_i * p.Ht, b0 = tb_i * p.Bt;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* a_dst = smem + s * S::STAGE_BYTES;
+        unsigned char* b_dst = a_dst + S::A_BYTES;
+        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        tma_load_4d(a_dst, tmS, &full_bar[s], mc, x0, y0, b0);
+        tma_load_4d(a_dst + WG_BOX_BYTES, tmS, &full_bar[s], mc + 64, x0, y0, b0);
+#pragma unroll
+        for (int kw = 0; kw < WG_TAPS; ++kw) {
+          const int dj = (kw + 1) / 2 - 1, rb = (kw + 1) & 1;
+#pragma unroll
+          for (int h = 0; h < NT / 64; ++h)
+            tma_load_5d(b_dst + kw * S::B_TAP_BYTES + h * WG_BOX_BYTES, &p.tmG, &full_bar[s], rb * p.N + n0 + h * 64,
+                        x0 + dj, ra, y0 + di, b0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(WG_M, NT, 1, 1);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+        for (int kw = 0; kw < WG_TAPS; ++kw) {
+#pragma unroll
+          for (int k = 0; k < WG_P / 16; ++k) {
+            // 16 pixels = two 8-row swizzle atoms = 2048 bytes further down the tile
+            const uint64_t ad = umma_smem_desc(a_addr + k * 2048, WG_BOX_BYTES, 1024);
+            const uint64_t bd = umma_smem_desc(b_addr + kw * S::B_TAP_BYTES + k * 2048, WG_BOX_BYTES, 1024);
+            umma_bf16(tmem_base + kw * NT, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int kw = 0; kw < WG_TAPS; ++kw) {
+      float* row = p.dw + ((size_t)m * 16 + kh * 4 + kw) * p.N + n0;
+#pragma unroll 1
+      for (int cc = 0; cc < NT; cc += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kw * NT + cc), v);
+        if (nkb > 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) red_add_v4(row + cc + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, S::TMEM_COLS);
+  }
+}
+
+bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+bool wg_geometry(int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
+  if (!pow2(Hs) || !pow2(Ws)) return false;
+  *Wt = Ws < WG_P ? Ws : WG_P;
+  int rest = WG_P / *Wt;
+  *Ht = Hs < rest ? Hs : rest;
+  *Bt = rest / *Ht;
+  return true;
+}
+
+template <int NT>
+int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t s) {
+  using S = WgradSmem<NT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADP_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    attr_set = true;
+  }
+  tc_wgrad_kernel<NT><<<grid, WG_THREADS, S::BYTES, s>>>(p);
+  adp_count_tc_launch();
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+}  // namespace
+
+bool tc_supported_wgrad(int B, int Hs, int Ws, int M0, int M1, int N) {
+  int Wt, Ht, Bt;
+  if (!adp_device_is_sm100() || !tc::encode_tiled_fn()) return false;
+  if (M0 <= 0 || M0 % WG_M || M1 % WG_M || N % 64 || B < 1) return false;
+  return wg_geometry(Hs, Ws, &Wt, &Ht, &Bt);
+}
+
+int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int N, float* dw, int B, int Hs, int Ws,
+             cudaStream_t s) {
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  ADP_CHECK_ARG(wg_geometry(Hs, Ws, &p.Wt, &p.Ht, &p.Bt), "tc_wgrad: unsupported spatial size %dx%d", Hs, Ws);
+  ADP_CHECK_ARG(M0 % WG_M == 0 && M1 % WG_M == 0 && N % 64 == 0, "tc_wgrad: unsupported channels");
+  const int NT = N % 128 == 0 ? 128 : 64;
+  p.tiles_w = Ws / p.Wt; p.tiles_h = Hs / p.Ht; p.tiles_b = adp_cdiv(B, p.Bt);
+  p.M0 = M0; p.M1 = M1; p.N = N; p.dw = dw;
+  p.kblocks = p.tiles_w * p.tiles_h * p.tiles_b;
+  for (int h = 0; h < 2; ++h) {
+    const int C = h == 0 ? M0 : M1;
+    if (C == 0) continue;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)Ws * C * 2, (uint64_t)Hs * Ws * C * 2};
+    uint32_t box[4] = {64, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
+    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmS0 : &p.tmS1, h == 0 ? s0 : s1, 4, dims, str, box));
+  }
+  {  // G [B, 2Hs, 2Ws, N] viewed as (2N | Ws | 2 | Hs | B)
+    const int Hg = 2 * Hs, Wg = 2 * Ws;
+    uint64_t dims[5] = {(uint64_t)2 * N, (uint64_t)Ws, 2, (uint64_t)Hs, (uint64_t)B};
+    uint64_t str[4] = {(uint64_t)2 * N * 2, (uint64_t)Wg * N * 2, (uint64_t)2 * Wg * N * 2, (uint64_t)Hg * Wg * N * 2};
+    uint32_t box[5] = {64, (uint32_t)p.Wt, 1, (uint32_t)p.Ht, (uint32_t)p.Bt};
+    ADP_TRY(make_tmap_bf16(&p.tmG, g, 5, dims, str, box));
+  }
+  const int m_tiles = (M0 + M1) / WG_M, n_tiles = N / NT;
+  const long long ctas = (long long)m_tiles * n_tiles * 4;
+  int splits = (int)((2LL * sm_count() + ctas - 1) / ctas);
+  if (splits > p.kblocks) splits = p.kblocks;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = adp_cdiv(p.kblocks, splits);
+  splits = adp_cdiv(p.kblocks, p.kb_per_split);
+  dim3 grid(m_tiles, n_tiles, 4 * splits);
+  if (NT == 128) return launch_wgrad<128>(p, grid, s);
+  return launch_wgrad<64>(p, grid, s);
+}
+
+}  // namespace adp

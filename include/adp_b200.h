@@ -182,6 +182,8 @@ int adp_clip_adamw_step(const adp_tensor_ref* refs_host, int n_tensors, const do
 /* ------------------------------------------------------------------ measurement
  * Kernel launches issued by this library since load (bench.py's gpu_launches). */
 long long adp_launch_count(void);
+/* ... of which tcgen05 tensor-core kernels. */
+long long adp_tc_launch_count(void);
 /* CUDA-event timing of the convolution kernel families on their launching stream.
  * adp_profile_enable(1) clears and starts, (0) stops; adp_profile_read (after the stream is
  * synchronised) fills 5-entry arrays {gather conv, parity convT, wgrad, thin first/last layers,
