@@ -67,6 +67,39 @@ __device__ __forceinline__ void st4(bf16* p, float4 v) {
   u.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = u;
 }
+// ---- 8-wide typed loads / stores (fp32: 2 x 16 B, bf16: 16 B) ---------------
+struct float8 { float v[8]; };
+__device__ __forceinline__ float8 ld8(const float* p) {
+  float8 r;
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ float8 ld8(const bf16* p) {
+  float8 r;
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+  return r;
+}
+__device__ __forceinline__ void st8(float* p, const float8& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_(float lo, float hi) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&a);
+}
+__device__ __forceinline__ void st8(bf16* p, const float8& r) {
+  uint4 u;
+  u.x = pack_bf16x2_(r.v[0], r.v[1]); u.y = pack_bf16x2_(r.v[2], r.v[3]);
+  u.z = pack_bf16x2_(r.v[4], r.v[5]); u.w = pack_bf16x2_(r.v[6], r.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
 __device__ __forceinline__ float ld1(const float* p) { return *p; }
 __device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
@@ -177,6 +210,23 @@ int last_convT_dgrad(int dtype, const float* du, const float* w, void* g0, int C
                      int B, int Hi, int Wi, cudaStream_t s);
 int last_convT_wgrad(int dtype, const void* x0, int C0, const void* x1, int C1, const float* du,
                      float* dw, int B, int Hi, int Wi, cudaStream_t s);
+
+// tiled thin-layer kernels (adp_thin.cu)
+bool thin_first_supported(int Cin, int N);
+int thin_first_conv_fprop(int dtype, const float* x, const float* w, float slope0, void* out0, float slope1, void* out1,
+                          int B, int H, int W, int Cin, int N, cudaStream_t s);
+int thin_first_conv_wgrad(int dtype, const float* x, const void* dy, float* dw, int B, int H, int W, int Cin, int N,
+                          cudaStream_t s);
+int thin_last_convT_dgrad(int dtype, const float* du, const float* w, void* g0, int C0, void* g1, int C1, int B, int Hi,
+                          int Wi, cudaStream_t s);
+int thin_last_convT_wgrad(int dtype, const void* x0, int C0, const void* x1, int C1, const float* du, float* dw, int B,
+                          int Hi, int Wi, cudaStream_t s);
+// P fp32 [B,Hi,Wi,16] -> y fp32 [B,1,2Hi,2Wi] = act(bias + col2im(P))
+int last_convT_col2im(const float* P, const float* bias, int final_sigmoid, float* y, int B, int Hi, int Wi, cudaStream_t s);
+// P[pixel][16 taps] = sum_c (x0|x1)[pixel][c] * w16[tap][c]   (w16: bf16 [16][C0+C1]) on tensor cores
+bool tc_supported_pointwise16(int B, int Hi, int Wi, int C0, int C1);
+int tc_pointwise16(const void* x0, int C0, const void* x1, int C1, const void* w16, float* P, int B, int Hi, int Wi,
+                   cudaStream_t s);
 
 // tcgen05 paths (adp_conv_tc.cu), bf16 operands, fp32 accumulate in TMEM.
 // w_nk: bf16 [N][16][C] (K-major B operand)

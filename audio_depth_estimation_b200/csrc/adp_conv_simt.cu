@@ -66,7 +66,6 @@ __global__ void __launch_bounds__(256) igemm_kernel(const P p) {
     p.storeC(ctx, m0 + ty * 4 + i, n0 + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
 }
 
-const float4 ZERO4 = {0.f, 0.f, 0.f, 0.f};
 #define Z4 make_float4(0.f, 0.f, 0.f, 0.f)
 
 struct CtxRange {
@@ -448,6 +447,8 @@ int simt_gather_conv(int dtype, const void* x, const float* w, void* y0, int N0,
 int first_conv_fprop(int dtype, const float* x, const float* w, float slope0, void* out0, float slope1,
                      void* out1, int B, int H, int W, int Cin, int N, cudaStream_t s) {
   ADP_CHECK_ARG(N % 4 == 0 && (16 * Cin) % 4 == 0 && H % 2 == 0 && W % 2 == 0, "first_conv: bad shape");
+  if (thin_first_supported(Cin, N))
+    return thin_first_conv_fprop(dtype, x, w, slope0, out0, slope1, out1, B, H, W, Cin, N, s);
   ADP_DISPATCH_T(dtype, {
     FirstConv<T> p;
     p.x = x; p.w = w; p.out0 = (T*)out0; p.out1 = (T*)out1; p.slope0 = slope0; p.slope1 = slope1;
@@ -495,6 +496,7 @@ int simt_wgrad(int dtype, const void* s0, int M0, const void* s1, int M1, const 
 int first_conv_wgrad(int dtype, const float* x, const void* dy, float* dw, int B, int H, int W, int Cin, int N,
                      cudaStream_t s) {
   ADP_CHECK_ARG(N % 4 == 0 && H % 2 == 0 && W % 2 == 0, "first_conv_wgrad: bad shape");
+  if (thin_first_supported(Cin, N)) return thin_first_conv_wgrad(dtype, x, dy, dw, B, H, W, Cin, N, s);
   ADP_DISPATCH_T(dtype, {
     FirstWgrad<T> p;
     p.x = x; p.dy = (const T*)dy; p.dw = dw; p.B = B; p.Hi = H; p.Wi = W; p.C = Cin; p.Ho = H / 2; p.Wo = W / 2;
@@ -528,6 +530,7 @@ int last_convT_fprop(int dtype, const void* x0, int C0, const void* x1, int C1, 
 int last_convT_dgrad(int dtype, const float* du, const float* w, void* g0, int C0, void* g1, int C1,
                      int B, int Hi, int Wi, cudaStream_t s) {
   ADP_CHECK_ARG(C0 % 4 == 0 && C1 % 4 == 0 && C0 + C1 <= 2048, "last_convT_dgrad: bad channel counts");
+  return thin_last_convT_dgrad(dtype, du, w, g0, C0, g1, C1, B, Hi, Wi, s);
   size_t smem = (size_t)16 * (C0 + C1) * 4;
   long long npix = (long long)B * Hi * Wi;
   ADP_DISPATCH_T(dtype, {
@@ -542,6 +545,7 @@ int last_convT_dgrad(int dtype, const float* du, const float* w, void* g0, int C
 int last_convT_wgrad(int dtype, const void* x0, int C0, const void* x1, int C1, const float* du, float* dw,
                      int B, int Hi, int Wi, cudaStream_t s) {
   ADP_CHECK_ARG(C0 % 4 == 0 && C1 % 4 == 0, "last_convT_wgrad: bad channel counts");
+  return thin_last_convT_wgrad(dtype, x0, C0, x1, C1, du, dw, B, Hi, Wi, s);
   long long npix = (long long)B * Hi * Wi;
   int grid = adp::sm_count() * 2;
   if ((long long)grid * (LAST_THREADS / 32) > npix) grid = (int)((npix + 7) / 8);

@@ -76,19 +76,20 @@ struct IgemmParams {
   // tile geometry over the "small" pixel grid (conv outputs for F1, convT inputs for F2)
   int Wt, Ht, Bt, tiles_w, tiles_h;
   int B, Hs, Ws;                      // small grid extent
-  int mode;                           // 0 = gather (F1), 1 = parity (F2)
+  int mode;                           // 0 = gather (F1), 1 = parity (F2), 2 = pointwise (1x1, fp32 rows out)
   int C0, C1, Ct;                     // input channels (concat halves)
   int N, N0, N1;                      // output channels and split
   int kblocks, splits, kb_per_split;
   bf16* y0; bf16* y1;
   float* partial;                     // fp32 [out pixels][N] when splits > 1
+  float* out_f32;                     // mode 2: fp32 [pixels][BLOCK_N] result
 };
 
 template <int BLOCK_N>
 struct IgemmSmem {
   static constexpr int B_STAGE_BYTES = BLOCK_N * TILE_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BLOCK_N <= 64 ? 6 : (BLOCK_N <= 128 ? 5 : 4);
+  static constexpr int STAGES = BLOCK_N <= 16 ? 2 : (BLOCK_N <= 64 ? 6 : (BLOCK_N <= 128 ? 5 : 4));
   static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -152,6 +153,10 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid
           const int dj = (kw + 1) / 2 - 1, rb = (kw + 1) & 1;
           tma_load_5d(a_dst, &p.tmA0, &full_bar[s], rb * p.Ct + c, x0 + dj, ra, y0c + di, b0);
           tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + c, n0);
+        } else if (p.mode == 2) {
+          if (c < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], c, x0, y0c, b0);
+          else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], c - p.C0, x0, y0c, b0);
+          tma_load_2d(b_dst, &p.tmW, &full_bar[s], c, n0);
         } else {
           const int th = tap >> 1, tw = tap & 1;
           const int cx = x0 + pb - 1 + tw, cy = y0c + pa - 1 + th;
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid
     const int b = b0 + bt, py = y0c + ht, px = x0 + wt;
     const bool valid = b < p.B && nkb > 0;
     size_t opix;
-    if (p.mode == 0) opix = ((size_t)b * p.Hs + py) * p.Ws + px;
+    if (p.mode != 1) opix = ((size_t)b * p.Hs + py) * p.Ws + px;
     else opix = ((size_t)b * 2 * p.Hs + 2 * py + pa) * (2 * p.Ws) + 2 * px + pb;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
@@ -201,7 +206,11 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
       if (!valid) continue;
       const int n = n0 + cc;
-      if (p.splits > 1) {
+      if (BLOCK_N == 16) {
+        float* dst = p.out_f32 + opix * 16;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      } else if (p.splits > 1) {
         float* dst = p.partial + opix * p.N + n;
 #pragma unroll
         for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
@@ -298,6 +307,7 @@ int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes,
     case 128: ADP_TRY(launch_igemm<128>(p, grid, s)); break;
     case 64: ADP_TRY(launch_igemm<64>(p, grid, s)); break;
     case 32: ADP_TRY(launch_igemm<32>(p, grid, s)); break;
+    case 16: ADP_TRY(launch_igemm<16>(p, grid, s)); break;
     default: adp_set_error("tc igemm: bad BLOCK_N %d", block_n); return ADP_ERR_ARG;
   }
   if (splits > 1) {
@@ -389,6 +399,41 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
     ADP_TRY(make_tmap_bf16(&p.tmW, w_nk, 2, dims, str, box));
   }
   return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
+}
+
+bool tc_supported_pointwise16(int B, int Hi, int Wi, int C0, int C1) {
+  int Wt, Ht, Bt;
+  if (!adp_device_is_sm100() || !encode_tiled_fn()) return false;
+  if (C0 % TILE_K || C1 % TILE_K || C0 <= 0 || B < 1) return false;
+  return tile_geometry(B, Hi, Wi, &Wt, &Ht, &Bt);
+}
+
+int tc_pointwise16(const void* x0, int C0, const void* x1, int C1, const void* w16, float* P, int B, int Hi, int Wi,
+                   cudaStream_t s) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  ADP_CHECK_ARG(tile_geometry(B, Hi, Wi, &p.Wt, &p.Ht, &p.Bt), "tc_pointwise16: unsupported spatial size %dx%d", Hi, Wi);
+  ADP_CHECK_ARG(C0 % TILE_K == 0 && C1 % TILE_K == 0 && C0 > 0, "tc_pointwise16: unsupported channels");
+  const int Ct = C0 + C1;
+  p.tiles_w = Wi / p.Wt; p.tiles_h = Hi / p.Ht;
+  p.B = B; p.Hs = Hi; p.Ws = Wi; p.mode = 2; p.C0 = C0; p.C1 = C1; p.Ct = Ct; p.N = 16; p.N0 = 16; p.N1 = 0;
+  p.kblocks = Ct / TILE_K;
+  p.out_f32 = P;
+  for (int h = 0; h < 2; ++h) {
+    const int C = h == 0 ? C0 : C1;
+    if (C == 0) continue;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)Wi * C * 2, (uint64_t)Hi * Wi * C * 2};
+    uint32_t box[4] = {TILE_K, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
+    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, box));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)Ct, 16};
+    uint64_t str[1] = {(uint64_t)Ct * 2};
+    uint32_t box[2] = {TILE_K, 16};
+    ADP_TRY(make_tmap_bf16(&p.tmW, w16, 2, dims, str, box));
+  }
+  return run_igemm(p, 16, nullptr, 0, s);
 }
 
 // wgrad on tensor cores: see adp_wgrad_tc.cu

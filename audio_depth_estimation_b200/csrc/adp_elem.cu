@@ -195,6 +195,186 @@ act_bn_bwd_apply_kernel(const T* __restrict__ x, long long n4, long long rows, i
   }
 }
 
+
+// ================================================================== 8-wide variants (C % 8 == 0)
+// Column reductions use blockDim = (tx, 256/tx) with tx = min(32, C/8): every thread owns 8 consecutive
+// channels and strides over rows, so narrow tensors (C = 64) still use all 256 threads.
+// Final stage: shuffle over the rows held by one warp, then one (channel, value) per thread.
+__device__ __forceinline__ void col_reduce16(float (&v)[16], int C, int c0_block, double* __restrict__ sums) {
+  __shared__ float red[8][32][17];
+  const int tx = blockDim.x;
+  const int tid = threadIdx.y * tx + threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int off = tx; off < 32; off <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+  }
+  if (lane < tx) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) red[warp][lane][i] = v[i];
+  }
+  __syncthreads();
+  // columns per warp-row: tx >= 32 means every lane is a distinct column group
+  const int groups = tx < 32 ? tx : 32;
+  const int nwarps = (tx * blockDim.y) >> 5;
+  for (int item = tid; item < groups * 16; item += tx * blockDim.y) {
+    const int x = item >> 4, i = item & 15;
+    double a = 0.0;
+    if (tx < 32) {
+      for (int w = 0; w < nwarps; ++w) a += (double)red[w][x][i];
+    } else {
+      for (int w = 0; w < nwarps; ++w) a += (double)red[w][x][i];
+    }
+    const int c = c0_block + x * 8;
+    if (c < C) atomicAdd(&sums[(i < 8 ? 0 : C) + c + (i & 7)], a);
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+bn_stats8_kernel(const T* __restrict__ x, long long rows, int C, double* __restrict__ sums) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  if (c < C) {
+    const long long step = (long long)gridDim.y * blockDim.y;
+    long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+    for (; r + step < rows; r += 2 * step) {   // two independent loads in flight
+      const float8 a = ld8(x + r * C + c), b = ld8(x + (r + step) * C + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] += a.v[i] + b.v[i];
+        v[8 + i] = fmaf(a.v[i], a.v[i], fmaf(b.v[i], b.v[i], v[8 + i]));
+      }
+    }
+    for (; r < rows; r += step) {
+      const float8 a = ld8(x + r * C + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] += a.v[i]; v[8 + i] = fmaf(a.v[i], a.v[i], v[8 + i]); }
+    }
+  }
+  col_reduce16(v, C, blockIdx.x * blockDim.x * 8, sums);
+}
+
+// Streaming kernels: a block covers 2048 consecutive elements per iteration, so when 2048 % C == 0 a
+// thread meets the SAME 8 channels in every iteration and its per-channel coefficients stay in registers.
+template <class T, bool FIXED>
+__global__ void __launch_bounds__(EW_THREADS)
+affine_act8_kernel(const T* __restrict__ x, long long n8, int C, const float* __restrict__ scale,
+                   const float* __restrict__ shift, float slope0, T* __restrict__ out0, float slope1, T* __restrict__ out1) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float8 sc, sh;
+  if (FIXED && scale) { const int c = (threadIdx.x * 8) % C; sc = ld8(scale + c); sh = ld8(shift + c); }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float8 v = ld8(x + 8 * i);
+    if (scale) {
+      if (!FIXED) { const int c = (int)((8 * i) % C); sc = ld8(scale + c); sh = ld8(shift + c); }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v.v[k] = fmaf(v.v[k], sc.v[k], sh.v[k]);
+    }
+    float8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = lrelu(v.v[k], slope0);
+    st8(out0 + 8 * i, o);
+    if (out1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = lrelu(v.v[k], slope1);
+      st8(out1 + 8 * i, o);
+    }
+  }
+}
+
+template <class T>
+__device__ __forceinline__ float8 gz8(const float8& xv, const float8* sc, const float8* sh, const T* gA, float slope0,
+                                      const T* gB, float slope1, long long off) {
+  float8 z = xv;
+  if (sc) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z.v[k] = fmaf(z.v[k], sc->v[k], sh->v[k]);
+  }
+  float8 g;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) g.v[k] = 0.f;
+  if (gA) {
+    const float8 a = ld8(gA + off);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = a.v[k] * lrelu_grad(z.v[k], slope0);
+  }
+  if (gB) {
+    const float8 b = ld8(gB + off);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = fmaf(b.v[k], lrelu_grad(z.v[k], slope1), g.v[k]);
+  }
+  return g;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+act_bn_bwd_reduce8_kernel(const T* __restrict__ x, long long rows, int C, const float* __restrict__ scale,
+                          const float* __restrict__ shift, const float* __restrict__ mean,
+                          const float* __restrict__ invstd, const T* __restrict__ gA, float slope0,
+                          const T* __restrict__ gB, float slope1, double* __restrict__ sums) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  if (c < C) {
+    const float8 mu = ld8(mean + c), is = ld8(invstd + c);
+    float8 sc, sh;
+    if (scale) { sc = ld8(scale + c); sh = ld8(shift + c); }
+    const long long step = (long long)gridDim.y * blockDim.y;
+    for (long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y; r < rows; r += step) {
+      const long long off = r * C + c;
+      const float8 xv = ld8(x + off);
+      const float8 g = gz8(xv, scale ? &sc : nullptr, &sh, gA, slope0, gB, slope1, off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] += g.v[i];
+        v[8 + i] = fmaf(g.v[i], (xv.v[i] - mu.v[i]) * is.v[i], v[8 + i]);
+      }
+    }
+  }
+  col_reduce16(v, C, blockIdx.x * blockDim.x * 8, sums);
+}
+
+// dx = A*gz + Bc*x + Cc  with  mode 0: A=1,Bc=Cc=0;  1: A=scale;  2: A=scale, Bc=-scale*invstd*s2/M,
+// Cc = -scale*s1/M + scale*invstd*mean*s2/M   (the batch-statistics BatchNorm backward)
+template <class T, bool FIXED>
+__global__ void __launch_bounds__(EW_THREADS)
+act_bn_bwd_apply8_kernel(const T* __restrict__ x, long long n8, long long rows, int C, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const T* __restrict__ gA, float slope0,
+                         const T* __restrict__ gB, float slope1, const double* __restrict__ sums, int mode,
+                         T* __restrict__ dx) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float inv_m = 1.f / (float)rows;
+  float8 sc, sh, cA, cB, cC;
+  auto coeffs = [&](int c) {
+    if (scale) { sc = ld8(scale + c); sh = ld8(shift + c); }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { cA.v[k] = 1.f; cB.v[k] = 0.f; cC.v[k] = 0.f; }
+    if (mode >= 1) cA = sc;
+    if (mode == 2) {
+      const float8 mu = ld8(mean + c), is = ld8(invstd + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float s1 = (float)sums[c + k] * inv_m, s2 = (float)sums[C + c + k] * inv_m;
+        cB.v[k] = -sc.v[k] * is.v[k] * s2;
+        cC.v[k] = -sc.v[k] * s1 - cB.v[k] * mu.v[k];
+      }
+    }
+  };
+  if (FIXED) coeffs((threadIdx.x * 8) % C);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    if (!FIXED) coeffs((int)((8 * i) % C));
+    const float8 xv = ld8(x + 8 * i);
+    float8 g = gz8(xv, scale ? &sc : nullptr, &sh, gA, slope0, gB, slope1, 8 * i);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = fmaf(cA.v[k], g.v[k], fmaf(cB.v[k], xv.v[k], cC.v[k]));
+    st8(dx + 8 * i, g);
+  }
+}
+
 __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
                                       float* __restrict__ dbeta) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,10 +433,25 @@ cast_transpose_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int
 
 int ew_grid(long long n4) {
   long long blocks = (n4 + EW_THREADS - 1) / EW_THREADS;
-  long long cap = (long long)adp::sm_count() * 16;
+  long long cap = (long long)adp::sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
+}
+
+struct ColLaunch { dim3 grid, block; };
+ColLaunch col_launch8(long long rows, int C) {
+  int tx = C / 8 < 32 ? C / 8 : 32;
+  int p2 = 1;
+  while (p2 * 2 <= tx) p2 *= 2;       // power of two so that 256 / tx is integral
+  tx = p2;
+  const int ty = 256 / tx;
+  const int gx = adp_cdiv(C, tx * 8);
+  long long gy = (rows + (long long)ty * 8 - 1) / ((long long)ty * 8);   // >= 8 rows per thread
+  long long cap = (long long)adp::sm_count() * 4 / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  return ColLaunch{dim3(gx, (unsigned)gy), dim3(tx, ty)};
 }
 
 dim3 col_grid(long long rows, int C) {
@@ -286,6 +481,12 @@ namespace adp {
 
 int bn_stats(int dtype, const void* x, long long rows, int C, double* sums, cudaStream_t s) {
   ADP_CHECK_ARG(C % 4 == 0, "bn_stats: C %% 4 != 0");
+  if (C % 8 == 0) {
+    ColLaunch L = col_launch8(rows, C);
+    ADP_DISPATCH_T(dtype, bn_stats8_kernel<T><<<L.grid, L.block, 0, s>>>((const T*)x, rows, C, sums);)
+    ADP_LAUNCH_CHECK();
+    return ADP_OK;
+  }
   ADP_DISPATCH_T(dtype, bn_stats_kernel<T><<<col_grid(rows, C), dim3(32, 8), 0, s>>>((const T*)x, rows, C, sums);)
   ADP_LAUNCH_CHECK();
   return ADP_OK;
@@ -303,6 +504,18 @@ int bn_finalize(const double* sums, long long rows, int C, const float* gamma, c
 int affine_act(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift,
                float slope0, void* out0, float slope1, void* out1, cudaStream_t s) {
   ADP_CHECK_ARG(C % 4 == 0, "affine_act: C %% 4 != 0");
+  if (C % 8 == 0) {
+    long long n8 = rows * C / 8;
+    if (2048 % C == 0) {
+      ADP_DISPATCH_T(dtype, (affine_act8_kernel<T, true><<<ew_grid(n8), EW_THREADS, 0, s>>>(
+                                (const T*)x, n8, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1));)
+    } else {
+      ADP_DISPATCH_T(dtype, (affine_act8_kernel<T, false><<<ew_grid(n8), EW_THREADS, 0, s>>>(
+                                (const T*)x, n8, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1));)
+    }
+    ADP_LAUNCH_CHECK();
+    return ADP_OK;
+  }
   long long n4 = rows * C / 4;
   ADP_DISPATCH_T(dtype, affine_act_kernel<T><<<ew_grid(n4), EW_THREADS, 0, s>>>(
                             (const T*)x, n4, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1);)
@@ -314,6 +527,14 @@ int act_bn_bwd_reduce(int dtype, const void* x, long long rows, int C, const flo
                       const float* mean, const float* invstd, const void* gA, float slope0, const void* gB,
                       float slope1, double* sums, cudaStream_t s) {
   ADP_CHECK_ARG(C % 4 == 0, "act_bn_bwd_reduce: C %% 4 != 0");
+  if (C % 8 == 0) {
+    ColLaunch L = col_launch8(rows, C);
+    ADP_DISPATCH_T(dtype, act_bn_bwd_reduce8_kernel<T><<<L.grid, L.block, 0, s>>>(
+                              (const T*)x, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0, (const T*)gB,
+                              slope1, sums);)
+    ADP_LAUNCH_CHECK();
+    return ADP_OK;
+  }
   ADP_DISPATCH_T(dtype, act_bn_bwd_reduce_kernel<T><<<col_grid(rows, C), dim3(32, 8), 0, s>>>(
                             (const T*)x, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
                             (const T*)gB, slope1, sums);)
@@ -325,6 +546,20 @@ int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const floa
                      const float* mean, const float* invstd, const void* gA, float slope0, const void* gB,
                      float slope1, const double* sums, int mode, void* dx, cudaStream_t s) {
   ADP_CHECK_ARG(C % 4 == 0, "act_bn_bwd_apply: C %% 4 != 0");
+  if (C % 8 == 0) {
+    long long n8 = rows * C / 8;
+    if (2048 % C == 0) {
+      ADP_DISPATCH_T(dtype, (act_bn_bwd_apply8_kernel<T, true><<<ew_grid(n8), EW_THREADS, 0, s>>>(
+                                (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
+                                (const T*)gB, slope1, sums, mode, (T*)dx));)
+    } else {
+      ADP_DISPATCH_T(dtype, (act_bn_bwd_apply8_kernel<T, false><<<ew_grid(n8), EW_THREADS, 0, s>>>(
+                                (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
+                                (const T*)gB, slope1, sums, mode, (T*)dx));)
+    }
+    ADP_LAUNCH_CHECK();
+    return ADP_OK;
+  }
   long long n4 = rows * C / 4;
   ADP_DISPATCH_T(dtype, act_bn_bwd_apply_kernel<T><<<ew_grid(n4), EW_THREADS, 0, s>>>(
                             (const T*)x, n4, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,

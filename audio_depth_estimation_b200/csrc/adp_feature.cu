@@ -161,18 +161,17 @@ resize_aa_kernel(const float* __restrict__ in, int H, int W, int S, float* __res
   }
   AxisTaps ah = aa_axis(p, H, S);
   AxisTaps aw = aa_axis(o, W, S);
+  const float ih = ah.total != 0.f ? 1.f / ah.total : 1.f, iw = aw.total != 0.f ? 1.f / aw.total : 1.f;
   const float* src = in + (size_t)row * H * W;
   float acc = 0.f;
   for (int jh = 0; jh < ah.size; ++jh) {
     const float* line = src + (size_t)(ah.lo + jh) * W + aw.lo;
     float hacc = 0.f;
-    for (int jw = 0; jw < aw.size; ++jw) {
-      float v = line[jw];
-      if (minmax) v = (v - mn) / den;
-      hacc += v * (aw.total != 0.f ? aa_w(aw, jw) / aw.total : aa_w(aw, jw));
-    }
-    acc += hacc * (ah.total != 0.f ? aa_w(ah, jh) / ah.total : aa_w(ah, jh));
+    for (int jw = 0; jw < aw.size; ++jw) hacc = fmaf(line[jw], aa_w(aw, jw) * iw, hacc);
+    acc = fmaf(hacc, aa_w(ah, jh) * ih, acc);
   }
+  // the weights sum to one, so the per-channel min-max commutes with the resize
+  if (minmax) acc = (acc - mn) / den;
   if (zero) acc = 0.f;
   out[((size_t)row * S + p) * S + o] = acc;
 }

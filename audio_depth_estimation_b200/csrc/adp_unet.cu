@@ -31,6 +31,7 @@ struct Plan {
   int D, B, esz;
   LevelPlan lv[ADP_MAX_LEVELS];
   size_t du;                     // float [B,1,S,S]
+  size_t p_last, w16_last;       // tensor-core head: P fp32 [B,H/2,W/2,16], bf16 weights [16][Ct]
   size_t tc_scratch, tc_scratch_bytes;  // fp32 split-K partial sums of the tensor-core convolutions
   size_t sums_begin, sums_end;   // forward BN sums region (zeroed every forward)
   size_t bsums_begin, bsums_end; // backward sums region
@@ -93,6 +94,8 @@ int make_plan(const adp_unet_desc* d, Plan* p) {
   // a layer only splits K when it has fewer tiles than SMs, i.e. fewer than ~148*128*128 outputs
   p->tc_scratch_bytes = d->dtype == ADP_BF16 ? (size_t)16 << 20 : 0;
   p->tc_scratch = take(p->tc_scratch_bytes);
+  p->p_last = take(d->dtype == ADP_BF16 ? (size_t)d->batch * p->lv[0].hout * p->lv[0].hout * 16 * sizeof(float) : 0);
+  p->w16_last = take((size_t)16 * (p->lv[0].cout + p->lv[0].t_c1) * 2);
   p->total = off;
   return ADP_OK;
 }
@@ -166,7 +169,11 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   const bool tc = use_tc(dt);
   tc_set_scratch(p.tc_scratch_bytes ? at(ws, p.tc_scratch) : nullptr, p.tc_scratch_bytes);
 
+  const bool tc_head = tc && d->out_ch == 1 &&
+                       tc_supported_pointwise16(B, p.lv[0].hout, p.lv[0].hout, p.lv[0].cout, p.lv[0].t_c1);
   if (tc && !d->reuse_weight_cache) {
+    if (tc_head)  // [Ct][16][1] -> [1][16][Ct]
+      ADP_TRY(cast_transpose_taps(params[0].convT_w, at(ws, p.w16_last), p.lv[0].cout + p.lv[0].t_c1, 1, s));
     for (int l = 0; l < D; ++l) {
       const LevelPlan& L = p.lv[l];
       if (l > 0) {
@@ -220,8 +227,15 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   }
   {
     const LevelPlan& L = p.lv[0];
-    ADP_TRY(last_convT_fprop(dt, at(ws, L.r), L.cout, at(ws, L.q), L.t_c1, params[0].convT_w, params[0].convT_bias,
-                             d->final_sigmoid, y, B, L.hout, L.hout, s));
+    ProfScope prof(PROF_THIN, s, 2.0 * B * L.hout * L.hout * 16.0 * (L.cout + L.t_c1));
+    if (tc_head) {
+      float* P = reinterpret_cast<float*>(at(ws, p.p_last));
+      ADP_TRY(tc_pointwise16(at(ws, L.r), L.cout, at(ws, L.q), L.t_c1, at(ws, p.w16_last), P, B, L.hout, L.hout, s));
+      ADP_TRY(last_convT_col2im(P, params[0].convT_bias, d->final_sigmoid, y, B, L.hout, L.hout, s));
+    } else {
+      ADP_TRY(last_convT_fprop(dt, at(ws, L.r), L.cout, at(ws, L.q), L.t_c1, params[0].convT_w, params[0].convT_bias,
+                               d->final_sigmoid, y, B, L.hout, L.hout, s));
+    }
   }
   return ADP_OK;
 }
