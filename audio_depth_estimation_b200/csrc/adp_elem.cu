@@ -284,10 +284,18 @@ affine_act8_kernel(const T* __restrict__ x, long long n8, int C, const float* __
   }
 }
 
+struct GzIn { float8 x, a, b; };
 template <class T>
-__device__ __forceinline__ float8 gz8(const float8& xv, const float8* sc, const float8* sh, const T* gA, float slope0,
-                                      const T* gB, float slope1, long long off) {
-  float8 z = xv;
+__device__ __forceinline__ GzIn gz_load(const T* x, const T* gA, const T* gB, long long off) {
+  GzIn r;
+  r.x = ld8(x + off);
+  if (gA) r.a = ld8(gA + off);
+  if (gB) r.b = ld8(gB + off);
+  return r;
+}
+__device__ __forceinline__ float8 gz_compute(const GzIn& in, const float8* sc, const float8* sh, bool hasA, float slope0,
+                                             bool hasB, float slope1) {
+  float8 z = in.x;
   if (sc) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) z.v[k] = fmaf(z.v[k], sc->v[k], sh->v[k]);
@@ -295,15 +303,13 @@ __device__ __forceinline__ float8 gz8(const float8& xv, const float8* sc, const 
   float8 g;
 #pragma unroll
   for (int k = 0; k < 8; ++k) g.v[k] = 0.f;
-  if (gA) {
-    const float8 a = ld8(gA + off);
+  if (hasA) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g.v[k] = a.v[k] * lrelu_grad(z.v[k], slope0);
+    for (int k = 0; k < 8; ++k) g.v[k] = in.a.v[k] * lrelu_grad(z.v[k], slope0);
   }
-  if (gB) {
-    const float8 b = ld8(gB + off);
+  if (hasB) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g.v[k] = fmaf(b.v[k], lrelu_grad(z.v[k], slope1), g.v[k]);
+    for (int k = 0; k < 8; ++k) g.v[k] = fmaf(in.b.v[k], lrelu_grad(z.v[k], slope1), g.v[k]);
   }
   return g;
 }
@@ -323,16 +329,22 @@ act_bn_bwd_reduce8_kernel(const T* __restrict__ x, long long rows, int C, const 
     float8 sc, sh;
     if (scale) { sc = ld8(scale + c); sh = ld8(shift + c); }
     const long long step = (long long)gridDim.y * blockDim.y;
-    for (long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y; r < rows; r += step) {
-      const long long off = r * C + c;
-      const float8 xv = ld8(x + off);
-      const float8 g = gz8(xv, scale ? &sc : nullptr, &sh, gA, slope0, gB, slope1, off);
+    const float8* scp = scale ? &sc : nullptr;
+    auto accumulate = [&](const GzIn& in) {
+      const float8 g = gz_compute(in, scp, &sh, gA != nullptr, slope0, gB != nullptr, slope1);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         v[i] += g.v[i];
-        v[8 + i] = fmaf(g.v[i], (xv.v[i] - mu.v[i]) * is.v[i], v[8 + i]);
+        v[8 + i] = fmaf(g.v[i], (in.x.v[i] - mu.v[i]) * is.v[i], v[8 + i]);
       }
+    };
+    long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+    for (; r + step < rows; r += 2 * step) {      // two rows in flight
+      const GzIn i0 = gz_load(x, gA, gB, r * C + c), i1 = gz_load(x, gA, gB, (r + step) * C + c);
+      accumulate(i0);
+      accumulate(i1);
     }
+    for (; r < rows; r += step) accumulate(gz_load(x, gA, gB, r * C + c));
   }
   col_reduce16(v, C, blockIdx.x * blockDim.x * 8, sums);
 }
@@ -365,13 +377,24 @@ act_bn_bwd_apply8_kernel(const T* __restrict__ x, long long n8, long long rows, 
     }
   };
   if (FIXED) coeffs((threadIdx.x * 8) % C);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
-    if (!FIXED) coeffs((int)((8 * i) % C));
-    const float8 xv = ld8(x + 8 * i);
-    float8 g = gz8(xv, scale ? &sc : nullptr, &sh, gA, slope0, gB, slope1, 8 * i);
+  const float8* scp = scale ? &sc : nullptr;
+  auto finish = [&](const GzIn& in, long long i) {
+    float8 g = gz_compute(in, scp, &sh, gA != nullptr, slope0, gB != nullptr, slope1);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g.v[k] = fmaf(cA.v[k], g.v[k], fmaf(cB.v[k], xv.v[k], cC.v[k]));
+    for (int k = 0; k < 8; ++k) g.v[k] = fmaf(cA.v[k], g.v[k], fmaf(cB.v[k], in.x.v[k], cC.v[k]));
     st8(dx + 8 * i, g);
+  };
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (FIXED) {
+    for (; i + stride < n8; i += 2 * stride) {    // two independent 16-byte loads per tensor in flight
+      const GzIn a = gz_load(x, gA, gB, 8 * i), b = gz_load(x, gA, gB, 8 * (i + stride));
+      finish(a, i);
+      finish(b, i + stride);
+    }
+  }
+  for (; i < n8; i += stride) {
+    if (!FIXED) coeffs((int)((8 * i) % C));
+    finish(gz_load(x, gA, gB, 8 * i), i);
   }
 }
 
