@@ -221,6 +221,17 @@ int thin_last_convT_dgrad(int dtype, const float* du, const float* w, void* g0, 
                           int Wi, cudaStream_t s);
 int thin_last_convT_wgrad(int dtype, const void* x0, int C0, const void* x1, int C1, const float* du, float* dw, int B,
                           int Hi, int Wi, cudaStream_t s);
+// tensor-core route for the thin layers: bf16 patch rows [pixels][64], padded weights, result folding
+int thin_patch_rows(const float* img, void* out, int B, int Cin, int H, int W, cudaStream_t s);
+int thin_pad_rows(const float* src, void* dst, int R, int K, cudaStream_t s);
+int thin_fold_wgrad(const float* D, float* dw, int mode, int K, cudaStream_t s);
+// y[pix][n] = sum_c (x0|x1)[pix][c] * w_nk[n][c] over NHWC pixels (adp_conv_tc.cu)
+int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_nk, void* y0, int N0, void* y1, int N1,
+                 int act_dual, float slope0, float slope1, int B, int Hi, int Wi, cudaStream_t s);
+// D[128][NT] (fp32, zeroed by the callee) = sum_rows A[row][0:128] * Bm[row][0:NT]; A = two 64-column halves
+// (a0: [rows][lda0] at column ca0, a1: [rows][lda1] at column ca1), Bm: [rows][ldb], all bf16 row-major (adp_wgrad_tc.cu)
+int tc_gemm_tn(const void* a0, int lda0, int ca0, const void* a1, int lda1, int ca1, const void* bm, int ldb, int NT,
+               long long rows, float* D, cudaStream_t s);
 // P fp32 [B,Hi,Wi,16] -> y fp32 [B,1,2Hi,2Wi] = act(bias + col2im(P))
 int last_convT_col2im(const float* P, const float* bias, int final_sigmoid, float* y, int B, int Hi, int Wi, cudaStream_t s);
 // P[pixel][16 taps] = sum_c (x0|x1)[pixel][c] * w16[tap][c]   (w16: bf16 [16][C0+C1]) on tensor cores

@@ -17,6 +17,7 @@
 //   * the epilogue (4 warps = 128 TMEM lanes) reads the accumulator with tcgen05.ld and writes bf16
 //     NHWC rows (strided by parity for F2, split into two tensors for a concat gradient), or
 //     accumulates fp32 partial sums when the K range is split across CTAs (deep, small-M layers).
+#include <stdlib.h>
 #include "adp_tc.cuh"
 
 namespace adp {
@@ -83,6 +84,9 @@ struct IgemmParams {
   bf16* y0; bf16* y1;
   float* partial;                     // fp32 [out pixels][N] when splits > 1
   float* out_f32;                     // mode 2: fp32 [pixels][BLOCK_N] result
+  int stages;                         // smem ring depth actually used (<= IgemmSmem::STAGES)
+  int act_dual;                       // mode 2: y0 = lrelu(D, slope0), y1 = lrelu(D, slope1), both [pixels][N]
+  float slope0, slope1;
 };
 
 template <int BLOCK_N>
@@ -96,7 +100,7 @@ struct IgemmSmem {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid_constant__ IgemmParams p) {
   using S = IgemmSmem<BLOCK_N>;
-  constexpr int STAGES = S::STAGES;
+  const int STAGES = p.stages;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
@@ -210,6 +214,23 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid
         float* dst = p.out_f32 + opix * 16;
 #pragma unroll
         for (int i = 0; i < 16; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      } else if (p.act_dual) {
+        bf16* d0 = p.y0 + opix * p.N + n;
+        bf16* d1 = p.y1 + opix * p.N + n;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u, w;
+          u.x = pack_bf16x2(lrelu(v[i + 0], p.slope0), lrelu(v[i + 1], p.slope0));
+          u.y = pack_bf16x2(lrelu(v[i + 2], p.slope0), lrelu(v[i + 3], p.slope0));
+          u.z = pack_bf16x2(lrelu(v[i + 4], p.slope0), lrelu(v[i + 5], p.slope0));
+          u.w = pack_bf16x2(lrelu(v[i + 6], p.slope0), lrelu(v[i + 7], p.slope0));
+          w.x = pack_bf16x2(lrelu(v[i + 0], p.slope1), lrelu(v[i + 1], p.slope1));
+          w.y = pack_bf16x2(lrelu(v[i + 2], p.slope1), lrelu(v[i + 3], p.slope1));
+          w.z = pack_bf16x2(lrelu(v[i + 4], p.slope1), lrelu(v[i + 5], p.slope1));
+          w.w = pack_bf16x2(lrelu(v[i + 6], p.slope1), lrelu(v[i + 7], p.slope1));
+          *reinterpret_cast<uint4*>(d0 + i) = u;
+          *reinterpret_cast<uint4*>(d1 + i) = w;
+        }
       } else if (p.splits > 1) {
         float* dst = p.partial + opix * p.N + n;
 #pragma unroll
@@ -268,15 +289,25 @@ bool tile_geometry(int B, int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
   return *Bt <= 256;
 }
 
+int g_force_stages = 0;   // ADP_TC_STAGES environment override (tuning)
+
 template <int BLOCK_N>
-int launch_igemm(const IgemmParams& p, dim3 grid, cudaStream_t s) {
+int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
   using S = IgemmSmem<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
     ADP_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
     attr_set = true;
   }
-  tc_igemm_kernel<BLOCK_N><<<grid, IGEMM_THREADS, S::BYTES, s>>>(p);
+  // Ring depth: at most what fits twice into an SM's shared memory, so that two CTAs are co-resident and one
+  // CTA's epilogue (TMEM -> global) overlaps the other's TMA/MMA main loop; never deeper than the K loop.
+  int max_stages = (108 * 1024) / S::STAGE_BYTES;
+  if (max_stages > S::STAGES) max_stages = S::STAGES;
+  if (max_stages < 2) max_stages = 2;
+  if (g_force_stages > 0) max_stages = g_force_stages < S::STAGES ? g_force_stages : S::STAGES;
+  p.stages = p.kb_per_split < max_stages ? (p.kb_per_split < 1 ? 1 : p.kb_per_split) : max_stages;
+  const int smem_bytes = p.stages * S::STAGE_BYTES + 1024 + 256;
+  tc_igemm_kernel<BLOCK_N><<<grid, IGEMM_THREADS, smem_bytes, s>>>(p);
   adp_count_tc_launch();
   ADP_LAUNCH_CHECK();
   return ADP_OK;
@@ -318,6 +349,13 @@ int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes,
   }
   return ADP_OK;
 }
+
+struct StagesEnvInit {
+  StagesEnvInit() {
+    const char* e = getenv("ADP_TC_STAGES");
+    if (e) g_force_stages = atoi(e);
+  }
+} g_stages_env_init;
 
 float* g_scratch = nullptr;
 size_t g_scratch_bytes = 0;
@@ -434,6 +472,40 @@ int tc_pointwise16(const void* x0, int C0, const void* x1, int C1, const void* w
     ADP_TRY(make_tmap_bf16(&p.tmW, w16, 2, dims, str, box));
   }
   return run_igemm(p, 16, nullptr, 0, s);
+}
+
+// Pointwise (1x1) GEMM over NHWC pixels with K = C0 + C1 (multiple of 64):
+//   y[pix][n] = sum_c (x0|x1)[pix][c] * w_nk[n][c]
+// act_dual = 0: bf16 output split (y0: n < N0 | y1: rest);  act_dual = 1: y0 = lrelu(., slope0), y1 = lrelu(., slope1).
+int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_nk, void* y0, int N0, void* y1, int N1,
+                 int act_dual, float slope0, float slope1, int B, int Hi, int Wi, cudaStream_t s) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  ADP_CHECK_ARG(tile_geometry(B, Hi, Wi, &p.Wt, &p.Ht, &p.Bt), "tc_pointwise: unsupported spatial size %dx%d", Hi, Wi);
+  const int N = act_dual ? N0 : N0 + N1;
+  const int bn = pick_block_n(N, N0, act_dual ? 0 : N1);
+  ADP_CHECK_ARG(bn >= 32 && C0 % TILE_K == 0 && C1 % TILE_K == 0 && C0 > 0, "tc_pointwise: unsupported channels");
+  const int Ct = C0 + C1;
+  p.tiles_w = Wi / p.Wt; p.tiles_h = Hi / p.Ht;
+  p.B = B; p.Hs = Hi; p.Ws = Wi; p.mode = 2; p.C0 = C0; p.C1 = C1; p.Ct = Ct; p.N = N; p.N0 = N0; p.N1 = act_dual ? 0 : N1;
+  p.kblocks = Ct / TILE_K;
+  p.y0 = (bf16*)y0; p.y1 = (bf16*)y1;
+  p.act_dual = act_dual; p.slope0 = slope0; p.slope1 = slope1;
+  for (int h = 0; h < 2; ++h) {
+    const int C = h == 0 ? C0 : C1;
+    if (C == 0) continue;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)Wi * C * 2, (uint64_t)Hi * Wi * C * 2};
+    uint32_t box[4] = {TILE_K, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
+    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, box));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)Ct, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)Ct * 2};
+    uint32_t box[2] = {TILE_K, (uint32_t)bn};
+    ADP_TRY(make_tmap_bf16(&p.tmW, w_nk, 2, dims, str, box));
+  }
+  return run_igemm(p, bn, nullptr, 0, s);
 }
 
 // wgrad on tensor cores: see adp_wgrad_tc.cu

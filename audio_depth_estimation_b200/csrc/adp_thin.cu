@@ -324,6 +324,63 @@ last_convT_col2im_kernel(const float* __restrict__ P, const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------ tensor-core route for the thin layers
+// Patch matrices (im2col rows padded to 64 bf16 = one 128-byte swizzled TMA row):
+//   mode 0: xp[pix][t], t = (kh*4+kw)*Cin + ci < 16*Cin, = x[b,ci,2oy-1+kh,2ox-1+kw]   (x NCHW fp32, Cin planes)
+//   mode 1: dp[pix][t], t = kh*4+kw < 16,              = du[b,2i-1+kh,2j-1+kw]          (same with Cin = 1)
+// One thread writes one 16-byte chunk (8 values).
+__global__ void __launch_bounds__(256)
+patch_rows_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int Cin, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * 8;
+  const int K = 16 * Cin;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx & 7);
+    const long long pix = idx >> 3;
+    float8 r;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r.v[e] = 0.f;
+    if (q * 8 < K) {
+      const int ox = (int)(pix % Wo);
+      const long long t2 = pix / Wo;
+      const int oy = (int)(t2 % Ho), b = (int)(t2 / Ho);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int t = q * 8 + e;
+        if (t < K) {
+          const int tap = t / Cin, ci = t - tap * Cin;
+          const int y = 2 * oy - 1 + (tap >> 2), x = 2 * ox - 1 + (tap & 3);
+          if (y >= 0 && y < H && x >= 0 && x < W) r.v[e] = img[(((size_t)b * Cin + ci) * H + y) * W + x];
+        }
+      }
+    }
+    st8(out + idx * 8, r);
+  }
+}
+
+// src fp32 [R][K] -> dst bf16 [R][64] zero padded (K <= 64)
+__global__ void pad_rows_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int R, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * 64) return;
+  const int r = i >> 6, k = i & 63;
+  dst[i] = __float2bfloat16_rn(k < K ? src[(size_t)r * K + k] : 0.f);
+}
+
+// D fp32 [128][NT] from the transposed-operand GEMM -> dw
+//   mode 0 (last convT): dw[c][t]   = D[c][t],                 c < 128, t < 16    (ldd = 64)
+//   mode 1 (first conv): dw[n][t]   = D[n][t] + D[64+n][64+t], n < 64,  t < K     (ldd = 128; pixel pairs folded)
+__global__ void fold_thin_wgrad_kernel(const float* __restrict__ D, float* __restrict__ dw, int mode, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == 0) {
+    if (i < 128 * 16) dw[i] = D[(i >> 4) * 64 + (i & 15)];
+  } else {
+    if (i < 64 * K) {
+      const int n = i / K, t = i - n * K;
+      dw[i] = D[n * 128 + t] + D[(64 + n) * 128 + 64 + t];
+    }
+  }
+}
+
 int tile_grid(int B, int Hs, int Ws, int per_sm) {
   long long tiles = (long long)B * ((Hs + TT_H - 1) / TT_H) * ((Ws + TT_W - 1) / TT_W);
   long long cap = (long long)adp::sm_count() * per_sm;
@@ -396,6 +453,30 @@ int thin_last_convT_wgrad(int dtype, const void* x0, int C0, const void* x1, int
     })
     ADP_LAUNCH_CHECK();
   }
+  return ADP_OK;
+}
+
+int thin_patch_rows(const float* img, void* out, int B, int Cin, int H, int W, cudaStream_t s) {
+  long long total = (long long)B * (H / 2) * (W / 2) * 8;
+  long long blocks = (total + 255) / 256;
+  long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  patch_rows_kernel<<<(int)blocks, 256, 0, s>>>(img, (bf16*)out, B, Cin, H, W);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int thin_pad_rows(const float* src, void* dst, int R, int K, cudaStream_t s) {
+  ADP_CHECK_ARG(K <= 64, "pad_rows: K > 64");
+  pad_rows_kernel<<<adp_cdiv((long long)R * 64, 256), 256, 0, s>>>(src, (bf16*)dst, R, K);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int thin_fold_wgrad(const float* D, float* dw, int mode, int K, cudaStream_t s) {
+  const int n = mode == 0 ? 128 * 16 : 64 * K;
+  fold_thin_wgrad_kernel<<<adp_cdiv(n, 256), 256, 0, s>>>(D, dw, mode, K);
+  ADP_LAUNCH_CHECK();
   return ADP_OK;
 }
 

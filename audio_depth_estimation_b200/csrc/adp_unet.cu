@@ -32,6 +32,8 @@ struct Plan {
   LevelPlan lv[ADP_MAX_LEVELS];
   size_t du;                     // float [B,1,S,S]
   size_t p_last, w16_last;       // tensor-core head: P fp32 [B,H/2,W/2,16], bf16 weights [16][Ct]
+  size_t xp0, dp0, w1pad, wLpad, dthin;  // tensor-core thin layers: patch rows [pix][64] bf16, padded weights, D fp32 [128][128]
+  bool thin_tc;
   size_t tc_scratch, tc_scratch_bytes;  // fp32 split-K partial sums of the tensor-core convolutions
   size_t sums_begin, sums_end;   // forward BN sums region (zeroed every forward)
   size_t bsums_begin, bsums_end; // backward sums region
@@ -96,6 +98,17 @@ int make_plan(const adp_unet_desc* d, Plan* p) {
   p->tc_scratch = take(p->tc_scratch_bytes);
   p->p_last = take(d->dtype == ADP_BF16 ? (size_t)d->batch * p->lv[0].hout * p->lv[0].hout * 16 * sizeof(float) : 0);
   p->w16_last = take((size_t)16 * (p->lv[0].cout + p->lv[0].t_c1) * 2);
+  {
+    const LevelPlan& L0 = p->lv[0];
+    p->thin_tc = d->dtype == ADP_BF16 && L0.cout == 64 && 16 * L0.cin <= 64 && L0.t_c1 == 64 && d->out_ch == 1 &&
+                 ((size_t)d->batch * L0.hout * L0.hout) % 2 == 0;
+    const size_t rows = (size_t)d->batch * L0.hout * L0.hout;
+    p->xp0 = take(p->thin_tc ? rows * 64 * 2 : 0);
+    p->dp0 = take(p->thin_tc ? rows * 64 * 2 : 0);
+    p->w1pad = take(64 * 64 * 2);
+    p->wLpad = take(128 * 64 * 2);
+    p->dthin = take(128 * 128 * sizeof(float));
+  }
   p->total = off;
   return ADP_OK;
 }
@@ -171,7 +184,12 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
 
   const bool tc_head = tc && d->out_ch == 1 &&
                        tc_supported_pointwise16(B, p.lv[0].hout, p.lv[0].hout, p.lv[0].cout, p.lv[0].t_c1);
+  const bool thin_tc = tc && tc_head && p.thin_tc;
   if (tc && !d->reuse_weight_cache) {
+    if (thin_tc) {
+      ADP_TRY(thin_pad_rows(params[0].conv_w, at(ws, p.w1pad), 64, 16 * p.lv[0].cin, s));
+      ADP_TRY(thin_pad_rows(params[0].convT_w, at(ws, p.wLpad), 128, 16, s));
+    }
     if (tc_head)  // [Ct][16][1] -> [1][16][Ct]
       ADP_TRY(cast_transpose_taps(params[0].convT_w, at(ws, p.w16_last), p.lv[0].cout + p.lv[0].t_c1, 1, s));
     for (int l = 0; l < D; ++l) {
@@ -190,8 +208,15 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   // ---- encoder
   {
     const LevelPlan& L = p.lv[0];
-    ADP_TRY(first_conv_fprop(dt, x, params[0].conv_w, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), B, L.hin, L.hin, L.cin,
-                             L.cout, s));
+    ProfScope prof(PROF_THIN, s, 2.0 * B * L.hout * L.hout * 16.0 * L.cin * L.cout);
+    if (thin_tc) {  // im2col rows (bf16, padded to 64) + pointwise tensor-core GEMM with both activations in the epilogue
+      ADP_TRY(thin_patch_rows(x, at(ws, p.xp0), B, L.cin, L.hin, L.hin, s));
+      ADP_TRY(tc_pointwise(at(ws, p.xp0), 64, nullptr, 0, at(ws, p.w1pad), at(ws, L.a), 64, at(ws, L.r), 0, 1, 0.2f, 0.f, B,
+                           L.hout, L.hout, s));
+    } else {
+      ADP_TRY(first_conv_fprop(dt, x, params[0].conv_w, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), B, L.hin, L.hin, L.cin,
+                               L.cout, s));
+    }
   }
   for (int l = 1; l < D; ++l) {
     const LevelPlan& L = p.lv[l];
@@ -251,6 +276,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
   const int D = p.D, B = p.B, dt = d->dtype;
   ADP_CHECK_ARG(stage_begin >= 0 && stage_end <= 2 * D && stage_begin <= stage_end, "unet_backward: bad stage range");
   const bool tc = use_tc(dt);
+  const bool thin_tc_bwd = tc && p.thin_tc && tc_supported_pointwise16(B, p.lv[0].hout, p.lv[0].hout, p.lv[0].cout, p.lv[0].t_c1);
   const int bn_mode = d->training ? 2 : 1;
   tc_set_scratch(p.tc_scratch_bytes ? at(ws, p.tc_scratch) : nullptr, p.tc_scratch_bytes);
 
@@ -279,10 +305,20 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       ADP_CHECK_ARG(grads[0].convT_bias, "unet_backward: level 0 convT bias gradient missing");
       ADP_CUDA(cudaMemsetAsync(grads[0].convT_bias, 0, sizeof(float), s));
       ADP_TRY(head_bwd(y, dy, (long long)B * d->size * d->size, d->final_sigmoid, du, grads[0].convT_bias, s));
-      ADP_CUDA(cudaMemsetAsync(grads[0].convT_w, 0, sizeof(float) * 16 * Ct, s));
-      ADP_TRY(last_convT_wgrad(dt, at(ws, L.r), L.cout, at(ws, L.q), L.t_c1, du, grads[0].convT_w, B, L.hout, L.hout, s));
-      ADP_TRY(last_convT_dgrad(dt, du, params[0].convT_w, at(ws, L.g_r), L.cout, at(ws, L.g_q), L.t_c1, B, L.hout,
-                               L.hout, s));
+      if (thin_tc_bwd) {
+        ProfScope prof(PROF_THIN, s, 4.0 * B * L.hout * L.hout * 16.0 * Ct);
+        float* Dt = reinterpret_cast<float*>(at(ws, p.dthin));
+        ADP_TRY(thin_patch_rows(du, at(ws, p.dp0), B, 1, d->size, d->size, s));
+        ADP_TRY(tc_gemm_tn(at(ws, L.r), 64, 0, at(ws, L.q), 64, 0, at(ws, p.dp0), 64, 64, (long long)B * L.hout * L.hout, Dt, s));
+        ADP_TRY(thin_fold_wgrad(Dt, grads[0].convT_w, 0, 16, s));
+        ADP_TRY(tc_pointwise(at(ws, p.dp0), 64, nullptr, 0, at(ws, p.wLpad), at(ws, L.g_r), 64, at(ws, L.g_q), 64, 0, 0.f,
+                             0.f, B, L.hout, L.hout, s));
+      } else {
+        ADP_CUDA(cudaMemsetAsync(grads[0].convT_w, 0, sizeof(float) * 16 * Ct, s));
+        ADP_TRY(last_convT_wgrad(dt, at(ws, L.r), L.cout, at(ws, L.q), L.t_c1, du, grads[0].convT_w, B, L.hout, L.hout, s));
+        ADP_TRY(last_convT_dgrad(dt, du, params[0].convT_w, at(ws, L.g_r), L.cout, at(ws, L.g_q), L.t_c1, B, L.hout,
+                                 L.hout, s));
+      }
       ADP_TRY(up_norm_bwd(0));
     } else if (st < D) {
       const int l = st;
@@ -315,7 +351,14 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
                                  at(ws, L.g_r), 0.f, nullptr, 0, at(ws, L.g_e), s));
       }
       ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, s));
-      if (l == 0) {
+      if (l == 0 && thin_tc_bwd) {
+        ProfScope prof(PROF_THIN, s, 2.0 * B * L.hout * L.hout * 16.0 * L.cin * L.cout);
+        float* Dt = reinterpret_cast<float*>(at(ws, p.dthin));
+        // pixel pairs folded into 128 "channels": D[(h,n)][(h',t)], the two diagonal blocks are the gradient
+        ADP_TRY(tc_gemm_tn(at(ws, L.g_e), 128, 0, at(ws, L.g_e), 128, 64, at(ws, p.xp0), 128, 128,
+                           (long long)B * L.hout * L.hout / 2, Dt, s));
+        ADP_TRY(thin_fold_wgrad(Dt, grads[0].conv_w, 1, 16 * L.cin, s));
+      } else if (l == 0) {
         ADP_TRY(first_conv_wgrad(dt, x, at(ws, L.g_e), grads[0].conv_w, B, L.hin, L.hin, L.cin, L.cout, s));
       } else {
         const LevelPlan& I = p.lv[l - 1];

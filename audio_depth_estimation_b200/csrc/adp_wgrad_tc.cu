@@ -159,6 +159,128 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   }
 }
 
+// ------------------------------------------------------------------ plain transposed-operand GEMM
+// D[128][NT] += sum_rows A[row][0:128] * Bm[row][0:NT]   (both operands row-major = MN-major for the MMA).
+// Used by the thin layers' weight gradients, whose operands are [pixels][channels] / [pixels][patch] matrices.
+struct GemmTnParams {
+  CUtensorMap tmA0, tmA1, tmB;
+  int ca0, ca1;
+  int kblocks, kb_per_split;
+  float* D;
+};
+
+template <int NT>
+struct GemmTnSmem {
+  static constexpr int A_BYTES = 2 * WG_BOX_BYTES;
+  static constexpr int B_BYTES = (NT / 64) * WG_BOX_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 4;
+  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(WG_THREADS, 1) tc_gemm_tn_kernel(const __grid_constant__ GemmTnParams p) {
+  using S = GemmTnSmem<NT>;
+  constexpr int STAGES = S::STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_begin = blockIdx.x * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.kblocks);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tmA0);
+    prefetch_tmap(&p.tmA1);
+    prefetch_tmap(&p.tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, NT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int it = 0; it < nkb; ++it) {
+        const int row0 = (kb_begin + it) * WG_P;
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* a_dst = smem + s * S::STAGE_BYTES;
+        unsigned char* b_dst = a_dst + S::A_BYTES;
+        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        tma_load_2d(a_dst, &p.tmA0, &full_bar[s], p.ca0, row0);
+        tma_load_2d(a_dst + WG_BOX_BYTES, &p.tmA1, &full_bar[s], p.ca1, row0);
+#pragma unroll
+        for (int h = 0; h < NT / 64; ++h) tma_load_2d(b_dst + h * WG_BOX_BYTES, &p.tmB, &full_bar[s], h * 64, row0);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(WG_M, NT, 1, 1);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_P / 16; ++k) {
+          const uint64_t ad = umma_smem_desc(a_addr + k * 2048, WG_BOX_BYTES, 1024);
+          const uint64_t bd = umma_smem_desc(b_addr + k * 2048, WG_BOX_BYTES, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    float* row = p.D + (size_t)m * NT;
+#pragma unroll 1
+    for (int cc = 0; cc < NT; cc += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+      if (nkb > 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) red_add_v4(row + cc + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, NT);
+  }
+}
+
+template <int NT>
+int launch_gemm_tn(const GemmTnParams& p, int splits, cudaStream_t s) {
+  using S = GemmTnSmem<NT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADP_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    attr_set = true;
+  }
+  tc_gemm_tn_kernel<NT><<<splits, WG_THREADS, S::BYTES, s>>>(p);
+  adp_count_tc_launch();
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 bool wg_geometry(int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
@@ -185,6 +307,33 @@ int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t s) {
 }
 
 }  // namespace
+
+int tc_gemm_tn(const void* a0, int lda0, int ca0, const void* a1, int lda1, int ca1, const void* bm, int ldb, int NT,
+               long long rows, float* D, cudaStream_t s) {
+  ADP_CHECK_ARG(NT == 64 || NT == 128, "tc_gemm_tn: NT must be 64 or 128");
+  ADP_CHECK_ARG(lda0 % 8 == 0 && lda1 % 8 == 0 && ldb % 8 == 0 && ldb >= NT && rows > 0 && rows < (1LL << 31),
+                "tc_gemm_tn: bad leading dimensions / rows");
+  GemmTnParams p;
+  memset(&p, 0, sizeof(p));
+  const void* bases[3] = {a0, a1, bm};
+  const int lds[3] = {lda0, lda1, ldb};
+  CUtensorMap* maps[3] = {&p.tmA0, &p.tmA1, &p.tmB};
+  for (int i = 0; i < 3; ++i) {
+    uint64_t dims[2] = {(uint64_t)lds[i], (uint64_t)rows};
+    uint64_t str[1] = {(uint64_t)lds[i] * 2};
+    uint32_t box[2] = {64, (uint32_t)WG_P};
+    ADP_TRY(tc::make_tmap_bf16(maps[i], bases[i], 2, dims, str, box));
+  }
+  p.ca0 = ca0; p.ca1 = ca1; p.D = D;
+  p.kblocks = (int)((rows + WG_P - 1) / WG_P);
+  int splits = 2 * sm_count();
+  if (splits > p.kblocks) splits = p.kblocks;
+  p.kb_per_split = adp_cdiv(p.kblocks, splits);
+  splits = adp_cdiv(p.kblocks, p.kb_per_split);
+  ADP_CUDA(cudaMemsetAsync(D, 0, sizeof(float) * 128 * NT, s));
+  if (NT == 128) return launch_gemm_tn<128>(p, splits, s);
+  return launch_gemm_tn<64>(p, splits, s);
+}
 
 bool tc_supported_wgrad(int B, int Hs, int Ws, int M0, int M1, int N) {
   int Wt, Ht, Bt;
