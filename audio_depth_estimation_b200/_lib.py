@@ -53,7 +53,7 @@ SIGNATURES = {
     "adp_depth_loss_sums": (_i, [_vp, _vp, _i64, _f, _f, _i, _vp, _vp]),
     "adp_depth_loss_value": (_i, [_vp, _f, _f, _f, _vp, _vp]),
     "adp_depth_loss_backward": (_i, [_vp, _vp, _i64, _f, _f, _i, _vp, _f, _f, _f, _vp, _vp, _vp]),
-    "adp_weight_operand": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "adp_weight_operand": (_i, [_vp, _i, _i, _vp, _vp]),
     "adp_conv2d_k4s2_fprop": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "adp_conv2d_k4s2_dgrad": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "adp_conv2d_k4s2_wgrad": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

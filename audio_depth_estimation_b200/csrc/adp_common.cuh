@@ -243,7 +243,8 @@ int tc_pointwise16(const void* x0, int C0, const void* x1, int C1, const void* w
 // w_nk: bf16 [N][16][C] (K-major B operand)
 int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, int N1,
                    int B, int Hi, int Wi, int C, cudaStream_t s);
-int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* w_nk, void* y,
+// w_kn: bf16 [C0+C1][16][N] (N-major B operand: the master layout of the weight, cast)
+int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* w_kn, void* y,
                     int B, int Hi, int Wi, int N, cudaStream_t s);
 int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int N,
              float* dw, int B, int Hs, int Ws, cudaStream_t s);

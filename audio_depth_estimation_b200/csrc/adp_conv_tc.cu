@@ -166,15 +166,20 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid
           const int cx = x0 + pb - 1 + tw, cy = y0c + pa - 1 + th;
           if (c < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], c, cx, cy, b0);
           else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], c - p.C0, cx, cy, b0);
+          // weights stay in their master layout [c][tap][n]: the B tile is fetched N-major (64-row boxes of
+          // 64 output channels) and handed to the MMA through an MN-major descriptor -- no transposed copy
           const int wtap = (3 - pa - 2 * th) * 4 + (3 - pb - 2 * tw);
-          tma_load_2d(b_dst, &p.tmW, &full_bar[s], wtap * p.Ct + c, n0);
+#pragma unroll
+          for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h)
+            tma_load_3d(b_dst + h * (TILE_K * 128), &p.tmW, &full_bar[s], n0 + h * 64, wtap, c);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
+      const bool b_mn = p.mode == 1;
+      const uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, 0, b_mn ? 1 : 0);
       for (int it = 0; it < nkb; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1;
@@ -185,7 +190,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid
 #pragma unroll
         for (int k = 0; k < TILE_K / 16; ++k) {
           const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
+          const uint64_t bd = b_mn ? umma_smem_desc(b_addr + k * 2048, TILE_K * 128, 1024)
+                                   : umma_smem_desc(b_addr + k * 32, 16, 1024);
           umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
@@ -380,7 +386,7 @@ bool tc_supported_parity(int B, int Hi, int Wi, int C0, int C1, int N) {
   if (!adp_device_is_sm100() || !encode_tiled_fn()) return false;
   if (C0 % TILE_K || C1 % TILE_K || C0 <= 0 || B < 1) return false;
   if (!tile_geometry(B, Hi, Wi, &Wt, &Ht, &Bt)) return false;
-  return pick_block_n(N, N, 0) != 0;
+  return pick_block_n(N, N, 0) >= 64;
 }
 
 int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, int N1, int B, int Hi, int Wi, int C,
@@ -410,13 +416,13 @@ int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, 
   return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
 }
 
-int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* w_nk, void* y, int B, int Hi, int Wi, int N,
+int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* w_kn, void* y, int B, int Hi, int Wi, int N,
                     cudaStream_t s) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   ADP_CHECK_ARG(tile_geometry(B, Hi, Wi, &p.Wt, &p.Ht, &p.Bt), "tc_parity_convT: unsupported spatial size %dx%d", Hi, Wi);
   const int bn = pick_block_n(N, N, 0);
-  ADP_CHECK_ARG(bn != 0 && C0 % TILE_K == 0 && C1 % TILE_K == 0, "tc_parity_convT: unsupported channels");
+  ADP_CHECK_ARG(bn >= 64 && C0 % TILE_K == 0 && C1 % TILE_K == 0, "tc_parity_convT: unsupported channels");
   const int Ct = C0 + C1;
   p.tiles_w = Wi / p.Wt; p.tiles_h = Hi / p.Ht;
   p.B = B; p.Hs = Hi; p.Ws = Wi; p.mode = 1; p.C0 = C0; p.C1 = C1; p.Ct = Ct; p.N = N; p.N0 = N; p.N1 = 0;
@@ -430,11 +436,11 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
     uint32_t box[4] = {TILE_K, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
     ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, box));
   }
-  {
-    uint64_t dims[2] = {(uint64_t)16 * Ct, (uint64_t)N};
-    uint64_t str[1] = {(uint64_t)16 * Ct * 2};
-    uint32_t box[2] = {TILE_K, (uint32_t)bn};
-    ADP_TRY(make_tmap_bf16(&p.tmW, w_nk, 2, dims, str, box));
+  {  // w_kn: bf16 [Ct][16][N] (the master layout, cast)
+    uint64_t dims[3] = {(uint64_t)N, 16, (uint64_t)Ct};
+    uint64_t str[2] = {(uint64_t)N * 2, (uint64_t)16 * N * 2};
+    uint32_t box[3] = {64, 1, TILE_K};
+    ADP_TRY(make_tmap_bf16(&p.tmW, w_kn, 3, dims, str, box));
   }
   return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
 }

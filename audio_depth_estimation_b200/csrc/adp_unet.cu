@@ -24,7 +24,7 @@ struct LevelPlan {
   size_t bn_down_f, bn_up_f;     // float[4*C]: scale, shift, mean, invstd
   size_t sums_down, sums_up;     // double[2C] forward statistics
   size_t bsums_down, bsums_up;   // double[2C] backward reductions
-  size_t wb_conv_nk, wb_conv_t, wb_convT_nk, wb_convT_t;
+  size_t wb_conv, wb_convT;      // bf16 casts of the two weights in their master layouts
 };
 
 struct Plan {
@@ -89,8 +89,8 @@ int make_plan(const adp_unet_desc* d, Plan* p) {
     if (l < D - 1) { L.t = take(act); L.q = take(act); L.g_q = take(act); L.g_t = take(act); }
     else { L.t = L.q = L.g_q = L.g_t = 0; }
     const size_t wc = (size_t)L.cout * 16 * L.cin * 2, wt = (size_t)(L.cout + L.t_c1) * 16 * L.t_cout * 2;
-    L.wb_conv_nk = take(wc); L.wb_conv_t = take(wc);
-    L.wb_convT_nk = take(wt); L.wb_convT_t = take(wt);
+    L.wb_conv = take(wc);
+    L.wb_convT = take(wt);
   }
   p->du = take((size_t)d->batch * d->size * d->size * sizeof(float));
   // a layer only splits K when it has fewer tiles than SMs, i.e. fewer than ~148*128*128 outputs
@@ -195,10 +195,8 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     for (int l = 0; l < D; ++l) {
       const LevelPlan& L = p.lv[l];
       if (l > 0) {
-        ADP_TRY(cast_f32_to_bf16(params[l].conv_w, at(ws, L.wb_conv_nk), (long long)L.cout * 16 * L.cin, s));
-        ADP_TRY(cast_transpose_taps(params[l].conv_w, at(ws, L.wb_conv_t), L.cout, L.cin, s));
-        ADP_TRY(cast_f32_to_bf16(params[l].convT_w, at(ws, L.wb_convT_nk), (long long)(L.cout + L.t_c1) * 16 * L.t_cout, s));
-        ADP_TRY(cast_transpose_taps(params[l].convT_w, at(ws, L.wb_convT_t), L.cout + L.t_c1, L.t_cout, s));
+        ADP_TRY(cast_f32_to_bf16(params[l].conv_w, at(ws, L.wb_conv), (long long)L.cout * 16 * L.cin, s));
+        ADP_TRY(cast_f32_to_bf16(params[l].convT_w, at(ws, L.wb_convT), (long long)(L.cout + L.t_c1) * 16 * L.t_cout, s));
       }
     }
   }
@@ -221,7 +219,7 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   for (int l = 1; l < D; ++l) {
     const LevelPlan& L = p.lv[l];
     const long long rows = (long long)B * L.hout * L.hout;
-    ADP_TRY(conv_gather(dt, at(ws, p.lv[l - 1].a), params[l].conv_w, tc ? at(ws, L.wb_conv_nk) : nullptr,
+    ADP_TRY(conv_gather(dt, at(ws, p.lv[l - 1].a), params[l].conv_w, tc ? at(ws, L.wb_conv) : nullptr,
                         at(ws, L.e), L.cout, nullptr, 0, B, L.hin, L.hin, L.cin, s));
     if (L.bn_down) {
       BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
@@ -241,7 +239,7 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     const LevelPlan& O = p.lv[l - 1];  // output lives at level l-1's resolution
     const long long rows = (long long)B * O.hout * O.hout;
     ADP_TRY(conv_parity(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, params[l].convT_w,
-                        tc ? at(ws, L.wb_convT_t) : nullptr, at(ws, O.t), B, L.hout, L.hout, L.t_cout, s));
+                        tc ? at(ws, L.wb_convT) : nullptr, at(ws, O.t), B, L.hout, L.hout, L.t_cout, s));
     BnBuf bn = bnbuf(ws, L.bn_up_f, L.t_cout);
     double* sums = reinterpret_cast<double*>(at(ws, L.sums_up));
     if (d->training) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));
@@ -328,7 +326,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       ADP_CUDA(cudaMemsetAsync(grads[l].convT_w, 0, sizeof(float) * 16 * (size_t)Ct * L.t_cout, s));
       ADP_TRY(conv_wgrad(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, at(ws, O.g_t), L.t_cout,
                          grads[l].convT_w, B, L.hout, L.hout, s));
-      ADP_TRY(conv_gather(dt, at(ws, O.g_t), params[l].convT_w, tc ? at(ws, L.wb_convT_nk) : nullptr, at(ws, L.g_r),
+      ADP_TRY(conv_gather(dt, at(ws, O.g_t), params[l].convT_w, tc ? at(ws, L.wb_convT) : nullptr, at(ws, L.g_r),
                           L.cout, L.t_c1 ? at(ws, L.g_q) : nullptr, L.t_c1, B, O.hout, O.hout, L.t_cout, s));
       if (l < D - 1) ADP_TRY(up_norm_bwd(l));
     } else {
@@ -364,7 +362,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         const LevelPlan& I = p.lv[l - 1];
         ADP_TRY(conv_wgrad(dt, at(ws, L.g_e), L.cout, nullptr, 0, at(ws, I.a), L.cin, grads[l].conv_w, B, L.hout,
                            L.hout, s));
-        ADP_TRY(conv_parity(dt, at(ws, L.g_e), L.cout, nullptr, 0, params[l].conv_w, tc ? at(ws, L.wb_conv_t) : nullptr,
+        ADP_TRY(conv_parity(dt, at(ws, L.g_e), L.cout, nullptr, 0, params[l].conv_w, tc ? at(ws, L.wb_conv) : nullptr,
                             at(ws, I.g_a), B, L.hout, L.hout, L.cin, s));
       }
     }
@@ -381,9 +379,8 @@ extern "C" int adp_unet_backward(const adp_unet_desc* d, const float* x, const f
 
 // ------------------------------------------------------------------ per-layer C ABI
 // (no workspace argument: the tensor-core kernels run without K-splitting here)
-extern "C" int adp_weight_operand(const float* w, int R, int C, int transpose, void* out, void* stream) {
+extern "C" int adp_weight_operand(const float* w, int R, int C, void* out, void* stream) {
   ADP_CHECK_ARG(w && out && R > 0 && C > 0, "weight_operand: bad arguments");
-  if (transpose) return cast_transpose_taps(w, out, R, C, (cudaStream_t)stream);
   ADP_CHECK_ARG(((long long)R * 16 * C) % 4 == 0, "weight_operand: size must be a multiple of 4");
   return cast_f32_to_bf16(w, out, (long long)R * 16 * C, (cudaStream_t)stream);
 }

@@ -98,10 +98,9 @@ int adp_depth_loss_backward(const float* pred, const float* gt, int64_t n, float
  *   x1/c1 : second half of a channel concat (decoder skip), NULL/0 if none;
  *   dw    : fp32, same layout as w, ACCUMULATED into (zero it first). */
 
-/* w [R][16][C] fp32 -> bf16 [R][16][C] (transpose = 0) or [C][16][R] (transpose = 1).
- * Operands: conv fprop  <- conv  weight, transpose 0;  conv dgrad  <- conv  weight, transpose 1;
- *           convT fprop <- convT weight, transpose 1;  convT dgrad <- convT weight, transpose 0. */
-int adp_weight_operand(const float* w, int R, int C, int transpose, void* out, void* stream);
+/* w [R][16][C] fp32 -> bf16 [R][16][C]: the tensor-core operand of a weight is its master layout cast to
+ * bf16 for all four uses (conv fprop / convT dgrad read it K-major, conv dgrad / convT fprop N-major). */
+int adp_weight_operand(const float* w, int R, int C, void* out, void* stream);
 
 int adp_conv2d_k4s2_fprop(int dtype, const void* x, const float* w, const void* w_op, void* y,
                           int B, int Hin, int Win, int Cin, int Cout, void* stream);

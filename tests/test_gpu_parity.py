@@ -162,9 +162,9 @@ def from_nhwc(t):
     return t.float().permute(0, 3, 1, 2).contiguous()
 
 
-def op_weights(lib, w_master, R, C, transpose):
+def op_weights(lib, w_master, R, C):
     out = torch.empty(R * 16 * C, device=DEV, dtype=torch.bfloat16)
-    _lib.check(lib.adp_weight_operand(w_master.data_ptr(), R, C, transpose, out.data_ptr(), None))
+    _lib.check(lib.adp_weight_operand(w_master.data_ptr(), R, C, out.data_ptr(), None))
     return out
 
 
@@ -192,8 +192,8 @@ def test_conv2d_k4s2_all_passes(mode, B, H, Cin, Cout):
     wm = w.permute(0, 2, 3, 1).contiguous()          # [Cout][4][4][Cin]
     wq = wm if mode == "fp32" else wm.to(torch.bfloat16).float()
     wq_nchw = wq.permute(0, 3, 1, 2).contiguous()
-    w_f = op_weights(lib, wm, Cout, Cin, 0) if mode == "bf16_tc" else None
-    w_t = op_weights(lib, wm, Cout, Cin, 1) if mode == "bf16_tc" else None
+    w_f = op_weights(lib, wm, Cout, Cin) if mode == "bf16_tc" else None
+    w_t = w_f
     wref = wq_nchw if mode == "bf16_tc" else w
     # fprop
     y = torch.empty(B, H // 2, H // 2, Cout, device=DEV, dtype=tdt)
@@ -249,8 +249,8 @@ def test_convT2d_k4s2_all_passes(mode, B, H, C0, C1, Cout):
     wm = w.permute(0, 2, 3, 1).contiguous()          # [Cin][4][4][Cout]
     wq = wm if mode == "fp32" else wm.to(torch.bfloat16).float()
     wq_nchw = wq.permute(0, 3, 1, 2).contiguous()
-    w_f = op_weights(lib, wm, Cin, Cout, 1) if mode == "bf16_tc" else None   # fprop operand [Cout][16][Cin]
-    w_d = op_weights(lib, wm, Cin, Cout, 0) if mode == "bf16_tc" else None   # dgrad operand [Cin][16][Cout]
+    w_f = op_weights(lib, wm, Cin, Cout) if mode == "bf16_tc" else None   # one operand serves fprop and dgrad
+    w_d = w_f
     wref = wq_nchw if mode == "bf16_tc" else w
     p = lambda t: t.data_ptr() if t is not None else None
     y = torch.empty(B, 2 * H, 2 * H, Cout, device=DEV, dtype=tdt)
