@@ -72,6 +72,7 @@ SIGNATURES = {
     "adp_profile_read": (_i, [_vp, _vp, _vp]),
     "adp_grad_sumsq": (_i, [C.POINTER(TensorRef), _i, _vp, _vp]),
     "adp_clip_adamw_step": (_i, [C.POINTER(TensorRef), _i, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
+    "adp_clip_adamw_step_graph": (_i, [C.POINTER(TensorRef), _i, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

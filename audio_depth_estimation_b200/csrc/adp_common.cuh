@@ -100,6 +100,33 @@ __device__ __forceinline__ void st8(bf16* p, const float8& r) {
   u.z = pack_bf16x2_(r.v[4], r.v[5]); u.w = pack_bf16x2_(r.v[6], r.v[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+// raw (unconverted) 8-element loads: several can be put in flight at 4 registers each for bf16
+struct raw8f { float4 a, b; };
+__device__ __forceinline__ raw8f ldraw8(const float* p) {
+  raw8f r;
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+  return r;
+}
+__device__ __forceinline__ uint4 ldraw8(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ float8 cvt8(const raw8f& r) {
+  float8 o;
+  o.v[0] = r.a.x; o.v[1] = r.a.y; o.v[2] = r.a.z; o.v[3] = r.a.w; o.v[4] = r.b.x; o.v[5] = r.b.y; o.v[6] = r.b.z; o.v[7] = r.b.w;
+  return o;
+}
+__device__ __forceinline__ float8 cvt8(const uint4& u) {
+  float8 o;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o.v[2 * i] = __uint_as_float(w[i] << 16);
+    o.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+  return o;
+}
+template <class T> struct Raw8;
+template <> struct Raw8<float> { typedef raw8f type; };
+template <> struct Raw8<bf16> { typedef uint4 type; };
 __device__ __forceinline__ float ld1(const float* p) { return *p; }
 __device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void st1(float* p, float v) { *p = v; }

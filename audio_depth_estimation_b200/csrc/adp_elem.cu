@@ -239,19 +239,16 @@ bn_stats8_kernel(const T* __restrict__ x, long long rows, int C, double* __restr
   if (c < C) {
     const long long step = (long long)gridDim.y * blockDim.y;
     long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
-    for (; r + step < rows; r += 2 * step) {   // two independent loads in flight
-      const float8 a = ld8(x + r * C + c), b = ld8(x + (r + step) * C + c);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v[i] += a.v[i] + b.v[i];
-        v[8 + i] = fmaf(a.v[i], a.v[i], fmaf(b.v[i], b.v[i], v[8 + i]));
-      }
-    }
-    for (; r < rows; r += step) {
-      const float8 a = ld8(x + r * C + c);
+    auto add = [&](const float8& a) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { v[i] += a.v[i]; v[8 + i] = fmaf(a.v[i], a.v[i], v[8 + i]); }
+    };
+    for (; r + 3 * step < rows; r += 4 * step) {   // four independent 16-byte loads in flight
+      typename Raw8<T>::type q0 = ldraw8(x + r * C + c), q1 = ldraw8(x + (r + step) * C + c),
+                             q2 = ldraw8(x + (r + 2 * step) * C + c), q3 = ldraw8(x + (r + 3 * step) * C + c);
+      add(cvt8(q0)); add(cvt8(q1)); add(cvt8(q2)); add(cvt8(q3));
     }
+    for (; r < rows; r += step) add(ld8(x + r * C + c));
   }
   col_reduce16(v, C, blockIdx.x * blockDim.x * 8, sums);
 }
@@ -314,37 +311,90 @@ __device__ __forceinline__ float8 gz_compute(const GzIn& in, const float8* sc, c
   return g;
 }
 
+// Register-free prefetch: every thread owns private 16-byte shared-memory slots that it fills with cp.async and
+// later reads back itself (no block synchronisation), so RED_ROWS rows x up to 3 tensors are in flight per thread.
+constexpr int RED_ROWS = 3, RED_STAGES = 2;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <class T>
 __global__ void __launch_bounds__(256)
 act_bn_bwd_reduce8_kernel(const T* __restrict__ x, long long rows, int C, const float* __restrict__ scale,
                           const float* __restrict__ shift, const float* __restrict__ mean,
                           const float* __restrict__ invstd, const T* __restrict__ gA, float slope0,
                           const T* __restrict__ gB, float slope1, double* __restrict__ sums) {
+  constexpr int CH16 = (int)(sizeof(T) * 8 / 16);                 // 16-byte chunks per 8 elements
+  extern __shared__ __align__(16) unsigned char red_smem[];      // [STAGES][ROWS][3][CH16][256] x 16 B
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  auto slot = [&](int stage, int j, int t, int h) -> unsigned char* {
+    return red_smem + ((((size_t)(stage * RED_ROWS + j) * 3 + t) * CH16 + h) * 256 + tid) * 16;
+  };
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.f;
   if (c < C) {
-    const float8 mu = ld8(mean + c), is = ld8(invstd + c);
     float8 sc, sh;
     if (scale) { sc = ld8(scale + c); sh = ld8(shift + c); }
-    const long long step = (long long)gridDim.y * blockDim.y;
+    const float8 mu = ld8(mean + c);
     const float8* scp = scale ? &sc : nullptr;
-    auto accumulate = [&](const GzIn& in) {
-      const float8 g = gz_compute(in, scp, &sh, gA != nullptr, slope0, gB != nullptr, slope1);
+    const long long step = (long long)gridDim.y * blockDim.y;
+    auto issue = [&](int stage, long long r0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v[i] += g.v[i];
-        v[8 + i] = fmaf(g.v[i], (in.x.v[i] - mu.v[i]) * is.v[i], v[8 + i]);
+      for (int j = 0; j < RED_ROWS; ++j) {
+        const long long r = r0 + j * step;
+        if (r < rows) {
+          const long long off = r * C + c;
+#pragma unroll
+          for (int h = 0; h < CH16; ++h) {
+            cp_async16(slot(stage, j, 0, h), reinterpret_cast<const unsigned char*>(x + off) + 16 * h);
+            if (gA) cp_async16(slot(stage, j, 1, h), reinterpret_cast<const unsigned char*>(gA + off) + 16 * h);
+            if (gB) cp_async16(slot(stage, j, 2, h), reinterpret_cast<const unsigned char*>(gB + off) + 16 * h);
+          }
+        }
       }
+      cp_async_commit();
+    };
+    auto read8 = [&](int stage, int j, int t) -> float8 {
+      if (CH16 == 1) return cvt8(*reinterpret_cast<const uint4*>(slot(stage, j, t, 0)));
+      raw8f q;
+      q.a = *reinterpret_cast<const float4*>(slot(stage, j, t, 0));
+      q.b = *reinterpret_cast<const float4*>(slot(stage, j, t, CH16 - 1));
+      return cvt8(q);
     };
     long long r = (long long)blockIdx.y * blockDim.y + threadIdx.y;
-    for (; r + step < rows; r += 2 * step) {      // two rows in flight
-      const GzIn i0 = gz_load(x, gA, gB, r * C + c), i1 = gz_load(x, gA, gB, (r + step) * C + c);
-      accumulate(i0);
-      accumulate(i1);
+    int stage = 0;
+    issue(0, r);
+    while (r < rows) {
+      const long long rn = r + RED_ROWS * step;
+      issue(stage ^ 1, rn);                 // empty group when rn >= rows
+      cp_async_wait<1>();
+#pragma unroll
+      for (int j = 0; j < RED_ROWS; ++j) {
+        if (r + j * step < rows) {
+          GzIn in;
+          in.x = read8(stage, j, 0);
+          if (gA) in.a = read8(stage, j, 1);
+          if (gB) in.b = read8(stage, j, 2);
+          const float8 g = gz_compute(in, scp, &sh, gA != nullptr, slope0, gB != nullptr, slope1);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[i] += g.v[i];
+            v[8 + i] = fmaf(g.v[i], in.x.v[i] - mu.v[i], v[8 + i]);
+          }
+        }
+      }
+      r = rn;
+      stage ^= 1;
     }
-    for (; r < rows; r += step) accumulate(gz_load(x, gA, gB, r * C + c));
+    cp_async_wait<0>();
+    const float8 is = ld8(invstd + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[8 + i] *= is.v[i];
   }
   col_reduce16(v, C, blockIdx.x * blockDim.x * 8, sums);
 }
@@ -552,7 +602,18 @@ int act_bn_bwd_reduce(int dtype, const void* x, long long rows, int C, const flo
   ADP_CHECK_ARG(C % 4 == 0, "act_bn_bwd_reduce: C %% 4 != 0");
   if (C % 8 == 0) {
     ColLaunch L = col_launch8(rows, C);
-    ADP_DISPATCH_T(dtype, act_bn_bwd_reduce8_kernel<T><<<L.grid, L.block, 0, s>>>(
+    const size_t smem = (size_t)RED_STAGES * RED_ROWS * 3 * 256 * (dtype == ADP_F32 ? 32 : 16);
+    {
+      static bool attr_set = false;
+      if (!attr_set) {
+        ADP_CUDA(cudaFuncSetAttribute(act_bn_bwd_reduce8_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      RED_STAGES * RED_ROWS * 3 * 256 * 32));
+        ADP_CUDA(cudaFuncSetAttribute(act_bn_bwd_reduce8_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      RED_STAGES * RED_ROWS * 3 * 256 * 16));
+        attr_set = true;
+      }
+    }
+    ADP_DISPATCH_T(dtype, act_bn_bwd_reduce8_kernel<T><<<L.grid, L.block, smem, s>>>(
                               (const T*)x, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0, (const T*)gB,
                               slope1, sums);)
     ADP_LAUNCH_CHECK();

@@ -143,37 +143,60 @@ __device__ __forceinline__ AxisTaps aa_axis(int i, int n_in, int n_out) {
   return a;
 }
 
-// in [rows,H,W] -> out [rows,S,S]; optional (x - min)/(max - min) per row applied on load.
+// in [rows,H,W] -> out [rows,S,S]; optional per-row (x - min)/(max - min).  The taps of an output pixel depend on
+// (p, o) only, so a thread computes them once (registers) and applies them to RESIZE_PLANES consecutive planes.
+constexpr int RESIZE_PLANES = 8;
+constexpr int RESIZE_HT = 6, RESIZE_VT = 4;   // register-resident taps; larger footprints take the generic loop
+
 __global__ void __launch_bounds__(256)
-resize_aa_kernel(const float* __restrict__ in, int H, int W, int S, float* __restrict__ out,
+resize_aa_kernel(const float* __restrict__ in, int rows, int H, int W, int S, float* __restrict__ out,
                  const int* __restrict__ minmax) {
-  const int row = blockIdx.z;
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   const int p = blockIdx.y;
   if (o >= S) return;
-  float mn = 0.f, den = 1.f;
-  bool zero = false;
-  if (minmax) {
-    mn = ordered_to_float(minmax[2 * row]);
-    float mx = ordered_to_float(minmax[2 * row + 1]);
-    zero = !(mx > mn);
-    den = mx - mn;
-  }
-  AxisTaps ah = aa_axis(p, H, S);
-  AxisTaps aw = aa_axis(o, W, S);
+  const AxisTaps ah = aa_axis(p, H, S);
+  const AxisTaps aw = aa_axis(o, W, S);
   const float ih = ah.total != 0.f ? 1.f / ah.total : 1.f, iw = aw.total != 0.f ? 1.f / aw.total : 1.f;
-  const float* src = in + (size_t)row * H * W;
-  float acc = 0.f;
-  for (int jh = 0; jh < ah.size; ++jh) {
-    const float* line = src + (size_t)(ah.lo + jh) * W + aw.lo;
-    float hacc = 0.f;
-    for (int jw = 0; jw < aw.size; ++jw) hacc = fmaf(line[jw], aa_w(aw, jw) * iw, hacc);
-    acc = fmaf(hacc, aa_w(ah, jh) * ih, acc);
+  const bool fast = aw.size <= RESIZE_HT && ah.size <= RESIZE_VT;
+  float wh[RESIZE_VT], ww[RESIZE_HT];
+  int cw[RESIZE_HT];
+#pragma unroll
+  for (int j = 0; j < RESIZE_VT; ++j) wh[j] = j < ah.size ? aa_w(ah, j) * ih : 0.f;
+#pragma unroll
+  for (int j = 0; j < RESIZE_HT; ++j) {
+    ww[j] = j < aw.size ? aa_w(aw, j) * iw : 0.f;
+    cw[j] = min(aw.lo + j, W - 1);          // clamped: taps beyond the footprint carry weight 0
   }
-  // the weights sum to one, so the per-channel min-max commutes with the resize
-  if (minmax) acc = (acc - mn) / den;
-  if (zero) acc = 0.f;
-  out[((size_t)row * S + p) * S + o] = acc;
+  const int row_end = min(rows, (int)(blockIdx.z + 1) * RESIZE_PLANES);
+  for (int row = blockIdx.z * RESIZE_PLANES; row < row_end; ++row) {
+    const float* src = in + (size_t)row * H * W;
+    float acc = 0.f;
+    if (fast) {
+#pragma unroll
+      for (int jh = 0; jh < RESIZE_VT; ++jh) {
+        if (jh < ah.size) {
+          const float* line = src + (size_t)(ah.lo + jh) * W;
+          float hacc = 0.f;
+#pragma unroll
+          for (int jw = 0; jw < RESIZE_HT; ++jw) hacc = fmaf(line[cw[jw]], ww[jw], hacc);
+          acc = fmaf(hacc, wh[jh], acc);
+        }
+      }
+    } else {
+      for (int jh = 0; jh < ah.size; ++jh) {
+        const float* line = src + (size_t)(ah.lo + jh) * W + aw.lo;
+        float hacc = 0.f;
+        for (int jw = 0; jw < aw.size; ++jw) hacc = fmaf(line[jw], aa_w(aw, jw) * iw, hacc);
+        acc = fmaf(hacc, aa_w(ah, jh) * ih, acc);
+      }
+    }
+    if (minmax) {
+      // the weights sum to one, so the per-channel min-max commutes with the resize
+      const float mn = ordered_to_float(minmax[2 * row]), mx = ordered_to_float(minmax[2 * row + 1]);
+      acc = mx > mn ? (acc - mn) / (mx - mn) : 0.f;
+    }
+    out[((size_t)row * S + p) * S + o] = acc;
+  }
 }
 
 int check_stft_args(int rows, int L, int pitch, int n_fft, int win, int hop) {
@@ -220,8 +243,8 @@ extern "C" size_t adp_feature_workspace_bytes(int rows, int L, int n_fft, int ho
 extern "C" int adp_resize_aa(const float* in, int rows, int H, int W, int out_size, float* out, void* stream) {
   ADP_CHECK_ARG(in && out && rows > 0 && H > 0 && W > 0 && out_size > 0, "resize: bad arguments");
   ADP_CHECK_ARG(rows <= 65535 && out_size <= 65535, "resize: rows/out_size too large for one launch");
-  dim3 grid(adp_cdiv(out_size, 256), out_size, rows);
-  resize_aa_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, H, W, out_size, out, nullptr);
+  dim3 grid(adp_cdiv(out_size, 256), out_size, adp_cdiv(rows, RESIZE_PLANES));
+  resize_aa_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, rows, H, W, out_size, out, nullptr);
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }
@@ -244,8 +267,8 @@ extern "C" int adp_feature_forward(const float* wave, int rows, int L, int wave_
     ADP_LAUNCH_CHECK();
   }
   ADP_TRY(launch_stft(wave, rows, L, wave_pitch, n_fft, win_length, hop, spec, log_minmax ? 1 : 0, minmax, s));
-  dim3 grid(adp_cdiv(out_size, 256), out_size, rows);
-  resize_aa_kernel<<<grid, 256, 0, s>>>(spec, F, T, out_size, out, log_minmax ? minmax : nullptr);
+  dim3 grid(adp_cdiv(out_size, 256), out_size, adp_cdiv(rows, RESIZE_PLANES));
+  resize_aa_kernel<<<grid, 256, 0, s>>>(spec, rows, F, T, out_size, out, log_minmax ? minmax : nullptr);
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }

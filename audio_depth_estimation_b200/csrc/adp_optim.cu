@@ -66,9 +66,20 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
   p = p - a.step_size * (m / denom);
 }
 
+// Device-resident step counter for CUDA-graph replay: scalars = {step_size, 1/sqrt(bias_correction2)}
+__global__ void adam_tick_kernel(int* __restrict__ step, float* __restrict__ scalars, float lr, float beta1, float beta2) {
+  const int t = *step + 1;
+  *step = t;
+  const double bc1 = 1.0 - pow((double)beta1, (double)t);
+  const double bc2 = 1.0 - pow((double)beta2, (double)t);
+  scalars[0] = (float)((double)lr / bc1);
+  scalars[1] = (float)(1.0 / sqrt(bc2));
+}
+
 __global__ void __launch_bounds__(OPT_THREADS)
-clip_adamw_kernel(const __grid_constant__ TensorTable tab, const double* __restrict__ sumsq, const AdamArgs a,
-                  float* __restrict__ norm_out) {
+clip_adamw_kernel(const __grid_constant__ TensorTable tab, const double* __restrict__ sumsq, AdamArgs a,
+                  float* __restrict__ norm_out, const float* __restrict__ dev_scalars) {
+  if (dev_scalars) { a.step_size = dev_scalars[0]; a.inv_bc2_sqrt = dev_scalars[1]; }
   const float total = (float)sqrt(*sumsq);
   float coef = a.max_norm > 0.f ? a.max_norm / (total + 1e-6f) : 1.f;
   coef = fminf(coef, 1.f);
@@ -141,7 +152,28 @@ extern "C" int adp_clip_adamw_step(const adp_tensor_ref* refs_host, int n_tensor
   a.step_size = (float)((double)lr / bc1);
   a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   return for_each_table(refs_host, n_tensors, [&](const TensorTable& tab, int blocks) -> int {
-    clip_adamw_kernel<<<blocks, OPT_THREADS, 0, s>>>(tab, sumsq, a, norm_out);
+    clip_adamw_kernel<<<blocks, OPT_THREADS, 0, s>>>(tab, sumsq, a, norm_out, nullptr);
+    ADP_LAUNCH_CHECK();
+    return ADP_OK;
+  });
+}
+
+// Same update with the step counter kept on the device (step_dev: int, incremented here; scratch: 2 floats), so
+// that the call can be captured once in a CUDA graph and replayed.
+extern "C" int adp_clip_adamw_step_graph(const adp_tensor_ref* refs_host, int n_tensors, const double* sumsq,
+                                         float max_norm, float lr, float beta1, float beta2, float eps,
+                                         float weight_decay, int* step_dev, float* scratch, float* norm_out,
+                                         void* stream) {
+  ADP_CHECK_ARG(refs_host && n_tensors > 0 && sumsq && step_dev && scratch, "clip_adamw_step_graph: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  AdamArgs a;
+  a.max_norm = max_norm; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+  a.decay_mul = 1.f - lr * weight_decay;
+  a.step_size = 0.f; a.inv_bc2_sqrt = 0.f;
+  adam_tick_kernel<<<1, 1, 0, s>>>(step_dev, scratch, lr, beta1, beta2);
+  ADP_LAUNCH_CHECK();
+  return for_each_table(refs_host, n_tensors, [&](const TensorTable& tab, int blocks) -> int {
+    clip_adamw_kernel<<<blocks, OPT_THREADS, 0, s>>>(tab, sumsq, a, norm_out, scratch);
     ADP_LAUNCH_CHECK();
     return ADP_OK;
   });

@@ -12,8 +12,11 @@ from . import _lib
 
 
 class FusedClipAdamW:
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=1.0):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=1.0,
+                 capturable=False):
+        """capturable=True keeps the step counter on the device so that step() can be recorded in a CUDA graph."""
         self.model = model
+        self.capturable = bool(capturable)
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
         self.max_norm = float(max_norm) if max_norm is not None else 0.0
         self.step_count = 0
@@ -27,7 +30,9 @@ class FusedClipAdamW:
             old = st
             st = dict(p_ptr=p.data_ptr(), m=torch.zeros_like(p), v=torch.zeros_like(p),
                       sumsq=torch.zeros(1, device=p.device, dtype=torch.float64),
-                      norm=torch.zeros(1, device=p.device, dtype=torch.float32))
+                      norm=torch.zeros(1, device=p.device, dtype=torch.float32),
+                      step_dev=torch.full((1,), self.step_count, device=p.device, dtype=torch.int32),
+                      scratch=torch.zeros(2, device=p.device, dtype=torch.float32))
             if old is not None and old["m"].numel() == p.numel():
                 st["m"].copy_(old["m"])
                 st["v"].copy_(old["v"])
@@ -48,9 +53,15 @@ class FusedClipAdamW:
             s = _lib.stream_ptr()
             st["sumsq"].zero_()
             _lib.check(lib.adp_grad_sumsq(ref, 1, st["sumsq"].data_ptr(), s))
-            _lib.check(lib.adp_clip_adamw_step(ref, 1, st["sumsq"].data_ptr(), self.max_norm, self.lr,
-                                               self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                               self.step_count, st["norm"].data_ptr(), s))
+            if self.capturable:
+                _lib.check(lib.adp_clip_adamw_step_graph(ref, 1, st["sumsq"].data_ptr(), self.max_norm, self.lr,
+                                                         self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                                         st["step_dev"].data_ptr(), st["scratch"].data_ptr(),
+                                                         st["norm"].data_ptr(), s))
+            else:
+                _lib.check(lib.adp_clip_adamw_step(ref, 1, st["sumsq"].data_ptr(), self.max_norm, self.lr,
+                                                   self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                                   self.step_count, st["norm"].data_ptr(), s))
         self.model.mark_weights_dirty()
         self.last_norm = st["norm"]
         return st["norm"]

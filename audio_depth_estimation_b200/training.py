@@ -68,15 +68,23 @@ class GradientReducer:
 
 class TrainStep:
     def __init__(self, cfg, model, lr=None, max_norm=1.0, process_group=None, stages_per_group=2,
-                 waveform_input=True):
+                 waveform_input=True, cuda_graph=False):
+        """cuda_graph=True records the whole step (feature -> forward -> loss -> backward -> clip+AdamW) once, after
+        two eager warm-up steps, and replays it for every later batch of the same shape (single-GPU only)."""
         self.cfg = cfg
+        self.cuda_graph = bool(cuda_graph)
+        self._graph = None
+        self._static = None
+        self._eager_calls = 0
         self.model = model
         self.transform = SpectrogramTransform.for_cfg(cfg) if waveform_input else None
         self.reducer = GradientReducer(model, process_group, stages_per_group)
         self.criterion = DepthCriterion.from_cfg(cfg, reduce_fn=self.reducer.reduce_loss_sums
                                                  if self.reducer.world > 1 else None)
         lr = lr if lr is not None else getattr(cfg.mode, "learning_rate", 1e-3)
-        self.optimizer = FusedClipAdamW(model, lr=lr, max_norm=max_norm)
+        if self.cuda_graph and self.reducer.world > 1:
+            raise NotImplementedError("cuda_graph=True is single-GPU for now")
+        self.optimizer = FusedClipAdamW(model, lr=lr, max_norm=max_norm, capturable=self.cuda_graph)
 
     def features(self, batch):
         return self.transform(batch) if self.transform is not None else batch
@@ -84,6 +92,11 @@ class TrainStep:
     def __call__(self, batch, gtdepth):
         """batch: waveform [B,2,L] (or features [B,2,S,S] when waveform_input=False), gtdepth [B,1,S,S];
         CUDA fp32.  Returns the loss as a 0-dim device tensor (no synchronisation)."""
+        if self.cuda_graph:
+            return self._graphed_step(batch, gtdepth)
+        return self._eager_step(batch, gtdepth)
+
+    def _eager_step(self, batch, gtdepth):
         self.model.train()
         x = self.features(batch)
         pred = self.model(x)
@@ -92,6 +105,31 @@ class TrainStep:
         self.reducer.wait()
         self.optimizer.step()
         return loss.detach()
+
+    def _graphed_step(self, batch, gtdepth):
+        key = (tuple(batch.shape), tuple(gtdepth.shape), batch.device)
+        if self._static is not None and self._static[0] != key:
+            self._graph, self._static, self._eager_calls = None, None, 0      # new shape: re-record
+        if self._graph is None:
+            if self._eager_calls < 2:                  # workspaces, tensor maps, func attributes: all set up eagerly
+                self._eager_calls += 1
+                return self._eager_step(batch, gtdepth)
+            sb, sg = batch.clone(), gtdepth.clone()
+            side = torch.cuda.Stream(device=batch.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._eager_step(sb, sg)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                sloss = self._eager_step(sb, sg)
+            self._graph, self._static = graph, (key, sb, sg, sloss)
+        _, sb, sg, sloss = self._static
+        sb.copy_(batch, non_blocking=True)
+        sg.copy_(gtdepth, non_blocking=True)
+        self._graph.replay()
+        self.optimizer.step_count += 1
+        return sloss
 
     @torch.no_grad()
     def evaluate(self, batch, gtdepth):

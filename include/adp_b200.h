@@ -190,6 +190,12 @@ long long adp_tc_launch_count(void);
 int adp_profile_enable(int on);
 int adp_profile_read(double* ms, double* work, long long* calls);
 
+/* adp_clip_adamw_step with the step counter on the device (int, incremented by the call; scratch = 2 floats):
+ * capturable in a CUDA graph. */
+int adp_clip_adamw_step_graph(const adp_tensor_ref* refs_host, int n_tensors, const double* sumsq,
+                              float max_norm, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, int* step_dev, float* scratch, float* norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
