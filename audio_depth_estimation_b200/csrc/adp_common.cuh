@@ -249,8 +249,8 @@ int thin_last_convT_dgrad(int dtype, const float* du, const float* w, void* g0, 
 int thin_last_convT_wgrad(int dtype, const void* x0, int C0, const void* x1, int C1, const float* du, float* dw, int B,
                           int Hi, int Wi, cudaStream_t s);
 // tensor-core route for the thin layers: bf16 patch rows [pixels][64], padded weights, result folding
-int thin_patch_rows(const float* img, void* out, int B, int Cin, int H, int W, cudaStream_t s);
-int thin_pad_rows(const float* src, void* dst, int R, int K, cudaStream_t s);
+int thin_patch_rows(const float* img, void* out, int B, int Cin, int H, int W, int split, cudaStream_t s);
+int thin_pad_rows(const float* src, void* dst, int R, int K, int dup, cudaStream_t s);
 int thin_fold_wgrad(const float* D, float* dw, int mode, int K, cudaStream_t s);
 // y[pix][n] = sum_c (x0|x1)[pix][c] * w_nk[n][c] over NHWC pixels (adp_conv_tc.cu)
 int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_nk, void* y0, int N0, void* y1, int N1,

@@ -436,11 +436,57 @@ act_bn_bwd_apply8_kernel(const T* __restrict__ x, long long n8, long long rows, 
   };
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (FIXED) {
-    for (; i + stride < n8; i += 2 * stride) {    // two independent 16-byte loads per tensor in flight
-      const GzIn a = gz_load(x, gA, gB, 8 * i), b = gz_load(x, gA, gB, 8 * (i + stride));
-      finish(a, i);
-      finish(b, i + stride);
+    // same register-free cp.async prefetch as the reduction: RED_ROWS iterations x up to 3 tensors in flight
+    constexpr int CH16 = (int)(sizeof(T) * 8 / 16);
+    extern __shared__ __align__(16) unsigned char red_smem[];
+    const int tid = threadIdx.x;
+    auto slot = [&](int stage, int j, int t, int h) -> unsigned char* {
+      return red_smem + ((((size_t)(stage * RED_ROWS + j) * 3 + t) * CH16 + h) * 256 + tid) * 16;
+    };
+    auto issue = [&](int stage, long long i0) {
+#pragma unroll
+      for (int j = 0; j < RED_ROWS; ++j) {
+        const long long ii = i0 + j * stride;
+        if (ii < n8) {
+#pragma unroll
+          for (int h = 0; h < CH16; ++h) {
+            cp_async16(slot(stage, j, 0, h), reinterpret_cast<const unsigned char*>(x + 8 * ii) + 16 * h);
+            if (gA) cp_async16(slot(stage, j, 1, h), reinterpret_cast<const unsigned char*>(gA + 8 * ii) + 16 * h);
+            if (gB) cp_async16(slot(stage, j, 2, h), reinterpret_cast<const unsigned char*>(gB + 8 * ii) + 16 * h);
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    auto read8 = [&](int stage, int j, int t) -> float8 {
+      if (CH16 == 1) return cvt8(*reinterpret_cast<const uint4*>(slot(stage, j, t, 0)));
+      raw8f q;
+      q.a = *reinterpret_cast<const float4*>(slot(stage, j, t, 0));
+      q.b = *reinterpret_cast<const float4*>(slot(stage, j, t, CH16 - 1));
+      return cvt8(q);
+    };
+    int stage = 0;
+    issue(0, i);
+    while (i < n8) {
+      const long long in_ = i + RED_ROWS * stride;
+      issue(stage ^ 1, in_);
+      cp_async_wait<1>();
+#pragma unroll
+      for (int j = 0; j < RED_ROWS; ++j) {
+        const long long ii = i + j * stride;
+        if (ii < n8) {
+          GzIn q;
+          q.x = read8(stage, j, 0);
+          if (gA) q.a = read8(stage, j, 1);
+          if (gB) q.b = read8(stage, j, 2);
+          finish(q, ii);
+        }
+      }
+      i = in_;
+      stage ^= 1;
     }
+    cp_async_wait<0>();
+    return;
   }
   for (; i < n8; i += stride) {
     if (!FIXED) coeffs((int)((8 * i) % C));
@@ -633,7 +679,16 @@ int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const floa
   if (C % 8 == 0) {
     long long n8 = rows * C / 8;
     if (2048 % C == 0) {
-      ADP_DISPATCH_T(dtype, (act_bn_bwd_apply8_kernel<T, true><<<ew_grid(n8), EW_THREADS, 0, s>>>(
+      const size_t smem = (size_t)RED_STAGES * RED_ROWS * 3 * 256 * (dtype == ADP_F32 ? 32 : 16);
+      static bool attr_set = false;
+      if (!attr_set) {
+        ADP_CUDA(cudaFuncSetAttribute(act_bn_bwd_apply8_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      RED_STAGES * RED_ROWS * 3 * 256 * 32));
+        ADP_CUDA(cudaFuncSetAttribute(act_bn_bwd_apply8_kernel<bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      RED_STAGES * RED_ROWS * 3 * 256 * 16));
+        attr_set = true;
+      }
+      ADP_DISPATCH_T(dtype, (act_bn_bwd_apply8_kernel<T, true><<<ew_grid(n8), EW_THREADS, smem, s>>>(
                                 (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
                                 (const T*)gB, slope1, sums, mode, (T*)dx));)
     } else {

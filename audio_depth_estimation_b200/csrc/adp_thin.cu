@@ -329,46 +329,52 @@ last_convT_col2im_kernel(const float* __restrict__ P, const float* __restrict__ 
 //   mode 0: xp[pix][t], t = (kh*4+kw)*Cin + ci < 16*Cin, = x[b,ci,2oy-1+kh,2ox-1+kw]   (x NCHW fp32, Cin planes)
 //   mode 1: dp[pix][t], t = kh*4+kw < 16,              = du[b,2i-1+kh,2j-1+kw]          (same with Cin = 1)
 // One thread writes one 16-byte chunk (8 values).
+// SPLIT (needs 16*CIN <= 32): columns 0..31 hold bf16(x) and columns 32..63 hold bf16(x - bf16(x)), so that the
+// network input keeps ~16 mantissa bits through the bf16 tensor-core GEMM (the weight rows are duplicated).
+template <int CIN, bool SPLIT>
 __global__ void __launch_bounds__(256)
-patch_rows_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int Cin, int H, int W) {
-  const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)B * Ho * Wo * 8;
-  const int K = 16 * Cin;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(idx & 7);
-    const long long pix = idx >> 3;
-    float8 r;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) r.v[e] = 0.f;
+patch_rows_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int H, int W, int lw, int lh) {
+  // Wo = 1 << lw, Ho = 1 << lh (the tensor-core path needs power-of-two grids); 32-bit indices
+  const int Wo = 1 << lw, Ho = 1 << lh;
+  const unsigned total = (unsigned)B * Ho * Wo * 8u;
+  constexpr int K = 16 * CIN;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int q8 = (int)(idx & 7u);
+    const bool lo_half = SPLIT && q8 >= 4;
+    const int q = SPLIT ? (q8 & 3) : q8;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
     if (q * 8 < K) {
-      const int ox = (int)(pix % Wo);
-      const long long t2 = pix / Wo;
-      const int oy = (int)(t2 % Ho), b = (int)(t2 / Ho);
+      const unsigned pix = idx >> 3;
+      const int ox = (int)(pix & (Wo - 1)), oy = (int)((pix >> lw) & (Ho - 1)), b = (int)(pix >> (lw + lh));
+      float r[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int t = q * 8 + e;
-        if (t < K) {
-          const int tap = t / Cin, ci = t - tap * Cin;
-          const int y = 2 * oy - 1 + (tap >> 2), x = 2 * ox - 1 + (tap & 3);
-          if (y >= 0 && y < H && x >= 0 && x < W) r.v[e] = img[(((size_t)b * Cin + ci) * H + y) * W + x];
-        }
+        const int t = q * 8 + e;                 // compile-time after unrolling except for q
+        const int tap = t / CIN, ci = t % CIN;
+        const int y = 2 * oy - 1 + (tap >> 2), x = 2 * ox - 1 + (tap & 3);
+        r[e] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(img + (((size_t)b * CIN + ci) * H + y) * W + x) : 0.f;
+        if (lo_half) r[e] -= __bfloat162float(__float2bfloat16_rn(r[e]));
       }
+      u.x = pack_bf16x2(r[0], r[1]); u.y = pack_bf16x2(r[2], r[3]);
+      u.z = pack_bf16x2(r[4], r[5]); u.w = pack_bf16x2(r[6], r[7]);
     }
-    st8(out + idx * 8, r);
+    *reinterpret_cast<uint4*>(out + (size_t)idx * 8) = u;
   }
 }
 
-// src fp32 [R][K] -> dst bf16 [R][64] zero padded (K <= 64)
-__global__ void pad_rows_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int R, int K) {
+// src fp32 [R][K] -> dst bf16 [R][64] zero padded (K <= 64); dup: columns 32..32+K-1 repeat columns 0..K-1 (K <= 32)
+__global__ void pad_rows_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int R, int K, int dup) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * 64) return;
   const int r = i >> 6, k = i & 63;
-  dst[i] = __float2bfloat16_rn(k < K ? src[(size_t)r * K + k] : 0.f);
+  const int kk = (dup && k >= 32) ? k - 32 : k;
+  dst[i] = __float2bfloat16_rn(kk < K ? src[(size_t)r * K + kk] : 0.f);
 }
 
 // D fp32 [128][NT] from the transposed-operand GEMM -> dw
 //   mode 0 (last convT): dw[c][t]   = D[c][t],                 c < 128, t < 16    (ldd = 64)
 //   mode 1 (first conv): dw[n][t]   = D[n][t] + D[64+n][64+t], n < 64,  t < K     (ldd = 128; pixel pairs folded)
+//   mode 2 (first conv, hi/lo split input): as mode 1 plus the low-order halves D[n][32+t] + D[64+n][96+t]
 __global__ void fold_thin_wgrad_kernel(const float* __restrict__ D, float* __restrict__ dw, int mode, int K) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (mode == 0) {
@@ -376,7 +382,9 @@ __global__ void fold_thin_wgrad_kernel(const float* __restrict__ D, float* __res
   } else {
     if (i < 64 * K) {
       const int n = i / K, t = i - n * K;
-      dw[i] = D[n * 128 + t] + D[(64 + n) * 128 + 64 + t];
+      float v = D[n * 128 + t] + D[(64 + n) * 128 + 64 + t];
+      if (mode == 2) v += D[n * 128 + 32 + t] + D[(64 + n) * 128 + 96 + t];
+      dw[i] = v;
     }
   }
 }
@@ -456,19 +464,34 @@ int thin_last_convT_wgrad(int dtype, const void* x0, int C0, const void* x1, int
   return ADP_OK;
 }
 
-int thin_patch_rows(const float* img, void* out, int B, int Cin, int H, int W, cudaStream_t s) {
-  long long total = (long long)B * (H / 2) * (W / 2) * 8;
+int thin_patch_rows(const float* img, void* out, int B, int Cin, int H, int W, int split, cudaStream_t s) {
+  const int Ho = H / 2, Wo = W / 2;
+  int lw = 0, lh = 0;
+  while ((1 << lw) < Wo) ++lw;
+  while ((1 << lh) < Ho) ++lh;
+  ADP_CHECK_ARG((1 << lw) == Wo && (1 << lh) == Ho && (long long)B * Ho * Wo * 8 < (1LL << 31),
+                "patch_rows: grid must be a power of two and fit 32-bit indexing");
+  long long total = (long long)B * Ho * Wo * 8;
   long long blocks = (total + 255) / 256;
   long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  patch_rows_kernel<<<(int)blocks, 256, 0, s>>>(img, (bf16*)out, B, Cin, H, W);
+  ADP_CHECK_ARG(!split || 16 * Cin <= 32, "patch_rows: hi/lo split needs 16*Cin <= 32");
+  switch (Cin * 2 + (split ? 1 : 0)) {
+    case 2: patch_rows_kernel<1, false><<<(int)blocks, 256, 0, s>>>(img, (bf16*)out, B, H, W, lw, lh); break;
+    case 3: patch_rows_kernel<1, true><<<(int)blocks, 256, 0, s>>>(img, (bf16*)out, B, H, W, lw, lh); break;
+    case 4: patch_rows_kernel<2, false><<<(int)blocks, 256, 0, s>>>(img, (bf16*)out, B, H, W, lw, lh); break;
+    case 5: patch_rows_kernel<2, true><<<(int)blocks, 256, 0, s>>>(img, (bf16*)out, B, H, W, lw, lh); break;
+    case 6: patch_rows_kernel<3, false><<<(int)blocks, 256, 0, s>>>(img, (bf16*)out, B, H, W, lw, lh); break;
+    case 8: patch_rows_kernel<4, false><<<(int)blocks, 256, 0, s>>>(img, (bf16*)out, B, H, W, lw, lh); break;
+    default: adp_set_error("patch_rows: Cin %d unsupported", Cin); return ADP_ERR_UNSUPPORTED;
+  }
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }
 
-int thin_pad_rows(const float* src, void* dst, int R, int K, cudaStream_t s) {
-  ADP_CHECK_ARG(K <= 64, "pad_rows: K > 64");
-  pad_rows_kernel<<<adp_cdiv((long long)R * 64, 256), 256, 0, s>>>(src, (bf16*)dst, R, K);
+int thin_pad_rows(const float* src, void* dst, int R, int K, int dup, cudaStream_t s) {
+  ADP_CHECK_ARG(K <= 64 && (!dup || K <= 32), "pad_rows: K too large");
+  pad_rows_kernel<<<adp_cdiv((long long)R * 64, 256), 256, 0, s>>>(src, (bf16*)dst, R, K, dup);
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }

@@ -187,8 +187,8 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   const bool thin_tc = tc && tc_head && p.thin_tc;
   if (tc && !d->reuse_weight_cache) {
     if (thin_tc) {
-      ADP_TRY(thin_pad_rows(params[0].conv_w, at(ws, p.w1pad), 64, 16 * p.lv[0].cin, s));
-      ADP_TRY(thin_pad_rows(params[0].convT_w, at(ws, p.wLpad), 128, 16, s));
+      ADP_TRY(thin_pad_rows(params[0].conv_w, at(ws, p.w1pad), 64, 16 * p.lv[0].cin, p.lv[0].cin <= 2, s));
+      ADP_TRY(thin_pad_rows(params[0].convT_w, at(ws, p.wLpad), 128, 16, 0, s));
     }
     if (tc_head)  // [Ct][16][1] -> [1][16][Ct]
       ADP_TRY(cast_transpose_taps(params[0].convT_w, at(ws, p.w16_last), p.lv[0].cout + p.lv[0].t_c1, 1, s));
@@ -208,7 +208,7 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     const LevelPlan& L = p.lv[0];
     ProfScope prof(PROF_THIN, s, 2.0 * B * L.hout * L.hout * 16.0 * L.cin * L.cout);
     if (thin_tc) {  // im2col rows (bf16, padded to 64) + pointwise tensor-core GEMM with both activations in the epilogue
-      ADP_TRY(thin_patch_rows(x, at(ws, p.xp0), B, L.cin, L.hin, L.hin, s));
+      ADP_TRY(thin_patch_rows(x, at(ws, p.xp0), B, L.cin, L.hin, L.hin, L.cin <= 2, s));
       ADP_TRY(tc_pointwise(at(ws, p.xp0), 64, nullptr, 0, at(ws, p.w1pad), at(ws, L.a), 64, at(ws, L.r), 0, 1, 0.2f, 0.f, B,
                            L.hout, L.hout, s));
     } else {
@@ -306,7 +306,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       if (thin_tc_bwd) {
         ProfScope prof(PROF_THIN, s, 4.0 * B * L.hout * L.hout * 16.0 * Ct);
         float* Dt = reinterpret_cast<float*>(at(ws, p.dthin));
-        ADP_TRY(thin_patch_rows(du, at(ws, p.dp0), B, 1, d->size, d->size, s));
+        ADP_TRY(thin_patch_rows(du, at(ws, p.dp0), B, 1, d->size, d->size, 0, s));
         ADP_TRY(tc_gemm_tn(at(ws, L.r), 64, 0, at(ws, L.q), 64, 0, at(ws, p.dp0), 64, 64, (long long)B * L.hout * L.hout, Dt, s));
         ADP_TRY(thin_fold_wgrad(Dt, grads[0].convT_w, 0, 16, s));
         ADP_TRY(tc_pointwise(at(ws, p.dp0), 64, nullptr, 0, at(ws, p.wLpad), at(ws, L.g_r), 64, at(ws, L.g_q), 64, 0, 0.f,
@@ -355,7 +355,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         // pixel pairs folded into 128 "channels": D[(h,n)][(h',t)], the two diagonal blocks are the gradient
         ADP_TRY(tc_gemm_tn(at(ws, L.g_e), 128, 0, at(ws, L.g_e), 128, 64, at(ws, p.xp0), 128, 128,
                            (long long)B * L.hout * L.hout / 2, Dt, s));
-        ADP_TRY(thin_fold_wgrad(Dt, grads[0].conv_w, 1, 16 * L.cin, s));
+        ADP_TRY(thin_fold_wgrad(Dt, grads[0].conv_w, L.cin <= 2 ? 2 : 1, 16 * L.cin, s));
       } else if (l == 0) {
         ADP_TRY(first_conv_wgrad(dt, x, at(ws, L.g_e), grads[0].conv_w, B, L.hin, L.hin, L.cin, L.cout, s));
       } else {

@@ -70,7 +70,8 @@ class TrainStep:
     def __init__(self, cfg, model, lr=None, max_norm=1.0, process_group=None, stages_per_group=2,
                  waveform_input=True, cuda_graph=False):
         """cuda_graph=True records the whole step (feature -> forward -> loss -> backward -> clip+AdamW) once, after
-        two eager warm-up steps, and replays it for every later batch of the same shape (single-GPU only)."""
+        two eager warm-up steps, and replays it for every later batch of the same shape.  With several ranks the NCCL
+        all-reduces are recorded into the graph as well (every rank must record and replay in lock-step)."""
         self.cfg = cfg
         self.cuda_graph = bool(cuda_graph)
         self._graph = None
@@ -82,8 +83,6 @@ class TrainStep:
         self.criterion = DepthCriterion.from_cfg(cfg, reduce_fn=self.reducer.reduce_loss_sums
                                                  if self.reducer.world > 1 else None)
         lr = lr if lr is not None else getattr(cfg.mode, "learning_rate", 1e-3)
-        if self.cuda_graph and self.reducer.world > 1:
-            raise NotImplementedError("cuda_graph=True is single-GPU for now")
         self.optimizer = FusedClipAdamW(model, lr=lr, max_norm=max_norm, capturable=self.cuda_graph)
 
     def features(self, batch):

@@ -173,7 +173,7 @@ def run_ours(args):
     cfg = make_cfg(args.precision)
     torch.manual_seed(0)
     net = define_G(cfg, 2, 1, 64, "unet_256", "batch", False, gpu_ids=[local])
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
     step = TrainStep(cfg, net, lr=0.002, stages_per_group=args.stages_per_group, cuda_graph=use_graph)
     wave_h = torch.from_numpy(synthetic.waveform(B, synthetic.V2_LEN, seed=1234 + rank)).pin_memory()
     gt_h = torch.from_numpy(synthetic.gt_depth(B, 256, 30.0, seed=4321 + rank)).pin_memory()
@@ -237,9 +237,18 @@ def run_ours(args):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
 
-    if rank != 0:
+    def finish():
+        # NCCL communicators recorded into a CUDA graph make destroy_process_group() hang: drop the graph, make sure
+        # every rank is done, then leave without running the collective teardown
+        sys.stdout.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     pk = peaks()
     ms_step = ms_total / args.steps
@@ -286,8 +295,7 @@ def run_ours(args):
         out["cpu_baseline"] = {"value": cb / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": "1 timed step of batch %d after 1 warm-up (fp32, %d torch threads)" % (cb, threads)}
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
