@@ -111,12 +111,14 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- tile coordinates
-  const int tm = blockIdx.x;
+  // parity mode: the four output-parity classes of one pixel tile read the same input pixels (different taps);
+  // they are adjacent in launch order so that the tile is fetched from HBM once and hit in L2 three times
+  const int tm = p.mode == 1 ? (int)(blockIdx.x >> 2) : (int)blockIdx.x;
   const int tw_i = tm % p.tiles_w, th_i = (tm / p.tiles_w) % p.tiles_h, tb_i = tm / (p.tiles_w * p.tiles_h);
   const int x0 = tw_i * p.Wt, y0c = th_i * p.Ht, b0 = tb_i * p.Bt;
   const int n0 = blockIdx.y * BLOCK_N;
-  const int zpar = p.mode == 1 ? (int)(blockIdx.z & 3) : 0;
-  const int split = p.mode == 1 ? (int)(blockIdx.z >> 2) : (int)blockIdx.z;
+  const int zpar = p.mode == 1 ? (int)(blockIdx.x & 3) : 0;
+  const int split = (int)blockIdx.z;
   const int pa = zpar >> 1, pb = zpar & 1;
   const int kb_begin = split * p.kb_per_split;
   const int kb_end = min(kb_begin + p.kb_per_split, p.kblocks);
@@ -240,7 +242,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid
       } else if (p.splits > 1) {
         float* dst = p.partial + opix * p.N + n;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
+        for (int i = 0; i < 32; i += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
+                       "f"(v[i + 2]), "f"(v[i + 3]) : "memory");
       } else {
         bf16* dst = n < p.N0 ? p.y0 + opix * p.N0 + n : p.y1 + opix * p.N1 + (n - p.N0);
 #pragma unroll
@@ -339,7 +343,7 @@ int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes,
   p.splits = splits;
   p.partial = splits > 1 ? scratch : nullptr;
   if (splits > 1) ADP_CUDA(cudaMemsetAsync(scratch, 0, (size_t)out_pixels * p.N * sizeof(float), s));
-  dim3 grid(m_tiles, n_tiles, par * splits);
+  dim3 grid(m_tiles * par, n_tiles, splits);
   switch (block_n) {
     case 128: ADP_TRY(launch_igemm<128>(p, grid, s)); break;
     case 64: ADP_TRY(launch_igemm<64>(p, grid, s)); break;
