@@ -19,7 +19,7 @@ namespace {
 using namespace tc;
 
 constexpr int WG_M = 128;            // weight-tile rows (channels of S)
-constexpr int WG_P = 64;             // pixels per k-block
+constexpr int WG_P = 32;             // pixels per k-block (two UMMA K steps): small stages -> a deep TMA ring
 constexpr int WG_TAPS = 4;           // taps accumulated per CTA (one kernel row kh)
 constexpr int WG_THREADS = 192;
 constexpr int WG_BOX_BYTES = WG_P * 128;   // one [64 pixels x 64 channels] bf16 box
@@ -37,7 +37,7 @@ struct WgradSmem {
   static constexpr int A_BYTES = 2 * WG_BOX_BYTES;
   static constexpr int B_TAP_BYTES = (NT / 64) * WG_BOX_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + WG_TAPS * B_TAP_BYTES;
-  static constexpr int STAGES = NT == 128 ? 2 : 4;
+  static constexpr int STAGES = NT == 128 ? 4 : 8;
   static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = WG_TAPS * NT;   // 512 or 256
 };
@@ -174,7 +174,7 @@ struct GemmTnSmem {
   static constexpr int A_BYTES = 2 * WG_BOX_BYTES;
   static constexpr int B_BYTES = (NT / 64) * WG_BOX_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = 8;
   static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
