@@ -113,12 +113,9 @@ class TrainStep:
             if self._eager_calls < 2:                  # workspaces, tensor maps, func attributes: all set up eagerly
                 self._eager_calls += 1
                 return self._eager_step(batch, gtdepth)
+            # (no side-stream warm-up step here: it would be an extra, real optimiser update)
             sb, sg = batch.clone(), gtdepth.clone()
-            side = torch.cuda.Stream(device=batch.device)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                self._eager_step(sb, sg)
-            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(batch.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 sloss = self._eager_step(sb, sg)

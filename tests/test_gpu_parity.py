@@ -474,3 +474,47 @@ def test_train_step_end_to_end_loss_decreases():
     losses = [step(wave, gt).item() for _ in range(6)]
     assert all(np.isfinite(losses))
     assert losses[-1] < losses[0]
+
+
+def test_cuda_graph_step_matches_eager_steps():
+    """TrainStep(cuda_graph=True) replays one recorded step; its losses must track the eager path step for step
+    (same weights, same batches), including the device-side AdamW step counter."""
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    from audio_depth_estimation_b200.training import TrainStep
+    cfg = make_cfg(False, 30.0, 128, "fp32")
+    sd = uo.ordered_state_dict(uo.make_state_dict(16, 7, seed=42), 7)
+    batches = [(cuda(synthetic.waveform(2, synthetic.V2_LEN, seed=50 + i)), cuda(synthetic.gt_depth(2, 128, 30.0, seed=60 + i)))
+               for i in range(6)]
+    losses = {}
+    for graph in (False, True):
+        net = define_G(cfg, 2, 1, 16, "unet_128", "batch", False, gpu_ids=[0])
+        net.load_state_dict({k: v.clone() for k, v in sd.items()})
+        step = TrainStep(cfg, net, lr=0.002, cuda_graph=graph)
+        losses[graph] = [float(step(w, g)) for w, g in batches]
+        torch.cuda.synchronize()
+    a, b = np.array(losses[False]), np.array(losses[True])
+    print("eager", a, "graph", b)
+    assert np.all(np.isfinite(a)) and np.all(np.isfinite(b))
+    # the first two (eager) steps are identical; afterwards fp32 atomics (split-K, wgrad) make even two eager runs
+    # drift by ~1e-3 on this tiny-batch problem, so the recorded step is held to 1e-2
+    assert np.abs(a[:2] - b[:2]).max() <= 1e-5 * np.abs(a).max(), (a, b)
+    assert np.abs(a - b).max() <= 1e-2 * np.abs(a).max(), (a, b)
+
+
+def test_eval_mode_inference_shapes_v1_v2():
+    """test.py:231-241 path: eval-mode forward from waveforms, BatVision V1 and V2 shapes, batch 1 and 5."""
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    from audio_depth_estimation_b200.feature import SpectrogramTransform
+    for name, L, dn, md in (("batvisionv2", synthetic.V2_LEN, False, 30.0), ("batvisionv1", synthetic.V1_LEN, True, 12.0)):
+        cfg = make_cfg(dn, md, 256, "bf16")
+        cfg.dataset.name = name
+        net = define_G(cfg, 2, 1, 64, "unet_256", "batch", False, gpu_ids=[0]).eval()
+        tr = SpectrogramTransform.for_cfg(cfg)
+        for B in (1, 5):
+            with torch.no_grad():
+                y = net(tr(cuda(synthetic.waveform(B, L, seed=B))))
+            assert y.shape == (B, 1, 256, 256) and torch.isfinite(y).all()
+            if dn:
+                assert float(y.min()) >= 0.0 and float(y.max()) <= 1.0
+            else:
+                assert float(y.min()) >= 0.0
