@@ -311,99 +311,6 @@ last_convT_fprop_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ 
   }
 }
 
-template <class T>
-__global__ void __launch_bounds__(LAST_THREADS)
-last_convT_dgrad_kernel(const float* __restrict__ du, const float* __restrict__ w, T* __restrict__ g0, int C0,
-                        T* __restrict__ g1, int C1, int B, int Hi, int Wi) {
-  extern __shared__ __align__(16) float ws[];  // [16][Ct]
-  const int Ct = C0 + C1;
-  for (int i = threadIdx.x; i < 16 * Ct; i += LAST_THREADS) {
-    int tap = i / Ct, c = i - tap * Ct;
-    ws[i] = w[(size_t)c * 16 + tap];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * LAST_THREADS + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * LAST_THREADS) >> 5;
-  const long long npix = (long long)B * Hi * Wi;
-  const int Ho = 2 * Hi, Wo = 2 * Wi;
-  for (long long p = warp; p < npix; p += nwarps) {
-    const int j = (int)(p % Wi);
-    const long long t = p / Wi;
-    const int i = (int)(t % Hi), b = (int)(t / Hi);
-    float d[16];
-#pragma unroll
-    for (int kh = 0; kh < 4; ++kh) {
-      const int oy = 2 * i - 1 + kh;
-#pragma unroll
-      for (int kw = 0; kw < 4; ++kw) {
-        const int ox = 2 * j - 1 + kw;
-        d[kh * 4 + kw] = (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) ? du[((size_t)b * Ho + oy) * Wo + ox] : 0.f;
-      }
-    }
-    for (int c = lane * 4; c < Ct; c += 128) {
-      float4 acc = Z4;
-#pragma unroll
-      for (int tap = 0; tap < 16; ++tap) {
-        float4 wv = *reinterpret_cast<const float4*>(&ws[tap * Ct + c]);
-        acc.x = fmaf(d[tap], wv.x, acc.x); acc.y = fmaf(d[tap], wv.y, acc.y);
-        acc.z = fmaf(d[tap], wv.z, acc.z); acc.w = fmaf(d[tap], wv.w, acc.w);
-      }
-      if (c < C0) st4(g0 + (size_t)p * C0 + c, acc);
-      else st4(g1 + (size_t)p * C1 + (c - C0), acc);
-    }
-  }
-}
-
-// requires Ct <= 128 per pass: lane owns channels 4*lane..4*lane+3 of the current 128-channel slab
-template <class T>
-__global__ void __launch_bounds__(LAST_THREADS)
-last_convT_wgrad_kernel(const T* __restrict__ x0, int C0, const T* __restrict__ x1, int C1,
-                        const float* __restrict__ du, float* __restrict__ dw, int B, int Hi, int Wi, int cbase) {
-  __shared__ float red[16][128];
-  const int Ct = C0 + C1;
-  for (int i = threadIdx.x; i < 16 * 128; i += LAST_THREADS) (&red[0][0])[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * LAST_THREADS + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * LAST_THREADS) >> 5;
-  const long long npix = (long long)B * Hi * Wi;
-  const int Ho = 2 * Hi, Wo = 2 * Wi;
-  const int c = cbase + lane * 4;
-  float acc[16][4];
-#pragma unroll
-  for (int t = 0; t < 16; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
-  if (c < Ct) {
-    for (long long p = warp; p < npix; p += nwarps) {
-      const int j = (int)(p % Wi);
-      const long long t = p / Wi;
-      const int i = (int)(t % Hi), b = (int)(t / Hi);
-      float4 v = ld_cat(x0, C0, x1, C1, (size_t)p, c);
-#pragma unroll
-      for (int kh = 0; kh < 4; ++kh) {
-        const int oy = 2 * i - 1 + kh;
-#pragma unroll
-        for (int kw = 0; kw < 4; ++kw) {
-          const int ox = 2 * j - 1 + kw;
-          float d = (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) ? du[((size_t)b * Ho + oy) * Wo + ox] : 0.f;
-          float* a = acc[kh * 4 + kw];
-          a[0] = fmaf(d, v.x, a[0]); a[1] = fmaf(d, v.y, a[1]);
-          a[2] = fmaf(d, v.z, a[2]); a[3] = fmaf(d, v.w, a[3]);
-        }
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < 16; ++t)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) atomicAdd(&red[t][lane * 4 + q], acc[t][q]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 16 * 128; i += LAST_THREADS) {
-    int t = i >> 7, cl = i & 127;
-    if (cbase + cl < Ct) atomicAdd(&dw[(size_t)(cbase + cl) * 16 + t], red[t][cl]);
-  }
-}
-
 int pix_grid(long long npix) {
   long long blocks = (npix + (LAST_THREADS / 32) * 4 - 1) / ((LAST_THREADS / 32) * 4);
   long long cap = (long long)adp::sm_count() * 8;
@@ -531,32 +438,12 @@ int last_convT_dgrad(int dtype, const float* du, const float* w, void* g0, int C
                      int B, int Hi, int Wi, cudaStream_t s) {
   ADP_CHECK_ARG(C0 % 4 == 0 && C1 % 4 == 0 && C0 + C1 <= 2048, "last_convT_dgrad: bad channel counts");
   return thin_last_convT_dgrad(dtype, du, w, g0, C0, g1, C1, B, Hi, Wi, s);
-  size_t smem = (size_t)16 * (C0 + C1) * 4;
-  long long npix = (long long)B * Hi * Wi;
-  ADP_DISPATCH_T(dtype, {
-    if (smem > 48 * 1024)
-      ADP_CUDA(cudaFuncSetAttribute(last_convT_dgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    last_convT_dgrad_kernel<T><<<pix_grid(npix), LAST_THREADS, smem, s>>>(du, w, (T*)g0, C0, (T*)g1, C1, B, Hi, Wi);
-  })
-  ADP_LAUNCH_CHECK();
-  return ADP_OK;
 }
 
 int last_convT_wgrad(int dtype, const void* x0, int C0, const void* x1, int C1, const float* du, float* dw,
                      int B, int Hi, int Wi, cudaStream_t s) {
   ADP_CHECK_ARG(C0 % 4 == 0 && C1 % 4 == 0, "last_convT_wgrad: bad channel counts");
   return thin_last_convT_wgrad(dtype, x0, C0, x1, C1, du, dw, B, Hi, Wi, s);
-  long long npix = (long long)B * Hi * Wi;
-  int grid = adp::sm_count() * 2;
-  if ((long long)grid * (LAST_THREADS / 32) > npix) grid = (int)((npix + 7) / 8);
-  if (grid < 1) grid = 1;
-  for (int cbase = 0; cbase < C0 + C1; cbase += 128) {
-    ADP_DISPATCH_T(dtype, {
-      last_convT_wgrad_kernel<T><<<grid, LAST_THREADS, 0, s>>>((const T*)x0, C0, (const T*)x1, C1, du, dw, B, Hi, Wi, cbase);
-    })
-    ADP_LAUNCH_CHECK();
-  }
-  return ADP_OK;
 }
 
 }  // namespace adp

@@ -251,6 +251,10 @@ def run_ours(args):
         finish()
         return
     pk = peaks()
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "r1_tc_dram_per_step.json")
+    if os.path.exists(tpath) and B == 64 and args.precision == "bf16":
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"]      # ncu capture of this workload, per launch
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
     e2e = B * world / (ms_e2e / args.steps / 1e3)
@@ -278,7 +282,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (gather + parity + wgrad families)",
                      "achieved": achieved, "peak": pk["tc_sustained"], "unit": "TFLOP/s",
-                     "frac": (achieved / pk["tc_sustained"]) if achieved else None, "traffic": None,
+                     "frac": (achieved / pk["tc_sustained"]) if achieved else None, "traffic": traffic,
+                     "traffic_note": "mean DRAM bytes per tcgen05 conv launch (ncu, profiles/r1_tc_dram_per_step.json)",
                      "peak_source": pk["source"] + " (sustained bf16, kernel timed inside a long step)",
                      "share_of_step": conv_ms / ms_eager if ms_eager > 0 else None, "families": families,
                      "timed_over": "the K eager steps (per-family CUDA events on the launching stream)"},
