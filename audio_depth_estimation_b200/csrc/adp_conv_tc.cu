@@ -85,6 +85,7 @@ struct IgemmParams {
   float* partial;                     // fp32 [out pixels][N] when splits > 1
   float* out_f32;                     // mode 2: fp32 [pixels][BLOCK_N] result
   int stages;                         // smem ring depth actually used (<= IgemmSmem::STAGES)
+  int gx, gy, gz, total_tiles;        // logical grid (x fastest) walked by the persistent kernel
   int act_dual;                       // mode 2: y0 = lrelu(D, slope0), y1 = lrelu(D, slope1), both [pixels][N]
   float slope0, slope1;
 };
@@ -265,6 +266,210 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid
   }
 }
 
+// ------------------------------------------------------------------ persistent variant
+// One CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x).  The smem ring and its phases run
+// continuously across tiles, the accumulator is double-buffered in tensor memory (2 x BLOCK_N columns), so the
+// epilogue of tile i (TMEM -> registers -> global) overlaps the TMA/MMA main loop of tile i+1, and TMEM allocation,
+// barrier initialisation and tensor-map prefetch are paid once per SM instead of once per tile.
+struct TileCoord { int x0, y0c, b0, n0, pa, pb, kb_begin, nkb; };
+
+template <int BLOCK_N>
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t) {
+  const int bx = t % p.gx, r = t / p.gx, by = r % p.gy, bz = r / p.gy;
+  TileCoord c;
+  const int tm = p.mode == 1 ? (bx >> 2) : bx;
+  const int tw_i = tm % p.tiles_w, th_i = (tm / p.tiles_w) % p.tiles_h, tb_i = tm / (p.tiles_w * p.tiles_h);
+  c.x0 = tw_i * p.Wt; c.y0c = th_i * p.Ht; c.b0 = tb_i * p.Bt;
+  c.n0 = by * BLOCK_N;
+  const int zpar = p.mode == 1 ? (bx & 3) : 0;
+  c.pa = zpar >> 1; c.pb = zpar & 1;
+  c.kb_begin = bz * p.kb_per_split;
+  c.nkb = min(c.kb_begin + p.kb_per_split, p.kblocks) - c.kb_begin;
+  return c;
+}
+
+template <int BLOCK_N>
+struct PersistSmem {
+  using S = IgemmSmem<BLOCK_N>;
+  static constexpr int STAGES = (196 * 1024) / S::STAGE_BYTES > 10 ? 10 : (196 * 1024) / S::STAGE_BYTES;
+  static constexpr int BYTES = STAGES * S::STAGE_BYTES + 1024 + 256;
+  static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
+  using S = IgemmSmem<BLOCK_N>;
+  using PS = PersistSmem<BLOCK_N>;
+  constexpr int STAGES = PS::STAGES;
+  constexpr int ACC = PS::ACC_COLS;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained by the 4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tmA0);
+    if (p.C1 > 0) prefetch_tmap(&p.tmA1);
+    prefetch_tmap(&p.tmW);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const int nchunk = p.Ct / TILE_K;
+      uint32_t g = 0;                                     // k-blocks issued so far (ring position)
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile<BLOCK_N>(p, t);
+        for (int it = 0; it < c.nkb; ++it, ++g) {
+          const int kb = c.kb_begin + it;
+          const int s = (int)(g % STAGES);
+          const uint32_t ph = (g / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          unsigned char* a_dst = smem + s * S::STAGE_BYTES;
+          unsigned char* b_dst = a_dst + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+          const int tap = kb / nchunk;
+          const int ch = (kb - tap * nchunk) * TILE_K;
+          if (p.mode == 0) {
+            const int kh = tap >> 2, kw = tap & 3;
+            const int di = (kh + 1) / 2 - 1, ra = (kh + 1) & 1;
+            const int dj = (kw + 1) / 2 - 1, rb = (kw + 1) & 1;
+            tma_load_5d(a_dst, &p.tmA0, &full_bar[s], rb * p.Ct + ch, c.x0 + dj, ra, c.y0c + di, c.b0);
+            tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + ch, c.n0);
+          } else if (p.mode == 2) {
+            if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, c.x0, c.y0c, c.b0);
+            else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, c.x0, c.y0c, c.b0);
+            tma_load_2d(b_dst, &p.tmW, &full_bar[s], ch, c.n0);
+          } else {
+            const int th = tap >> 1, tw = tap & 1;
+            const int cx = c.x0 + c.pb - 1 + tw, cy = c.y0c + c.pa - 1 + th;
+            if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, cx, cy, c.b0);
+            else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, cx, cy, c.b0);
+            const int wtap = (3 - c.pa - 2 * th) * 4 + (3 - c.pb - 2 * tw);
+#pragma unroll
+            for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h)
+              tma_load_3d(b_dst + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const bool b_mn = p.mode == 1;
+      const uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, 0, b_mn ? 1 : 0);
+      uint32_t g = 0, local = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
+        const TileCoord c = decode_tile<BLOCK_N>(p, t);
+        const uint32_t buf = local & 1u, use = local >> 1;
+        mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);    // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * ACC;
+        for (int it = 0; it < c.nkb; ++it, ++g) {
+          const int s = (int)(g % STAGES);
+          const uint32_t ph = (g / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < TILE_K / 16; ++k) {
+            const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = b_mn ? umma_smem_desc(b_addr + k * 2048, TILE_K * 128, 1024)
+                                     : umma_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(tacc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
+    uint32_t local = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
+      const TileCoord c = decode_tile<BLOCK_N>(p, t);
+      const uint32_t buf = local & 1u, use = local >> 1;
+      const int b = c.b0 + bt, py = c.y0c + ht, px = c.x0 + wt;
+      const bool valid = b < p.B && c.nkb > 0;
+      size_t opix;
+      if (p.mode != 1) opix = ((size_t)b * p.Hs + py) * p.Ws + px;
+      else opix = ((size_t)b * 2 * p.Hs + 2 * py + c.pa) * (2 * p.Ws) + 2 * px + c.pb;
+      mbar_wait(&tfull_bar[buf], use & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * ACC + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < BLOCK_N; cc += 32) {
+        float v[32];
+        tmem_ld32(tacc + (uint32_t)cc, v);
+        if (!valid) continue;
+        const int n = c.n0 + cc;
+        if (BLOCK_N == 16) {
+          float* dst = p.out_f32 + opix * 16;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        } else if (p.act_dual) {
+          bf16* d0 = p.y0 + opix * p.N + n;
+          bf16* d1 = p.y1 + opix * p.N + n;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 u, w;
+            u.x = pack_bf16x2(lrelu(v[i + 0], p.slope0), lrelu(v[i + 1], p.slope0));
+            u.y = pack_bf16x2(lrelu(v[i + 2], p.slope0), lrelu(v[i + 3], p.slope0));
+            u.z = pack_bf16x2(lrelu(v[i + 4], p.slope0), lrelu(v[i + 5], p.slope0));
+            u.w = pack_bf16x2(lrelu(v[i + 6], p.slope0), lrelu(v[i + 7], p.slope0));
+            w.x = pack_bf16x2(lrelu(v[i + 0], p.slope1), lrelu(v[i + 1], p.slope1));
+            w.y = pack_bf16x2(lrelu(v[i + 2], p.slope1), lrelu(v[i + 3], p.slope1));
+            w.z = pack_bf16x2(lrelu(v[i + 4], p.slope1), lrelu(v[i + 5], p.slope1));
+            w.w = pack_bf16x2(lrelu(v[i + 6], p.slope1), lrelu(v[i + 7], p.slope1));
+            *reinterpret_cast<uint4*>(d0 + i) = u;
+            *reinterpret_cast<uint4*>(d1 + i) = w;
+          }
+        } else if (p.splits > 1) {
+          float* dst = p.partial + opix * p.N + n;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
+                         "f"(v[i + 2]), "f"(v[i + 3]) : "memory");
+        } else {
+          bf16* dst = n < p.N0 ? p.y0 + opix * p.N0 + n : p.y1 + opix * p.N1 + (n - p.N0);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(v[i + 0], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
+            u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+            *reinterpret_cast<uint4*>(dst + i) = u;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);      // this warp's quarter of the accumulator is free again
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * ACC);
+  }
+}
+
 // fp32 partial sums [pixels][N] -> bf16 outputs (split at N0)
 __global__ void __launch_bounds__(256)
 finish_partial_kernel(const float* __restrict__ partial, long long pixels, int N, int N0, int N1, bf16* __restrict__ y0,
@@ -300,6 +505,7 @@ bool tile_geometry(int B, int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
 }
 
 int g_force_stages = 0;   // ADP_TC_STAGES environment override (tuning)
+int g_persistent = 1;     // ADP_TC_PERSISTENT=0 selects the one-tile-per-CTA kernel
 
 template <int BLOCK_N>
 int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
@@ -308,6 +514,21 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
   if (!attr_set) {
     ADP_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
     attr_set = true;
+  }
+  p.gx = grid.x; p.gy = grid.y; p.gz = grid.z;
+  p.total_tiles = (int)(grid.x * grid.y * grid.z);
+  if (g_persistent) {
+    using PS = PersistSmem<BLOCK_N>;
+    static bool pattr_set = false;
+    if (!pattr_set) {
+      ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
+      pattr_set = true;
+    }
+    const int ctas = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    tc_igemm_persist_kernel<BLOCK_N><<<ctas, IGEMM_THREADS, PS::BYTES, s>>>(p);
+    adp_count_tc_launch();
+    ADP_LAUNCH_CHECK();
+    return ADP_OK;
   }
   // Ring depth: at most what fits twice into an SM's shared memory, so that two CTAs are co-resident and one
   // CTA's epilogue (TMEM -> global) overlaps the other's TMA/MMA main loop; never deeper than the K loop.
@@ -364,6 +585,8 @@ struct StagesEnvInit {
   StagesEnvInit() {
     const char* e = getenv("ADP_TC_STAGES");
     if (e) g_force_stages = atoi(e);
+    const char* pe = getenv("ADP_TC_PERSISTENT");
+    if (pe) g_persistent = atoi(pe);
   }
 } g_stages_env_init;
 
