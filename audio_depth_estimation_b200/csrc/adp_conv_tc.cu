@@ -487,10 +487,12 @@ finish_partial_kernel(const float* __restrict__ partial, long long pixels, int N
 
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+int g_max_block_n = 256;   // ADP_TC_MAX_BN environment override (tuning)
+
 int pick_block_n(int N, int N0, int N1) {
-  const int cands[3] = {128, 64, 32};
+  const int cands[4] = {256, 128, 64, 32};
   for (int c : cands)
-    if (N % c == 0 && (N1 == 0 || N0 % c == 0)) return c;
+    if (c <= g_max_block_n && N % c == 0 && (N1 == 0 || N0 % c == 0)) return c;
   return 0;
 }
 
@@ -566,6 +568,7 @@ int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes,
   if (splits > 1) ADP_CUDA(cudaMemsetAsync(scratch, 0, (size_t)out_pixels * p.N * sizeof(float), s));
   dim3 grid(m_tiles * par, n_tiles, splits);
   switch (block_n) {
+    case 256: ADP_TRY(launch_igemm<256>(p, grid, s)); break;
     case 128: ADP_TRY(launch_igemm<128>(p, grid, s)); break;
     case 64: ADP_TRY(launch_igemm<64>(p, grid, s)); break;
     case 32: ADP_TRY(launch_igemm<32>(p, grid, s)); break;
@@ -587,6 +590,8 @@ struct StagesEnvInit {
     if (e) g_force_stages = atoi(e);
     const char* pe = getenv("ADP_TC_PERSISTENT");
     if (pe) g_persistent = atoi(pe);
+    const char* be = getenv("ADP_TC_MAX_BN");
+    if (be) g_max_block_n = atoi(be);
   }
 } g_stages_env_init;
 

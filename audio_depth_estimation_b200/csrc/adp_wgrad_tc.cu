@@ -11,6 +11,7 @@
 // accumulates a [128 x NT] weight tile for FOUR taps at once in tensor memory (4*NT <= 512
 // columns), re-using the S tile across the taps.  The pixel range is split across CTAs until
 // the grid fills the GPU; partial tiles are reduced with fp32 red.global.add.
+#include <stdlib.h>
 #include "adp_tc.cuh"
 
 namespace adp {
@@ -369,7 +370,9 @@ int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int 
   }
   const int m_tiles = (M0 + M1) / WG_M, n_tiles = N / NT;
   const long long ctas = (long long)m_tiles * n_tiles * 4;
-  int splits = (int)((2LL * sm_count() + ctas - 1) / ctas);
+  // one resident CTA per SM (160 KB of smem, all 512 TMEM columns): aim at ADP_WG_WAVES (default 1) full waves
+  static int waves = getenv("ADP_WG_WAVES") ? atoi(getenv("ADP_WG_WAVES")) : 1;
+  int splits = (int)(((long long)waves * sm_count() + ctas / 2) / ctas);
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits < 1) splits = 1;
   p.kb_per_split = adp_cdiv(p.kblocks, splits);

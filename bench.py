@@ -145,7 +145,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "UNetBaseline(unet_256, ngf 64) full training step, BatVision-V2 shapes, CPU batch %d" % B},
+        "config": {"workload": "UNetBaseline(unet_256, ngf 64, 54.4M params) full training step: STFT(512,64,16)+log+minmax+"
+                               "resize -> U-Net fwd/bwd -> Combined L1+SIlog loss -> clip+AdamW; BatVision-V2 shapes "
+                               "[B,2,7782] -> [B,1,256,256]",
+                   "per_gpu_batch": 64, "cpu_sample_batch": B, "parallelism": "cpu"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -212,11 +215,11 @@ def run_ours(args):
         g = gt_h.to(dev, non_blocking=True)
         return step(w, g).item()
 
-    for _ in range(max(args.warmup, 3)):
-        resident_step()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.start()      # sampled from the warm-up on, through every timed region (all of it is under load)
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
     if not use_graph:
         lib.adp_profile_enable(1)
     ms_total = timed(resident_step, args.steps)
@@ -229,13 +232,13 @@ def run_ours(args):
         lib.adp_profile_enable(0)
     else:
         ms_eager = ms_total
-    clocks = sampler.stop() if sampler else None
     pms, pwork, pcalls = (ctypes.c_double * 5)(), (ctypes.c_double * 5)(), (ctypes.c_longlong * 5)()
     _lib.check(lib.adp_profile_read(pms, pwork, pcalls))
 
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if sampler else None
 
     def finish():
         # NCCL communicators recorded into a CUDA graph make destroy_process_group() hang: drop the graph, make sure
