@@ -74,6 +74,7 @@ constexpr int IGEMM_THREADS = 192;    // warp 0: TMA, warp 1: MMA + TMEM alloc, 
 
 struct IgemmParams {
   CUtensorMap tmA0, tmA1, tmW;
+  CUtensorMap tmWh;                   // cluster mode: half-height weight boxes (each CTA of a pair multicasts one half)
   // tile geometry over the "small" pixel grid (conv outputs for F1, convT inputs for F2)
   int Wt, Ht, Bt, tiles_w, tiles_h;
   int B, Hs, Ws;                      // small grid extent
@@ -86,6 +87,8 @@ struct IgemmParams {
   float* out_f32;                     // mode 2: fp32 [pixels][BLOCK_N] result
   int stages;                         // smem ring depth actually used (<= IgemmSmem::STAGES)
   int gx, gy, gz, total_tiles;        // logical grid (x fastest) walked by the persistent kernel
+  int total_pair_tiles;               // cluster mode: tiles of two adjacent m-tiles
+  int has_half_map;                   // tmWh encoded
   int act_dual;                       // mode 2: y0 = lrelu(D, slope0), y1 = lrelu(D, slope1), both [pixels][N]
   float slope0, slope1;
 };
@@ -288,6 +291,24 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t) {
   return c;
 }
 
+// Pair tiles for the 2-CTA cluster variant: both CTAs take the same (n-tile, split, parity) and adjacent m-tiles,
+// so the weight tile is identical and each CTA fetches (and multicasts) only half of it.
+template <int BLOCK_N>
+__device__ __forceinline__ TileCoord decode_pair_tile(const IgemmParams& p, int u, int rank) {
+  const int gxp = p.mode == 1 ? ((p.gx / 4 + 1) / 2) * 4 : (p.gx + 1) / 2;
+  const int bxp = u % gxp, r = u / gxp, by = r % p.gy, bz = r / p.gy;
+  TileCoord c;
+  const int zpar = p.mode == 1 ? (bxp & 3) : 0;
+  const int tm = (p.mode == 1 ? (bxp >> 2) : bxp) * 2 + rank;
+  const int tw_i = tm % p.tiles_w, th_i = (tm / p.tiles_w) % p.tiles_h, tb_i = tm / (p.tiles_w * p.tiles_h);
+  c.x0 = tw_i * p.Wt; c.y0c = th_i * p.Ht; c.b0 = tb_i * p.Bt;     // tb_i past the batch: zero-filled, nothing stored
+  c.n0 = by * BLOCK_N;
+  c.pa = zpar >> 1; c.pb = zpar & 1;
+  c.kb_begin = bz * p.kb_per_split;
+  c.nkb = min(c.kb_begin + p.kb_per_split, p.kblocks) - c.kb_begin;
+  return c;
+}
+
 template <int BLOCK_N>
 struct PersistSmem {
   using S = IgemmSmem<BLOCK_N>;
@@ -296,10 +317,15 @@ struct PersistSmem {
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool CLUSTER>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
   using S = IgemmSmem<BLOCK_N>;
   using PS = PersistSmem<BLOCK_N>;
+  const int crank = CLUSTER ? (int)cluster_ctarank() : 0;
+  const int worker = CLUSTER ? (int)cluster_id_x() : (int)blockIdx.x;      // index of this CTA (pair) in the tile walk
+  const int nworkers = CLUSTER ? (int)cluster_count_x() : (int)gridDim.x;
+  const int ntiles = CLUSTER ? p.total_pair_tiles : p.total_tiles;
+  auto tile_at = [&](int t) { return CLUSTER ? decode_pair_tile<BLOCK_N>(p, t, crank) : decode_tile<BLOCK_N>(p, t); };
   constexpr int STAGES = PS::STAGES;
   constexpr int ACC = PS::ACC_COLS;
   extern __shared__ unsigned char smem_raw[];
@@ -315,13 +341,15 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
     prefetch_tmap(&p.tmA0);
     if (p.C1 > 0) prefetch_tmap(&p.tmA1);
     prefetch_tmap(&p.tmW);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    // cluster mode: a stage may be refilled only when BOTH CTAs have consumed it (each multicasts into the other)
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER ? 2 : 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC);
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();                        // peer barriers are initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -330,8 +358,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
     if (elect_one()) {
       const int nchunk = p.Ct / TILE_K;
       uint32_t g = 0;                                     // k-blocks issued so far (ring position)
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord c = decode_tile<BLOCK_N>(p, t);
+      for (int t = worker; t < ntiles; t += nworkers) {
+        const TileCoord c = tile_at(t);
         for (int it = 0; it < c.nkb; ++it, ++g) {
           const int kb = c.kb_begin + it;
           const int s = (int)(g % STAGES);
@@ -347,11 +375,18 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
             const int di = (kh + 1) / 2 - 1, ra = (kh + 1) & 1;
             const int dj = (kw + 1) / 2 - 1, rb = (kw + 1) & 1;
             tma_load_5d(a_dst, &p.tmA0, &full_bar[s], rb * p.Ct + ch, c.x0 + dj, ra, c.y0c + di, c.b0);
-            tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + ch, c.n0);
+            if (CLUSTER)
+              tma_load_2d_mc(b_dst + crank * (S::B_STAGE_BYTES / 2), &p.tmWh, &full_bar[s], 3, tap * p.Ct + ch,
+                             c.n0 + crank * (BLOCK_N / 2));
+            else
+              tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + ch, c.n0);
           } else if (p.mode == 2) {
             if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, c.x0, c.y0c, c.b0);
             else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, c.x0, c.y0c, c.b0);
-            tma_load_2d(b_dst, &p.tmW, &full_bar[s], ch, c.n0);
+            if (CLUSTER)
+              tma_load_2d_mc(b_dst + crank * (S::B_STAGE_BYTES / 2), &p.tmWh, &full_bar[s], 3, ch, c.n0 + crank * (BLOCK_N / 2));
+            else
+              tma_load_2d(b_dst, &p.tmW, &full_bar[s], ch, c.n0);
           } else {
             const int th = tap >> 1, tw = tap & 1;
             const int cx = c.x0 + c.pb - 1 + tw, cy = c.y0c + c.pa - 1 + th;
@@ -359,8 +394,13 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
             else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, cx, cy, c.b0);
             const int wtap = (3 - c.pa - 2 * th) * 4 + (3 - c.pb - 2 * tw);
 #pragma unroll
-            for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h)
-              tma_load_3d(b_dst + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
+            for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h) {
+              if (CLUSTER)   // every 64-row box is fetched as two 32-row halves, one per CTA
+                tma_load_3d_mc(b_dst + h * (TILE_K * 128) + crank * (TILE_K * 64), &p.tmWh, &full_bar[s], 3, c.n0 + h * 64,
+                               wtap, ch + crank * (TILE_K / 2));
+              else
+                tma_load_3d(b_dst + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
+            }
           }
         }
       }
@@ -371,8 +411,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
       const bool b_mn = p.mode == 1;
       const uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, 0, b_mn ? 1 : 0);
       uint32_t g = 0, local = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
-        const TileCoord c = decode_tile<BLOCK_N>(p, t);
+      for (int t = worker; t < ntiles; t += nworkers, ++local) {
+        const TileCoord c = tile_at(t);
         const uint32_t buf = local & 1u, use = local >> 1;
         mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);    // epilogue has drained this accumulator
         tc_fence_after();
@@ -391,7 +431,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
                                      : umma_smem_desc(b_addr + k * 32, 16, 1024);
             umma_bf16(tacc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          if (CLUSTER) umma_commit_mc(&empty_bar[s], 3);
+          else umma_commit(&empty_bar[s]);
         }
         umma_commit(&tfull_bar[buf]);
       }
@@ -402,8 +443,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
     const int r = q * 32 + lane;
     const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
     uint32_t local = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++local) {
-      const TileCoord c = decode_tile<BLOCK_N>(p, t);
+    for (int t = worker; t < ntiles; t += nworkers, ++local) {
+      const TileCoord c = tile_at(t);
       const uint32_t buf = local & 1u, use = local >> 1;
       const int b = c.b0 + bt, py = c.y0c + ht, px = c.x0 + wt;
       const bool valid = b < p.B && c.nkb > 0;
@@ -464,6 +505,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();                        // no multicast / remote arrive may target a CTA that has left
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * ACC);
@@ -508,6 +550,7 @@ bool tile_geometry(int B, int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
 
 int g_force_stages = 0;   // ADP_TC_STAGES environment override (tuning)
 int g_persistent = 1;     // ADP_TC_PERSISTENT=0 selects the one-tile-per-CTA kernel
+int g_cluster = 0;        // ADP_TC_CLUSTER=1: 2-CTA clusters, weight tile halves multicast between the pair
 
 template <int BLOCK_N>
 int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
@@ -523,11 +566,34 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
     using PS = PersistSmem<BLOCK_N>;
     static bool pattr_set = false;
     if (!pattr_set) {
-      ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
+      ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
+      ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
       pattr_set = true;
     }
+    const int m_groups = p.mode == 1 ? (int)grid.x / 4 : (int)grid.x;
+    if (g_cluster && p.has_half_map && m_groups >= 2) {
+      const int gxp = p.mode == 1 ? ((m_groups + 1) / 2) * 4 : (m_groups + 1) / 2;
+      p.total_pair_tiles = gxp * (int)grid.y * (int)grid.z;
+      int pairs = sm_count() / 2;
+      if (pairs > p.total_pair_tiles) pairs = p.total_pair_tiles;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2 * pairs);
+      cfg.blockDim = dim3(IGEMM_THREADS);
+      cfg.dynamicSmemBytes = PS::BYTES;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      ADP_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_persist_kernel<BLOCK_N, true>, p));
+      adp_count_tc_launch();
+      ADP_LAUNCH_CHECK();
+      return ADP_OK;
+    }
     const int ctas = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    tc_igemm_persist_kernel<BLOCK_N><<<ctas, IGEMM_THREADS, PS::BYTES, s>>>(p);
+    tc_igemm_persist_kernel<BLOCK_N, false><<<ctas, IGEMM_THREADS, PS::BYTES, s>>>(p);
     adp_count_tc_launch();
     ADP_LAUNCH_CHECK();
     return ADP_OK;
@@ -590,6 +656,8 @@ struct StagesEnvInit {
     if (e) g_force_stages = atoi(e);
     const char* pe = getenv("ADP_TC_PERSISTENT");
     if (pe) g_persistent = atoi(pe);
+    const char* ce = getenv("ADP_TC_CLUSTER");
+    if (ce) g_cluster = atoi(ce);
     const char* be = getenv("ADP_TC_MAX_BN");
     if (be) g_max_block_n = atoi(be);
   }
@@ -644,6 +712,9 @@ int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, 
     uint64_t str[1] = {(uint64_t)16 * C * 2};
     uint32_t box[2] = {TILE_K, (uint32_t)bn};
     ADP_TRY(make_tmap_bf16(&p.tmW, w_nk, 2, dims, str, box));
+    uint32_t hbox[2] = {TILE_K, (uint32_t)bn / 2};
+    ADP_TRY(make_tmap_bf16(&p.tmWh, w_nk, 2, dims, str, hbox));
+    p.has_half_map = 1;
   }
   return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
 }
@@ -673,6 +744,9 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
     uint64_t str[2] = {(uint64_t)N * 2, (uint64_t)16 * N * 2};
     uint32_t box[3] = {64, 1, TILE_K};
     ADP_TRY(make_tmap_bf16(&p.tmW, w_kn, 3, dims, str, box));
+    uint32_t hbox[3] = {64, 1, TILE_K / 2};
+    ADP_TRY(make_tmap_bf16(&p.tmWh, w_kn, 3, dims, str, hbox));
+    p.has_half_map = 1;
   }
   return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
 }
@@ -742,6 +816,9 @@ int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_n
     uint64_t str[1] = {(uint64_t)Ct * 2};
     uint32_t box[2] = {TILE_K, (uint32_t)bn};
     ADP_TRY(make_tmap_bf16(&p.tmW, w_nk, 2, dims, str, box));
+    uint32_t hbox[2] = {TILE_K, (uint32_t)bn / 2};
+    ADP_TRY(make_tmap_bf16(&p.tmWh, w_nk, 2, dims, str, hbox));
+    p.has_half_map = 1;
   }
   return run_igemm(p, bn, nullptr, 0, s);
 }
