@@ -357,19 +357,16 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
     // ===================== TMA producer =====================
     if (elect_one()) {
       const int nchunk = p.Ct / TILE_K;
-      uint32_t g = 0;                                     // k-blocks issued so far (ring position)
+      int s = 0;                                          // ring position and its phase bit
+      uint32_t ph = 0;
       for (int t = worker; t < ntiles; t += nworkers) {
         const TileCoord c = tile_at(t);
-        for (int it = 0; it < c.nkb; ++it, ++g) {
-          const int kb = c.kb_begin + it;
-          const int s = (int)(g % STAGES);
-          const uint32_t ph = (g / STAGES) & 1u;
+        int tap = c.kb_begin / nchunk, ch = (c.kb_begin - tap * nchunk) * TILE_K;
+        for (int it = 0; it < c.nkb; ++it) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           unsigned char* a_dst = smem + s * S::STAGE_BYTES;
           unsigned char* b_dst = a_dst + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-          const int tap = kb / nchunk;
-          const int ch = (kb - tap * nchunk) * TILE_K;
           if (p.mode == 0) {
             const int kh = tap >> 2, kw = tap & 3;
             const int di = (kh + 1) / 2 - 1, ra = (kh + 1) & 1;
@@ -402,6 +399,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
                 tma_load_3d(b_dst + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
             }
           }
+          ch += TILE_K;
+          if (ch == p.Ct) { ch = 0; ++tap; }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -410,29 +410,31 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
     if (elect_one()) {
       const bool b_mn = p.mode == 1;
       const uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, 0, b_mn ? 1 : 0);
-      uint32_t g = 0, local = 0;
+      // descriptors differ from stage to stage only in the 14-bit start-address field: build them once
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t a_desc0 = umma_smem_desc(smem_base, 16, 1024);
+      const uint64_t b_desc0 = b_mn ? umma_smem_desc(smem_base + A_STAGE_BYTES, TILE_K * 128, 1024)
+                                    : umma_smem_desc(smem_base + A_STAGE_BYTES, 16, 1024);
+      const uint32_t b_kstep = b_mn ? (2048u >> 4) : (32u >> 4);
+      int s = 0;
+      uint32_t ph = 0, local = 0;
       for (int t = worker; t < ntiles; t += nworkers, ++local) {
         const TileCoord c = tile_at(t);
         const uint32_t buf = local & 1u, use = local >> 1;
         mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);    // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * ACC;
-        for (int it = 0; it < c.nkb; ++it, ++g) {
-          const int s = (int)(g % STAGES);
-          const uint32_t ph = (g / STAGES) & 1u;
+        for (int it = 0; it < c.nkb; ++it) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const uint64_t stage_off = (uint64_t)((uint32_t)(s * S::STAGE_BYTES) >> 4);
+          const uint64_t ad0 = a_desc0 + stage_off, bd0 = b_desc0 + stage_off;
 #pragma unroll
-          for (int k = 0; k < TILE_K / 16; ++k) {
-            const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = b_mn ? umma_smem_desc(b_addr + k * 2048, TILE_K * 128, 1024)
-                                     : umma_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(tacc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < TILE_K / 16; ++k)
+            umma_bf16(tacc, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * b_kstep), idesc, (it | k) != 0 ? 1u : 0u);
           if (CLUSTER) umma_commit_mc(&empty_bar[s], 3);
           else umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         umma_commit(&tfull_bar[buf]);
       }
