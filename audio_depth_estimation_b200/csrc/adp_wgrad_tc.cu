@@ -87,10 +87,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
       const CUtensorMap* tmS = second ? &p.tmS1 : &p.tmS0;
       const int mc = second ? m0 - p.M0 : m0;
       const int di = (kh + 1) / 2 - 1, ra = (kh + 1) & 1;
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < nkb; ++it) {
         const int kb = kb_begin + it;
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
         const int tw_i = kb % p.tiles_w, th_i = (kb / p.tiles_w) % p.tiles_h, tb_i = kb / (p.tiles_w * p.tiles_h);
         const int x0 = tw_i * p.Wt, y0 = th_i * p.Ht, b0 = tb_i * p.Bt;
         mbar_wait(&empty_bar[s], ph ^ 1);
@@ -107,29 +107,34 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
             tma_load_5d(b_dst + kw * S::B_TAP_BYTES + h * WG_BOX_BYTES, &p.tmG, &full_bar[s], rb * p.N + n0 + h * 64,
                         x0 + dj, ra, y0 + di, b0);
         }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(WG_M, NT, 1, 1);
+      // descriptors differ between stages / taps / K steps only in the start-address field: build once, then add
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t a_desc0 = umma_smem_desc(smem_base, WG_BOX_BYTES, 1024);
+      const uint64_t b_desc0 = umma_smem_desc(smem_base + S::A_BYTES, WG_BOX_BYTES, 1024);
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + S::A_BYTES;
+        const uint64_t stage_off = (uint64_t)((uint32_t)(s * S::STAGE_BYTES) >> 4);
 #pragma unroll
         for (int kw = 0; kw < WG_TAPS; ++kw) {
 #pragma unroll
           for (int k = 0; k < WG_P / 16; ++k) {
             // 16 pixels = two 8-row swizzle atoms = 2048 bytes further down the tile
-            const uint64_t ad = umma_smem_desc(a_addr + k * 2048, WG_BOX_BYTES, 1024);
-            const uint64_t bd = umma_smem_desc(b_addr + kw * S::B_TAP_BYTES + k * 2048, WG_BOX_BYTES, 1024);
+            const uint64_t ad = a_desc0 + stage_off + (uint64_t)((k * 2048) >> 4);
+            const uint64_t bd = b_desc0 + stage_off + (uint64_t)((kw * S::B_TAP_BYTES + k * 2048) >> 4);
             umma_bf16(tmem_base + kw * NT, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
       umma_commit(accum_bar);
     }
