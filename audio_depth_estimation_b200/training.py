@@ -66,6 +66,52 @@ class GradientReducer:
         self.model.mark_weights_dirty()
 
 
+class DevicePrefetcher:
+    """Double-buffered host -> device input pipeline: while step i runs, the (pinned) host tensors of step i+1 are
+    copied on a side stream.  Iterating yields device tensors that are safe to use on the current stream.
+
+        for wave, gt in DevicePrefetcher(loader, device):       # loader yields tuples of pinned CPU tensors
+            loss = step(wave, gt)
+    """
+
+    def __init__(self, batches, device):
+        self.batches = iter(batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.i = 0
+        self._issue(0)
+
+    def _issue(self, k):
+        try:
+            host = next(self.batches)
+        except StopIteration:
+            self.slots[k] = None
+            return
+        # the slot was last read by the step before the previous one, which the compute stream has passed
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            if self.slots[k] is None or any(d.shape != h.shape for d, h in zip(self.slots[k], host)):
+                self.slots[k] = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host)
+            for d, h in zip(self.slots[k], host):
+                d.copy_(h, non_blocking=True)
+            self.events[k].record(self.stream)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        k = self.i & 1
+        if self.slots[k] is None:
+            raise StopIteration
+        cur = self.slots[k]
+        torch.cuda.current_stream(self.device).wait_event(self.events[k])
+        self.i += 1
+        self._issue(self.i & 1)          # next batch travels while the caller computes on `cur`
+        return cur
+
+
 class TrainStep:
     def __init__(self, cfg, model, lr=None, max_norm=1.0, process_group=None, stages_per_group=2,
                  waveform_input=True, cuda_graph=False):

@@ -518,3 +518,13 @@ def test_eval_mode_inference_shapes_v1_v2():
                 assert float(y.min()) >= 0.0 and float(y.max()) <= 1.0
             else:
                 assert float(y.min()) >= 0.0
+
+
+def test_device_prefetcher_yields_every_batch_in_order():
+    from audio_depth_estimation_b200.training import DevicePrefetcher
+    host = [(torch.full((4, 8), float(i)).pin_memory(), torch.full((2,), float(-i)).pin_memory()) for i in range(5)]
+    got = [(a.clone(), b.clone()) for a, b in DevicePrefetcher(iter(host), DEV)]
+    torch.cuda.synchronize()
+    assert len(got) == 5
+    for i, (a, b) in enumerate(got):
+        assert a.is_cuda and float(a[0, 0]) == float(i) and float(b[1]) == float(-i)
