@@ -266,6 +266,12 @@ bool tc_supported_pointwise16(int B, int Hi, int Wi, int C0, int C1);
 int tc_pointwise16(const void* x0, int C0, const void* x1, int C1, const void* w16, float* P, int B, int Hi, int Wi,
                    cudaStream_t s);
 
+// STFT magnitude as a split-bf16 DFT GEMM on tensor cores (win_length 64); spec [rows][F][T] fp32
+bool tc_supported_stft(int rows, int L, int n_fft, int win, int hop);
+size_t tc_stft_workspace_bytes(int rows, int L, int n_fft, int hop);
+int tc_stft_mag(const float* wave, int rows, int L, int pitch, int n_fft, int hop, float* spec, int log_mode, int* minmax,
+                void* workspace, cudaStream_t s);
+
 // tcgen05 paths (adp_conv_tc.cu), bf16 operands, fp32 accumulate in TMEM.
 // w_nk: bf16 [N][16][C] (K-major B operand)
 int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, int N1,

@@ -71,10 +71,12 @@ constexpr int TILE_M = 128;
 constexpr int TILE_K = 64;            // bf16 elements = one 128-byte swizzled row
 constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;
 constexpr int IGEMM_THREADS = 192;    // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int PERSIST_THREADS = 320;  // persistent kernel: warps 2-9 = two epilogue groups (alternate 32-column chunks)
 
 struct IgemmParams {
   CUtensorMap tmA0, tmA1, tmW;
   CUtensorMap tmWh;                   // cluster mode: half-height weight boxes (each CTA of a pair multicasts one half)
+  CUtensorMap tmA2;                   // mode 3: third bf16 slice of the frames
   // tile geometry over the "small" pixel grid (conv outputs for F1, convT inputs for F2)
   int Wt, Ht, Bt, tiles_w, tiles_h;
   int B, Hs, Ws;                      // small grid extent
@@ -91,6 +93,8 @@ struct IgemmParams {
   int has_half_map;                   // tmWh encoded
   int act_dual;                       // mode 2: y0 = lrelu(D, slope0), y1 = lrelu(D, slope1), both [pixels][N]
   float slope0, slope1;
+  // mode 3 (STFT as a split-bf16 DFT GEMM): rows = frames, columns = (re, im) pairs of the bins
+  float* spec; int F, T, log_mode; int* minmax;
 };
 
 template <int BLOCK_N>
@@ -317,8 +321,9 @@ struct PersistSmem {
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
-template <int BLOCK_N, bool CLUSTER>
-__global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
+// EG = number of epilogue warp groups (4 warps each): 1 for the convolutions, 2 for the math-heavy STFT epilogue
+template <int BLOCK_N, bool CLUSTER, int EG>
+__global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
   using S = IgemmSmem<BLOCK_N>;
   using PS = PersistSmem<BLOCK_N>;
   const int crank = CLUSTER ? (int)cluster_ctarank() : 0;
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
     prefetch_tmap(&p.tmW);
     // cluster mode: a stage may be refilled only when BOTH CTAs have consumed it (each multicasts into the other)
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER ? 2 : 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4 * EG); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC);
@@ -377,6 +382,12 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
                              c.n0 + crank * (BLOCK_N / 2));
             else
               tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + ch, c.n0);
+          } else if (p.mode == 3) {
+            // six K blocks x0*W0, x0*W1, x1*W0, x0*W2, x1*W1, x2*W0 of the three-way bf16 split (A slice 0,0,1,0,1,2)
+            const int kbi = ch / TILE_K;
+            const CUtensorMap* am = (kbi == 2 || kbi == 4) ? &p.tmA1 : (kbi == 5 ? &p.tmA2 : &p.tmA0);
+            tma_load_4d(a_dst, am, &full_bar[s], 0, c.x0, c.y0c, c.b0);
+            tma_load_2d(b_dst, &p.tmW, &full_bar[s], ch, c.n0);
           } else if (p.mode == 2) {
             if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, c.x0, c.y0c, c.b0);
             else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, c.x0, c.y0c, c.b0);
@@ -441,7 +452,10 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
     }
   } else {
     // ===================== epilogue =====================
+    // 8 warps: warp & 3 selects the TMEM lane quarter (hardware rule), (warp - 2) / 4 the group; the two groups
+    // take alternate 32-column chunks so that twice as many warps hide the tcgen05.ld / math / store latency
     const int q = warp & 3;
+    const int egroup = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
     uint32_t local = 0;
@@ -456,10 +470,31 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
       mbar_wait(&tfull_bar[buf], use & 1u);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * ACC + ((uint32_t)(q * 32) << 16);
+      float vmin = INFINITY, vmax = -INFINITY;
 #pragma unroll 1
-      for (int cc = 0; cc < BLOCK_N; cc += 32) {
+      for (int cc = egroup * 32; cc < BLOCK_N; cc += 32 * EG) {
         float v[32];
         tmem_ld32(tacc + (uint32_t)cc, v);
+        if (EG == 2) {   // STFT instantiation only (mode 3)
+          // row = frame px of waveform row b; columns (2k, 2k+1) = (Re, Im) of bin k -> |X| (optionally log)
+          if (b < p.B && px < p.T) {
+            const int k0 = (c.n0 + cc) >> 1;
+            float* dst = p.spec + ((size_t)b * p.F + k0) * p.T + px;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (k0 + i < p.F) {
+                float m = sqrtf(v[2 * i] * v[2 * i] + v[2 * i + 1] * v[2 * i + 1]);
+                if (p.log_mode) {
+                  m = __logf(m + 1e-8f);          // lg2.approx: absolute error ~1e-7 on a value range of ~10
+                  vmin = fminf(vmin, m);
+                  vmax = fmaxf(vmax, m);
+                }
+                dst[(size_t)i * p.T] = m;
+              }
+            }
+          }
+          continue;
+        }
         if (!valid) continue;
         const int n = c.n0 + cc;
         if (BLOCK_N == 16) {
@@ -498,6 +533,14 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_persist_kernel(cons
             u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
             *reinterpret_cast<uint4*>(dst + i) = u;
           }
+        }
+      }
+      if (EG == 2 && p.log_mode) {
+        vmin = warp_min(vmin);
+        vmax = warp_max(vmax);
+        if (lane == 0 && vmin <= vmax && b < p.B) {
+          atomicMin(&p.minmax[2 * b], float_to_ordered(vmin));
+          atomicMax(&p.minmax[2 * b + 1], float_to_ordered(vmax));
         }
       }
       tc_fence_before();
@@ -568,12 +611,15 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
     using PS = PersistSmem<BLOCK_N>;
     static bool pattr_set = false;
     if (!pattr_set) {
-      ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
-      ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
+      ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
+      ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
+      if (BLOCK_N == 128)
+        ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<128, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PersistSmem<128>::BYTES));
       pattr_set = true;
     }
     const int m_groups = p.mode == 1 ? (int)grid.x / 4 : (int)grid.x;
-    if (g_cluster && p.has_half_map && m_groups >= 2) {
+    if (g_cluster && p.has_half_map && m_groups >= 2 && p.mode != 3) {
       const int gxp = p.mode == 1 ? ((m_groups + 1) / 2) * 4 : (m_groups + 1) / 2;
       p.total_pair_tiles = gxp * (int)grid.y * (int)grid.z;
       int pairs = sm_count() / 2;
@@ -589,13 +635,18 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      ADP_CUDA(cudaLaunchKernelEx(&cfg, tc_igemm_persist_kernel<BLOCK_N, true>, p));
+      ADP_CUDA(cudaLaunchKernelEx(&cfg, (tc_igemm_persist_kernel<BLOCK_N, true, 1>), p));
       adp_count_tc_launch();
       ADP_LAUNCH_CHECK();
       return ADP_OK;
     }
     const int ctas = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    tc_igemm_persist_kernel<BLOCK_N, false><<<ctas, IGEMM_THREADS, PS::BYTES, s>>>(p);
+    if (p.mode == 3) {
+      if (BLOCK_N != 128) { adp_set_error("stft: BLOCK_N must be 128"); return ADP_ERR_ARG; }
+      tc_igemm_persist_kernel<128, false, 2><<<ctas, PERSIST_THREADS, PersistSmem<128>::BYTES, s>>>(p);
+    } else {
+      tc_igemm_persist_kernel<BLOCK_N, false, 1><<<ctas, IGEMM_THREADS, PS::BYTES, s>>>(p);
+    }
     adp_count_tc_launch();
     ADP_LAUNCH_CHECK();
     return ADP_OK;
@@ -823,6 +874,127 @@ int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_n
     p.has_half_map = 1;
   }
   return run_igemm(p, bn, nullptr, 0, s);
+}
+
+// ------------------------------------------------------------------ STFT magnitude as a tensor-core DFT
+// S[k,t] = | sum_{n<64} hann[n] x[hop*t + n - 32] e^{-2 pi i k n / n_fft} |  is the GEMM
+//   [frames x 64] * [64 x 2F]  (columns = Re/Im of the windowed twiddles).  bf16 operands would cost 3 digits, so both
+// operands are split x = hi + lo (two bf16 each) and the product is accumulated as hi*Whi + hi*Wlo + lo*Whi in fp32:
+// Three-way splits (24 mantissa bits) and the six leading product terms: K = 384, fp32-level accuracy.
+namespace {
+
+__global__ void __launch_bounds__(256)
+stft_frames_kernel(const float* __restrict__ wave, int L, int pitch, int hop, int T, int Tp, int rows,
+                   bf16* __restrict__ A0, bf16* __restrict__ A1, bf16* __restrict__ A2) {
+  const long long total = (long long)rows * Tp * 8;                 // one thread = 8 consecutive taps of one frame
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx & 7);
+    const long long fr = idx >> 3;
+    const int t = (int)(fr % Tp), row = (int)(fr / Tp);
+    uint4 s0, s1, s2;
+    uint32_t* p0 = &s0.x; uint32_t* p1 = &s1.x; uint32_t* p2 = &s2.x;
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      float x[2], a[2], b[2], cc[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        x[u] = 0.f;
+        if (t < T) {
+          int j = hop * t + q * 8 + e + u - 32;
+          if (j < 0) j = -j;
+          if (j >= L) j = 2 * (L - 1) - j;
+          j = min(max(j, 0), L - 1);
+          x[u] = wave[(size_t)row * pitch + j];
+        }
+        a[u] = __bfloat162float(__float2bfloat16_rn(x[u]));
+        b[u] = __bfloat162float(__float2bfloat16_rn(x[u] - a[u]));
+        cc[u] = x[u] - a[u] - b[u];
+      }
+      p0[e / 2] = pack_bf16x2(a[0], a[1]);
+      p1[e / 2] = pack_bf16x2(b[0], b[1]);
+      p2[e / 2] = pack_bf16x2(cc[0], cc[1]);
+    }
+    *reinterpret_cast<uint4*>(A0 + idx * 8) = s0;
+    *reinterpret_cast<uint4*>(A1 + idx * 8) = s1;
+    *reinterpret_cast<uint4*>(A2 + idx * 8) = s2;
+  }
+}
+
+// Wm bf16 [Npad][384]: row j = 2k (Re) / 2k+1 (Im); 64-column blocks W0, W1, W0, W2, W1, W0 (three-way split of w)
+__global__ void stft_dft_matrix_kernel(bf16* __restrict__ Wm, int n_fft, int F, int Npad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad * 64) return;
+  const int j = i >> 6, n = i & 63;
+  float w = 0.f;
+  if (j < 2 * F) {
+    const int k = j >> 1;
+    const double hann = 0.5 - 0.5 * cospi(2.0 * n / 64.0);
+    double sv, cv;
+    sincospi(2.0 * (double)((k * n) % n_fft) / (double)n_fft, &sv, &cv);
+    w = (float)(hann * ((j & 1) ? -sv : cv));
+  }
+  const float w0 = __bfloat162float(__float2bfloat16_rn(w));
+  const float w1 = __bfloat162float(__float2bfloat16_rn(w - w0));
+  const float w2 = w - w0 - w1;
+  bf16* rowp = Wm + (size_t)j * 384;
+  const bf16 b0 = __float2bfloat16_rn(w0), b1 = __float2bfloat16_rn(w1), b2 = __float2bfloat16_rn(w2);
+  rowp[n] = b0; rowp[64 + n] = b1; rowp[128 + n] = b0; rowp[192 + n] = b2; rowp[256 + n] = b1; rowp[320 + n] = b0;
+}
+
+}  // namespace
+
+size_t tc_stft_workspace_bytes(int rows, int L, int n_fft, int hop) {
+  const int T = 1 + L / hop;
+  int Tp = 128;
+  while (Tp < T) Tp *= 2;
+  const int Npad = ((2 * (n_fft / 2 + 1) + 127) / 128) * 128;
+  return adp_align_up((size_t)rows * Tp * 64 * 2, 1024) * 3 + adp_align_up((size_t)Npad * 384 * 2, 1024);
+}
+
+bool tc_supported_stft(int rows, int L, int n_fft, int win, int hop) {
+  if (!g_persistent || !adp_device_is_sm100() || !encode_tiled_fn()) return false;
+  return win == 64 && hop > 0 && n_fft >= 64 && n_fft <= 2048 && rows >= 1 && L > 32 && (1 + L / hop) <= 32768;
+}
+
+int tc_stft_mag(const float* wave, int rows, int L, int pitch, int n_fft, int hop, float* spec, int log_mode, int* minmax,
+                void* workspace, cudaStream_t s) {
+  const int T = 1 + L / hop, F = n_fft / 2 + 1;
+  int Tp = 128;
+  while (Tp < T) Tp *= 2;
+  const int Npad = ((2 * F + 127) / 128) * 128;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const size_t abytes = adp_align_up((size_t)rows * Tp * 64 * 2, 1024);
+  bf16* A0 = reinterpret_cast<bf16*>(ws);
+  bf16* A1 = reinterpret_cast<bf16*>(ws + abytes);
+  bf16* A2 = reinterpret_cast<bf16*>(ws + 2 * abytes);
+  bf16* Wm = reinterpret_cast<bf16*>(ws + 3 * abytes);
+  {
+    long long total = (long long)rows * Tp * 8, blocks = (total + 255) / 256, cap = (long long)sm_count() * 16;
+    stft_frames_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, s>>>(wave, L, pitch, hop, T, Tp, rows, A0, A1, A2);
+    ADP_LAUNCH_CHECK();
+    stft_dft_matrix_kernel<<<adp_cdiv((long long)Npad * 64, 256), 256, 0, s>>>(Wm, n_fft, F, Npad);
+    ADP_LAUNCH_CHECK();
+  }
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  ADP_CHECK_ARG(tile_geometry(rows, 1, Tp, &p.Wt, &p.Ht, &p.Bt), "tc_stft: unsupported frame count %d", Tp);
+  p.tiles_w = Tp / p.Wt; p.tiles_h = 1;
+  p.B = rows; p.Hs = 1; p.Ws = Tp; p.mode = 3; p.C0 = 64; p.C1 = 64; p.Ct = 384; p.N = Npad; p.N0 = Npad; p.N1 = 0;
+  p.kblocks = 6;
+  p.spec = spec; p.F = F; p.T = T; p.log_mode = log_mode; p.minmax = minmax;
+  for (int h = 0; h < 3; ++h) {
+    uint64_t dims[4] = {64, (uint64_t)Tp, 1, (uint64_t)rows};
+    uint64_t str[3] = {64 * 2, (uint64_t)Tp * 64 * 2, (uint64_t)Tp * 64 * 2};
+    uint32_t box[4] = {TILE_K, (uint32_t)p.Wt, 1, 1};
+    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : (h == 1 ? &p.tmA1 : &p.tmA2), h == 0 ? A0 : (h == 1 ? A1 : A2), 4, dims, str, box));
+  }
+  {
+    uint64_t dims[2] = {384, (uint64_t)Npad};
+    uint64_t str[1] = {384 * 2};
+    uint32_t box[2] = {TILE_K, 128};
+    ADP_TRY(make_tmap_bf16(&p.tmW, Wm, 2, dims, str, box));
+  }
+  return run_igemm(p, 128, nullptr, 0, s);
 }
 
 // wgrad on tensor cores: see adp_wgrad_tc.cu

@@ -237,7 +237,8 @@ extern "C" int adp_stft_mag(const float* wave, int rows, int L, int wave_pitch, 
 extern "C" size_t adp_feature_workspace_bytes(int rows, int L, int n_fft, int hop) {
   if (rows <= 0 || L <= 0 || n_fft <= 0 || hop <= 0) return 0;
   size_t T = 1 + (size_t)L / hop, F = (size_t)n_fft / 2 + 1;
-  return adp_align_up((size_t)rows * F * T * 4, 256) + adp_align_up((size_t)rows * 8, 256);
+  return adp_align_up((size_t)rows * F * T * 4, 1024) + adp_align_up((size_t)rows * 8, 1024) +
+         adp::tc_stft_workspace_bytes(rows, L, n_fft, hop);
 }
 
 extern "C" int adp_resize_aa(const float* in, int rows, int H, int W, int out_size, float* out, void* stream) {
@@ -260,13 +261,18 @@ extern "C" int adp_feature_forward(const float* wave, int rows, int L, int wave_
                 "feature: workspace too small (%zu)", workspace_bytes);
   const int T = 1 + L / hop, F = n_fft / 2 + 1;
   float* spec = reinterpret_cast<float*>(workspace);
-  int* minmax = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) +
-                                       adp_align_up((size_t)rows * F * T * 4, 256));
+  char* wsb = reinterpret_cast<char*>(workspace);
+  int* minmax = reinterpret_cast<int*>(wsb + adp_align_up((size_t)rows * F * T * 4, 1024));
+  void* tc_ws = wsb + adp_align_up((size_t)rows * F * T * 4, 1024) + adp_align_up((size_t)rows * 8, 1024);
   if (log_minmax) {
     init_minmax_kernel<<<adp_cdiv(rows, 256), 256, 0, s>>>(minmax, rows);
     ADP_LAUNCH_CHECK();
   }
-  ADP_TRY(launch_stft(wave, rows, L, wave_pitch, n_fft, win_length, hop, spec, log_minmax ? 1 : 0, minmax, s));
+  if (adp::tc_enabled() && adp::tc_supported_stft(rows, L, n_fft, win_length, hop)) {
+    ADP_TRY(adp::tc_stft_mag(wave, rows, L, wave_pitch, n_fft, hop, spec, log_minmax ? 1 : 0, minmax, tc_ws, s));
+  } else {
+    ADP_TRY(launch_stft(wave, rows, L, wave_pitch, n_fft, win_length, hop, spec, log_minmax ? 1 : 0, minmax, s));
+  }
   dim3 grid(adp_cdiv(out_size, 256), out_size, adp_cdiv(rows, RESIZE_PLANES));
   resize_aa_kernel<<<grid, 256, 0, s>>>(spec, rows, F, T, out_size, out, log_minmax ? minmax : nullptr);
   ADP_LAUNCH_CHECK();
