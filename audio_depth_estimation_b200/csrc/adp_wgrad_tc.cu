@@ -377,7 +377,8 @@ int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int 
   const long long ctas = (long long)m_tiles * n_tiles * 4;
   // one resident CTA per SM (160 KB of smem, all 512 TMEM columns): aim at ADP_WG_WAVES (default 1) full waves
   static int waves = getenv("ADP_WG_WAVES") ? atoi(getenv("ADP_WG_WAVES")) : 1;
-  int splits = (int)(((long long)waves * sm_count() + ctas / 2) / ctas);
+  const int eff_waves = NT == 64 ? 2 * waves : waves;      // the narrow-N tiles are short: two waves balance better
+  int splits = (int)(((long long)eff_waves * sm_count() + ctas / 2) / ctas);
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits < 1) splits = 1;
   p.kb_per_split = adp_cdiv(p.kblocks, splits);
