@@ -23,10 +23,9 @@ class BatvisionV1Dataset(Dataset):
         self.audio_format = cfg.dataset.audio_format
         self.device = torch.device("cuda") if torch.cuda.is_available() else None
         self.instances = pd.read_csv(os.path.join(self.root_dir, annotation_file))
-        if location_blacklist:
-            keep = ~self.instances["depth path"].astype(str).apply(
-                lambda p: any(b in p for b in location_blacklist))
-            self.instances = self.instances[keep]
+        if location_blacklist:      # reference :25-31 filters on the left-ear audio path
+            for location in location_blacklist:
+                self.instances = self.instances[~self.instances["audio path left"].str.contains(location)]
 
     def __len__(self):
         return len(self.instances)
@@ -34,8 +33,10 @@ class BatvisionV1Dataset(Dataset):
     def __getitem__(self, idx):
         inst = self.instances.iloc[idx]
         d = np.load(os.path.join(self.root_dir, inst["depth path"])).astype(np.float32)
-        d[~np.isfinite(d)] = 0.0
-        d = d / 1000.0
+        d = np.nan_to_num(d)          # reference :49-52: nan -> 0, +-inf -> +-float max (then clipped below)
+        d[d == -np.inf] = 0
+        d[d == np.inf] = 0
+        d = d / 1000
         if self.cfg.dataset.max_depth:
             d[d > self.cfg.dataset.max_depth] = self.cfg.dataset.max_depth
         d[d < 0] = 0
