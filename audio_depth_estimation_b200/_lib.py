@@ -49,10 +49,15 @@ SIGNATURES = {
     "adp_stft_mag": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "adp_feature_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "adp_feature_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "adp_mel_spectrogram": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _sz, _vp]),
+    "adp_feature_mel_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "adp_feature_forward_mel": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _i, _i, _vp, _vp, _sz, _vp]),
     "adp_resize_aa": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "adp_depth_loss_sums": (_i, [_vp, _vp, _i64, _f, _f, _i, _vp, _vp]),
     "adp_depth_loss_value": (_i, [_vp, _f, _f, _f, _vp, _vp]),
     "adp_depth_loss_backward": (_i, [_vp, _vp, _i64, _f, _f, _i, _vp, _f, _f, _f, _vp, _vp, _vp]),
+    "adp_depth_metrics_workspace_bytes": (_sz, [_i]),
+    "adp_depth_metrics": (_i, [_vp, _vp, _i, _i64, _f, _i, _f, _f, _vp, _vp, _sz, _vp]),
     "adp_weight_operand": (_i, [_vp, _i, _i, _vp, _vp]),
     "adp_conv2d_k4s2_fprop": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "adp_conv2d_k4s2_dgrad": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -120,6 +120,71 @@ __global__ void init_minmax_kernel(int* mm, int rows) {
   }
 }
 
+// torchaudio.functional.melscale_fbanks(n_freqs, f_min, f_max, n_mels, sample_rate, norm=None, mel_scale="htk")
+// followed by MelScale's matmul: mel[m,t] = sum_f spec[f,t] * fb[f,m]   (BatvisionV2_Dataset.py:187-197).
+// grid (ceil(T/64), rows); smem: fb[F][n_mels] | f_pts[n_mels+2] | band lo/hi [2*n_mels].  The triangular bank is
+// rebuilt per block (a few thousand flops) so that the call needs no persistent state.
+constexpr int MEL_THREADS = 256;
+constexpr int MEL_FRAMES = 64;
+
+__global__ void __launch_bounds__(MEL_THREADS)
+mel_contract_kernel(const float* __restrict__ spec, int F, int T, int n_mels, float nyquist, float f_min, float f_max,
+                    float* __restrict__ mel, int log_mode, int* __restrict__ minmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* fb = reinterpret_cast<float*>(smem_raw);
+  float* fpts = fb + (size_t)F * n_mels;
+  int* band = reinterpret_cast<int*>(fpts + n_mels + 2);
+  const int row = blockIdx.y, t0 = blockIdx.x * MEL_FRAMES;
+
+  for (int i = threadIdx.x; i < n_mels + 2; i += MEL_THREADS) {
+    const double m_lo = 2595.0 * log10(1.0 + (double)f_min / 700.0), m_hi = 2595.0 * log10(1.0 + (double)f_max / 700.0);
+    const float m = (float)(m_lo + (m_hi - m_lo) * (double)i / (double)(n_mels + 1));
+    fpts[i] = (float)(700.0 * (pow(10.0, (double)m / 2595.0) - 1.0));
+  }
+  __syncthreads();
+  const float fstep = nyquist / (float)(F - 1);
+  for (int i = threadIdx.x; i < F * n_mels; i += MEL_THREADS) {
+    const int f = i / n_mels, m = i - f * n_mels;
+    const float freq = f < F / 2 ? fstep * (float)f : nyquist - fstep * (float)(F - 1 - f);    // torch.linspace's rule
+    const float down = (freq - fpts[m]) / (fpts[m + 1] - fpts[m]);
+    const float up = (fpts[m + 2] - freq) / (fpts[m + 2] - fpts[m + 1]);
+    fb[i] = fmaxf(0.f, fminf(down, up));
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < n_mels; m += MEL_THREADS) {
+    int lo = F, hi = -1;
+    for (int f = 0; f < F; ++f)
+      if (fb[f * n_mels + m] != 0.f) { lo = min(lo, f); hi = f; }
+    band[2 * m] = lo;
+    band[2 * m + 1] = hi;
+  }
+  __syncthreads();
+
+  const int t = t0 + (threadIdx.x & (MEL_FRAMES - 1));
+  float vmin = INFINITY, vmax = -INFINITY;
+  if (t < T) {
+    const float* src = spec + (size_t)row * F * T + t;
+    for (int m = threadIdx.x / MEL_FRAMES; m < n_mels; m += MEL_THREADS / MEL_FRAMES) {
+      float acc = 0.f;
+      for (int f = band[2 * m]; f <= band[2 * m + 1]; ++f) acc = fmaf(src[(size_t)f * T], fb[f * n_mels + m], acc);
+      if (log_mode) {
+        acc = logf(acc + 1e-8f);
+        vmin = fminf(vmin, acc);
+        vmax = fmaxf(vmax, acc);
+      }
+      mel[((size_t)row * n_mels + m) * T + t] = acc;
+    }
+  }
+  if (log_mode) {
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0 && vmin <= vmax) {
+      atomicMin(&minmax[2 * row], float_to_ordered(vmin));
+      atomicMax(&minmax[2 * row + 1], float_to_ordered(vmax));
+    }
+  }
+}
+
 // aten::_upsample_bilinear2d_aa index/weight rule for one axis (align_corners = False)
 struct AxisTaps {
   int lo, size;
@@ -208,6 +273,8 @@ int check_stft_args(int rows, int L, int pitch, int n_fft, int win, int hop) {
   return ADP_OK;
 }
 
+size_t mel_smem(int F, int n_mels) { return ((size_t)F * n_mels + n_mels + 2) * 4 + (size_t)n_mels * 8; }
+
 size_t stft_smem(int n_fft, int win, int hop) {
   return (size_t)n_fft * 8 + (size_t)win * 4 + (size_t)((FRAMES_PER_BLOCK - 1) * hop + win) * 4;
 }
@@ -250,6 +317,55 @@ extern "C" int adp_resize_aa(const float* in, int rows, int H, int W, int out_si
   return ADP_OK;
 }
 
+namespace {
+
+struct FeatureWs {
+  float* spec;
+  int* minmax;
+  void* tc_ws;
+  float* mel;
+};
+
+FeatureWs carve_feature_ws(void* workspace, int rows, int L, int n_fft, int hop) {
+  const size_t T = 1 + (size_t)L / hop, F = (size_t)n_fft / 2 + 1;
+  char* wsb = reinterpret_cast<char*>(workspace);
+  FeatureWs w;
+  w.spec = reinterpret_cast<float*>(wsb);
+  w.minmax = reinterpret_cast<int*>(wsb + adp_align_up((size_t)rows * F * T * 4, 1024));
+  w.tc_ws = wsb + adp_align_up((size_t)rows * F * T * 4, 1024) + adp_align_up((size_t)rows * 8, 1024);
+  w.mel = reinterpret_cast<float*>(wsb + adp_feature_workspace_bytes(rows, L, n_fft, hop));
+  return w;
+}
+
+int run_stft(const float* wave, int rows, int L, int pitch, int n_fft, int win, int hop, const FeatureWs& w, int log_mode,
+             cudaStream_t s) {
+  if (adp::tc_enabled() && adp::tc_supported_stft(rows, L, n_fft, win, hop))
+    return adp::tc_stft_mag(wave, rows, L, pitch, n_fft, hop, w.spec, log_mode, w.minmax, w.tc_ws, s);
+  return launch_stft(wave, rows, L, pitch, n_fft, win, hop, w.spec, log_mode, w.minmax, s);
+}
+
+int check_mel_args(int n_fft, int n_mels, float sample_rate, float f_min, float f_max) {
+  ADP_CHECK_ARG(n_mels >= 1 && n_mels <= 512, "mel: n_mels %d unsupported", n_mels);
+  ADP_CHECK_ARG(sample_rate > 0.f && f_min >= 0.f && f_max > f_min, "mel: bad sample_rate/f_min/f_max");
+  ADP_CHECK_ARG(mel_smem(n_fft / 2 + 1, n_mels) <= 200 * 1024, "mel: filterbank %d x %d does not fit shared memory",
+                n_fft / 2 + 1, n_mels);
+  return ADP_OK;
+}
+
+int launch_mel(const float* spec, int rows, int F, int T, int n_mels, float sample_rate, float f_min, float f_max, float* mel,
+               int log_mode, int* minmax, cudaStream_t s) {
+  const size_t smem = mel_smem(F, n_mels);
+  if (smem > 48 * 1024)
+    ADP_CUDA(cudaFuncSetAttribute(mel_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const float nyquist = (float)((long long)sample_rate / 2);      // MelScale uses sample_rate // 2
+  dim3 grid(adp_cdiv(T, MEL_FRAMES), rows);
+  mel_contract_kernel<<<grid, MEL_THREADS, smem, s>>>(spec, F, T, n_mels, nyquist, f_min, f_max, mel, log_mode, minmax);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+}  // namespace
+
 extern "C" int adp_feature_forward(const float* wave, int rows, int L, int wave_pitch, int n_fft, int win_length,
                                    int hop, int log_minmax, int out_size, float* out, void* workspace,
                                    size_t workspace_bytes, void* stream) {
@@ -260,21 +376,58 @@ extern "C" int adp_feature_forward(const float* wave, int rows, int L, int wave_
   ADP_CHECK_ARG(workspace_bytes >= adp_feature_workspace_bytes(rows, L, n_fft, hop),
                 "feature: workspace too small (%zu)", workspace_bytes);
   const int T = 1 + L / hop, F = n_fft / 2 + 1;
-  float* spec = reinterpret_cast<float*>(workspace);
-  char* wsb = reinterpret_cast<char*>(workspace);
-  int* minmax = reinterpret_cast<int*>(wsb + adp_align_up((size_t)rows * F * T * 4, 1024));
-  void* tc_ws = wsb + adp_align_up((size_t)rows * F * T * 4, 1024) + adp_align_up((size_t)rows * 8, 1024);
+  const FeatureWs w = carve_feature_ws(workspace, rows, L, n_fft, hop);
   if (log_minmax) {
-    init_minmax_kernel<<<adp_cdiv(rows, 256), 256, 0, s>>>(minmax, rows);
+    init_minmax_kernel<<<adp_cdiv(rows, 256), 256, 0, s>>>(w.minmax, rows);
     ADP_LAUNCH_CHECK();
   }
-  if (adp::tc_enabled() && adp::tc_supported_stft(rows, L, n_fft, win_length, hop)) {
-    ADP_TRY(adp::tc_stft_mag(wave, rows, L, wave_pitch, n_fft, hop, spec, log_minmax ? 1 : 0, minmax, tc_ws, s));
-  } else {
-    ADP_TRY(launch_stft(wave, rows, L, wave_pitch, n_fft, win_length, hop, spec, log_minmax ? 1 : 0, minmax, s));
-  }
+  ADP_TRY(run_stft(wave, rows, L, wave_pitch, n_fft, win_length, hop, w, log_minmax ? 1 : 0, s));
   dim3 grid(adp_cdiv(out_size, 256), out_size, adp_cdiv(rows, RESIZE_PLANES));
-  resize_aa_kernel<<<grid, 256, 0, s>>>(spec, rows, F, T, out_size, out, log_minmax ? minmax : nullptr);
+  resize_aa_kernel<<<grid, 256, 0, s>>>(w.spec, rows, F, T, out_size, out, log_minmax ? w.minmax : nullptr);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+extern "C" size_t adp_feature_mel_workspace_bytes(int rows, int L, int n_fft, int hop, int n_mels) {
+  if (rows <= 0 || L <= 0 || n_fft <= 0 || hop <= 0 || n_mels <= 0) return 0;
+  return adp_feature_workspace_bytes(rows, L, n_fft, hop) + adp_align_up((size_t)rows * n_mels * (1 + (size_t)L / hop) * 4, 1024);
+}
+
+extern "C" int adp_mel_spectrogram(const float* wave, int rows, int L, int wave_pitch, int n_fft, int win_length, int hop,
+                                   int n_mels, float sample_rate, float f_min, float f_max, float* mel, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ADP_TRY(check_stft_args(rows, L, wave_pitch, n_fft, win_length, hop));
+  ADP_TRY(check_mel_args(n_fft, n_mels, sample_rate, f_min, f_max));
+  ADP_CHECK_ARG(wave && mel && workspace, "mel: null pointer");
+  ADP_CHECK_ARG(rows <= 65535, "mel: too many rows");
+  ADP_CHECK_ARG(workspace_bytes >= adp_feature_workspace_bytes(rows, L, n_fft, hop), "mel: workspace too small (%zu)",
+                workspace_bytes);
+  const FeatureWs w = carve_feature_ws(workspace, rows, L, n_fft, hop);
+  ADP_TRY(run_stft(wave, rows, L, wave_pitch, n_fft, win_length, hop, w, 0, s));
+  return launch_mel(w.spec, rows, n_fft / 2 + 1, 1 + L / hop, n_mels, sample_rate, f_min, f_max, mel, 0, nullptr, s);
+}
+
+extern "C" int adp_feature_forward_mel(const float* wave, int rows, int L, int wave_pitch, int n_fft, int win_length,
+                                       int hop, int n_mels, float sample_rate, float f_min, float f_max, int log_minmax,
+                                       int out_size, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ADP_TRY(check_stft_args(rows, L, wave_pitch, n_fft, win_length, hop));
+  ADP_TRY(check_mel_args(n_fft, n_mels, sample_rate, f_min, f_max));
+  ADP_CHECK_ARG(wave && out && workspace, "feature_mel: null pointer");
+  ADP_CHECK_ARG(out_size > 0 && out_size <= 65535 && rows <= 65535, "feature_mel: bad out_size/rows");
+  ADP_CHECK_ARG(workspace_bytes >= adp_feature_mel_workspace_bytes(rows, L, n_fft, hop, n_mels),
+                "feature_mel: workspace too small (%zu)", workspace_bytes);
+  const int T = 1 + L / hop, F = n_fft / 2 + 1;
+  const FeatureWs w = carve_feature_ws(workspace, rows, L, n_fft, hop);
+  if (log_minmax) {
+    init_minmax_kernel<<<adp_cdiv(rows, 256), 256, 0, s>>>(w.minmax, rows);
+    ADP_LAUNCH_CHECK();
+  }
+  ADP_TRY(run_stft(wave, rows, L, wave_pitch, n_fft, win_length, hop, w, 0, s));   // log/min-max follow the mel contraction
+  ADP_TRY(launch_mel(w.spec, rows, F, T, n_mels, sample_rate, f_min, f_max, w.mel, log_minmax ? 1 : 0, w.minmax, s));
+  dim3 grid(adp_cdiv(out_size, 256), out_size, adp_cdiv(rows, RESIZE_PLANES));
+  resize_aa_kernel<<<grid, 256, 0, s>>>(w.mel, rows, n_mels, T, out_size, out, log_minmax ? w.minmax : nullptr);
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }

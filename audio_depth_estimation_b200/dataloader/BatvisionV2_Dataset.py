@@ -64,14 +64,14 @@ class BatvisionV2Dataset(Dataset):
             waveform = waveform[:, :feature.cut_length(self.cfg.dataset.max_depth, sr)]
             n_fft, win_length, hop_length = feature.stft_params(self.cfg.dataset.max_depth)
         if "spectrogram" in self.audio_format:
-            if "mel" in self.audio_format:
-                raise NotImplementedError("mel_spectrogram (reference :187-197) is not on the B200 hot path yet; "
-                                          "use audio_format='spectrogram' or 'waveform'")
             if "resize" not in str(self.cfg.dataset.preprocess):
                 raise NotImplementedError("the fused feature kernel always resizes (cfg.dataset.preprocess='resize')")
             # STFT + log + per-channel min-max + Resize (reference :117-135) as one fused library call
+            # ('mel_spectrogram': the mel bank sits between magnitude and log, hop = win_length // 2, :111-114)
+            mel = "mel" in self.audio_format
             fused = feature.SpectrogramTransform(self.cfg.dataset.images_size, self.cfg.dataset.max_depth,
-                                                 log_minmax=True, cut=False, stft=(n_fft, win_length, hop_length))
+                                                 log_minmax=True, cut=False, mel={} if mel else None,
+                                                 stft=(n_fft, win_length, win_length // 2 if mel else hop_length))
             return fused(self._to_device(waveform)), gt_depth
         if "waveform" in self.audio_format:
             return waveform, gt_depth
@@ -85,3 +85,7 @@ class BatvisionV2Dataset(Dataset):
 
     def _get_spectrogram(self, waveform, n_fft=400, power=1.0, win_length=400, hop_length=100):
         return feature.spectrogram(waveform, n_fft=n_fft, power=power, win_length=win_length, hop_length=hop_length)
+
+    def _get_melspectrogram(self, waveform, n_fft=400, power=1.0, win_length=400, f_min=20.0, f_max=20000.0):
+        return feature.melspectrogram(waveform, n_fft=n_fft, power=power, win_length=win_length, f_min=f_min, f_max=f_max,
+                                      n_mels=32, sample_rate=44100)

@@ -67,6 +67,21 @@ int adp_feature_forward(const float* wave, int rows, int L, int wave_pitch,
                         int n_fft, int win_length, int hop, int log_minmax,
                         int out_size, float* out, void* workspace, size_t workspace_bytes,
                         void* stream);
+/* The mel branch of the V2 transform (audio_format 'mel_spectrogram', the default of
+ * conf/dataset/batvisionv2.yaml:8): _get_melspectrogram, BatvisionV2_Dataset.py:187-197 ==
+ * T.MelSpectrogram(sample_rate, n_fft, win_length, hop = win_length/2, power=1, f_min, f_max,
+ * n_mels, norm=None, mel_scale='htk'): |STFT| then the [n_fft/2+1 -> n_mels] triangular
+ * filterbank.  mel: [rows, n_mels, T].  workspace: adp_feature_workspace_bytes (or the mel one). */
+int adp_mel_spectrogram(const float* wave, int rows, int L, int wave_pitch, int n_fft, int win_length,
+                        int hop, int n_mels, float sample_rate, float f_min, float f_max, float* mel,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* ... followed by log(x+1e-8), per-channel min-max and Resize((S,S)) (:117-135):
+ * wave [B*C rows, L] -> out [B*C, S, S]. */
+size_t adp_feature_mel_workspace_bytes(int rows, int L, int n_fft, int hop, int n_mels);
+int adp_feature_forward_mel(const float* wave, int rows, int L, int wave_pitch, int n_fft,
+                            int win_length, int hop, int n_mels, float sample_rate, float f_min,
+                            float f_max, int log_minmax, int out_size, float* out, void* workspace,
+                            size_t workspace_bytes, void* stream);
 /* utils_dataset.py:18-20 alone: [rows, H, W] -> [rows, S, S]. */
 int adp_resize_aa(const float* in, int rows, int H, int W, int out_size, float* out, void* stream);
 
@@ -85,6 +100,18 @@ int adp_depth_loss_value(const double* sums, float l1_w, float silog_w, float la
 int adp_depth_loss_backward(const float* pred, const float* gt, int64_t n, float scale, float eps,
                             int use_mask, const double* sums, float l1_w, float silog_w, float lam,
                             const float* grad_scale, float* dpred, void* stream);
+
+/* ------------------------------------------------------------------ metrics
+ * Validation / test metrics of a batch without leaving the device:
+ * utils_criterion.py:6-90 (compute_errors) applied per sample, after the preparation of
+ * train.py:807-825 / test.py:251-270 when prepare = 1 (pred, gt scaled by `scale` = max_depth
+ * if depth_norm else 1; pred clipped to [clip_lo, clip_hi]; gt >= 0).  prepare = 0, scale = 1
+ * is compute_errors itself.  pred, gt: [batch, n_per_sample] fp32.
+ * metrics: [batch, 7] doubles = (abs_rel, rmse, a1, a2, a3, log_10, mae). */
+size_t adp_depth_metrics_workspace_bytes(int batch);
+int adp_depth_metrics(const float* pred, const float* gt, int batch, int64_t n_per_sample, float scale,
+                      int prepare, float clip_lo, float clip_hi, double* metrics, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* --------------------------------------------------------------------- convs
  * nn.Conv2d(k4,s2,p1,bias=False)  models/unetbaseline_model.py:187 and

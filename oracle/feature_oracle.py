@@ -12,6 +12,8 @@ are restated here; parity is anchored on the reference's own call sites:
 
 * dataloader/BatvisionV2_Dataset.py:96-135, :177-185  (cut, STFT params, log,
   per-channel min-max, Resize)
+* dataloader/BatvisionV2_Dataset.py:111-114, :187-197 (mel branch: T.MelSpectrogram -> MelScale ->
+  torchaudio.functional.melscale_fbanks, HTK scale, norm=None)
 * dataloader/BatvisionV1_Dataset.py:70-78, :86-95     (STFT, Resize; no log)
 * dataloader/utils_dataset.py:10-28                   (Resize((S,S)))
 """
@@ -147,4 +149,39 @@ def feature_v1(wave, images_size=256, do_resize=True):
     """BatvisionV1Dataset.__getitem__ audio branch (BatvisionV1_Dataset.py:68-78):
     Spectrogram(512, 64, hop 16), no log, no min-max, Resize."""
     spec = stft_mag(wave, 512, 64, 16)
+    return resize(spec, images_size) if do_resize else spec
+
+
+def mel_fbanks(n_freqs, f_min, f_max, n_mels, sample_rate):
+    """torchaudio.functional.melscale_fbanks(..., norm=None, mel_scale='htk') in float32, the bank
+    T.MelSpectrogram builds for _get_melspectrogram (BatvisionV2_Dataset.py:187-197).  [n_freqs, n_mels]."""
+    f32 = np.float32
+    all_freqs = np.linspace(0, sample_rate // 2, n_freqs).astype(f32)
+    m_min = 2595.0 * np.log10(1.0 + f_min / 700.0)
+    m_max = 2595.0 * np.log10(1.0 + f_max / 700.0)
+    m_pts = np.linspace(m_min, m_max, n_mels + 2).astype(f32)
+    f_pts = (f32(700.0) * (np.power(f32(10.0), m_pts / f32(2595.0)) - f32(1.0))).astype(f32)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts[None, :] - all_freqs[:, None]
+    down = -slopes[:, :-2] / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return np.maximum(f32(0.0), np.minimum(down, up)).astype(f32)
+
+
+def mel_spectrogram(wave, n_fft=400, win_length=400, f_min=20.0, f_max=20000.0, n_mels=32, sample_rate=44100,
+                    hop_length=None):
+    """T.MelSpectrogram(sample_rate, n_fft, win_length, power=1.0, f_min, f_max, n_mels): hop defaults to
+    win_length // 2; mel = (spec^T @ fb)^T.  wave [..., L] -> [..., n_mels, 1 + L // hop]."""
+    hop = hop_length if hop_length else win_length // 2
+    spec = stft_mag(wave, n_fft, win_length, hop).astype(np.float64)
+    fb = mel_fbanks(n_fft // 2 + 1, f_min, f_max, n_mels, sample_rate).astype(np.float64)
+    return np.einsum("...ft,fm->...mt", spec, fb).astype(np.float32)
+
+
+def feature_v2_mel(wave, max_depth=30.0, images_size=256, sr=44100, do_resize=True):
+    """BatvisionV2Dataset.__getitem__ audio branch, 'mel_spectrogram' format (BatvisionV2_Dataset.py:92-135)."""
+    n_fft, win, _ = stft_params(max_depth)
+    if max_depth:
+        wave = wave[:, :cut_length(max_depth, sr)]
+    spec = log_minmax(mel_spectrogram(wave, n_fft, win))
     return resize(spec, images_size) if do_resize else spec

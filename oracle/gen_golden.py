@@ -174,9 +174,75 @@ def gen_loss():
     print("loss.npz")
 
 
+def gen_feature_mel():
+    """Mel branch of the V2 transform: BatvisionV2_Dataset.py:111-135, :187-197, the reference's own methods."""
+    import torchaudio.transforms as T  # noqa: F401
+    from dataloader.BatvisionV2_Dataset import BatvisionV2Dataset
+    from dataloader.utils_dataset import get_transform
+    out = {}
+    cfg = ref_cfg(False, 30.0)
+    ds2 = BatvisionV2Dataset.__new__(BatvisionV2Dataset)
+    ds2.cfg = cfg
+    for name, echo, seed in (("mel", False, 21), ("melecho", True, 22)):
+        w = torch.from_numpy(synthetic.waveform(1, 8000, seed=seed, echo=echo)[0])
+        wc = w[:, :int((2 * cfg.dataset.max_depth / 340) * 44100)]
+        spec = ds2._get_melspectrogram(wc, n_fft=512, power=1.0, win_length=64)
+        out[name + "_spec"] = spec.numpy().copy()
+        spec = torch.log(spec + 1e-8)
+        for c in range(spec.shape[0]):
+            lo, hi = spec[c].min(), spec[c].max()
+            spec[c] = (spec[c] - lo) / (hi - lo) if hi > lo else torch.zeros_like(spec[c])
+        out[name + "_feat"] = get_transform(cfg, convert=False)(spec).numpy()
+    w = torch.from_numpy(synthetic.waveform(1, 3000, seed=23)[0])
+    out["small_mel_400"] = ds2._get_melspectrogram(w).numpy()             # the method's defaults: n_fft 400, win 400
+    np.savez_compressed(os.path.join(OUT, "feature_mel.npz"), **out)
+    print("feature_mel.npz", {k: v.shape for k, v in out.items()})
+
+
+def gen_metrics():
+    """utils_criterion.compute_errors after the per-sample preparation of train.py:807-825."""
+    from utils_criterion import compute_errors
+    out = {}
+    cases = [("m30", False, 30.0, 64, 0), ("n12", True, 12.0, 48, 1), ("zeros", False, 30.0, 32, 2),
+             ("negpred", False, 30.0, 32, 3), ("emptygt", False, 30.0, 32, 4)]
+    for name, dn, md, size, k in cases:
+        rng = np.random.default_rng(900 + k)
+        gt = synthetic.gt_depth(3, size, md, seed=910 + k, normalised=dn)
+        pred = (gt + rng.normal(0, 0.15 * (1.0 if dn else md), gt.shape)).astype(np.float32)
+        if name == "zeros":
+            pred[:] = 0.0
+        if name == "negpred":
+            pred = -np.abs(pred) - 1.0
+        if name == "emptygt":
+            gt[1] = 0.0
+        rows = []
+        for i in range(gt.shape[0]):
+            g, p = gt[i, 0].copy(), pred[i, 0].copy()
+            if dn:
+                g, p = g * md, p * md
+            eps = 1e-3 if dn else 1e-6
+            p = np.clip(p, eps, md)
+            g = np.maximum(g, 0.0)
+            rows.append([float(v) for v in compute_errors(g, p, min_depth_threshold=0.0)])
+        out[name + "_pred"] = pred
+        out[name + "_errors"] = np.array(rows, dtype=np.float64)
+    # compute_errors called directly (no clipping): its own fall-back branches (:38-54)
+    rng = np.random.default_rng(950)
+    g = rng.uniform(0.5, 20.0, size=(40, 40)).astype(np.float32)
+    g[rng.uniform(size=g.shape) < 0.2] = 0.0
+    p = (g + rng.normal(0, 2.0, g.shape)).astype(np.float32)
+    out["raw_gt"], out["raw_pred"] = g, p
+    out["raw_errors"] = np.array([float(v) for v in compute_errors(g, p)])
+    out["rawneg_errors"] = np.array([float(v) for v in compute_errors(g, -np.abs(p) - 1.0)])
+    out["rawsmall_errors"] = np.array([float(v) for v in compute_errors(g / 100.0, np.abs(p) / 100.0)])
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
+    print("metrics.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    gen_feature()
-    gen_loss()
-    gen_unet()
+    which = sys.argv[1:] or ["feature", "feature_mel", "metrics", "loss", "unet"]
+    for name in which:
+        {"feature": gen_feature, "feature_mel": gen_feature_mel, "metrics": gen_metrics, "loss": gen_loss,
+         "unet": gen_unet}[name]()

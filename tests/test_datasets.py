@@ -117,8 +117,6 @@ def test_spectrogram_branch_needs_cuda_or_fails_loudly(v2_tree):
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             ds[0]
-    with pytest.raises(NotImplementedError):
-        BatvisionV2Dataset(cfg_v2(root, "mel_spectrogram"), "train.csv")[0] if torch.cuda.is_available() else (_ for _ in ()).throw(NotImplementedError())
 
 
 @pytest.mark.gpu
@@ -134,6 +132,12 @@ def test_v2_and_v1_spectrogram_getitem_on_gpu(v2_tree, tmp_path):
     assert np.abs(x.cpu().numpy() - ref).max() <= 5e-4
     spec = ds._get_spectrogram(torch.from_numpy(waves[(first_loc, 1)][:, :4000]).cuda(), n_fft=512, power=1.0, win_length=64, hop_length=16)
     assert spec.shape == (2, 257, 251)
+    # the default audio_format of conf/dataset/batvisionv2.yaml
+    dm = BatvisionV2Dataset(cfg_v2(root, "mel_spectrogram", size=256), "train.csv")
+    xm, _ = dm[1]
+    refm = fo.feature_v2_mel(waves[(first_loc, 1)], 30.0, 256)
+    assert xm.shape == (2, 256, 256) and np.abs(xm.cpu().numpy() - refm).max() <= 5e-4
+    assert dm._get_melspectrogram(torch.from_numpy(waves[(first_loc, 1)][:, :4000]).cuda(), n_fft=512, win_length=64).shape == (2, 32, 126)
     # V1
     v1 = tmp_path / "v1"
     v1.mkdir()

@@ -145,3 +145,70 @@ def test_unet_oracle(golden_dir, name):
     head = np.stack([p.reshape(-1)[:16].numpy() if p.numel() >= 16 else
                      np.pad(p.reshape(-1).numpy(), (0, 16 - p.numel())) for p in params])
     assert np.abs(head - g["param_head_after"]).max() <= 2e-4
+
+
+# ---- mel branch ---------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def melgold(golden_dir):
+    return np.load(os.path.join(golden_dir, "feature_mel.npz"))
+
+
+def test_mel_fbanks_match_torchaudio():
+    ta = pytest.importorskip("torchaudio")
+    ref = ta.functional.melscale_fbanks(257, 20.0, 20000.0, 32, 44100, norm=None, mel_scale="htk").numpy()
+    got = fo.mel_fbanks(257, 20.0, 20000.0, 32, 44100)
+    # float32 cancellation in f_pts - all_freqs: weights agree to a few 1e-6 absolute (peak weight is 1)
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name,echo,seed", [("mel", False, 21), ("melecho", True, 22)])
+def test_feature_v2_mel(melgold, name, echo, seed):
+    w = synthetic.waveform(1, 8000, seed=seed, echo=echo)[0]
+    spec = fo.mel_spectrogram(w[:, :fo.cut_length(30.0)], 512, 64)
+    assert spec.shape == (2, 32, 244)
+    assert rel_to_max(spec, melgold[name + "_spec"]) <= 1e-5
+    got = fo.feature_v2_mel(w, 30.0, 256)
+    # a mel band sums >= 1 magnitude bins, so the near-zero-bin problem of the linear branch does not arise
+    assert np.abs(got - melgold[name + "_feat"]).max() <= 5e-5
+
+
+def test_mel_defaults_400(melgold):
+    w = synthetic.waveform(1, 3000, seed=23)[0]
+    got = fo.mel_spectrogram(w)                      # n_fft 400, win 400, hop 200
+    assert got.shape == melgold["small_mel_400"].shape
+    assert rel_to_max(got, melgold["small_mel_400"]) <= 1e-5
+
+
+# ---- evaluation metrics -------------------------------------------------------------------------
+METRIC_CASES = [("m30", False, 30.0, 64, 0), ("n12", True, 12.0, 48, 1), ("zeros", False, 30.0, 32, 2),
+                ("negpred", False, 30.0, 32, 3), ("emptygt", False, 30.0, 32, 4)]
+
+
+def metric_case_inputs(g, name, dn, md, size, k):
+    gt = synthetic.gt_depth(3, size, md, seed=910 + k, normalised=dn)
+    if name == "emptygt":
+        gt[1] = 0.0
+    return gt, g[name + "_pred"]
+
+
+@pytest.mark.parametrize("case", METRIC_CASES, ids=[c[0] for c in METRIC_CASES])
+def test_metrics_oracle(golden_dir, case):
+    from oracle import metrics_oracle as mo
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    name, dn, md, size, k = case
+    gt, pred = metric_case_inputs(g, *case)
+    got = mo.batch_errors(gt, pred, dn, md)
+    ref = g[name + "_errors"]
+    # the reference evaluates in float32 numpy; the oracle in float64
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_metrics_oracle_raw_branches(golden_dir):
+    from oracle import metrics_oracle as mo
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    gt, pred = g["raw_gt"], g["raw_pred"]
+    for key, (a, b) in {"raw": (gt, pred), "rawneg": (gt, -np.abs(pred) - 1.0),
+                        "rawsmall": (gt / 100.0, np.abs(pred) / 100.0)}.items():
+        got = np.array(mo.compute_errors(a, b))
+        ref = g[key + "_errors"]
+        assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), key
