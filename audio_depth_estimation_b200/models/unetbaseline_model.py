@@ -281,7 +281,10 @@ class UnetGenerator(nn.Module):
     def flat_buffers(self):
         """(flat parameters, flat gradients, per-stage (begin, end) element offsets)."""
         if self._flat is None:
-            raise RuntimeError("parameters are flattened on the first CUDA forward")
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("parameters are flattened on the first CUDA forward (or once the module is on a CUDA device)")
+            self._flatten(dev)
         return self._flat["p"], self._flat["g"], self._flat["stage_slices"]
 
     # ------------------------------------------------------------------ C structs

@@ -66,17 +66,54 @@ class FusedClipAdamW:
         self.last_norm = st["norm"]
         return st["norm"]
 
+    # ---- checkpointing: the layout torch.optim.AdamW.state_dict() has in the reference's checkpoints
+    # (train.py:1006-1011 saves 'optimizer': optimizer.state_dict()), parameters in model.parameters() order.
+    def _moment_views(self):
+        _, st, _ = self._buffers()
+        flat = self.model._flat
+        off_of = {id(q): o for q, o in zip(flat["params"], flat["offs"])}
+        return [(self.model._view_like(st["m"], off_of[id(q)], q), self.model._view_like(st["v"], off_of[id(q)], q))
+                for q in self.model.parameters()]
+
     def state_dict(self):
-        st = self._state
-        return dict(step=self.step_count, lr=self.lr, betas=self.betas, eps=self.eps,
-                    weight_decay=self.weight_decay, max_norm=self.max_norm,
-                    exp_avg=None if st is None else st["m"].clone(),
-                    exp_avg_sq=None if st is None else st["v"].clone())
+        n = len(list(self.model.parameters()))
+        state = {}
+        if self._state is not None or self.model._flat is not None:
+            if self.capturable and self._state is not None:
+                self.step_count = int(self._state["step_dev"].item())
+            if self.step_count > 0:
+                for i, (m, v) in enumerate(self._moment_views()):
+                    state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": m.detach().clone().contiguous(),
+                                "exp_avg_sq": v.detach().clone().contiguous()}
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay, amsgrad=False,
+                     maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                     params=list(range(n)))
+        return {"state": state, "param_groups": [group], "max_norm": self.max_norm}
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.lr = float(sd.get("lr", self.lr))
-        if sd.get("exp_avg") is not None:
-            _, st, _ = self._buffers()
-            st["m"].copy_(sd["exp_avg"])
-            st["v"].copy_(sd["exp_avg_sq"])
+        """Accepts the dictionary above, i.e. also a stock torch.optim.AdamW state_dict saved by the reference."""
+        group = sd["param_groups"][0]
+        self.lr = float(group.get("lr", self.lr))
+        self.betas = tuple(group.get("betas", self.betas))
+        self.eps = float(group.get("eps", self.eps))
+        self.weight_decay = float(group.get("weight_decay", self.weight_decay))
+        if "max_norm" in sd:
+            self.max_norm = float(sd["max_norm"])
+        state = sd.get("state", {})
+        if not state:
+            self.step_count = 0
+            return
+        views = self._moment_views()
+        if len(state) != len(views):
+            raise ValueError("optimizer state has %d entries, the model %d parameters" % (len(state), len(views)))
+        steps = set()
+        with torch.no_grad():
+            for i, (m, v) in enumerate(views):
+                ent = state[i] if i in state else state[str(i)]
+                m.copy_(ent["exp_avg"])
+                v.copy_(ent["exp_avg_sq"])
+                steps.add(int(float(ent["step"])))
+        if len(steps) != 1:
+            raise ValueError("per-parameter step counts differ: %s" % sorted(steps))
+        self.step_count = steps.pop()
+        self._state["step_dev"].fill_(self.step_count)

@@ -20,6 +20,7 @@ import torch.distributed as dist
 
 from .feature import SpectrogramTransform
 from .optim import FusedClipAdamW
+from .utils_criterion import METRIC_NAMES, batch_errors
 from .utils_loss import DepthCriterion
 
 
@@ -174,8 +175,28 @@ class TrainStep:
         return sloss
 
     @torch.no_grad()
-    def evaluate(self, batch, gtdepth):
-        """test.py:231-241: eval-mode forward + masked criterion."""
+    def evaluate(self, batch, gtdepth, metrics=False, protocol="train"):
+        """test.py:231-241 / train.py:770-838: eval-mode forward + masked criterion; metrics=True adds the [B,7]
+        per-sample error table (utils_criterion.batch_errors; still no host synchronisation)."""
         self.model.eval()
         pred = self.model(self.features(batch))
-        return pred, self.criterion(pred, gtdepth)
+        loss = self.criterion(pred, gtdepth)
+        if metrics:
+            return pred, loss, batch_errors(gtdepth, pred, self.cfg, protocol=protocol)
+        return pred, loss
+
+
+@torch.no_grad()
+def evaluate_loader(step, batches, protocol="test"):
+    """The evaluation loop of test.py:231-300 (or the validation pass of train.py:770-845 with protocol='train')
+    over an iterable of device (input, gt) pairs.  One device -> host copy at the end instead of two per sample.
+    Returns {'loss': mean batch loss, 'abs_rel', 'rmse', 'delta1', 'delta2', 'delta3', 'log10', 'mae': sample means}."""
+    losses, tables = [], []
+    for batch, gt in batches:
+        _, loss, errs = step.evaluate(batch, gt, metrics=True, protocol=protocol)
+        losses.append(loss.reshape(1).double())
+        tables.append(errs)
+    if not tables:
+        raise ValueError("evaluate_loader: no batches")
+    row = torch.cat([torch.cat(losses).mean().reshape(1), torch.cat(tables).mean(0)]).tolist()
+    return dict(zip(("loss",) + METRIC_NAMES, row))

@@ -28,12 +28,19 @@ def _run(gt, pred, batch, scale, prepare, lo, hi):
     return out
 
 
-def batch_errors(gt, pred, cfg=None, depth_norm=None, max_depth=None):
-    """gt, pred: [B,1,H,W] CUDA fp32 (network output and loader ground truth, un-denormalised).  -> [B,7] float64."""
+def batch_errors(gt, pred, cfg=None, depth_norm=None, max_depth=None, protocol="train"):
+    """gt, pred: [B,1,H,W] CUDA fp32 (network output and loader ground truth, un-denormalised).  -> [B,7] float64.
+    protocol 'train': the validation pass of train.py:807-825 (pred clipped to [eps, max_depth]);
+    protocol 'test' : test.py:262-276 (pred and gt only clipped at 0)."""
     if cfg is not None:
         depth_norm, max_depth = bool(cfg.dataset.depth_norm), float(cfg.dataset.max_depth)
+    scale = max_depth if depth_norm else 1.0
+    if protocol == "test":
+        return _run(gt, pred, pred.shape[0], scale, 1, 0.0, float("inf"))
+    if protocol != "train":
+        raise ValueError("protocol must be 'train' or 'test', got %r" % (protocol,))
     eps = 1e-3 if depth_norm else 1e-6                       # train.py:823
-    return _run(gt, pred, pred.shape[0], max_depth if depth_norm else 1.0, 1, eps, max_depth)
+    return _run(gt, pred, pred.shape[0], scale, 1, eps, max_depth)
 
 
 def compute_errors(gt, pred, min_depth_threshold=0.0):

@@ -109,3 +109,89 @@ def test_metrics_batch_vs_oracle_full_size():
     got = uc.batch_errors(torch.from_numpy(gt).cuda(), torch.from_numpy(pred).cuda(), depth_norm=False, max_depth=30.0)
     ref = mo.batch_errors(gt, pred, False, 30.0)
     assert np.abs(got.cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_metrics_test_protocol_and_eval_loop():
+    """test.py:262-276 protocol (clip at 0 only) and the evaluation loop with one D2H at the end."""
+    from audio_depth_estimation_b200 import utils_criterion as uc
+    from audio_depth_estimation_b200.config_loader import load_config
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    from audio_depth_estimation_b200.training import TrainStep, evaluate_loader
+    from oracle import metrics_oracle as mo
+    rng = np.random.default_rng(6)
+    gt = synthetic.gt_depth(4, 64, 12.0, seed=43, normalised=True)
+    pred = (gt + rng.normal(0, 0.2, gt.shape)).astype(np.float32)      # plenty of negative predictions
+    got = uc.batch_errors(torch.from_numpy(gt).cuda(), torch.from_numpy(pred).cuda(), depth_norm=True, max_depth=12.0,
+                          protocol="test")
+    ref = mo.batch_errors(gt, pred, True, 12.0, protocol="test")
+    assert np.abs(got.cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+    cfg = load_config()
+    cfg.dataset.images_size, cfg.model.generator, cfg.model.precision = 128, "unet_128", "fp32"
+    torch.manual_seed(0)
+    net = define_G(cfg, 2, 1, 16, "unet_128", "batch", False, gpu_ids=[0])
+    step = TrainStep(cfg, net, waveform_input=False)
+    batches = []
+    for i in range(3):
+        x = torch.from_numpy(synthetic.feature_like(2, 128, seed=50 + i)).cuda()
+        g = torch.from_numpy(synthetic.gt_depth(2, 128, cfg.dataset.max_depth, seed=60 + i,
+                                                normalised=bool(cfg.dataset.depth_norm))).cuda()
+        batches.append((x, g))
+    res = evaluate_loader(step, batches, protocol="test")
+    tabs, losses = [], []
+    for x, g in batches:
+        y, loss = step.evaluate(x, g)
+        losses.append(float(loss))
+        tabs.append(mo.batch_errors(g.cpu().numpy(), y.cpu().numpy(), bool(cfg.dataset.depth_norm),
+                                    float(cfg.dataset.max_depth), protocol="test"))
+    want = np.concatenate(tabs).mean(0)
+    assert abs(res["loss"] - np.mean(losses)) <= 1e-6 * max(1.0, abs(np.mean(losses)))
+    for k, name in enumerate(uc.METRIC_NAMES):
+        assert abs(res[name] - want[k]) <= 2e-5 * max(1.0, abs(want[k])), name
+
+
+def test_checkpoint_round_trip_reference_format(tmp_path):
+    """train.py:1003-1017 / :600-606: {'epoch','state_dict','optimizer'}; the optimizer entry has torch.optim.AdamW's
+    layout, so moments saved by the reference load here and vice versa; training resumes bit-identically."""
+    from audio_depth_estimation_b200.checkpoint import checkpoint_path, load_checkpoint, save_checkpoint
+    from audio_depth_estimation_b200.config_loader import load_config
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    from audio_depth_estimation_b200.training import TrainStep
+    cfg = load_config()
+    cfg.dataset.images_size, cfg.model.generator, cfg.model.precision = 128, "unet_128", "fp32"
+
+    def make():
+        torch.manual_seed(1)
+        net = define_G(cfg, 2, 1, 16, "unet_128", "batch", False, gpu_ids=[0])
+        return net, TrainStep(cfg, net, lr=1e-3, waveform_input=False)
+
+    def batch(i):
+        return (torch.from_numpy(synthetic.feature_like(2, 128, seed=70 + i)).cuda(),
+                torch.from_numpy(synthetic.gt_depth(2, 128, 30.0, seed=80 + i, normalised=False)).cuda())
+
+    net, step = make()
+    for i in range(3):
+        step(*batch(i))
+    path = save_checkpoint(checkpoint_path("exp", 7, root=str(tmp_path)), 7, net, step.optimizer, data_parallel_keys=True)
+    assert path.endswith(os.path.join("exp", "checkpoint_7.pth"))
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"epoch", "state_dict", "optimizer"} and all(k.startswith("module.") for k in ck["state_dict"])
+    # a stock torch AdamW over a same-shaped module accepts the optimizer entry (the reference's optimizer class)
+    shadow = [torch.nn.Parameter(torch.zeros_like(p, device="cpu")) for p in net.parameters()]
+    topt = torch.optim.AdamW(shadow, lr=1e-3)
+    topt.load_state_dict({"state": ck["optimizer"]["state"], "param_groups": ck["optimizer"]["param_groups"]})
+    assert int(topt.state[shadow[0]]["step"]) == 3 and topt.state[shadow[0]]["exp_avg"].shape == shadow[0].shape
+    loss_a = step(*batch(3))
+    net2, step2 = make()
+    with torch.no_grad():
+        for p in net2.parameters():
+            p.add_(1.0)                                   # make sure the load is what restores them
+    assert load_checkpoint(path, net2, step2.optimizer) == 8
+    loss_b = step2(*batch(3))
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-5 * abs(float(loss_a))
+    for (k, a), b in zip(net.state_dict().items(), net2.state_dict().values()):
+        if a.dtype.is_floating_point:
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), k
+    # and the reverse direction: moments written by torch.optim.AdamW.state_dict()
+    step2.optimizer.load_state_dict(topt.state_dict())
+    assert step2.optimizer.step_count == 3
