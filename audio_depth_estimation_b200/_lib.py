@@ -53,6 +53,7 @@ SIGNATURES = {
     "adp_feature_mel_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "adp_feature_forward_mel": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _i, _i, _vp, _vp, _sz, _vp]),
     "adp_resize_aa": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "adp_depth_prepare": (_i, [_vp, _i, _i, _i, _i, _i, _f, _i, _f, _vp, _vp]),
     "adp_depth_loss_sums": (_i, [_vp, _vp, _i64, _f, _f, _i, _vp, _vp]),
     "adp_depth_loss_value": (_i, [_vp, _f, _f, _f, _vp, _vp]),
     "adp_depth_loss_backward": (_i, [_vp, _vp, _i64, _f, _f, _i, _vp, _f, _f, _f, _vp, _vp, _vp]),

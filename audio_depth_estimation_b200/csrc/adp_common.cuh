@@ -187,9 +187,20 @@ struct ProfScope {
 // sums[0:C] += sum x, sums[C:2C] += sum x^2
 int bn_stats(int dtype, const void* x, long long rows, int C, double* sums, cudaStream_t s);
 // training: batch statistics from sums (+ running-stat update); eval: running statistics.
-int bn_finalize(const double* sums, long long rows, int C, const float* gamma, const float* beta,
-                float* running_mean, float* running_var, int training, float eps, float momentum,
-                float* scale, float* shift, float* mean, float* invstd, cudaStream_t s);
+struct BnFin {
+  const double* sums;     // [2C] sum x, sum x^2 (training)
+  double inv_rows;        // 1 / rows
+  float unbias;           // rows / (rows - 1) (1 when rows == 1): biased -> unbiased variance for the running estimate
+  const float *gamma, *beta;
+  float *rm, *rv;         // running statistics (updated when training)
+  int training;
+  float eps, momentum;
+  float *scale, *shift, *mean, *invstd;   // outputs, kept for the backward pass
+};
+int bn_finalize(const BnFin& f, int C, cudaStream_t s);
+// finalize + (z = x*scale+shift; out0 = lrelu(z, slope0); out1 (optional) = lrelu(z, slope1)) in one launch
+int bn_affine_act(int dtype, const void* x, long long rows, int C, const BnFin& f, float slope0, void* out0, float slope1,
+                  void* out1, cudaStream_t s);
 // z = x*scale+shift (scale==NULL: z = x); out0 = lrelu(z, slope0); out1 (optional) = lrelu(z, slope1)
 int affine_act(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift,
                float slope0, void* out0, float slope1, void* out1, cudaStream_t s);
@@ -199,9 +210,11 @@ int act_bn_bwd_reduce(int dtype, const void* x, long long rows, int C, const flo
                       const float* mean, const float* invstd, const void* gA, float slope0,
                       const void* gB, float slope1, double* sums, cudaStream_t s);
 // mode 0: dx = gz (no BN); 1: dx = gz*scale (eval BN); 2: dx = scale*(gz - s1/M - xhat*s2/M) (batch stats)
+// dgamma/dbeta (optional, both or none): dgamma[c] = sums[C+c], dbeta[c] = sums[c], written by the same launch
 int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift,
                      const float* mean, const float* invstd, const void* gA, float slope0,
-                     const void* gB, float slope1, const double* sums, int mode, void* dx, cudaStream_t s);
+                     const void* gB, float slope1, const double* sums, int mode, void* dx, float* dgamma, float* dbeta,
+                     cudaStream_t s);
 // dgamma[c] = sums[C+c], dbeta[c] = sums[c]
 int bn_param_grads(const double* sums, int C, float* dgamma, float* dbeta, cudaStream_t s);
 // final head: y = act(u + bias); du = dy*act'(y) ; dbias[0] += sum du   (out_ch == 1)

@@ -317,7 +317,8 @@ template <int BLOCK_N>
 struct PersistSmem {
   using S = IgemmSmem<BLOCK_N>;
   static constexpr int STAGES = (196 * 1024) / S::STAGE_BYTES > 10 ? 10 : (196 * 1024) / S::STAGE_BYTES;
-  static constexpr int BYTES = STAGES * S::STAGE_BYTES + 1024 + 256;
+  static constexpr int STAGING = 4 * 4096;        // epilogue transpose buffers: 4 warps x (32 rows x 128 B)
+  static constexpr int BYTES = STAGES * S::STAGE_BYTES + 1024 + 256 + STAGING;
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
@@ -458,6 +459,9 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     const int egroup = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
+    constexpr bool STAGED_OK = BLOCK_N >= 64 && EG == 1;
+    unsigned char* stg = smem + STAGES * S::STAGE_BYTES + 256 + (STAGED_OK ? (warp - 2) * 4096 : 0);
+    const bool staged = p.splits <= 1 && p.mode != 3 && (p.act_dual || p.N1 == 0 || p.N0 % 64 == 0);
     uint32_t local = 0;
     for (int t = worker; t < ntiles; t += nworkers, ++local) {
       const TileCoord c = tile_at(t);
@@ -471,6 +475,50 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * ACC + ((uint32_t)(q * 32) << 16);
       float vmin = INFINITY, vmax = -INFINITY;
+      if (STAGED_OK && staged) {
+        // bf16 outputs, 64 columns at a time: every lane packs its own pixel row (128 B) into the warp's swizzled
+        // staging buffer, then 8 lanes write one row -- full 128-byte lines per store instead of 32 scattered
+        // 16-byte pieces (the L1 tag stage processes one line per cycle, which bounded the thin layers).
+        const uint32_t okm = __ballot_sync(0xffffffffu, valid);
+        unsigned long long orow[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) orow[i] = __shfl_sync(0xffffffffu, (unsigned long long)opix, 4 * i + (lane >> 3));
+        auto emit = [&](const float (&v)[64], bf16* base, int ldn, float slope, bool act) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = act ? lrelu(v[8 * j + k], slope) : v[8 * j + k];
+            uint4 u;
+            u.x = pack_bf16x2(w[0], w[1]); u.y = pack_bf16x2(w[2], w[3]);
+            u.z = pack_bf16x2(w[4], w[5]); u.w = pack_bf16x2(w[6], w[7]);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = u;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+            if ((okm >> rr) & 1u) *reinterpret_cast<uint4*>(base + orow[i] * (unsigned long long)ldn + (lane & 7) * 8) = u;
+          }
+          __syncwarp();
+        };
+#pragma unroll 1
+        for (int cc = 0; cc < BLOCK_N; cc += 64) {
+          float v[64];
+          tmem_ld32(tacc + (uint32_t)cc, v);
+          tmem_ld32(tacc + (uint32_t)cc + 32u, v + 32);
+          const int n = c.n0 + cc;
+          if (p.act_dual) {
+            emit(v, p.y0 + n, p.N, p.slope0, true);
+            emit(v, p.y1 + n, p.N, p.slope1, true);
+          } else if (n < p.N0) {
+            emit(v, p.y0 + n, p.N0, 0.f, false);
+          } else {
+            emit(v, p.y1 + (n - p.N0), p.N1, 0.f, false);
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int cc = egroup * 32; cc < BLOCK_N; cc += 32 * EG) {
         float v[32];
@@ -534,6 +582,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
             *reinterpret_cast<uint4*>(dst + i) = u;
           }
         }
+      }
       }
       if (EG == 2 && p.log_mode) {
         vmin = warp_min(vmin);

@@ -47,34 +47,42 @@ bn_stats_kernel(const T* __restrict__ x, long long rows, int C, double* __restri
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long rows, int C,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ rm, float* __restrict__ rv, int training, float eps,
-                                   float momentum, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_o, float* __restrict__ invstd_o) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float mean, invstd;
-  if (training) {
-    double m = sums[c] / (double)rows;
-    double var = sums[C + c] / (double)rows - m * m;
+// Per-channel BatchNorm coefficients from the accumulated sums (training) or the running statistics (eval).  One
+// definition, used by the stand-alone finalize kernel AND by every thread of the fused normalise kernel, so that the
+// stored scale/shift (read by the backward pass) are bit-identical with what the forward pass applied.
+struct BnCoef { float mean, invstd, scale, shift, unbiased; };
+__device__ __forceinline__ BnCoef bn_coef(const adp::BnFin& f, int C, int c) {
+  BnCoef o;
+  if (f.training) {
+    const double m = f.sums[c] * f.inv_rows;                 // (no double division on the per-channel path)
+    double var = fma(-m, m, f.sums[C + c] * f.inv_rows);
     if (var < 0.0) var = 0.0;
-    mean = (float)m;
-    invstd = (float)(1.0 / sqrt(var + (double)eps));
-    if (rm) {
-      double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
-      rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
-      rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
-    }
+    o.mean = (float)m;
+    o.invstd = 1.f / sqrtf((float)var + f.eps);
+    o.unbiased = (float)var * f.unbias;
   } else {
-    mean = rm[c];
-    invstd = rsqrtf(rv[c] + eps);
+    o.mean = f.rm[c];
+    o.invstd = 1.f / sqrtf(f.rv[c] + f.eps);
+    o.unbiased = 0.f;
   }
-  float sc = gamma[c] * invstd;
-  scale[c] = sc;
-  shift[c] = beta[c] - mean * sc;
-  mean_o[c] = mean;
-  invstd_o[c] = invstd;
+  o.scale = f.gamma[c] * o.invstd;
+  o.shift = f.beta[c] - o.mean * o.scale;
+  return o;
+}
+__device__ __forceinline__ void bn_store(const adp::BnFin& f, int c, const BnCoef& o) {
+  if (f.training && f.rm) {
+    f.rm[c] = (1.f - f.momentum) * f.rm[c] + f.momentum * o.mean;
+    f.rv[c] = (1.f - f.momentum) * f.rv[c] + f.momentum * o.unbiased;
+  }
+  f.scale[c] = o.scale;
+  f.shift[c] = o.shift;
+  f.mean[c] = o.mean;
+  f.invstd[c] = o.invstd;
+}
+
+__global__ void bn_finalize_kernel(const adp::BnFin f, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) bn_store(f, c, bn_coef(f, C, c));
 }
 
 // ------------------------------------------------------------------ normalise + activation
@@ -281,6 +289,44 @@ affine_act8_kernel(const T* __restrict__ x, long long n8, int C, const float* __
   }
 }
 
+// BatchNorm finalize + normalise + activation in one launch (2048 % C == 0): every thread derives the coefficients of
+// its own 8 channels from the accumulated sums, block 0 additionally stores scale/shift/mean/invstd for the backward
+// pass and updates the running statistics.
+template <class T>
+__global__ void __launch_bounds__(EW_THREADS)
+bn_affine_act8_kernel(const T* __restrict__ x, long long n8, int C, const adp::BnFin f, float slope0, T* __restrict__ out0,
+                      float slope1, T* __restrict__ out1) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // the block derives the C coefficient pairs once (C <= 2048), every thread then picks up its 8 channels
+  __shared__ float2 coef_s[2048];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const BnCoef o = bn_coef(f, C, c);
+    coef_s[c] = make_float2(o.scale, o.shift);
+    if (blockIdx.x == 0) bn_store(f, c, o);      // (training: nobody reads rm/rv; eval: nobody writes them)
+  }
+  __syncthreads();
+  float8 sc, sh;
+  {
+    const int c = (threadIdx.x * 8) % C;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float2 t = coef_s[c + k]; sc.v[k] = t.x; sh.v[k] = t.y; }
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float8 v = ld8(x + 8 * i);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] = fmaf(v.v[k], sc.v[k], sh.v[k]);
+    float8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = lrelu(v.v[k], slope0);
+    st8(out0 + 8 * i, o);
+    if (out1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = lrelu(v.v[k], slope1);
+      st8(out1 + 8 * i, o);
+    }
+  }
+}
+
 struct GzIn { float8 x, a, b; };
 template <class T>
 __device__ __forceinline__ GzIn gz_load(const T* x, const T* gA, const T* gB, long long off) {
@@ -407,9 +453,12 @@ act_bn_bwd_apply8_kernel(const T* __restrict__ x, long long n8, long long rows, 
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const T* __restrict__ gA, float slope0,
                          const T* __restrict__ gB, float slope1, const double* __restrict__ sums, int mode,
-                         T* __restrict__ dx) {
+                         T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const float inv_m = 1.f / (float)rows;
+  if (dgamma && blockIdx.x == 0) {     // dbeta = sum gz, dgamma = sum gz * xhat
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta[c] = (float)sums[c]; dgamma[c] = (float)sums[C + c]; }
+  }
   float8 sc, sh, cA, cB, cC;
   auto coeffs = [&](int c) {
     if (scale) { sc = ld8(scale + c); sh = ld8(shift + c); }
@@ -611,13 +660,23 @@ int bn_stats(int dtype, const void* x, long long rows, int C, double* sums, cuda
   return ADP_OK;
 }
 
-int bn_finalize(const double* sums, long long rows, int C, const float* gamma, const float* beta,
-                float* running_mean, float* running_var, int training, float eps, float momentum,
-                float* scale, float* shift, float* mean, float* invstd, cudaStream_t s) {
-  bn_finalize_kernel<<<adp_cdiv(C, 128), 128, 0, s>>>(sums, rows, C, gamma, beta, running_mean, running_var,
-                                                      training, eps, momentum, scale, shift, mean, invstd);
+int bn_finalize(const BnFin& f, int C, cudaStream_t s) {
+  bn_finalize_kernel<<<adp_cdiv(C, 128), 128, 0, s>>>(f, C);
   ADP_LAUNCH_CHECK();
   return ADP_OK;
+}
+
+int bn_affine_act(int dtype, const void* x, long long rows, int C, const BnFin& f, float slope0, void* out0, float slope1,
+                  void* out1, cudaStream_t s) {
+  if (C % 8 == 0 && 2048 % C == 0) {
+    const long long n8 = rows * C / 8;
+    ADP_DISPATCH_T(dtype, (bn_affine_act8_kernel<T><<<ew_grid(n8), EW_THREADS, 0, s>>>((const T*)x, n8, C, f, slope0, (T*)out0,
+                                                                                     slope1, (T*)out1));)
+    ADP_LAUNCH_CHECK();
+    return ADP_OK;
+  }
+  ADP_TRY(bn_finalize(f, C, s));
+  return affine_act(dtype, x, rows, C, f.scale, f.shift, slope0, out0, slope1, out1, s);
 }
 
 int affine_act(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift,
@@ -674,8 +733,9 @@ int act_bn_bwd_reduce(int dtype, const void* x, long long rows, int C, const flo
 
 int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift,
                      const float* mean, const float* invstd, const void* gA, float slope0, const void* gB,
-                     float slope1, const double* sums, int mode, void* dx, cudaStream_t s) {
+                     float slope1, const double* sums, int mode, void* dx, float* dgamma, float* dbeta, cudaStream_t s) {
   ADP_CHECK_ARG(C % 4 == 0, "act_bn_bwd_apply: C %% 4 != 0");
+  ADP_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr) && (!dgamma || sums), "act_bn_bwd_apply: dgamma/dbeta need sums");
   if (C % 8 == 0) {
     long long n8 = rows * C / 8;
     if (2048 % C == 0) {
@@ -690,11 +750,11 @@ int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const floa
       }
       ADP_DISPATCH_T(dtype, (act_bn_bwd_apply8_kernel<T, true><<<ew_grid(n8), EW_THREADS, smem, s>>>(
                                 (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
-                                (const T*)gB, slope1, sums, mode, (T*)dx));)
+                                (const T*)gB, slope1, sums, mode, (T*)dx, dgamma, dbeta));)
     } else {
       ADP_DISPATCH_T(dtype, (act_bn_bwd_apply8_kernel<T, false><<<ew_grid(n8), EW_THREADS, 0, s>>>(
                                 (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
-                                (const T*)gB, slope1, sums, mode, (T*)dx));)
+                                (const T*)gB, slope1, sums, mode, (T*)dx, dgamma, dbeta));)
     }
     ADP_LAUNCH_CHECK();
     return ADP_OK;
@@ -704,6 +764,7 @@ int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const floa
                             (const T*)x, n4, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
                             (const T*)gB, slope1, sums, mode, (T*)dx);)
   ADP_LAUNCH_CHECK();
+  if (dgamma) return bn_param_grads(sums, C, dgamma, dbeta, s);
   return ADP_OK;
 }
 

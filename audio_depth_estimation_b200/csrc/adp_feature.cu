@@ -431,3 +431,49 @@ extern "C" int adp_feature_forward_mel(const float* wave, int rows, int L, int w
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ground-truth depth preparation (BatvisionV2_Dataset.py:68-78, BatvisionV1_Dataset.py:47-65): mm -> m, clip to
+// [0, max_depth], cv2.INTER_NEAREST resize to S x S, optional / max_depth.  Every step but the resize is
+// element-wise, so the kernel gathers first; fp32 IEEE division keeps it bit-exact with the numpy code.
+namespace {
+
+template <class T>
+__global__ void __launch_bounds__(256)
+depth_prepare_kernel(const T* __restrict__ raw, int H, int W, int S, float max_depth, int nan_to_num, float norm_div,
+                     float* __restrict__ out) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y, row = blockIdx.z;
+  if (o >= S) return;
+  // cv2 resizeNN: sx = min(floor(dx * (1 / ((double)S / W))), W - 1)
+  const double ify = 1.0 / ((double)S / (double)H), ifx = 1.0 / ((double)S / (double)W);
+  const int sy = min((int)floor((double)p * ify), H - 1), sx = min((int)floor((double)o * ifx), W - 1);
+  float d = (float)raw[((size_t)row * H + sy) * W + sx];
+  if (nan_to_num) {                                   // np.nan_to_num: nan -> 0, +-inf -> +-float max (V1 :49-52)
+    if (d != d) d = 0.f;
+    else if (isinf(d)) d = d > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+  }
+  d = d / 1000.0f;
+  if (max_depth > 0.f && d > max_depth) d = max_depth;
+  if (d < 0.f) d = 0.f;
+  if (norm_div > 0.f) d = d / norm_div;
+  out[((size_t)row * S + p) * S + o] = d;
+}
+
+}  // namespace
+
+extern "C" int adp_depth_prepare(const void* raw, int raw_dtype, int rows, int H, int W, int out_size, float max_depth,
+                                 int nan_to_num, float norm_div, float* out, void* stream) {
+  ADP_CHECK_ARG(raw && out && rows > 0 && rows <= 65535 && H > 0 && W > 0 && out_size > 0 && out_size <= 65535,
+                "depth_prepare: bad arguments");
+  ADP_CHECK_ARG(raw_dtype == 0 || raw_dtype == 1, "depth_prepare: raw_dtype %d (0 = fp32, 1 = uint16)", raw_dtype);
+  dim3 grid(adp_cdiv(out_size, 256), out_size, rows);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (raw_dtype == 0)
+    depth_prepare_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(raw), H, W, out_size, max_depth,
+                                                     nan_to_num, norm_div, out);
+  else
+    depth_prepare_kernel<unsigned short><<<grid, 256, 0, s>>>(reinterpret_cast<const unsigned short*>(raw), H, W, out_size,
+                                                              max_depth, 0, norm_div, out);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}

@@ -225,10 +225,9 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
       BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
       double* sums = reinterpret_cast<double*>(at(ws, L.sums_down));
       if (d->training) ADP_TRY(bn_stats(dt, at(ws, L.e), rows, L.cout, sums, s));
-      ADP_TRY(bn_finalize(sums, rows, L.cout, params[l].bn_down_w, params[l].bn_down_b, params[l].bn_down_rm,
-                          params[l].bn_down_rv, d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean,
-                          bn.invstd, s));
-      ADP_TRY(affine_act(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), s));
+      const BnFin fin{sums, 1.0 / (double)rows, rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f, params[l].bn_down_w, params[l].bn_down_b, params[l].bn_down_rm, params[l].bn_down_rv,
+                      d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd};
+      ADP_TRY(bn_affine_act(dt, at(ws, L.e), rows, L.cout, fin, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), s));
     } else {
       ADP_TRY(affine_act(dt, at(ws, L.e), rows, L.cout, nullptr, nullptr, 0.f, at(ws, L.r), 0.f, nullptr, s));
     }
@@ -243,10 +242,9 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     BnBuf bn = bnbuf(ws, L.bn_up_f, L.t_cout);
     double* sums = reinterpret_cast<double*>(at(ws, L.sums_up));
     if (d->training) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));
-    ADP_TRY(bn_finalize(sums, rows, L.t_cout, params[l].bn_up_w, params[l].bn_up_b, params[l].bn_up_rm,
-                        params[l].bn_up_rv, d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean,
-                        bn.invstd, s));
-    ADP_TRY(affine_act(dt, at(ws, O.t), rows, L.t_cout, bn.scale, bn.shift, 0.f, at(ws, O.q), 0.f, nullptr, s));
+    const BnFin fin{sums, 1.0 / (double)rows, rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f, params[l].bn_up_w, params[l].bn_up_b, params[l].bn_up_rm, params[l].bn_up_rv,
+                    d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd};
+    ADP_TRY(bn_affine_act(dt, at(ws, O.t), rows, L.t_cout, fin, 0.f, at(ws, O.q), 0.f, nullptr, s));
   }
   {
     const LevelPlan& L = p.lv[0];
@@ -289,8 +287,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
     ADP_TRY(act_bn_bwd_reduce(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f,
                               nullptr, 0.f, bs, s));
     ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f,
-                             nullptr, 0.f, bs, bn_mode, at(ws, L.g_t), s));
-    ADP_TRY(bn_param_grads(bs, C, grads[l + 1].bn_up_w, grads[l + 1].bn_up_b, s));
+                             nullptr, 0.f, bs, bn_mode, at(ws, L.g_t), grads[l + 1].bn_up_w, grads[l + 1].bn_up_b, s));
     return ADP_OK;
   };
 
@@ -335,18 +332,18 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       const long long rows = (long long)B * L.hout * L.hout;
       if (l == D - 1) {
         ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.e), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_r), 0.f,
-                                 nullptr, 0.f, nullptr, 0, at(ws, L.g_e), s));
+                                 nullptr, 0.f, nullptr, 0, at(ws, L.g_e), nullptr, nullptr, s));
       } else if (L.bn_down) {
         BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
         double* bs = reinterpret_cast<double*>(at(ws, L.bsums_down));
         ADP_TRY(act_bn_bwd_reduce(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd,
                                   at(ws, L.g_a), 0.2f, at(ws, L.g_r), 0.f, bs, s));
         ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_a),
-                                 0.2f, at(ws, L.g_r), 0.f, bs, bn_mode, at(ws, L.g_e), s));
-        ADP_TRY(bn_param_grads(bs, L.cout, grads[l].bn_down_w, grads[l].bn_down_b, s));
+                                 0.2f, at(ws, L.g_r), 0.f, bs, bn_mode, at(ws, L.g_e), grads[l].bn_down_w,
+                                 grads[l].bn_down_b, s));
       } else {  // level 0: no norm; sign(e) == sign(a)
         ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.a), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_a), 0.2f,
-                                 at(ws, L.g_r), 0.f, nullptr, 0, at(ws, L.g_e), s));
+                                 at(ws, L.g_r), 0.f, nullptr, 0, at(ws, L.g_e), nullptr, nullptr, s));
       }
       ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, s));
       if (l == 0 && thin_tc_bwd) {

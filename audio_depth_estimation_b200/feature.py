@@ -144,3 +144,40 @@ class SpectrogramTransform:
                                                1 if self.log_minmax else 0, self.size, out.data_ptr(),
                                                self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()))
         return out.reshape(*lead, self.size, self.size)
+
+
+class DepthTransform:
+    """Raw depth maps [B,H,W] in millimetres (CUDA fp32, or uint16 viewed as int16/uint16) -> gt_depth [B,1,S,S]:
+    the depth half of __getitem__ (BatvisionV2_Dataset.py:68-78; BatvisionV1_Dataset.py:47-65) for a whole batch,
+    bit-exact with the reference's numpy + cv2.INTER_NEAREST code."""
+
+    def __init__(self, images_size=256, max_depth=30.0, depth_norm=False, nan_to_num=False):
+        self.size = int(images_size)
+        self.max_depth = float(max_depth) if max_depth else 0.0
+        self.norm_div = self.max_depth if depth_norm else 0.0
+        self.nan_to_num = bool(nan_to_num)
+
+    @classmethod
+    def for_cfg(cls, cfg):
+        v1 = "v1" in str(getattr(cfg.dataset, "name", "batvisionv2")).lower()
+        # V2 never normalises the depth in the dataset (its __getitem__ has no depth_norm branch)
+        return cls(cfg.dataset.images_size, cfg.dataset.max_depth, depth_norm=v1 and bool(cfg.dataset.depth_norm),
+                   nan_to_num=v1)
+
+    def __call__(self, raw):
+        if not raw.is_cuda:
+            raise RuntimeError("DepthTransform needs a CUDA tensor (no CPU fallback)")
+        if raw.dtype == torch.float32:
+            code = 0
+        elif raw.dtype in (torch.uint16, torch.int16):
+            code = 1
+        else:
+            raise TypeError("raw depth must be float32 or uint16, got %s" % raw.dtype)
+        raw = raw.contiguous()
+        H, W = raw.shape[-2:]
+        rows = raw.numel() // (H * W)
+        out = torch.empty((rows, 1, self.size, self.size), device=raw.device, dtype=torch.float32)
+        _lib.check(_lib.load().adp_depth_prepare(raw.data_ptr(), code, rows, H, W, self.size, self.max_depth,
+                                                 1 if self.nan_to_num else 0, self.norm_div, out.data_ptr(),
+                                                 _lib.stream_ptr()))
+        return out

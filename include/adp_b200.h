@@ -85,6 +85,13 @@ int adp_feature_forward_mel(const float* wave, int rows, int L, int wave_pitch, 
 /* utils_dataset.py:18-20 alone: [rows, H, W] -> [rows, S, S]. */
 int adp_resize_aa(const float* in, int rows, int H, int W, int out_size, float* out, void* stream);
 
+/* Ground-truth depth preparation of __getitem__ (BatvisionV2_Dataset.py:68-78; V1 :47-65 with
+ * nan_to_num = 1 and norm_div = max_depth when depth_norm): raw [rows,H,W] millimetres
+ * (raw_dtype 0 = fp32, 1 = uint16) -> out [rows,S,S] fp32 metres, clipped to [0, max_depth]
+ * (max_depth <= 0: no upper clip), cv2.INTER_NEAREST sampling, bit-exact with the numpy code. */
+int adp_depth_prepare(const void* raw, int raw_dtype, int rows, int H, int W, int out_size,
+                      float max_depth, int nan_to_num, float norm_div, float* out, void* stream);
+
 /* --------------------------------------------------------------------- loss
  * train.py:646-669 + utils_loss.py:29-49.  Three phases so that data-parallel
  * ranks can all-reduce the four sufficient statistics in between

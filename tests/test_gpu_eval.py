@@ -195,3 +195,34 @@ def test_checkpoint_round_trip_reference_format(tmp_path):
     # and the reverse direction: moments written by torch.optim.AdamW.state_dict()
     step2.optimizer.load_state_dict(topt.state_dict())
     assert step2.optimizer.step_count == 3
+
+
+def test_depth_prepare_bit_exact_with_numpy_cv2():
+    cv2 = pytest.importorskip("cv2")
+    from audio_depth_estimation_b200.feature import DepthTransform
+    rng = np.random.default_rng(8)
+    for (H, W, S) in ((720, 1280, 256), ((90, 160, 64)), ((100, 100, 256)), ((257, 33, 17))):
+        raw = rng.uniform(-800, 45000, size=(3, H, W)).astype(np.float32)
+        # V2 (:68-78)
+        got = DepthTransform(S, 30.0)(torch.from_numpy(raw).cuda()).cpu().numpy()
+        for b in range(3):
+            d = raw[b].copy() / 1000.0
+            d[d > 30.0] = 30.0
+            d[d < 0] = 0
+            assert np.array_equal(got[b, 0], cv2.resize(d, (S, S), interpolation=cv2.INTER_NEAREST))
+        # V1 (:47-65): nan / inf handling and normalisation
+        raw[:, 0, :7] = np.nan; raw[:, 1, :7] = np.inf; raw[:, 2, :7] = -np.inf
+        got = DepthTransform(S, 12.0, depth_norm=True, nan_to_num=True)(torch.from_numpy(raw).cuda()).cpu().numpy()
+        for b in range(3):
+            d = np.nan_to_num(raw[b].copy())
+            d = d / 1000
+            d[d > 12.0] = 12.0
+            d[d < 0.0] = 0.0
+            d = cv2.resize(d, (S, S), interpolation=cv2.INTER_NEAREST) / 12.0
+            assert np.array_equal(got[b, 0], d.astype(np.float32))
+    u16 = rng.integers(0, 65535, size=(2, 96, 128), dtype=np.uint16)
+    got = DepthTransform(64, 30.0)(torch.from_numpy(u16.view(np.int16)).cuda()).cpu().numpy()
+    for b in range(2):
+        d = u16[b].astype(np.float32) / 1000.0
+        d[d > 30.0] = 30.0
+        assert np.array_equal(got[b, 0], cv2.resize(d, (64, 64), interpolation=cv2.INTER_NEAREST))
