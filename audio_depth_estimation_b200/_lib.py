@@ -27,7 +27,7 @@ class UnetDesc(C.Structure):
 
 
 _LEVEL_SLOTS = ("conv_w", "convT_w", "convT_bias", "bn_down_w", "bn_down_b", "bn_down_rm", "bn_down_rv",
-                "bn_up_w", "bn_up_b", "bn_up_rm", "bn_up_rv")
+                "bn_up_w", "bn_up_b", "bn_up_rm", "bn_up_rv", "conv_w_bf16", "convT_w_bf16")
 
 
 class UnetLevel(C.Structure):
@@ -35,7 +35,8 @@ class UnetLevel(C.Structure):
 
 
 class TensorRef(C.Structure):
-    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64)]
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64),
+                ("p_bf16", C.c_void_p)]
 
 
 _vp, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64

@@ -88,7 +88,9 @@ clip_adamw_kernel(const __grid_constant__ TensorTable tab, const double* __restr
   const adp_tensor_ref r = tab.refs[ti];
   const long long base = (long long)(blockIdx.x - tab.block_start[ti]) * OPT_ELEMS_PER_BLOCK;
   const long long end = min(base + (long long)OPT_ELEMS_PER_BLOCK, (long long)r.n);
-  const bool aligned = ((((uintptr_t)r.p) | ((uintptr_t)r.g) | ((uintptr_t)r.m) | ((uintptr_t)r.v)) & 15) == 0;
+  __nv_bfloat16* p16 = reinterpret_cast<__nv_bfloat16*>(r.p_bf16);
+  const bool aligned = ((((uintptr_t)r.p) | ((uintptr_t)r.g) | ((uintptr_t)r.m) | ((uintptr_t)r.v)) & 15) == 0 &&
+                       (((uintptr_t)r.p_bf16) & 7) == 0;
   if (aligned) {
     long long i = base + threadIdx.x * 4;
     for (; i + 3 < end; i += OPT_THREADS * 4) {
@@ -98,10 +100,22 @@ clip_adamw_kernel(const __grid_constant__ TensorTable tab, const double* __restr
       adam1(p.z, g.z, m.z, v.z, coef, a);
       adam1(p.w, g.w, m.w, v.w, coef, a);
       st4(r.p + i, p); st4(r.m + i, m); st4(r.v + i, v);
+      if (p16) {   // i % 4 == 0 and the mirror is 8-byte aligned with p 16-byte aligned
+        uint2 u;
+        u.x = pack_bf16x2_(p.x, p.y);
+        u.y = pack_bf16x2_(p.z, p.w);
+        *reinterpret_cast<uint2*>(p16 + i) = u;
+      }
     }
-    for (; i < end; ++i) adam1(r.p[i], r.g[i], r.m[i], r.v[i], coef, a);
+    for (; i < end; ++i) {
+      adam1(r.p[i], r.g[i], r.m[i], r.v[i], coef, a);
+      if (p16) p16[i] = __float2bfloat16(r.p[i]);
+    }
   } else {
-    for (long long i = base + threadIdx.x; i < end; i += OPT_THREADS) adam1(r.p[i], r.g[i], r.m[i], r.v[i], coef, a);
+    for (long long i = base + threadIdx.x; i < end; i += OPT_THREADS) {
+      adam1(r.p[i], r.g[i], r.m[i], r.v[i], coef, a);
+      if (p16) p16[i] = __float2bfloat16(r.p[i]);
+    }
   }
 }
 

@@ -179,6 +179,7 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   ADP_CHECK_ARG(x && y && ws && ws_bytes >= p.total, "unet_forward: null pointer or workspace too small (%zu < %zu)",
                 ws_bytes, p.total);
   const int D = p.D, B = p.B, dt = d->dtype;
+  auto w16 = [&](const void* mirror, size_t off) -> void* { return mirror ? const_cast<void*>(mirror) : (void*)at(ws, off); };
   const bool tc = use_tc(dt);
   tc_set_scratch(p.tc_scratch_bytes ? at(ws, p.tc_scratch) : nullptr, p.tc_scratch_bytes);
 
@@ -194,9 +195,11 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
       ADP_TRY(cast_transpose_taps(params[0].convT_w, at(ws, p.w16_last), p.lv[0].cout + p.lv[0].t_c1, 1, s));
     for (int l = 0; l < D; ++l) {
       const LevelPlan& L = p.lv[l];
-      if (l > 0) {
-        ADP_TRY(cast_f32_to_bf16(params[l].conv_w, at(ws, L.wb_conv), (long long)L.cout * 16 * L.cin, s));
-        ADP_TRY(cast_f32_to_bf16(params[l].convT_w, at(ws, L.wb_convT), (long long)(L.cout + L.t_c1) * 16 * L.t_cout, s));
+      if (l > 0) {   // (skipped where the caller maintains a bf16 mirror, e.g. written by the fused AdamW step)
+        if (!params[l].conv_w_bf16)
+          ADP_TRY(cast_f32_to_bf16(params[l].conv_w, at(ws, L.wb_conv), (long long)L.cout * 16 * L.cin, s));
+        if (!params[l].convT_w_bf16)
+          ADP_TRY(cast_f32_to_bf16(params[l].convT_w, at(ws, L.wb_convT), (long long)(L.cout + L.t_c1) * 16 * L.t_cout, s));
       }
     }
   }
@@ -219,7 +222,7 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   for (int l = 1; l < D; ++l) {
     const LevelPlan& L = p.lv[l];
     const long long rows = (long long)B * L.hout * L.hout;
-    ADP_TRY(conv_gather(dt, at(ws, p.lv[l - 1].a), params[l].conv_w, tc ? at(ws, L.wb_conv) : nullptr,
+    ADP_TRY(conv_gather(dt, at(ws, p.lv[l - 1].a), params[l].conv_w, tc ? w16(params[l].conv_w_bf16, L.wb_conv) : nullptr,
                         at(ws, L.e), L.cout, nullptr, 0, B, L.hin, L.hin, L.cin, s));
     if (L.bn_down) {
       BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
@@ -238,7 +241,7 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     const LevelPlan& O = p.lv[l - 1];  // output lives at level l-1's resolution
     const long long rows = (long long)B * O.hout * O.hout;
     ADP_TRY(conv_parity(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, params[l].convT_w,
-                        tc ? at(ws, L.wb_convT) : nullptr, at(ws, O.t), B, L.hout, L.hout, L.t_cout, s));
+                        tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, O.t), B, L.hout, L.hout, L.t_cout, s));
     BnBuf bn = bnbuf(ws, L.bn_up_f, L.t_cout);
     double* sums = reinterpret_cast<double*>(at(ws, L.sums_up));
     if (d->training) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));
@@ -270,6 +273,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
   ADP_TRY(check_params(d, p, params));
   ADP_CHECK_ARG(x && y && dy && grads && ws && ws_bytes >= p.total, "unet_backward: null pointer or workspace too small");
   const int D = p.D, B = p.B, dt = d->dtype;
+  auto w16 = [&](const void* mirror, size_t off) -> void* { return mirror ? const_cast<void*>(mirror) : (void*)at(ws, off); };
   ADP_CHECK_ARG(stage_begin >= 0 && stage_end <= 2 * D && stage_begin <= stage_end, "unet_backward: bad stage range");
   const bool tc = use_tc(dt);
   const bool thin_tc_bwd = tc && p.thin_tc && tc_supported_pointwise16(B, p.lv[0].hout, p.lv[0].hout, p.lv[0].cout, p.lv[0].t_c1);
@@ -323,7 +327,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       ADP_CUDA(cudaMemsetAsync(grads[l].convT_w, 0, sizeof(float) * 16 * (size_t)Ct * L.t_cout, s));
       ADP_TRY(conv_wgrad(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, at(ws, O.g_t), L.t_cout,
                          grads[l].convT_w, B, L.hout, L.hout, s));
-      ADP_TRY(conv_gather(dt, at(ws, O.g_t), params[l].convT_w, tc ? at(ws, L.wb_convT) : nullptr, at(ws, L.g_r),
+      ADP_TRY(conv_gather(dt, at(ws, O.g_t), params[l].convT_w, tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, L.g_r),
                           L.cout, L.t_c1 ? at(ws, L.g_q) : nullptr, L.t_c1, B, O.hout, O.hout, L.t_cout, s));
       if (l < D - 1) ADP_TRY(up_norm_bwd(l));
     } else {
@@ -359,7 +363,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         const LevelPlan& I = p.lv[l - 1];
         ADP_TRY(conv_wgrad(dt, at(ws, L.g_e), L.cout, nullptr, 0, at(ws, I.a), L.cin, grads[l].conv_w, B, L.hout,
                            L.hout, s));
-        ADP_TRY(conv_parity(dt, at(ws, L.g_e), L.cout, nullptr, 0, params[l].conv_w, tc ? at(ws, L.wb_conv) : nullptr,
+        ADP_TRY(conv_parity(dt, at(ws, L.g_e), L.cout, nullptr, 0, params[l].conv_w, tc ? w16(params[l].conv_w_bf16, L.wb_conv) : nullptr,
                             at(ws, I.g_a), B, L.hout, L.hout, L.cin, s));
       }
     }

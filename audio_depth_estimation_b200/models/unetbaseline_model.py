@@ -174,6 +174,9 @@ class UnetGenerator(nn.Module):
         self._fwd_token = 0
         self._wcache_key = None
         self._dirty = True
+        self._dirty_epoch = 0         # bumped by every mark_weights_dirty() (optimiser steps, loads, broadcasts)
+        self._mirror = None           # bf16 copy of the flat parameters kept current by FusedClipAdamW
+        self._fwd_mirror = False
         self._anchor = None
         self.grad_ready_hook = None   # callable(stage_group_index) used by the data-parallel trainer
         self.stage_groups = None      # list of (stage_begin, stage_end)
@@ -193,6 +196,26 @@ class UnetGenerator(nn.Module):
 
     def mark_weights_dirty(self):
         self._dirty = True
+        self._dirty_epoch += 1
+
+    # bf16 weight mirror: the fused optimiser writes bf16(p) next to every fp32 update, so the forward pass does not
+    # have to cast the 54 M weights again.  Valid only while nothing else has touched the parameters since.
+    def _weights_token(self):
+        return (self._dirty_epoch, self._flat["p"].data_ptr(), tuple(p._version for p in self._flat["params"]))
+
+    def bf16_mirror(self):
+        flat_p = self.flat_buffers()[0]
+        if self._mirror is None or self._mirror["buf"].numel() != flat_p.numel() or self._mirror["buf"].device != flat_p.device:
+            self._mirror = dict(buf=torch.empty(flat_p.numel(), device=flat_p.device, dtype=torch.bfloat16), token=None)
+        return self._mirror["buf"]
+
+    def mirror_written(self):
+        """Called by the optimiser right after a step that rewrote the whole mirror."""
+        self._mirror["token"] = self._weights_token()
+
+    def _mirror_ok(self):
+        return (self._dtype == _lib.ADP_BF16 and self._mirror is not None and self._mirror["token"] is not None
+                and self._mirror["token"] == self._weights_token())
 
     # ------------------------------------------------------------------ module-tree views
     def levels(self):
@@ -277,6 +300,7 @@ class UnetGenerator(nn.Module):
                         bn.num_batches_tracked = bn.num_batches_tracked.to(device)
         self._anchor = torch.zeros(1, device=device, requires_grad=True)
         self._dirty = True
+        self._mirror = None
 
     def flat_buffers(self):
         """(flat parameters, flat gradients, per-stage (begin, end) element offsets)."""
@@ -288,9 +312,11 @@ class UnetGenerator(nn.Module):
         return self._flat["p"], self._flat["g"], self._flat["stage_slices"]
 
     # ------------------------------------------------------------------ C structs
-    def _level_array(self, use_grads):
+    def _level_array(self, use_grads, mirror=False):
         f = self._flat
         grad_of = {id(p): g for p, g in zip(f["params"], f["gviews"])} if use_grads else None
+        off_of = {id(p): o for p, o in zip(f["params"], f["offs"])} if mirror else None
+        base16 = self._mirror["buf"].data_ptr() if mirror else 0
 
         def ptr(t):
             if t is None:
@@ -305,6 +331,9 @@ class UnetGenerator(nn.Module):
             a.conv_w = ptr(lv["conv"].weight)
             a.convT_w = ptr(lv["convT"].weight)
             a.convT_bias = ptr(lv["convT"].bias)
+            if mirror and i > 0:
+                a.conv_w_bf16 = base16 + 2 * off_of[id(lv["conv"].weight)]
+                a.convT_w_bf16 = base16 + 2 * off_of[id(lv["convT"].weight)]
             for tag in ("bn_down", "bn_up"):
                 bn = lv[tag]
                 if bn is not None:
@@ -353,7 +382,8 @@ class UnetGenerator(nn.Module):
             reuse = False
             desc.reuse_weight_cache = 0
         y = torch.empty((B, self.output_nc, S, S), device=x.device, dtype=torch.float32)
-        params = self._level_array(False)
+        self._fwd_mirror = self._mirror_ok()
+        params = self._level_array(False, self._fwd_mirror)
         with torch.cuda.device(x.device):
             _lib.check(lib.adp_unet_forward(ctypes.byref(desc), x.data_ptr(), params, self._ws.data_ptr(),
                                             self._ws.numel(), y.data_ptr(), _lib.stream_ptr()))
@@ -377,7 +407,7 @@ class UnetGenerator(nn.Module):
         dy = dy.contiguous()
         if dy.dtype != torch.float32:
             dy = dy.float()
-        params, grads = self._level_array(False), self._level_array(True)
+        params, grads = self._level_array(False, self._fwd_mirror), self._level_array(True)
         groups = self.stage_groups or [(0, 2 * self.num_downs)]
         with torch.cuda.device(x.device):
             for gi, (b, e) in enumerate(groups):

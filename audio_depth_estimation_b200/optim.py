@@ -40,6 +40,9 @@ class FusedClipAdamW:
         ref = (_lib.TensorRef * 1)()
         ref[0].p, ref[0].g, ref[0].m, ref[0].v, ref[0].n = (p.data_ptr(), g.data_ptr(), st["m"].data_ptr(),
                                                            st["v"].data_ptr(), p.numel())
+        # bf16 models: the update also writes bf16(p) into the model's mirror, which replaces the per-forward casts
+        self._mirrored = getattr(self.model, "precision", None) == "bf16" and hasattr(self.model, "bf16_mirror")
+        ref[0].p_bf16 = self.model.bf16_mirror().data_ptr() if self._mirrored else None
         return p, st, ref
 
     def zero_grad(self, set_to_none=True):
@@ -63,6 +66,8 @@ class FusedClipAdamW:
                                                    self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                                    self.step_count, st["norm"].data_ptr(), s))
         self.model.mark_weights_dirty()
+        if self._mirrored:
+            self.model.mirror_written()
         self.last_norm = st["norm"]
         return st["norm"]
 

@@ -124,6 +124,7 @@ class TrainStep:
         self._graph = None
         self._static = None
         self._eager_calls = 0
+        self._epoch = None
         self.model = model
         self.transform = SpectrogramTransform.for_cfg(cfg) if waveform_input else None
         self.reducer = GradientReducer(model, process_group, stages_per_group)
@@ -154,8 +155,10 @@ class TrainStep:
 
     def _graphed_step(self, batch, gtdepth):
         key = (tuple(batch.shape), tuple(gtdepth.shape), batch.device)
-        if self._static is not None and self._static[0] != key:
-            self._graph, self._static, self._eager_calls = None, None, 0      # new shape: re-record
+        if self._static is not None and (self._static[0] != key or self._epoch != self.model._dirty_epoch):
+            # new shape, or the parameters were replaced behind the graph's back (load_state_dict, broadcast):
+            # the recorded step reads the optimiser-maintained bf16 weight mirror, so record again
+            self._graph, self._static, self._eager_calls = None, None, 0
         if self._graph is None:
             if self._eager_calls < 2:                  # workspaces, tensor maps, func attributes: all set up eagerly
                 self._eager_calls += 1
@@ -167,6 +170,7 @@ class TrainStep:
             with torch.cuda.graph(graph):
                 sloss = self._eager_step(sb, sg)
             self._graph, self._static = graph, (key, sb, sg, sloss)
+            self._epoch = self.model._dirty_epoch
         _, sb, sg, sloss = self._static
         sb.copy_(batch, non_blocking=True)
         sg.copy_(gtdepth, non_blocking=True)

@@ -178,6 +178,10 @@ typedef struct adp_unet_level {      /* level 0 = outermost block */
   float* convT_bias;   /* [out_ch] (outermost only) or NULL */
   float* bn_down_w; float* bn_down_b; float* bn_down_rm; float* bn_down_rv;  /* NULL where the block has no down-norm */
   float* bn_up_w;   float* bn_up_b;   float* bn_up_rm;   float* bn_up_rv;
+  /* Optional bf16 copies of conv_w / convT_w in the same element order, kept up to date by the caller
+   * (adp_clip_adamw_step writes them through adp_tensor_ref.p_bf16).  NULL: the forward casts the fp32
+   * weights itself.  Ignored for level 0 and in fp32 mode. */
+  const void* conv_w_bf16; const void* convT_w_bf16;
 } adp_unet_level;
 
 size_t adp_unet_workspace_bytes(const adp_unet_desc* d);
@@ -203,7 +207,10 @@ int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, const float
 /* ----------------------------------------------------------------- optimiser
  * clip_grad_norm_(max_norm) + AdamW.step  train.py:471-476, :689-691.
  * Multi-tensor: n tensors described by device-visible pointer tables. */
-typedef struct adp_tensor_ref { float* p; float* g; float* m; float* v; int64_t n; } adp_tensor_ref;
+typedef struct adp_tensor_ref {
+  float* p; float* g; float* m; float* v; int64_t n;
+  void* p_bf16;   /* optional: bf16 mirror of p (n elements), rewritten by the AdamW step; NULL = none */
+} adp_tensor_ref;
 /* sumsq[0] += sum g^2 over all tensors (double, device) */
 int adp_grad_sumsq(const adp_tensor_ref* refs_host, int n_tensors, double* sumsq, void* stream);
 /* p,m,v updated in place; clip coefficient min(1, max_norm/(sqrt(sumsq)+1e-6)) taken

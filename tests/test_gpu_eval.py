@@ -226,3 +226,54 @@ def test_depth_prepare_bit_exact_with_numpy_cv2():
         d = u16[b].astype(np.float32) / 1000.0
         d[d > 30.0] = 30.0
         assert np.array_equal(got[b, 0], cv2.resize(d, (64, 64), interpolation=cv2.INTER_NEAREST))
+
+
+def test_bf16_weight_mirror_follows_every_parameter_change():
+    """FusedClipAdamW keeps a bf16 copy of the weights for the forward pass; any other writer (load_state_dict,
+    in-place edits, a recorded CUDA graph whose weights are replaced) must invalidate it."""
+    from audio_depth_estimation_b200.config_loader import load_config
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    from audio_depth_estimation_b200.training import TrainStep
+    cfg = load_config()
+    cfg.dataset.images_size, cfg.model.generator, cfg.model.precision = 128, "unet_128", "bf16"
+
+    def make(seed):
+        torch.manual_seed(seed)
+        return define_G(cfg, 2, 1, 16, "unet_128", "batch", False, gpu_ids=[0])
+
+    def batch(i):
+        return (torch.from_numpy(synthetic.feature_like(2, 128, seed=170 + i)).cuda(),
+                torch.from_numpy(synthetic.gt_depth(2, 128, 30.0, seed=180 + i, normalised=False)).cuda())
+
+    def eval_out(net, x):
+        net.eval()
+        with torch.no_grad():
+            return net(x).clone()
+
+    def close(a, b):
+        return float((a - b).norm() / b.norm().clamp_min(1e-12)) <= 2e-2
+
+    x = batch(9)[0]
+    for graph in (False, True):
+        net = make(1)
+        step = TrainStep(cfg, net, lr=1e-3, waveform_input=False, cuda_graph=graph)
+        for i in range(4):
+            step(*batch(i))
+        assert net._mirror_ok()                                   # the optimiser's mirror is what the forward uses
+        trained = eval_out(net, x)
+        other = make(2)
+        sd = {k: v.clone() for k, v in other.state_dict().items()}
+        want = eval_out(other.cuda(), x)
+        net.load_state_dict(sd)
+        assert not net._mirror_ok()
+        got = eval_out(net, x)
+        assert close(got, want) and not close(got, trained)
+        # training continues from the loaded weights (graph mode records again)
+        ref = TrainStep(cfg, other, lr=1e-3, waveform_input=False)
+        ref.optimizer.load_state_dict(step.optimizer.state_dict())          # same moments and step count
+        for i in range(4, 7):
+            la, lb = float(step(*batch(i))), float(ref(*batch(i)))
+            assert abs(la - lb) <= (2e-3 if i == 4 else 5e-2) * abs(lb), (graph, i, la, lb)
+        with torch.no_grad():
+            next(net.parameters()).mul_(0.5)                      # in-place edit bumps the version counter
+        assert not net._mirror_ok()
