@@ -1,0 +1,67 @@
+"""Turn an ncu CSV of (dram__bytes_read.sum, dram__bytes_write.sum, gpu__time_duration.sum) per tc_* launch of ONE
+training step into profiles/<name>.json (what bench.py reports as roofline.traffic).
+
+    ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+        -k regex:tc_ -s 192 -c 48 --csv --log-file gpurun_out/tc_dram.csv \
+        python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph
+    python tools/dram_per_step.py gpurun_out/tc_dram.csv profiles/r1_tc_dram_per_step.json
+"""
+import csv
+import io
+import json
+import sys
+
+
+def main(src, dst):
+    txt = open(src).read().splitlines()
+    start = [k for k, line in enumerate(txt) if line.startswith('"ID"')][0]
+    rows = list(csv.DictReader(io.StringIO("\n".join(txt[start:]))))
+    by_id = {}
+    for r in rows:
+        e = by_id.setdefault(r["ID"], {"kernel": r["Kernel Name"], "grid": r["Grid Size"]})
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r["Metric Unit"]
+        if r["Metric Name"].startswith("dram__bytes"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+            e["read" if "read" in r["Metric Name"] else "write"] = v * scale
+        else:
+            e["us"] = v * {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "nsecond": 1e-3, "ms": 1e3, "msecond": 1e3}[unit]
+    launches = list(by_id.values())
+
+    def family(e):
+        k = e["kernel"]
+        if "tc_wgrad" in k:
+            return "conv"
+        if "tc_igemm_persist_kernel" in k:
+            return "conv"
+        return "other"
+
+    # the conv families of bench.py's roofline = gather + parity + wgrad over E2-E8 / D8-D2; the thin first/last layers
+    # (pointwise GEMMs: <16>, gemm_tn, the two 1M-pixel <64> pointwise launches) and the STFT GEMM are listed but not averaged
+    per = []
+    for e in launches:
+        name = e["kernel"].split("(")[0].replace("void adp::<unnamed>::", "")
+        per.append({"kernel": name, "grid": e["grid"], "read_MB": round(e.get("read", 0) / 1e6, 1),
+                    "write_MB": round(e.get("write", 0) / 1e6, 1), "us": round(e.get("us", 0), 1)})
+    def is_thin(e):
+        k = e["kernel"]
+        return "gemm_tn" in k or "<16," in k or "(int)16" in k or ", 2>" in k or "(int)2>" in k
+    thin = [i for i, e in enumerate(per) if is_thin(e)]
+    # the E1 pointwise GEMM is the launch right after the STFT GEMM, the last-layer dgrad the one right after gemm_tn<64>
+    for i, e in enumerate(per[:-1]):
+        if (", 2>" in e["kernel"] or "(int)2>" in e["kernel"] or "gemm_tn_kernel<64>" in e["kernel"]
+                or "gemm_tn_kernel<(int)64>" in e["kernel"]):
+            thin.append(i + 1)
+    conv = [i for i in range(len(per)) if i not in thin]
+    tot = sum((launches[i].get("read", 0) + launches[i].get("write", 0)) for i in conv)
+    out = {"what": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the tcgen05 launches of ONE training step, "
+                   "B=64 bf16, 1xB200; averaged over the conv-family launches (everything but the STFT GEMM, gemm_tn and "
+                   "the <16> head GEMM)",
+           "launches": len(conv), "dram_bytes_per_step": tot, "dram_bytes_per_launch": tot / max(len(conv), 1),
+           "ncu_time_us_per_step": sum(per[i]["us"] for i in conv), "per_launch": per}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(dst, "launches", len(conv), "MB/launch %.1f" % (out["dram_bytes_per_launch"] / 1e6), "us", out["ncu_time_us_per_step"])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])
