@@ -67,6 +67,11 @@ SIGNATURES = {
     "adp_convT2d_k4s2_fprop": (_i, [_i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "adp_convT2d_k4s2_dgrad": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "adp_convT2d_k4s2_wgrad": (_i, [_i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "adp_cast_bf16": (_i, [_vp, _vp, _i64, _vp]),
+    "adp_conv2d_k3s1_fprop": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "adp_conv2d_k3s1_dgrad": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "adp_conv2d_k3s1_wgrad": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "adp_gemm_rows_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i64, _vp]),
     "adp_unet_workspace_bytes": (_sz, [C.POINTER(UnetDesc)]),
     "adp_unet_forward": (_i, [C.POINTER(UnetDesc), _vp, C.POINTER(UnetLevel), _vp, _sz, _vp, _vp]),
     "adp_unet_backward": (_i, [C.POINTER(UnetDesc), _vp, _vp, _vp, C.POINTER(UnetLevel), C.POINTER(UnetLevel),

@@ -294,6 +294,18 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
                     int B, int Hi, int Wi, int N, cudaStream_t s);
 int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int N,
              float* dw, int B, int Hs, int Ws, cudaStream_t s);
+// 3x3 / stride 1 / pad 1 on the same kernel (binaural_attention_model.py DoubleConv).  wmode 0: w = bf16 [N][9][Ct]
+// (forward); wmode 1: w = bf16 [Ct][9][N] read MN-major with reversed taps (data gradient through the forward weight).
+// scratch: fp32 [pixels][N] for split-K on small grids, or NULL.
+bool tc_supported_conv3x3(int B, int H, int W, int C0, int C1, int N0, int N1);
+int tc_conv3x3(const void* x0, int C0, const void* x1, int C1, const void* w, int wmode, void* y0, int N0, void* y1, int N1,
+               int B, int H, int W, void* scratch, size_t scratch_bytes, cudaStream_t s);
+bool tc_supported_wgrad3x3(int B, int H, int W, int M, int N);
+int tc_wgrad3x3(const void* sgrad, int M, const void* g, int N, int ldn, int n_off, float* dw, int B, int H, int W,
+                cudaStream_t s);
+// C[m][n] = sum_k (A0|A1)[m][k] * (b_kn ? Bm[k][n] : Bm[n][k]); bf16 (split N0|N1) or fp32 output; any M >= 1
+int tc_gemm_rows(const void* a0, int K0, const void* a1, int K1, const void* bm, int b_kn, void* c16_0, int N0, void* c16_1,
+                 int N1, float* c32, long long M, cudaStream_t s);
 // fp32 scratch used to split the K range of deep, small-M layers across CTAs (NULL: never split)
 void tc_set_scratch(void* ptr, size_t bytes);
 bool tc_supported_gather(int B, int Hi, int Wi, int C, int N0, int N1);

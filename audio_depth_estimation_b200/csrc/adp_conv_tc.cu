@@ -80,7 +80,7 @@ struct IgemmParams {
   // tile geometry over the "small" pixel grid (conv outputs for F1, convT inputs for F2)
   int Wt, Ht, Bt, tiles_w, tiles_h;
   int B, Hs, Ws;                      // small grid extent
-  int mode;                           // 0 = gather (F1), 1 = parity (F2), 2 = pointwise (1x1, fp32 rows out)
+  int mode;                           // 0 = gather (F1), 1 = parity (F2), 2 = pointwise (1x1), 3 = STFT, 4 = 3x3 stride 1 pad 1
   int C0, C1, Ct;                     // input channels (concat halves)
   int N, N0, N1;                      // output channels and split
   int kblocks, splits, kb_per_split;
@@ -91,6 +91,9 @@ struct IgemmParams {
   int gx, gy, gz, total_tiles;        // logical grid (x fastest) walked by the persistent kernel
   int total_pair_tiles;               // cluster mode: tiles of two adjacent m-tiles
   int has_half_map;                   // tmWh encoded
+  int wmode;                          // modes 2/4: 1 = weights through the MN-major 3-D map (N | taps | Ct), taps reversed
+  int f32_rows;                       // modes 2/4: write fp32 [pixels][N] to out_f32 instead of bf16 (any BLOCK_N)
+  long long rows_guard;               // > 0: output rows (opix) >= rows_guard are not stored (ragged GEMM M)
   int act_dual;                       // mode 2: y0 = lrelu(D, slope0), y1 = lrelu(D, slope1), both [pixels][N]
   float slope0, slope1;
   // mode 3 (STFT as a split-bf16 DFT GEMM): rows = frames, columns = (re, im) pairs of the bins
@@ -389,6 +392,20 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
             const CUtensorMap* am = (kbi == 2 || kbi == 4) ? &p.tmA1 : (kbi == 5 ? &p.tmA2 : &p.tmA0);
             tma_load_4d(a_dst, am, &full_bar[s], 0, c.x0, c.y0c, c.b0);
             tma_load_2d(b_dst, &p.tmW, &full_bar[s], ch, c.n0);
+          } else if (p.mode == 4 || (p.mode == 2 && p.wmode)) {
+            // 3x3 / stride 1 / pad 1 (or a 1x1 with MN-major weights): tap (th, tw) reads the input shifted by (th-1, tw-1)
+            const int th = p.mode == 4 ? tap / 3 : 1, tw = p.mode == 4 ? tap - 3 * th : 1;
+            const int cx = c.x0 + tw - 1, cy = c.y0c + th - 1;
+            if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, cx, cy, c.b0);
+            else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, cx, cy, c.b0);
+            if (p.wmode) {   // data gradient: w[k = cout][8 - tap][n = cin], n contiguous
+              const int wtap = p.mode == 4 ? 8 - tap : 0;
+#pragma unroll
+              for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h)
+                tma_load_3d(b_dst + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
+            } else {
+              tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + ch, c.n0);
+            }
           } else if (p.mode == 2) {
             if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, c.x0, c.y0c, c.b0);
             else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, c.x0, c.y0c, c.b0);
@@ -420,7 +437,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      const bool b_mn = p.mode == 1;
+      const bool b_mn = p.mode == 1 || p.wmode != 0;
       const uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, 0, b_mn ? 1 : 0);
       // descriptors differ from stage to stage only in the 14-bit start-address field: build them once
       const uint32_t smem_base = smem_u32(smem);
@@ -461,16 +478,16 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
     constexpr bool STAGED_OK = BLOCK_N >= 64 && EG == 1;
     unsigned char* stg = smem + STAGES * S::STAGE_BYTES + 256 + (STAGED_OK ? (warp - 2) * 4096 : 0);
-    const bool staged = p.splits <= 1 && p.mode != 3 && (p.act_dual || p.N1 == 0 || p.N0 % 64 == 0);
+    const bool staged = p.splits <= 1 && p.mode != 3 && !p.f32_rows && (p.act_dual || p.N1 == 0 || p.N0 % 64 == 0);
     uint32_t local = 0;
     for (int t = worker; t < ntiles; t += nworkers, ++local) {
       const TileCoord c = tile_at(t);
       const uint32_t buf = local & 1u, use = local >> 1;
       const int b = c.b0 + bt, py = c.y0c + ht, px = c.x0 + wt;
-      const bool valid = b < p.B && c.nkb > 0;
       size_t opix;
       if (p.mode != 1) opix = ((size_t)b * p.Hs + py) * p.Ws + px;
       else opix = ((size_t)b * 2 * p.Hs + 2 * py + c.pa) * (2 * p.Ws) + 2 * px + c.pb;
+      const bool valid = b < p.B && c.nkb > 0 && (p.rows_guard <= 0 || (long long)opix < p.rows_guard);
       mbar_wait(&tfull_bar[buf], use & 1u);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * ACC + ((uint32_t)(q * 32) << 16);
@@ -545,7 +562,11 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
         }
         if (!valid) continue;
         const int n = c.n0 + cc;
-        if (BLOCK_N == 16) {
+        if (p.f32_rows && BLOCK_N != 16 && p.splits <= 1) {
+          float* dst = p.out_f32 + opix * p.N + n;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        } else if (BLOCK_N == 16) {
           float* dst = p.out_f32 + opix * 16;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
@@ -722,16 +743,18 @@ int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes,
   // split the K range when the tile count cannot fill the machine (deep layers: small M, huge K)
   int splits = 1;
   const long long ctas = (long long)m_tiles * n_tiles * par;
-  if (scratch && ctas < sm_count()) {
+  if ((scratch || p.f32_rows) && ctas < sm_count()) {
     splits = (int)((sm_count() + ctas - 1) / ctas);
     const int max_by_k = p.kblocks / 4 > 0 ? p.kblocks / 4 : 1;
     if (splits > max_by_k) splits = max_by_k;
     if (splits > 32) splits = 32;
-    if ((size_t)out_pixels * p.N * sizeof(float) > scratch_bytes) splits = 1;
+    if (!p.f32_rows && (size_t)out_pixels * p.N * sizeof(float) > scratch_bytes) splits = 1;
+    if (p.rows_guard > 0) splits = 1;      // (ragged row counts: keep the guarded direct store)
   }
   p.kb_per_split = adp_cdiv(p.kblocks, splits);
   splits = adp_cdiv(p.kblocks, p.kb_per_split);
   p.splits = splits;
+  if (p.f32_rows && splits > 1) scratch = p.out_f32;      // fp32 result: the split-K partial sums ARE the output
   p.partial = splits > 1 ? scratch : nullptr;
   if (splits > 1) ADP_CUDA(cudaMemsetAsync(scratch, 0, (size_t)out_pixels * p.N * sizeof(float), s));
   dim3 grid(m_tiles * par, n_tiles, splits);
@@ -743,7 +766,7 @@ int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes,
     case 16: ADP_TRY(launch_igemm<16>(p, grid, s)); break;
     default: adp_set_error("tc igemm: bad BLOCK_N %d", block_n); return ADP_ERR_ARG;
   }
-  if (splits > 1) {
+  if (splits > 1 && !p.f32_rows) {
     long long n4 = out_pixels * p.N / 4;
     int blocks = (int)((n4 + 255) / 256 < (long long)sm_count() * 8 ? (n4 + 255) / 256 : (long long)sm_count() * 8);
     finish_partial_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, s>>>(scratch, out_pixels, p.N, p.N0, p.N1, p.y0, p.y1);
@@ -921,6 +944,100 @@ int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_n
     uint32_t hbox[2] = {TILE_K, (uint32_t)bn / 2};
     ADP_TRY(make_tmap_bf16(&p.tmWh, w_nk, 2, dims, str, hbox));
     p.has_half_map = 1;
+  }
+  return run_igemm(p, bn, nullptr, 0, s);
+}
+
+// ------------------------------------------------------------------ 3x3 / stride 1 / pad 1 convolution (mode 4)
+// models/binaural_attention_model.py:22-39 (DoubleConv).  Forward: w_nk = bf16 [N][9][Ct] (the nn.Conv2d weight in
+// channels_last memory), wmode 0.  Data gradient: the SAME bf16 weight tensor [Cout][9][Cin] read through an
+// MN-major (N = Cin | tap | K = Cout) map with the taps reversed (wmode 1), dy as the input, dx split N0 | N1.
+bool tc_supported_conv3x3(int B, int H, int W, int C0, int C1, int N0, int N1) {
+  int Wt, Ht, Bt;
+  if (!g_persistent || !adp_device_is_sm100() || !encode_tiled_fn()) return false;
+  if (C0 <= 0 || C0 % TILE_K || C1 % TILE_K || B < 1) return false;
+  if (!tile_geometry(B, H, W, &Wt, &Ht, &Bt)) return false;
+  return pick_block_n(N0 + N1, N0, N1) >= 64;
+}
+
+int tc_conv3x3(const void* x0, int C0, const void* x1, int C1, const void* w, int wmode, void* y0, int N0, void* y1, int N1,
+               int B, int H, int W, void* scratch, size_t scratch_bytes, cudaStream_t s) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  ADP_CHECK_ARG(g_persistent, "tc_conv3x3 needs the persistent kernel (ADP_TC_PERSISTENT=0 is set)");
+  ADP_CHECK_ARG(tile_geometry(B, H, W, &p.Wt, &p.Ht, &p.Bt), "tc_conv3x3: unsupported spatial size %dx%d", H, W);
+  const int N = N0 + N1, Ct = C0 + C1;
+  const int bn = pick_block_n(N, N0, N1);
+  ADP_CHECK_ARG(bn >= 64 && C0 > 0 && C0 % TILE_K == 0 && C1 % TILE_K == 0, "tc_conv3x3: unsupported channels %d+%d -> %d+%d",
+                C0, C1, N0, N1);
+  p.tiles_w = W / p.Wt; p.tiles_h = H / p.Ht;
+  p.B = B; p.Hs = H; p.Ws = W; p.mode = 4; p.wmode = wmode; p.C0 = C0; p.C1 = C1; p.Ct = Ct; p.N = N; p.N0 = N0; p.N1 = N1;
+  p.kblocks = 9 * (Ct / TILE_K);
+  p.y0 = (bf16*)y0; p.y1 = (bf16*)y1;
+  for (int h = 0; h < 2; ++h) {
+    const int C = h == 0 ? C0 : C1;
+    if (C == 0) continue;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {TILE_K, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
+    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, box));
+  }
+  if (wmode) {   // w = [K = Ct][9][N]
+    uint64_t dims[3] = {(uint64_t)N, 9, (uint64_t)Ct};
+    uint64_t str[2] = {(uint64_t)N * 2, (uint64_t)9 * N * 2};
+    uint32_t box[3] = {64, 1, TILE_K};
+    ADP_TRY(make_tmap_bf16(&p.tmW, w, 3, dims, str, box));
+  } else {       // w = [N][9][Ct]
+    uint64_t dims[2] = {(uint64_t)9 * Ct, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)9 * Ct * 2};
+    uint32_t box[2] = {TILE_K, (uint32_t)bn};
+    ADP_TRY(make_tmap_bf16(&p.tmW, w, 2, dims, str, box));
+  }
+  return run_igemm(p, bn, reinterpret_cast<float*>(scratch), scratch_bytes, s);
+}
+
+// ------------------------------------------------------------------ row GEMMs on the same kernel (mode 2)
+//   C[m][n] = sum_k (A0|A1)[m][k] * Bop      m < M (any M >= 1), K = K0 + K1 (multiples of 64), N % 64 == 0
+//   b_kn = 0: Bop = Bm[n][k] (K contiguous, "NT");  b_kn = 1: Bop = Bm[k][n] (N contiguous, "NN").
+//   Output bf16 (c16, split N0 | N1 over two tensors) or fp32 (c32, one tensor).
+// Used for the 1x1 convolutions and the attention products of models/binaural_attention_model.py:81-153.
+int tc_gemm_rows(const void* a0, int K0, const void* a1, int K1, const void* bm, int b_kn, void* c16_0, int N0, void* c16_1,
+                 int N1, float* c32, long long M, cudaStream_t s) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  ADP_CHECK_ARG(g_persistent && adp_device_is_sm100() && encode_tiled_fn(), "tc_gemm_rows: tcgen05 path unavailable");
+  const int N = N0 + N1, Kt = K0 + K1;
+  const int bn = pick_block_n(N, N0, N1);
+  ADP_CHECK_ARG(bn >= 64 && K0 > 0 && K0 % TILE_K == 0 && K1 % TILE_K == 0 && M >= 1 && M < (1LL << 31),
+                "tc_gemm_rows: unsupported shape M=%lld N=%d+%d K=%d+%d", M, N0, N1, K0, K1);
+  ADP_CHECK_ARG((c32 != nullptr) != (c16_0 != nullptr), "tc_gemm_rows: exactly one of the bf16 / fp32 outputs");
+  const int mt = (int)((M + TILE_M - 1) / TILE_M);
+  p.Wt = TILE_M; p.Ht = 1; p.Bt = 1; p.tiles_w = mt; p.tiles_h = 1;
+  p.B = 1; p.Hs = 1; p.Ws = mt * TILE_M;           // one "image" of height 1 whose width is the (padded) row count
+  p.mode = 2; p.wmode = b_kn; p.C0 = K0; p.C1 = K1; p.Ct = Kt; p.N = N; p.N0 = N0; p.N1 = N1;
+  p.kblocks = Kt / TILE_K;
+  p.rows_guard = M % TILE_M ? M : 0;
+  p.y0 = (bf16*)c16_0; p.y1 = (bf16*)c16_1;
+  p.out_f32 = c32; p.f32_rows = c32 ? 1 : 0;
+  for (int h = 0; h < 2; ++h) {
+    const int K = h == 0 ? K0 : K1;
+    if (K == 0) continue;
+    // rows beyond M are outside the tensor: zero-filled by TMA
+    uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
+    uint64_t str[3] = {(uint64_t)K * 2, (uint64_t)M * K * 2, (uint64_t)M * K * 2};
+    uint32_t box[4] = {TILE_K, (uint32_t)TILE_M, 1, 1};
+    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? a0 : a1, 4, dims, str, box));
+  }
+  if (b_kn) {    // Bm = [K][N]
+    uint64_t dims[3] = {(uint64_t)N, 1, (uint64_t)Kt};
+    uint64_t str[2] = {(uint64_t)N * 2, (uint64_t)N * 2};
+    uint32_t box[3] = {64, 1, TILE_K};
+    ADP_TRY(make_tmap_bf16(&p.tmW, bm, 3, dims, str, box));
+  } else {       // Bm = [N][K]
+    uint64_t dims[2] = {(uint64_t)Kt, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)Kt * 2};
+    uint32_t box[2] = {TILE_K, (uint32_t)bn};
+    ADP_TRY(make_tmap_bf16(&p.tmW, bm, 2, dims, str, box));
   }
   return run_igemm(p, bn, nullptr, 0, s);
 }

@@ -31,6 +31,11 @@ struct WgradParams {
   int M0, M1, N;
   int kblocks, kb_per_split;
   float* dw;
+  // k3 = 1: 3x3 / stride 1 / pad 1 (binaural_attention_model.py DoubleConv): 3 rows of 3 taps, G at S's resolution.
+  int k3;
+  int ntaps;          // taps per CTA (= per kernel row): 4 or 3
+  int taps_total;     // 16 or 9
+  int ldn, n_off;     // dw row pitch per tap (total input channels) and column offset of this G tensor
 };
 
 template <int NT>
@@ -61,8 +66,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * WG_M;
   const int n0 = blockIdx.y * NT;
-  const int kh = blockIdx.z & 3;                 // tap group = kernel row
-  const int split = blockIdx.z >> 2;
+  const int kh = blockIdx.z % p.ntaps;           // tap group = kernel row
+  const int split = blockIdx.z / p.ntaps;
   const int kb_begin = split * p.kb_per_split;
   const int kb_end = min(kb_begin + p.kb_per_split, p.kblocks);
   const int nkb = kb_end - kb_begin;
@@ -96,16 +101,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* a_dst = smem + s * S::STAGE_BYTES;
         unsigned char* b_dst = a_dst + S::A_BYTES;
-        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        mbar_expect_tx(&full_bar[s], S::A_BYTES + p.ntaps * S::B_TAP_BYTES);
         tma_load_4d(a_dst, tmS, &full_bar[s], mc, x0, y0, b0);
-        tma_load_4d(a_dst + WG_BOX_BYTES, tmS, &full_bar[s], mc + 64, x0, y0, b0);
+        tma_load_4d(a_dst + WG_BOX_BYTES, tmS, &full_bar[s], mc + 64, x0, y0, b0);   // (rows past M: zero-filled)
 #pragma unroll
         for (int kw = 0; kw < WG_TAPS; ++kw) {
+          if (kw >= p.ntaps) break;
           const int dj = (kw + 1) / 2 - 1, rb = (kw + 1) & 1;
 #pragma unroll
-          for (int h = 0; h < NT / 64; ++h)
-            tma_load_5d(b_dst + kw * S::B_TAP_BYTES + h * WG_BOX_BYTES, &p.tmG, &full_bar[s], rb * p.N + n0 + h * 64,
-                        x0 + dj, ra, y0 + di, b0);
+          for (int h = 0; h < NT / 64; ++h) {
+            unsigned char* dst = b_dst + kw * S::B_TAP_BYTES + h * WG_BOX_BYTES;
+            if (p.k3) tma_load_4d(dst, &p.tmG, &full_bar[s], n0 + h * 64, x0 + kw - 1, y0 + kh - 1, b0);
+            else tma_load_5d(dst, &p.tmG, &full_bar[s], rb * p.N + n0 + h * 64, x0 + dj, ra, y0 + di, b0);
+          }
         }
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
@@ -125,6 +133,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         const uint64_t stage_off = (uint64_t)((uint32_t)(s * S::STAGE_BYTES) >> 4);
 #pragma unroll
         for (int kw = 0; kw < WG_TAPS; ++kw) {
+          if (kw >= p.ntaps) break;
 #pragma unroll
           for (int k = 0; k < WG_P / 16; ++k) {
             // 16 pixels = two 8-row swizzle atoms = 2048 bytes further down the tile
@@ -144,13 +153,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
     mbar_wait(accum_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int kw = 0; kw < WG_TAPS; ++kw) {
-      float* row = p.dw + ((size_t)m * 16 + kh * 4 + kw) * p.N + n0;
+    for (int kw = 0; kw < p.ntaps; ++kw) {
+      float* row = p.dw + ((size_t)m * p.taps_total + kh * p.ntaps + kw) * p.ldn + p.n_off + n0;
 #pragma unroll 1
       for (int cc = 0; cc < NT; cc += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kw * NT + cc), v);
-        if (nkb > 0) {
+        if (nkb > 0 && m < p.M0 + p.M1) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) red_add_v4(row + cc + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
@@ -357,6 +366,7 @@ int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int 
   const int NT = N % 128 == 0 ? 128 : 64;
   p.tiles_w = Ws / p.Wt; p.tiles_h = Hs / p.Ht; p.tiles_b = adp_cdiv(B, p.Bt);
   p.M0 = M0; p.M1 = M1; p.N = N; p.dw = dw;
+  p.k3 = 0; p.ntaps = 4; p.taps_total = 16; p.ldn = N; p.n_off = 0;
   p.kblocks = p.tiles_w * p.tiles_h * p.tiles_b;
   for (int h = 0; h < 2; ++h) {
     const int C = h == 0 ? M0 : M1;
@@ -384,6 +394,52 @@ int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int 
   p.kb_per_split = adp_cdiv(p.kblocks, splits);
   splits = adp_cdiv(p.kblocks, p.kb_per_split);
   dim3 grid(m_tiles, n_tiles, 4 * splits);
+  if (NT == 128) return launch_wgrad<128>(p, grid, s);
+  return launch_wgrad<64>(p, grid, s);
+}
+
+// Weight gradient of the 3x3 / stride 1 / pad 1 convolution:
+//   dw[m][kh,kw][n_off + n] += sum_{b,i,j} S[b,i,j,m] * G[b,i+kh-1,j+kw-1,n]     (S = dL/dy [M], G = layer input [N])
+// dw is fp32 [M][9][ldn]; a concatenated input is handled by one call per half (n_off = 0 / C0).  M % 64 == 0
+// (a 64-row tail is zero-filled by TMA and not stored), N % 64 == 0.
+bool tc_supported_wgrad3x3(int B, int H, int W, int M, int N) {
+  int Wt, Ht, Bt;
+  if (!adp_device_is_sm100() || !tc::encode_tiled_fn()) return false;
+  if (M <= 0 || M % 64 || N % 64 || N <= 0 || B < 1) return false;
+  return wg_geometry(H, W, &Wt, &Ht, &Bt);
+}
+
+int tc_wgrad3x3(const void* sgrad, int M, const void* g, int N, int ldn, int n_off, float* dw, int B, int H, int W,
+                cudaStream_t s) {
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  ADP_CHECK_ARG(wg_geometry(H, W, &p.Wt, &p.Ht, &p.Bt), "tc_wgrad3x3: unsupported spatial size %dx%d", H, W);
+  ADP_CHECK_ARG(M % 64 == 0 && N % 64 == 0 && ldn >= n_off + N && ldn % 4 == 0 && n_off % 4 == 0, "tc_wgrad3x3: unsupported channels");
+  const int NT = N % 128 == 0 ? 128 : 64;
+  p.tiles_w = W / p.Wt; p.tiles_h = H / p.Ht; p.tiles_b = adp_cdiv(B, p.Bt);
+  p.M0 = M; p.M1 = 0; p.N = N; p.dw = dw;
+  p.k3 = 1; p.ntaps = 3; p.taps_total = 9; p.ldn = ldn; p.n_off = n_off;
+  p.kblocks = p.tiles_w * p.tiles_h * p.tiles_b;
+  {
+    uint64_t dims[4] = {(uint64_t)M, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)M * 2, (uint64_t)W * M * 2, (uint64_t)H * W * M * 2};
+    uint32_t box[4] = {64, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
+    ADP_TRY(make_tmap_bf16(&p.tmS0, sgrad, 4, dims, str, box));
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)N, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)N * 2, (uint64_t)W * N * 2, (uint64_t)H * W * N * 2};
+    uint32_t box[4] = {64, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
+    ADP_TRY(make_tmap_bf16(&p.tmG, g, 4, dims, str, box));
+  }
+  const int m_tiles = adp_cdiv(M, WG_M), n_tiles = N / NT;
+  const long long ctas = (long long)m_tiles * n_tiles * 3;
+  int splits = (int)(((long long)(NT == 64 ? 2 : 1) * sm_count() + ctas / 2) / ctas);
+  if (splits > p.kblocks) splits = p.kblocks;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = adp_cdiv(p.kblocks, splits);
+  splits = adp_cdiv(p.kblocks, p.kb_per_split);
+  dim3 grid(m_tiles, n_tiles, 3 * splits);
   if (NT == 128) return launch_wgrad<128>(p, grid, s);
   return launch_wgrad<64>(p, grid, s);
 }

@@ -204,6 +204,27 @@ int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, const float
                              void* workspace, size_t workspace_bytes, int stage_begin, int stage_end,
                              void* stream);
 
+/* ------------------------------------------------- binaural attention network
+ * Building blocks of BASELINE config 4 (models/binaural_attention_model.py), bf16 NHWC
+ * activations, tcgen05 kernels shared with the U-Net convolutions.
+ * nn.Conv2d(C0+C1, Cout, 3, padding=1, bias=False) (:29,:32) over the channel concat (x0|x1)
+ * (:75 torch.cat([x2, x1])): w_bf16 = the weight in channels_last memory [Cout][3][3][C0+C1]
+ * cast to bf16 (adp_cast_bf16); the data gradient reads the SAME tensor.  Needs power-of-two
+ * H, W and channel counts that are multiples of 64.  scratch: optional fp32 [B*H*W][N] used to
+ * split the reduction on small grids (NULL: never split).  wgrad OVERWRITES dw (fp32, weight layout). */
+int adp_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+int adp_conv2d_k3s1_fprop(const void* x0, int C0, const void* x1, int C1, const void* w_bf16, void* y,
+                          int B, int H, int W, int Cout, void* scratch, size_t scratch_bytes, void* stream);
+int adp_conv2d_k3s1_dgrad(const void* dy, int Cout, const void* w_bf16, void* dx0, int C0, void* dx1, int C1,
+                          int B, int H, int W, void* scratch, size_t scratch_bytes, void* stream);
+int adp_conv2d_k3s1_wgrad(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw,
+                          int B, int H, int W, void* stream);
+/* Row GEMM C[m][n] = sum_k (A0|A1)[m][k] * (b_kn ? B[k][n] : B[n][k]), bf16 operands, fp32
+ * accumulate; output bf16 split over two tensors (N0 | N1) or one fp32 tensor.  The 1x1
+ * convolutions (:97-103, :241, :263) and the attention products (:120-131) of config 4. */
+int adp_gemm_rows_bf16(const void* a0, int K0, const void* a1, int K1, const void* b, int b_kn,
+                       void* c_bf16_0, int N0, void* c_bf16_1, int N1, float* c_f32, int64_t M, void* stream);
+
 /* ----------------------------------------------------------------- optimiser
  * clip_grad_norm_(max_norm) + AdamW.step  train.py:471-476, :689-691.
  * Multi-tensor: n tensors described by device-visible pointer tables. */
