@@ -72,6 +72,22 @@ SIGNATURES = {
     "adp_conv2d_k3s1_dgrad": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "adp_conv2d_k3s1_wgrad": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp]),
     "adp_gemm_rows_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i64, _vp]),
+    "adp_conv2d_k3s1_c1_fprop": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "adp_conv2d_k3s1_c1_wgrad": (_i, [_vp, _vp, _i64, _vp, _i, _i, _i, _i, _vp]),
+    "adp_bn_act_forward": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "adp_bn_act_backward": (_i, [_vp, _i64, _i, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "adp_maxpool2_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "adp_maxpool2_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "adp_upsample2x_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "adp_upsample2x_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "adp_rows_op": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "adp_rows_reduce": (_i, [_i, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "adp_softmax_rows": (_i, [_vp, _i64, _i, _f, _vp, _vp, _vp, _vp]),
+    "adp_softmax_apply": (_i, [_vp, _i64, _i, _f, _vp, _vp, _i, _vp, _vp]),
+    "adp_softmax_backward": (_i, [_vp, _vp, _i64, _i, _f, _vp, _i, _vp, _vp]),
+    "adp_gemm_tn_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i64, _vp]),
+    "adp_depth_head_forward": (_i, [_vp, _vp, _vp, _f, _i64, _i, _vp, _vp]),
+    "adp_depth_head_backward": (_i, [_vp, _vp, _vp, _f, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
     "adp_unet_workspace_bytes": (_sz, [C.POINTER(UnetDesc)]),
     "adp_unet_forward": (_i, [C.POINTER(UnetDesc), _vp, C.POINTER(UnetLevel), _vp, _sz, _vp, _vp]),
     "adp_unet_backward": (_i, [C.POINTER(UnetDesc), _vp, _vp, _vp, C.POINTER(UnetLevel), C.POINTER(UnetLevel),

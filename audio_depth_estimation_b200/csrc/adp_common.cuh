@@ -272,6 +272,8 @@ int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_n
 // (a0: [rows][lda0] at column ca0, a1: [rows][lda1] at column ca1), Bm: [rows][ldb], all bf16 row-major (adp_wgrad_tc.cu)
 int tc_gemm_tn(const void* a0, int lda0, int ca0, const void* a1, int lda1, int ca1, const void* bm, int ldb, int NT,
                long long rows, float* D, cudaStream_t s);
+// dw[m][n] += sum_rows a[row][m] * bm[row][n]  (fp32 [M][ldd], caller zeroes; M, N multiples of 64): 1x1-conv weight gradients
+int tc_gemm_tn_full(const void* a, int M, const void* bm, int N, float* dw, int ldd, long long rows, cudaStream_t s);
 // P fp32 [B,Hi,Wi,16] -> y fp32 [B,1,2Hi,2Wi] = act(bias + col2im(P))
 int last_convT_col2im(const float* P, const float* bias, int final_sigmoid, float* y, int B, int Hi, int Wi, cudaStream_t s);
 // P[pixel][16 taps] = sum_c (x0|x1)[pixel][c] * w16[tap][c]   (w16: bf16 [16][C0+C1]) on tensor cores

@@ -182,6 +182,8 @@ struct GemmTnParams {
   int ca0, ca1;
   int kblocks, kb_per_split;
   float* D;
+  int cb;            // first column of Bm used by this launch
+  int ldd, m_valid;  // row pitch of D and number of valid rows (<= 128)
 };
 
 template <int NT>
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_gemm_tn_kernel(const __grid_
         tma_load_2d(a_dst, &p.tmA0, &full_bar[s], p.ca0, row0);
         tma_load_2d(a_dst + WG_BOX_BYTES, &p.tmA1, &full_bar[s], p.ca1, row0);
 #pragma unroll
-        for (int h = 0; h < NT / 64; ++h) tma_load_2d(b_dst + h * WG_BOX_BYTES, &p.tmB, &full_bar[s], h * 64, row0);
+        for (int h = 0; h < NT / 64; ++h) tma_load_2d(b_dst + h * WG_BOX_BYTES, &p.tmB, &full_bar[s], p.cb + h * 64, row0);
       }
     }
   } else if (warp == 1) {
@@ -263,12 +265,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_gemm_tn_kernel(const __grid_
     const int m = q * 32 + lane;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    float* row = p.D + (size_t)m * NT;
+    float* row = p.D + (size_t)m * p.ldd;
 #pragma unroll 1
     for (int cc = 0; cc < NT; cc += 32) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
-      if (nkb > 0) {
+      if (nkb > 0 && m < p.m_valid) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) red_add_v4(row + cc + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
@@ -340,6 +342,7 @@ int tc_gemm_tn(const void* a0, int lda0, int ca0, const void* a1, int lda1, int 
     ADP_TRY(tc::make_tmap_bf16(maps[i], bases[i], 2, dims, str, box));
   }
   p.ca0 = ca0; p.ca1 = ca1; p.D = D;
+  p.cb = 0; p.ldd = NT; p.m_valid = 128;
   p.kblocks = (int)((rows + WG_P - 1) / WG_P);
   int splits = 2 * sm_count();
   if (splits > p.kblocks) splits = p.kblocks;
@@ -348,6 +351,49 @@ int tc_gemm_tn(const void* a0, int lda0, int ca0, const void* a1, int lda1, int 
   ADP_CUDA(cudaMemsetAsync(D, 0, sizeof(float) * 128 * NT, s));
   if (NT == 128) return launch_gemm_tn<128>(p, splits, s);
   return launch_gemm_tn<64>(p, splits, s);
+}
+
+// dw[m][n] += sum_rows A[row][m] * Bm[row][n]  for an [M x N] fp32 matrix (row pitch ldd), M % 64 == 0, N % 64 == 0:
+// the weight gradient of a 1x1 convolution (A = dL/dy [pixels][Cout], Bm = layer input [pixels][Cin]).  One launch per
+// [128 x NT] block of dw; the caller zeroes dw.
+int tc_gemm_tn_full(const void* a, int M, const void* bm, int N, float* dw, int ldd, long long rows, cudaStream_t s) {
+  ADP_CHECK_ARG(M > 0 && M % 64 == 0 && N > 0 && N % 64 == 0 && rows > 0 && rows < (1LL << 31) && ldd >= N,
+                "tc_gemm_tn_full: unsupported shape M=%d N=%d rows=%lld", M, N, rows);
+  GemmTnParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    uint64_t dims[2] = {(uint64_t)M, (uint64_t)rows};
+    uint64_t str[1] = {(uint64_t)M * 2};
+    uint32_t box[2] = {64, (uint32_t)WG_P};
+    ADP_TRY(tc::make_tmap_bf16(&p.tmA0, a, 2, dims, str, box));
+    p.tmA1 = p.tmA0;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)rows};
+    uint64_t str[1] = {(uint64_t)N * 2};
+    uint32_t box[2] = {64, (uint32_t)WG_P};
+    ADP_TRY(tc::make_tmap_bf16(&p.tmB, bm, 2, dims, str, box));
+  }
+  const int NT = N % 128 == 0 ? 128 : 64;
+  p.kblocks = (int)((rows + WG_P - 1) / WG_P);
+  const int blocks = adp_cdiv(M, 128) * (N / NT);
+  int splits = adp_cdiv(2 * sm_count(), blocks);
+  if (splits > p.kblocks) splits = p.kblocks;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = adp_cdiv(p.kblocks, splits);
+  splits = adp_cdiv(p.kblocks, p.kb_per_split);
+  p.ldd = ldd;
+  for (int m0 = 0; m0 < M; m0 += 128) {
+    p.ca0 = m0; p.ca1 = m0 + 64;                   // (a half past M is outside the tensor: zero-filled, not stored)
+    p.m_valid = M - m0 < 128 ? M - m0 : 128;
+    for (int n0 = 0; n0 < N; n0 += NT) {
+      p.cb = n0;
+      p.D = dw + (size_t)m0 * ldd + n0;
+      if (NT == 128) ADP_TRY(launch_gemm_tn<128>(p, splits, s));
+      else ADP_TRY(launch_gemm_tn<64>(p, splits, s));
+    }
+  }
+  return ADP_OK;
 }
 
 bool tc_supported_wgrad(int B, int Hs, int Ws, int M0, int M1, int N) {

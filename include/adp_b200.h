@@ -225,6 +225,56 @@ int adp_conv2d_k3s1_wgrad(const void* dy, int Cout, const void* x0, int C0, cons
 int adp_gemm_rows_bf16(const void* a0, int K0, const void* a1, int K1, const void* b, int b_kn,
                        void* c_bf16_0, int N0, void* c_bf16_1, int N1, float* c_f32, int64_t M, void* stream);
 
+/* First convolution of an encoder (:166 DoubleConv(1, C)): one fp32 input plane per sample
+ * (x + b * x_batch_stride; the left / right channel of the [B,2,H,W] network input),
+ * w fp32 [Cout][3][3]; y bf16 NHWC.  wgrad OVERWRITES dw. */
+int adp_conv2d_k3s1_c1_fprop(const float* x, int64_t x_batch_stride, const float* w, void* y,
+                             int B, int H, int W, int Cout, void* stream);
+int adp_conv2d_k3s1_c1_wgrad(const void* dy, const float* x, int64_t x_batch_stride, float* dw,
+                             int B, int H, int W, int Cout, void* stream);
+/* nn.BatchNorm2d + ReLU (slope 0) over bf16 rows [rows = B*H*W][C] (:30-34, :242-243).
+ * conv_bias (may be NULL): bias of the preceding convolution, NOT added to x -- it cancels in the
+ * normalised output and is folded into the running mean.  saved: float [4C] kept for the backward
+ * pass; sums_ws: double [2C] scratch.  backward: dy is the gradient of the activation output;
+ * dgamma / dbeta are overwritten. */
+int adp_bn_act_forward(const void* x, int64_t rows, int C, const float* gamma, const float* beta,
+                       const float* conv_bias, float* running_mean, float* running_var, int training,
+                       float eps, float momentum, float slope, void* y, float* saved, double* sums_ws,
+                       void* stream);
+int adp_bn_act_backward(const void* x, int64_t rows, int C, const float* saved, const void* dy, float slope,
+                        int training, void* dx, float* dgamma, float* dbeta, double* sums_ws, void* stream);
+/* nn.MaxPool2d(2) (:48) on bf16 NHWC, x [B,2Ho,2Wo,C] -> y [B,Ho,Wo,C]; backward recomputes the
+ * arg-max (first maximum in scan order, as ATen) from the saved input. */
+int adp_maxpool2_forward(const void* x, void* y, int B, int Ho, int Wo, int C, void* stream);
+int adp_maxpool2_backward(const void* x, const void* dy, void* dx, int B, int Ho, int Wo, int C, void* stream);
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (:62): x [B,H,W,C] -> [B,2H,2W,C];
+ * backward is the exact adjoint in gather form (no atomics). */
+int adp_upsample2x_forward(const void* x, void* y, int B, int H, int W, int C, void* stream);
+int adp_upsample2x_backward(const void* dy, void* dx, int B, int H, int W, int C, void* stream);
+/* bf16 row helpers ([rows][C]).  adp_rows_op: 0: x += bias[c] (a == y, g = bias);
+ * 1: y = a + g[0]*b (:134 residual with the learnable gamma); 2: y = a + b; 3: y = g[0]*a.
+ * adp_rows_reduce: 0: out[c] = sum_r a[r][c] (bias gradients; sums_ws double [2C]);
+ * 1: out[r] = sum_c a[r][c]*b[r][c]; 2: out[0] = sum a*b. */
+int adp_rows_op(int op, const void* a, const void* b, const float* g, void* y, int64_t rows, int C, void* stream);
+int adp_rows_reduce(int op, const void* a, const void* b, int64_t rows, int C, float* out, double* sums_ws, void* stream);
+/* Attention softmax (:119-123) on materialised fp32 scores S [R][N] (row = query):
+ * rows: P = softmax(scale*S) in bf16, m = row max of scale*S, l = row sum of exp(scale*S - m);
+ * apply: P = exp(scale*S - m)/l with the statistics indexed by row (by_col 0) or column (1: S is
+ * the transposed score matrix); backward: dS = scale * P * (dP - delta[query]). */
+int adp_softmax_rows(const float* S, int64_t R, int N, float scale, void* P, float* m, float* l, void* stream);
+int adp_softmax_apply(const float* S, int64_t R, int N, float scale, const float* m, const float* l, int by_col,
+                      void* P, void* stream);
+int adp_softmax_backward(const void* P, const float* dP, int64_t R, int N, float scale, const float* delta,
+                         int by_col, void* dS, void* stream);
+/* dw[m][n] += sum_r a[r][m]*b[r][n] (fp32 [M][ldd], caller zeroes): 1x1-convolution weight gradients. */
+int adp_gemm_tn_bf16(const void* a, int M, const void* b, int N, float* dw, int ldd, int64_t rows, void* stream);
+/* Output head (:262-265, :318-332): y = clamp(max_depth * sigmoid(x . w + bias), 0, max_depth), fp32 [rows];
+ * backward overwrites dx (bf16), dw [C], db [1]. */
+int adp_depth_head_forward(const void* x, const float* w, const float* bias, float max_depth, int64_t rows, int C,
+                           float* y, void* stream);
+int adp_depth_head_backward(const void* x, const float* w, const float* bias, float max_depth, const float* dy,
+                            int64_t rows, int C, void* dx, float* dw, float* db, void* stream);
+
 /* ----------------------------------------------------------------- optimiser
  * clip_grad_norm_(max_norm) + AdamW.step  train.py:471-476, :689-691.
  * Multi-tensor: n tensors described by device-visible pointer tables. */

@@ -239,10 +239,48 @@ def gen_metrics():
     print("metrics.npz", {k: v.shape for k, v in out.items()})
 
 
+def gen_binaural():
+    """BASELINE config 4: the unmodified BinauralAttentionDepthNet (models/binaural_attention_model.py:181-340), train-mode
+    forward + backward of L = sum(y * r) and an eval-mode forward afterwards.  The weights are the reference's own
+    initialisation under torch.manual_seed(0) (the mirror creates its modules in the same order, so the same seed gives
+    the same tensors); the attention gammas are set to 0.5 so that the attention branch contributes."""
+    from models.binaural_attention_model import BinauralAttentionDepthNet
+    out = {}
+    for name, levels, batch in (("lv345_b2", [3, 4, 5], 2), ("lv2345_b2", [2, 3, 4, 5], 2)):
+        torch.manual_seed(0)
+        net = BinauralAttentionDepthNet(base_channels=64, bilinear=True, output_size=128, max_depth=30.0, attention_levels=levels)
+        with torch.no_grad():
+            for m in net.attention_modules.values():
+                m.gamma.fill_(0.5)
+            net.outc[0].weight.mul_(0.1)          # un-saturate the sigmoid head of the untrained network (logits ~ N(12, 7))
+            net.outc[0].bias.fill_(-1.2)
+        x = torch.from_numpy(synthetic.feature_like(batch, 128, seed=301))
+        r = torch.from_numpy(np.random.default_rng(302).normal(0, 1, (batch, 1, 128, 128)).astype(np.float32))
+        net.train()
+        y = net(x)
+        (y * r).sum().backward()
+        out[name + "_y"] = y.detach().numpy()
+        names, norms, heads = [], [], []
+        for k, p_ in net.named_parameters():
+            g = p_.grad.detach().reshape(-1)
+            names.append(k)
+            norms.append(float(g.double().norm()))
+            heads.append(np.pad(g[:64].numpy(), (0, max(0, 64 - g.numel()))))
+        out[name + "_grad_names"] = np.array(names)
+        out[name + "_grad_norms"] = np.array(norms)
+        out[name + "_grad_heads"] = np.stack(heads)
+        out[name + "_rm_fusion3"] = net.fusion_layers["fusion_3"][1].running_mean.numpy().copy()
+        net.eval()
+        with torch.no_grad():
+            out[name + "_y_eval"] = net(x).numpy()
+    np.savez_compressed(os.path.join(OUT, "binaural.npz"), **out)
+    print("binaural.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["feature", "feature_mel", "metrics", "loss", "unet"]
+    which = sys.argv[1:] or ["feature", "feature_mel", "metrics", "loss", "unet", "binaural"]
     for name in which:
         {"feature": gen_feature, "feature_mel": gen_feature_mel, "metrics": gen_metrics, "loss": gen_loss,
-         "unet": gen_unet}[name]()
+         "unet": gen_unet, "binaural": gen_binaural}[name]()

