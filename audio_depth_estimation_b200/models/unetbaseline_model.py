@@ -175,6 +175,7 @@ class UnetGenerator(nn.Module):
         self._wcache_key = None
         self._dirty = True
         self._dirty_epoch = 0         # bumped by every mark_weights_dirty() (optimiser steps, loads, broadcasts)
+        self._external_epoch = 0      # ... only by writers other than the fused optimiser
         self._mirror = None           # bf16 copy of the flat parameters kept current by FusedClipAdamW
         self._fwd_mirror = False
         self._anchor = None
@@ -194,9 +195,11 @@ class UnetGenerator(nn.Module):
         self._dtype = _lib.ADP_BF16 if precision == "bf16" else _lib.ADP_F32
         return self
 
-    def mark_weights_dirty(self):
+    def mark_weights_dirty(self, by_optimizer=False):
         self._dirty = True
         self._dirty_epoch += 1
+        if not by_optimizer:          # load_state_dict, broadcasts, user code: a recorded CUDA graph must be re-recorded
+            self._external_epoch += 1
 
     # bf16 weight mirror: the fused optimiser writes bf16(p) next to every fp32 update, so the forward pass does not
     # have to cast the 54 M weights again.  Valid only while nothing else has touched the parameters since.

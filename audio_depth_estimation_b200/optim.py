@@ -65,7 +65,7 @@ class FusedClipAdamW:
                 _lib.check(lib.adp_clip_adamw_step(ref, 1, st["sumsq"].data_ptr(), self.max_norm, self.lr,
                                                    self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                                    self.step_count, st["norm"].data_ptr(), s))
-        self.model.mark_weights_dirty()
+        self.model.mark_weights_dirty(by_optimizer=True)
         if self._mirrored:
             self.model.mirror_written()
         self.last_norm = st["norm"]

@@ -155,7 +155,7 @@ class TrainStep:
 
     def _graphed_step(self, batch, gtdepth):
         key = (tuple(batch.shape), tuple(gtdepth.shape), batch.device)
-        if self._static is not None and (self._static[0] != key or self._epoch != self.model._dirty_epoch):
+        if self._static is not None and (self._static[0] != key or self._epoch != self.model._external_epoch):
             # new shape, or the parameters were replaced behind the graph's back (load_state_dict, broadcast):
             # the recorded step reads the optimiser-maintained bf16 weight mirror, so record again
             self._graph, self._static, self._eager_calls = None, None, 0
@@ -170,7 +170,7 @@ class TrainStep:
             with torch.cuda.graph(graph):
                 sloss = self._eager_step(sb, sg)
             self._graph, self._static = graph, (key, sb, sg, sloss)
-            self._epoch = self.model._dirty_epoch
+            self._epoch = self.model._external_epoch
         _, sb, sg, sloss = self._static
         sb.copy_(batch, non_blocking=True)
         sg.copy_(gtdepth, non_blocking=True)
