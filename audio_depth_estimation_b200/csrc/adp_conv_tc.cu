@@ -91,6 +91,8 @@ struct IgemmParams {
   int gx, gy, gz, total_tiles;        // logical grid (x fastest) walked by the persistent kernel
   int total_pair_tiles;               // cluster mode: tiles of two adjacent m-tiles
   int has_half_map;                   // tmWh encoded
+  int* tile_counter;                  // dynamic tile scheduler of the persistent kernel (NULL: static round-robin):
+  int* done_counter;                  //   next tile index / CTAs finished; the last CTA resets both for the next launch
   int wmode;                          // modes 2/4: 1 = weights through the MN-major 3-D map (N | taps | Ct), taps reversed
   int f32_rows;                       // modes 2/4: write fp32 [pixels][N] to out_f32 instead of bf16 (any BLOCK_N)
   long long rows_guard;               // > 0: output rows (opix) >= rows_guard are not stored (ragged GEMM M)
@@ -321,7 +323,8 @@ struct PersistSmem {
   using S = IgemmSmem<BLOCK_N>;
   static constexpr int STAGES = (196 * 1024) / S::STAGE_BYTES > 10 ? 10 : (196 * 1024) / S::STAGE_BYTES;
   static constexpr int STAGING = 4 * 4096;        // epilogue transpose buffers: 4 warps x (32 rows x 128 B)
-  static constexpr int BYTES = STAGES * S::STAGE_BYTES + 1024 + 256 + STAGING;
+  static constexpr int BAR_BYTES = 512;           // pipeline barriers, TMEM slot, tile queue
+  static constexpr int BYTES = STAGES * S::STAGE_BYTES + 1024 + BAR_BYTES + STAGING;
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
@@ -344,6 +347,13 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
   uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready for the epilogue
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained by the 4 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // Dynamic tile scheduling: the producer thread draws tile indices from a global counter and hands them to the MMA
+  // thread and the epilogue warps through a 4-deep shared-memory queue.  A CTA that gets its SM late (e.g. while NCCL
+  // kernels of the gradient all-reduce occupy SMs) then simply takes fewer tiles instead of delaying the whole launch.
+  uint64_t* tq_full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + 256);
+  uint64_t* tq_empty = tq_full + 4;
+  volatile int* tile_q = reinterpret_cast<volatile int*>(tq_empty + 4);
+  const bool dyn = !CLUSTER && p.tile_counter != nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -353,8 +363,29 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     // cluster mode: a stage may be refilled only when BOTH CTAs have consumed it (each multicasts into the other)
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER ? 2 : 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4 * EG); }
+    for (int q = 0; q < 4; ++q) { mbar_init(&tq_full[q], 1); mbar_init(&tq_empty[q], 1 + 4 * EG); }
     fence_barrier_init();
   }
+  // consumer side of the tile queue (MMA thread: leader = true; epilogue warps: lane 0 arrives after the warp has read)
+  auto next_tile = [&](uint32_t& qi, bool single_thread) -> int {
+    int t;
+    if (dyn) {
+      const uint32_t qs = qi & 3u;
+      mbar_wait(&tq_full[qs], (qi >> 2) & 1u);
+      t = tile_q[qs];
+      if (single_thread) {
+        mbar_arrive(&tq_empty[qs]);
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tq_empty[qs]);
+      }
+    } else {
+      t = worker + (int)qi * nworkers;
+      if (t >= ntiles) t = -1;
+    }
+    ++qi;
+    return t;
+  };
   if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC);
   tc_fence_before();
   __syncthreads();
@@ -368,7 +399,20 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
       const int nchunk = p.Ct / TILE_K;
       int s = 0;                                          // ring position and its phase bit
       uint32_t ph = 0;
-      for (int t = worker; t < ntiles; t += nworkers) {
+      for (uint32_t qi = 0;; ++qi) {
+        int t;
+        if (dyn) {
+          const uint32_t qs = qi & 3u;
+          mbar_wait(&tq_empty[qs], ((qi >> 2) & 1u) ^ 1u);
+          t = atomicAdd(p.tile_counter, 1);
+          if (t >= ntiles) t = -1;
+          tile_q[qs] = t;
+          mbar_arrive(&tq_full[qs]);
+        } else {
+          t = worker + (int)qi * nworkers;
+          if (t >= ntiles) t = -1;
+        }
+        if (t < 0) break;
         const TileCoord c = tile_at(t);
         int tap = c.kb_begin / nchunk, ch = (c.kb_begin - tap * nchunk) * TILE_K;
         for (int it = 0; it < c.nkb; ++it) {
@@ -446,8 +490,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
                                     : umma_smem_desc(smem_base + A_STAGE_BYTES, 16, 1024);
       const uint32_t b_kstep = b_mn ? (2048u >> 4) : (32u >> 4);
       int s = 0;
-      uint32_t ph = 0, local = 0;
-      for (int t = worker; t < ntiles; t += nworkers, ++local) {
+      uint32_t ph = 0, local = 0, qi = 0;
+      for (int t = next_tile(qi, true); t >= 0; t = next_tile(qi, true), ++local) {
         const TileCoord c = tile_at(t);
         const uint32_t buf = local & 1u, use = local >> 1;
         mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);    // epilogue has drained this accumulator
@@ -477,10 +521,10 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     const int r = q * 32 + lane;
     const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
     constexpr bool STAGED_OK = BLOCK_N >= 64 && EG == 1;
-    unsigned char* stg = smem + STAGES * S::STAGE_BYTES + 256 + (STAGED_OK ? (warp - 2) * 4096 : 0);
+    unsigned char* stg = smem + STAGES * S::STAGE_BYTES + PS::BAR_BYTES + (STAGED_OK ? (warp - 2) * 4096 : 0);
     const bool staged = p.splits <= 1 && p.mode != 3 && !p.f32_rows && (p.act_dual || p.N1 == 0 || p.N0 % 64 == 0);
-    uint32_t local = 0;
-    for (int t = worker; t < ntiles; t += nworkers, ++local) {
+    uint32_t local = 0, qi = 0;
+    for (int t = next_tile(qi, false); t >= 0; t = next_tile(qi, false), ++local) {
       const TileCoord c = tile_at(t);
       const uint32_t buf = local & 1u, use = local >> 1;
       const int b = c.b0 + bt, py = c.y0c + ht, px = c.x0 + wt;
@@ -625,6 +669,14 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * ACC);
   }
+  if (dyn && threadIdx.x == 0) {                          // the last CTA to leave re-arms the scheduler for the next launch
+    __threadfence();
+    if (atomicAdd(p.done_counter, 1) == (int)gridDim.x - 1) {
+      *p.tile_counter = 0;
+      *p.done_counter = 0;
+      __threadfence();
+    }
+  }
 }
 
 // fp32 partial sums [pixels][N] -> bf16 outputs (split at N0)
@@ -666,6 +718,28 @@ bool tile_geometry(int B, int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
 int g_force_stages = 0;   // ADP_TC_STAGES environment override (tuning)
 int g_persistent = 1;     // ADP_TC_PERSISTENT=0 selects the one-tile-per-CTA kernel
 int g_cluster = 0;        // ADP_TC_CLUSTER=1: 2-CTA clusters, weight tile halves multicast between the pair
+
+// Scheduler cells of the persistent kernel: 8192 (tile counter, done counter) pairs per device, handed out round-robin.
+// Every launch leaves its pair zeroed, so a captured launch can be replayed with the pair baked into its parameters.
+int g_tc_sms = 0;          // ADP_TC_SMS=n: persistent kernels use at most n CTAs (leave SMs to concurrent NCCL kernels)
+int g_dynamic_tiles = 0;   // ADP_TC_DYNAMIC=1: dynamic tile scheduler (parity-validated; measured 2 % slower than static, off)
+int sched_slot(int** tile_counter, int** done_counter) {
+  constexpr int SLOTS = 8192, MAX_DEV = 64;
+  static int* base[MAX_DEV] = {nullptr};
+  static unsigned next[MAX_DEV] = {0};
+  int dev = 0;
+  ADP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEV) { *tile_counter = nullptr; *done_counter = nullptr; return ADP_OK; }
+  if (!base[dev]) {
+    // (the first launch of a process is an eager warm-up step, never inside a stream capture)
+    ADP_CUDA(cudaMalloc(&base[dev], sizeof(int) * 2 * SLOTS));
+    ADP_CUDA(cudaMemset(base[dev], 0, sizeof(int) * 2 * SLOTS));
+  }
+  const unsigned k = next[dev]++ % SLOTS;
+  *tile_counter = base[dev] + 2 * k;
+  *done_counter = base[dev] + 2 * k + 1;
+  return ADP_OK;
+}
 
 template <int BLOCK_N>
 int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
@@ -710,7 +784,9 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
       ADP_LAUNCH_CHECK();
       return ADP_OK;
     }
-    const int ctas = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    const int sms = g_tc_sms > 0 && g_tc_sms < sm_count() ? g_tc_sms : sm_count();
+    const int ctas = p.total_tiles < sms ? p.total_tiles : sms;
+    if (g_dynamic_tiles) ADP_TRY(sched_slot(&p.tile_counter, &p.done_counter));
     if (p.mode == 3) {
       if (BLOCK_N != 128) { adp_set_error("stft: BLOCK_N must be 128"); return ADP_ERR_ARG; }
       tc_igemm_persist_kernel<128, false, 2><<<ctas, PERSIST_THREADS, PersistSmem<128>::BYTES, s>>>(p);
@@ -783,6 +859,10 @@ struct StagesEnvInit {
     if (pe) g_persistent = atoi(pe);
     const char* ce = getenv("ADP_TC_CLUSTER");
     if (ce) g_cluster = atoi(ce);
+    const char* se = getenv("ADP_TC_SMS");
+    if (se) g_tc_sms = atoi(se);
+    const char* de = getenv("ADP_TC_DYNAMIC");
+    if (de) g_dynamic_tiles = atoi(de);
     const char* be = getenv("ADP_TC_MAX_BN");
     if (be) g_max_block_n = atoi(be);
   }

@@ -15,6 +15,8 @@ GPU 0) by one process per GPU over torch.distributed/NCCL:
     of backward are still running (NCCL's stream overlaps the compute stream);
   * the clip norm is computed after the all-reduce, hence identical on every rank.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -22,6 +24,11 @@ from .feature import SpectrogramTransform
 from .optim import FusedClipAdamW
 from .utils_criterion import METRIC_NAMES, batch_errors
 from .utils_loss import DepthCriterion
+
+
+# measurement only (tools/nccl_sweep.sh): ADP_SKIP_GRAD_ALLREDUCE=1 drops the gradient all-reduce (WRONG training) to
+# separate the cost of the collective from the cost of running next to it
+_SKIP_GRAD_ALLREDUCE = os.environ.get("ADP_SKIP_GRAD_ALLREDUCE", "0") == "1"
 
 
 def default_stage_groups(num_downs, stages_per_group=2):
@@ -44,7 +51,7 @@ class GradientReducer:
         _, flat_g, slices = self.model.flat_buffers()
         b, e = self.model.stage_groups[gi]
         lo, hi = slices[b][0], slices[e - 1][1]
-        if hi > lo:
+        if hi > lo and not _SKIP_GRAD_ALLREDUCE:
             self.pending.append(dist.all_reduce(flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def reduce_loss_sums(self, sums):
