@@ -85,6 +85,8 @@ SIGNATURES = {
     "adp_softmax_rows": (_i, [_vp, _i64, _i, _f, _vp, _vp, _vp, _vp]),
     "adp_softmax_apply": (_i, [_vp, _i64, _i, _f, _vp, _vp, _i, _vp, _vp]),
     "adp_softmax_backward": (_i, [_vp, _vp, _i64, _i, _f, _vp, _i, _vp, _vp]),
+    "adp_softmax_stats_init": (_i, [_vp, _vp, _i64, _vp]),
+    "adp_gemm_rows_softmax": (_i, [_vp, _i, _vp, _i, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "adp_gemm_tn_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i64, _vp]),
     "adp_depth_head_forward": (_i, [_vp, _vp, _vp, _f, _i64, _i, _vp, _vp]),
     "adp_depth_head_backward": (_i, [_vp, _vp, _vp, _f, _vp, _i64, _i, _vp, _vp, _vp, _vp]),

@@ -674,3 +674,36 @@ extern "C" int adp_depth_head_backward(const void* x, const float* w, const floa
              (long long)rows, C, (bf16*)dx, dw, db);
   return ADP_OK;
 }
+
+// ---- fused attention epilogues: the score matrix never leaves the GEMM in fp32 -----------------------------------------
+namespace {
+__global__ void stats_init_kernel(int* __restrict__ m, float* __restrict__ l, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    m[i] = float_to_ordered(-INFINITY);
+    l[i] = 0.f;
+  }
+}
+}  // namespace
+
+extern "C" int adp_softmax_stats_init(int* stat_m, float* stat_l, int64_t n, void* stream) {
+  ADP_CHECK_ARG(stat_m && stat_l && n > 0, "softmax_stats_init: bad arguments");
+  stats_init_kernel<<<adp_cdiv((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(stat_m, stat_l, (long long)n);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+// D[m][n] = sum_k a[m][k] * b[n][k] (bf16, K % 64 == 0, N % 64 == 0) followed by one of the softmax epilogues:
+//   mode 1: stat_m[m] = max(stat_m[m], max_n scale*D)   (stat_m holds order-preserving int images of floats)
+//   mode 2: stat_l[m] += sum_n exp(scale*D - stat_m[m])
+//   mode 3: out[m][n] = exp(scale*D - stat_m[i]) / stat_l[i]
+//   mode 4: out[m][n] = scale * pmat[m][n] * (D - delta[i])
+// with i = m, or i = n when by_col (D is then the transposed score matrix, statistics stay per query).
+extern "C" int adp_gemm_rows_softmax(const void* a, int K, const void* b, int N, int64_t M, int mode, int by_col, float scale,
+                                     int* stat_m, float* stat_l, const float* delta, const void* pmat, void* out_bf16,
+                                     void* stream) {
+  ADP_CHECK_ARG(a && b && mode >= 1 && mode <= 4, "gemm_rows_softmax: bad arguments");
+  GemmEpilogue e{mode, by_col, scale, stat_m, stat_l, delta, pmat};
+  return tc_gemm_rows(a, K, nullptr, 0, b, 0, mode >= 3 ? out_bf16 : nullptr, N, nullptr, 0, nullptr, (long long)M,
+                      (cudaStream_t)stream, &e);
+}

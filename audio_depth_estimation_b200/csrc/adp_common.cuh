@@ -306,8 +306,16 @@ bool tc_supported_wgrad3x3(int B, int H, int W, int M, int N);
 int tc_wgrad3x3(const void* sgrad, int M, const void* g, int N, int ldn, int n_off, float* dw, int B, int H, int W,
                 cudaStream_t s);
 // C[m][n] = sum_k (A0|A1)[m][k] * (b_kn ? Bm[k][n] : Bm[n][k]); bf16 (split N0|N1) or fp32 output; any M >= 1
+// optional attention epilogue (score tile D, row = m, column = n):  mode 1: stat_m[m] = max(., scale*D) (ordered int);
+// 2: stat_l[m] += sum exp(scale*D - m[m]);  3: C = exp(scale*D - m[i]) / l[i];  4: C = scale * pmat[m][n] * (D - delta[i]);
+// i = m, or n when by_col (the transposed score matrix).  Modes 1/2 write no matrix.
+struct GemmEpilogue {
+  int mode, by_col;
+  float scale;
+  int* stat_m; float* stat_l; const float* delta; const void* pmat;
+};
 int tc_gemm_rows(const void* a0, int K0, const void* a1, int K1, const void* bm, int b_kn, void* c16_0, int N0, void* c16_1,
-                 int N1, float* c32, long long M, cudaStream_t s);
+                 int N1, float* c32, long long M, cudaStream_t s, const GemmEpilogue* epi = nullptr);
 // fp32 scratch used to split the K range of deep, small-M layers across CTAs (NULL: never split)
 void tc_set_scratch(void* ptr, size_t bytes);
 bool tc_supported_gather(int B, int Hi, int Wi, int C, int N0, int N1);

@@ -91,8 +91,14 @@ struct IgemmParams {
   int gx, gy, gz, total_tiles;        // logical grid (x fastest) walked by the persistent kernel
   int total_pair_tiles;               // cluster mode: tiles of two adjacent m-tiles
   int has_half_map;                   // tmWh encoded
-  int* tile_counter;                  // dynamic tile scheduler of the persistent kernel (NULL: static round-robin):
-  int* done_counter;                  //   next tile index / CTAs finished; the last CTA resets both for the next launch
+  // Attention epilogues of the row GEMM (mode 2): D = A * B^T is a tile of the score matrix (row = opix, column = n)
+  //   epi 1: stat_m[row] = max(stat_m[row], max_n scale*D)                     (ordered-int atomicMax)
+  //   epi 2: stat_l[row] += sum_n exp(scale*D - m[row])
+  //   epi 3: out bf16 = exp(scale*D - m[i]) / l[i]            i = row, or i = column when stat_by_col (transposed scores)
+  //   epi 4: out bf16 = scale * pmat[row][n] * (D - delta[i])                  (softmax backward, D = dP)
+  int epi, stat_by_col;
+  float escale;
+  int* stat_m; float* stat_l; const float* delta; const bf16* pmat;
   int wmode;                          // modes 2/4: 1 = weights through the MN-major 3-D map (N | taps | Ct), taps reversed
   int f32_rows;                       // modes 2/4: write fp32 [pixels][N] to out_f32 instead of bf16 (any BLOCK_N)
   long long rows_guard;               // > 0: output rows (opix) >= rows_guard are not stored (ragged GEMM M)
@@ -329,7 +335,8 @@ struct PersistSmem {
 };
 
 // EG = number of epilogue warp groups (4 warps each): 1 for the convolutions, 2 for the math-heavy STFT epilogue
-template <int BLOCK_N, bool CLUSTER, int EG>
+// ATT = attention (softmax) epilogues of the row GEMM compiled in (kept out of the convolution instantiations)
+template <int BLOCK_N, bool CLUSTER, int EG, bool ATT = false>
 __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
   using S = IgemmSmem<BLOCK_N>;
   using PS = PersistSmem<BLOCK_N>;
@@ -347,13 +354,6 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
   uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready for the epilogue
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained by the 4 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  // Dynamic tile scheduling: the producer thread draws tile indices from a global counter and hands them to the MMA
-  // thread and the epilogue warps through a 4-deep shared-memory queue.  A CTA that gets its SM late (e.g. while NCCL
-  // kernels of the gradient all-reduce occupy SMs) then simply takes fewer tiles instead of delaying the whole launch.
-  uint64_t* tq_full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + 256);
-  uint64_t* tq_empty = tq_full + 4;
-  volatile int* tile_q = reinterpret_cast<volatile int*>(tq_empty + 4);
-  const bool dyn = !CLUSTER && p.tile_counter != nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -363,29 +363,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     // cluster mode: a stage may be refilled only when BOTH CTAs have consumed it (each multicasts into the other)
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER ? 2 : 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4 * EG); }
-    for (int q = 0; q < 4; ++q) { mbar_init(&tq_full[q], 1); mbar_init(&tq_empty[q], 1 + 4 * EG); }
     fence_barrier_init();
   }
-  // consumer side of the tile queue (MMA thread: leader = true; epilogue warps: lane 0 arrives after the warp has read)
-  auto next_tile = [&](uint32_t& qi, bool single_thread) -> int {
-    int t;
-    if (dyn) {
-      const uint32_t qs = qi & 3u;
-      mbar_wait(&tq_full[qs], (qi >> 2) & 1u);
-      t = tile_q[qs];
-      if (single_thread) {
-        mbar_arrive(&tq_empty[qs]);
-      } else {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tq_empty[qs]);
-      }
-    } else {
-      t = worker + (int)qi * nworkers;
-      if (t >= ntiles) t = -1;
-    }
-    ++qi;
-    return t;
-  };
   if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC);
   tc_fence_before();
   __syncthreads();
@@ -399,20 +378,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
       const int nchunk = p.Ct / TILE_K;
       int s = 0;                                          // ring position and its phase bit
       uint32_t ph = 0;
-      for (uint32_t qi = 0;; ++qi) {
-        int t;
-        if (dyn) {
-          const uint32_t qs = qi & 3u;
-          mbar_wait(&tq_empty[qs], ((qi >> 2) & 1u) ^ 1u);
-          t = atomicAdd(p.tile_counter, 1);
-          if (t >= ntiles) t = -1;
-          tile_q[qs] = t;
-          mbar_arrive(&tq_full[qs]);
-        } else {
-          t = worker + (int)qi * nworkers;
-          if (t >= ntiles) t = -1;
-        }
-        if (t < 0) break;
+      for (int t = worker; t < ntiles; t += nworkers) {
         const TileCoord c = tile_at(t);
         int tap = c.kb_begin / nchunk, ch = (c.kb_begin - tap * nchunk) * TILE_K;
         for (int it = 0; it < c.nkb; ++it) {
@@ -430,6 +396,21 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
                              c.n0 + crank * (BLOCK_N / 2));
             else
               tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + ch, c.n0);
+          } else if (p.mode == 1) {
+            const int th = tap >> 1, tw = tap & 1;
+            const int cx = c.x0 + c.pb - 1 + tw, cy = c.y0c + c.pa - 1 + th;
+            if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, cx, cy, c.b0);
+            else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, cx, cy, c.b0);
+            const int wtap = (3 - c.pa - 2 * th) * 4 + (3 - c.pb - 2 * tw);
+#pragma unroll
+            for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h) {
+              if (CLUSTER)   // every 64-row box is fetched as two 32-row halves, one per CTA
+                tma_load_3d_mc(b_dst + h * (TILE_K * 128) + crank * (TILE_K * 64), &p.tmWh, &full_bar[s], 3, c.n0 + h * 64,
+                               wtap, ch + crank * (TILE_K / 2));
+              else
+                tma_load_3d(b_dst + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
+            }
+          
           } else if (p.mode == 3) {
             // six K blocks x0*W0, x0*W1, x1*W0, x0*W2, x1*W1, x2*W0 of the three-way bf16 split (A slice 0,0,1,0,1,2)
             const int kbi = ch / TILE_K;
@@ -457,20 +438,6 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
               tma_load_2d_mc(b_dst + crank * (S::B_STAGE_BYTES / 2), &p.tmWh, &full_bar[s], 3, ch, c.n0 + crank * (BLOCK_N / 2));
             else
               tma_load_2d(b_dst, &p.tmW, &full_bar[s], ch, c.n0);
-          } else {
-            const int th = tap >> 1, tw = tap & 1;
-            const int cx = c.x0 + c.pb - 1 + tw, cy = c.y0c + c.pa - 1 + th;
-            if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, cx, cy, c.b0);
-            else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, cx, cy, c.b0);
-            const int wtap = (3 - c.pa - 2 * th) * 4 + (3 - c.pb - 2 * tw);
-#pragma unroll
-            for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h) {
-              if (CLUSTER)   // every 64-row box is fetched as two 32-row halves, one per CTA
-                tma_load_3d_mc(b_dst + h * (TILE_K * 128) + crank * (TILE_K * 64), &p.tmWh, &full_bar[s], 3, c.n0 + h * 64,
-                               wtap, ch + crank * (TILE_K / 2));
-              else
-                tma_load_3d(b_dst + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
-            }
           }
           ch += TILE_K;
           if (ch == p.Ct) { ch = 0; ++tap; }
@@ -490,8 +457,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
                                     : umma_smem_desc(smem_base + A_STAGE_BYTES, 16, 1024);
       const uint32_t b_kstep = b_mn ? (2048u >> 4) : (32u >> 4);
       int s = 0;
-      uint32_t ph = 0, local = 0, qi = 0;
-      for (int t = next_tile(qi, true); t >= 0; t = next_tile(qi, true), ++local) {
+      uint32_t ph = 0, local = 0;
+      for (int t = worker; t < ntiles; t += nworkers, ++local) {
         const TileCoord c = tile_at(t);
         const uint32_t buf = local & 1u, use = local >> 1;
         mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);    // epilogue has drained this accumulator
@@ -522,9 +489,10 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
     constexpr bool STAGED_OK = BLOCK_N >= 64 && EG == 1;
     unsigned char* stg = smem + STAGES * S::STAGE_BYTES + PS::BAR_BYTES + (STAGED_OK ? (warp - 2) * 4096 : 0);
-    const bool staged = p.splits <= 1 && p.mode != 3 && !p.f32_rows && (p.act_dual || p.N1 == 0 || p.N0 % 64 == 0);
-    uint32_t local = 0, qi = 0;
-    for (int t = next_tile(qi, false); t >= 0; t = next_tile(qi, false), ++local) {
+    const bool staged = p.splits <= 1 && p.mode != 3 && !p.f32_rows && !(ATT && (p.epi == 1 || p.epi == 2)) &&
+                        (p.act_dual || p.N1 == 0 || p.N0 % 64 == 0);
+    uint32_t local = 0;
+    for (int t = worker; t < ntiles; t += nworkers, ++local) {
       const TileCoord c = tile_at(t);
       const uint32_t buf = local & 1u, use = local >> 1;
       const int b = c.b0 + bt, py = c.y0c + ht, px = c.x0 + wt;
@@ -564,12 +532,52 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
           }
           __syncwarp();
         };
+        float row_m = 0.f, row_il = 0.f, row_d = 0.f;
+        if (ATT && p.epi >= 3 && !p.stat_by_col && valid) {
+          if (p.epi == 3) { row_m = ordered_to_float(p.stat_m[opix]); row_il = 1.f / p.stat_l[opix]; }
+          else row_d = p.delta[opix];
+        }
 #pragma unroll 1
         for (int cc = 0; cc < BLOCK_N; cc += 64) {
           float v[64];
           tmem_ld32(tacc + (uint32_t)cc, v);
           tmem_ld32(tacc + (uint32_t)cc + 32u, v + 32);
           const int n = c.n0 + cc;
+          if (ATT && p.epi == 3) {
+            if (p.stat_by_col) {
+#pragma unroll
+              for (int k4 = 0; k4 < 64; k4 += 4) {          // (full unroll: v[] must keep static indices to stay in registers)
+                const int4 mm = *reinterpret_cast<const int4*>(p.stat_m + n + k4);
+                const float4 ll = ld4(p.stat_l + n + k4);
+                v[k4 + 0] = __expf(v[k4 + 0] * p.escale - ordered_to_float(mm.x)) * __frcp_rn(ll.x);
+                v[k4 + 1] = __expf(v[k4 + 1] * p.escale - ordered_to_float(mm.y)) * __frcp_rn(ll.y);
+                v[k4 + 2] = __expf(v[k4 + 2] * p.escale - ordered_to_float(mm.z)) * __frcp_rn(ll.z);
+                v[k4 + 3] = __expf(v[k4 + 3] * p.escale - ordered_to_float(mm.w)) * __frcp_rn(ll.w);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 64; ++k) v[k] = __expf(v[k] * p.escale - row_m) * row_il;
+            }
+          } else if (ATT && p.epi == 4) {
+            if (valid) {
+              const bf16* prow = p.pmat + opix * (size_t)p.N + n;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float8 pv = ld8(prow + 8 * j);
+#pragma unroll
+                float dl[8];
+                if (p.stat_by_col) {
+                  const float4 d0 = ld4(p.delta + n + 8 * j), d1 = ld4(p.delta + n + 8 * j + 4);
+                  dl[0] = d0.x; dl[1] = d0.y; dl[2] = d0.z; dl[3] = d0.w; dl[4] = d1.x; dl[5] = d1.y; dl[6] = d1.z; dl[7] = d1.w;
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) dl[k] = row_d;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[8 * j + k] = p.escale * pv.v[k] * (v[8 * j + k] - dl[k]);
+              }
+            }
+          }
           if (p.act_dual) {
             emit(v, p.y0 + n, p.N, p.slope0, true);
             emit(v, p.y1 + n, p.N, p.slope1, true);
@@ -606,7 +614,14 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
         }
         if (!valid) continue;
         const int n = c.n0 + cc;
-        if (p.f32_rows && BLOCK_N != 16 && p.splits <= 1) {
+        if (ATT && p.epi == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) vmax = fmaxf(vmax, v[i] * p.escale);
+        } else if (ATT && p.epi == 2) {
+          if (cc == 0) { vmin = ordered_to_float(p.stat_m[opix]); vmax = 0.f; }    // (vmin = row max, vmax = running sum)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) vmax += __expf(v[i] * p.escale - vmin);
+        } else if (p.f32_rows && BLOCK_N != 16 && p.splits <= 1) {
           float* dst = p.out_f32 + opix * p.N + n;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
@@ -649,6 +664,10 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
         }
       }
       }
+      if (ATT && EG == 1 && valid) {
+        if (p.epi == 1) atomicMax(&p.stat_m[opix], float_to_ordered(vmax));
+        else if (p.epi == 2) atomicAdd(&p.stat_l[opix], vmax);
+      }
       if (EG == 2 && p.log_mode) {
         vmin = warp_min(vmin);
         vmax = warp_max(vmax);
@@ -668,14 +687,6 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * ACC);
-  }
-  if (dyn && threadIdx.x == 0) {                          // the last CTA to leave re-arms the scheduler for the next launch
-    __threadfence();
-    if (atomicAdd(p.done_counter, 1) == (int)gridDim.x - 1) {
-      *p.tile_counter = 0;
-      *p.done_counter = 0;
-      __threadfence();
-    }
   }
 }
 
@@ -719,28 +730,7 @@ int g_force_stages = 0;   // ADP_TC_STAGES environment override (tuning)
 int g_persistent = 1;     // ADP_TC_PERSISTENT=0 selects the one-tile-per-CTA kernel
 int g_cluster = 0;        // ADP_TC_CLUSTER=1: 2-CTA clusters, weight tile halves multicast between the pair
 
-// Scheduler cells of the persistent kernel: 8192 (tile counter, done counter) pairs per device, handed out round-robin.
-// Every launch leaves its pair zeroed, so a captured launch can be replayed with the pair baked into its parameters.
-int g_tc_sms = 0;          // ADP_TC_SMS=n: persistent kernels use at most n CTAs (leave SMs to concurrent NCCL kernels)
-int g_dynamic_tiles = 0;   // ADP_TC_DYNAMIC=1: dynamic tile scheduler (parity-validated; measured 2 % slower than static, off)
-int sched_slot(int** tile_counter, int** done_counter) {
-  constexpr int SLOTS = 8192, MAX_DEV = 64;
-  static int* base[MAX_DEV] = {nullptr};
-  static unsigned next[MAX_DEV] = {0};
-  int dev = 0;
-  ADP_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= MAX_DEV) { *tile_counter = nullptr; *done_counter = nullptr; return ADP_OK; }
-  if (!base[dev]) {
-    // (the first launch of a process is an eager warm-up step, never inside a stream capture)
-    ADP_CUDA(cudaMalloc(&base[dev], sizeof(int) * 2 * SLOTS));
-    ADP_CUDA(cudaMemset(base[dev], 0, sizeof(int) * 2 * SLOTS));
-  }
-  const unsigned k = next[dev]++ % SLOTS;
-  *tile_counter = base[dev] + 2 * k;
-  *done_counter = base[dev] + 2 * k + 1;
-  return ADP_OK;
-}
-
+int g_tc_sms = 0;          // ADP_TC_SMS=n: persistent kernels use at most n CTAs (measured: no gain next to NCCL)
 template <int BLOCK_N>
 int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
   using S = IgemmSmem<BLOCK_N>;
@@ -786,12 +776,22 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
     }
     const int sms = g_tc_sms > 0 && g_tc_sms < sm_count() ? g_tc_sms : sm_count();
     const int ctas = p.total_tiles < sms ? p.total_tiles : sms;
-    if (g_dynamic_tiles) ADP_TRY(sched_slot(&p.tile_counter, &p.done_counter));
     if (p.mode == 3) {
       if (BLOCK_N != 128) { adp_set_error("stft: BLOCK_N must be 128"); return ADP_ERR_ARG; }
       tc_igemm_persist_kernel<128, false, 2><<<ctas, PERSIST_THREADS, PersistSmem<128>::BYTES, s>>>(p);
     } else {
-      tc_igemm_persist_kernel<BLOCK_N, false, 1><<<ctas, IGEMM_THREADS, PS::BYTES, s>>>(p);
+      if (p.epi != 0) {
+        if (BLOCK_N < 64) { adp_set_error("attention epilogues need BLOCK_N >= 64"); return ADP_ERR_ARG; }
+        static bool aattr_set = false;
+        if (!aattr_set) {
+          ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<(BLOCK_N < 64 ? 64 : BLOCK_N), false, 1, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, PersistSmem<(BLOCK_N < 64 ? 64 : BLOCK_N)>::BYTES));
+          aattr_set = true;
+        }
+        tc_igemm_persist_kernel<(BLOCK_N < 64 ? 64 : BLOCK_N), false, 1, true><<<ctas, IGEMM_THREADS, PS::BYTES, s>>>(p);
+      } else {
+        tc_igemm_persist_kernel<BLOCK_N, false, 1><<<ctas, IGEMM_THREADS, PS::BYTES, s>>>(p);
+      }
     }
     adp_count_tc_launch();
     ADP_LAUNCH_CHECK();
@@ -861,8 +861,6 @@ struct StagesEnvInit {
     if (ce) g_cluster = atoi(ce);
     const char* se = getenv("ADP_TC_SMS");
     if (se) g_tc_sms = atoi(se);
-    const char* de = getenv("ADP_TC_DYNAMIC");
-    if (de) g_dynamic_tiles = atoi(de);
     const char* be = getenv("ADP_TC_MAX_BN");
     if (be) g_max_block_n = atoi(be);
   }
@@ -1082,15 +1080,25 @@ int tc_conv3x3(const void* x0, int C0, const void* x1, int C1, const void* w, in
 //   Output bf16 (c16, split N0 | N1 over two tensors) or fp32 (c32, one tensor).
 // Used for the 1x1 convolutions and the attention products of models/binaural_attention_model.py:81-153.
 int tc_gemm_rows(const void* a0, int K0, const void* a1, int K1, const void* bm, int b_kn, void* c16_0, int N0, void* c16_1,
-                 int N1, float* c32, long long M, cudaStream_t s) {
+                 int N1, float* c32, long long M, cudaStream_t s, const GemmEpilogue* epi) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
+  if (epi && epi->mode) {
+    p.epi = epi->mode; p.stat_by_col = epi->by_col; p.escale = epi->scale;
+    p.stat_m = epi->stat_m; p.stat_l = epi->stat_l; p.delta = epi->delta; p.pmat = reinterpret_cast<const bf16*>(epi->pmat);
+  }
   ADP_CHECK_ARG(g_persistent && adp_device_is_sm100() && encode_tiled_fn(), "tc_gemm_rows: tcgen05 path unavailable");
   const int N = N0 + N1, Kt = K0 + K1;
   const int bn = pick_block_n(N, N0, N1);
   ADP_CHECK_ARG(bn >= 64 && K0 > 0 && K0 % TILE_K == 0 && K1 % TILE_K == 0 && M >= 1 && M < (1LL << 31),
                 "tc_gemm_rows: unsupported shape M=%lld N=%d+%d K=%d+%d", M, N0, N1, K0, K1);
-  ADP_CHECK_ARG((c32 != nullptr) != (c16_0 != nullptr), "tc_gemm_rows: exactly one of the bf16 / fp32 outputs");
+  if (p.epi == 1 || p.epi == 2) {
+    ADP_CHECK_ARG(!c32 && !c16_0 && p.stat_m && (p.epi == 1 || p.stat_l) && bn >= 64, "tc_gemm_rows: reduction epilogue arguments");
+  } else {
+    ADP_CHECK_ARG((c32 != nullptr) != (c16_0 != nullptr), "tc_gemm_rows: exactly one of the bf16 / fp32 outputs");
+    ADP_CHECK_ARG(p.epi == 0 || (c16_0 && N1 == 0 && (p.epi == 3 ? (p.stat_m && p.stat_l) : (p.delta && p.pmat))),
+                  "tc_gemm_rows: softmax epilogue arguments");
+  }
   const int mt = (int)((M + TILE_M - 1) / TILE_M);
   p.Wt = TILE_M; p.Ht = 1; p.Bt = 1; p.tiles_w = mt; p.tiles_h = 1;
   p.B = 1; p.Hs = 1; p.Ws = mt * TILE_M;           // one "image" of height 1 whose width is the (padded) row count

@@ -52,9 +52,10 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int NT>
+template <int NT, bool K3>
 __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
   using S = WgradSmem<NT>;
+  constexpr int NTAPS = K3 ? 3 : 4;               // taps per CTA = one kernel row (compile time: the tap loops unroll)
   constexpr int STAGES = S::STAGES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -66,8 +67,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * WG_M;
   const int n0 = blockIdx.y * NT;
-  const int kh = blockIdx.z % p.ntaps;           // tap group = kernel row
-  const int split = blockIdx.z / p.ntaps;
+  const int kh = blockIdx.z % NTAPS;             // tap group = kernel row
+  const int split = blockIdx.z / NTAPS;
   const int kb_begin = split * p.kb_per_split;
   const int kb_end = min(kb_begin + p.kb_per_split, p.kblocks);
   const int nkb = kb_end - kb_begin;
@@ -101,17 +102,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* a_dst = smem + s * S::STAGE_BYTES;
         unsigned char* b_dst = a_dst + S::A_BYTES;
-        mbar_expect_tx(&full_bar[s], S::A_BYTES + p.ntaps * S::B_TAP_BYTES);
+        mbar_expect_tx(&full_bar[s], S::A_BYTES + NTAPS * S::B_TAP_BYTES);
         tma_load_4d(a_dst, tmS, &full_bar[s], mc, x0, y0, b0);
         tma_load_4d(a_dst + WG_BOX_BYTES, tmS, &full_bar[s], mc + 64, x0, y0, b0);   // (rows past M: zero-filled)
 #pragma unroll
-        for (int kw = 0; kw < WG_TAPS; ++kw) {
-          if (kw >= p.ntaps) break;
+        for (int kw = 0; kw < NTAPS; ++kw) {
           const int dj = (kw + 1) / 2 - 1, rb = (kw + 1) & 1;
 #pragma unroll
           for (int h = 0; h < NT / 64; ++h) {
             unsigned char* dst = b_dst + kw * S::B_TAP_BYTES + h * WG_BOX_BYTES;
-            if (p.k3) tma_load_4d(dst, &p.tmG, &full_bar[s], n0 + h * 64, x0 + kw - 1, y0 + kh - 1, b0);
+            if (K3) tma_load_4d(dst, &p.tmG, &full_bar[s], n0 + h * 64, x0 + kw - 1, y0 + kh - 1, b0);
             else tma_load_5d(dst, &p.tmG, &full_bar[s], rb * p.N + n0 + h * 64, x0 + dj, ra, y0 + di, b0);
           }
         }
@@ -132,8 +132,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         tc_fence_after();
         const uint64_t stage_off = (uint64_t)((uint32_t)(s * S::STAGE_BYTES) >> 4);
 #pragma unroll
-        for (int kw = 0; kw < WG_TAPS; ++kw) {
-          if (kw >= p.ntaps) break;
+        for (int kw = 0; kw < NTAPS; ++kw) {
 #pragma unroll
           for (int k = 0; k < WG_P / 16; ++k) {
             // 16 pixels = two 8-row swizzle atoms = 2048 bytes further down the tile
@@ -153,8 +152,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
     mbar_wait(accum_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int kw = 0; kw < p.ntaps; ++kw) {
-      float* row = p.dw + ((size_t)m * p.taps_total + kh * p.ntaps + kw) * p.ldn + p.n_off + n0;
+    for (int kw = 0; kw < NTAPS; ++kw) {
+      float* row = p.dw + ((size_t)m * (NTAPS * NTAPS) + kh * NTAPS + kw) * p.ldn + p.n_off + n0;
 #pragma unroll 1
       for (int cc = 0; cc < NT; cc += 32) {
         float v[32];
@@ -184,6 +183,7 @@ struct GemmTnParams {
   float* D;
   int cb;            // first column of Bm used by this launch
   int ldd, m_valid;  // row pitch of D and number of valid rows (<= 128)
+  int m_total;       // > 0: blockIdx.y / blockIdx.z select the [128 x NT] block of an [m_total x N] result
 };
 
 template <int NT>
@@ -209,6 +209,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_gemm_tn_kernel(const __grid_
   const int kb_begin = blockIdx.x * p.kb_per_split;
   const int kb_end = min(kb_begin + p.kb_per_split, p.kblocks);
   const int nkb = kb_end - kb_begin;
+  const int mb = p.m_total > 0 ? (int)blockIdx.y : 0, nb = p.m_total > 0 ? (int)blockIdx.z : 0;
+  const int ca0 = p.ca0 + mb * 128, ca1 = p.ca1 + mb * 128, cb = p.cb + nb * NT;
+  const int m_valid = p.m_total > 0 ? min(128, p.m_total - mb * 128) : p.m_valid;
+  float* const Dblk = p.D + (size_t)mb * 128 * p.ldd + (size_t)nb * NT;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&p.tmA0);
@@ -234,10 +238,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_gemm_tn_kernel(const __grid_
         unsigned char* a_dst = smem + s * S::STAGE_BYTES;
         unsigned char* b_dst = a_dst + S::A_BYTES;
         mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        tma_load_2d(a_dst, &p.tmA0, &full_bar[s], p.ca0, row0);
-        tma_load_2d(a_dst + WG_BOX_BYTES, &p.tmA1, &full_bar[s], p.ca1, row0);
+        tma_load_2d(a_dst, &p.tmA0, &full_bar[s], ca0, row0);
+        tma_load_2d(a_dst + WG_BOX_BYTES, &p.tmA1, &full_bar[s], ca1, row0);
 #pragma unroll
-        for (int h = 0; h < NT / 64; ++h) tma_load_2d(b_dst + h * WG_BOX_BYTES, &p.tmB, &full_bar[s], p.cb + h * 64, row0);
+        for (int h = 0; h < NT / 64; ++h) tma_load_2d(b_dst + h * WG_BOX_BYTES, &p.tmB, &full_bar[s], cb + h * 64, row0);
       }
     }
   } else if (warp == 1) {
@@ -265,12 +269,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_gemm_tn_kernel(const __grid_
     const int m = q * 32 + lane;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    float* row = p.D + (size_t)m * p.ldd;
+    float* row = Dblk + (size_t)m * p.ldd;
 #pragma unroll 1
     for (int cc = 0; cc < NT; cc += 32) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
-      if (nkb > 0 && m < p.m_valid) {
+      if (nkb > 0 && m < m_valid) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) red_add_v4(row + cc + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
@@ -285,14 +289,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_gemm_tn_kernel(const __grid_
 }
 
 template <int NT>
-int launch_gemm_tn(const GemmTnParams& p, int splits, cudaStream_t s) {
+int launch_gemm_tn(const GemmTnParams& p, int splits, cudaStream_t s, int mblocks = 1, int nblocks = 1) {
   using S = GemmTnSmem<NT>;
   static bool attr_set = false;
   if (!attr_set) {
     ADP_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
     attr_set = true;
   }
-  tc_gemm_tn_kernel<NT><<<splits, WG_THREADS, S::BYTES, s>>>(p);
+  tc_gemm_tn_kernel<NT><<<dim3(splits, mblocks, nblocks), WG_THREADS, S::BYTES, s>>>(p);
   adp_count_tc_launch();
   ADP_LAUNCH_CHECK();
   return ADP_OK;
@@ -309,15 +313,15 @@ bool wg_geometry(int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
   return true;
 }
 
-template <int NT>
+template <int NT, bool K3>
 int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t s) {
   using S = WgradSmem<NT>;
   static bool attr_set = false;
   if (!attr_set) {
-    ADP_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    ADP_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<NT, K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
     attr_set = true;
   }
-  tc_wgrad_kernel<NT><<<grid, WG_THREADS, S::BYTES, s>>>(p);
+  tc_wgrad_kernel<NT, K3><<<grid, WG_THREADS, S::BYTES, s>>>(p);
   adp_count_tc_launch();
   ADP_LAUNCH_CHECK();
   return ADP_OK;
@@ -354,8 +358,9 @@ int tc_gemm_tn(const void* a0, int lda0, int ca0, const void* a1, int lda1, int 
 }
 
 // dw[m][n] += sum_rows A[row][m] * Bm[row][n]  for an [M x N] fp32 matrix (row pitch ldd), M % 64 == 0, N % 64 == 0:
-// the weight gradient of a 1x1 convolution (A = dL/dy [pixels][Cout], Bm = layer input [pixels][Cin]).  One launch per
-// [128 x NT] block of dw; the caller zeroes dw.
+// the weight gradient of a 1x1 convolution (A = dL/dy [pixels][Cout], Bm = layer input [pixels][Cin]) and the
+// transposed products of the attention backward (dV = P^T dO, dK = dS^T Q).  One launch, one CTA per ([128 x NT] block,
+// row split); the caller zeroes dw.
 int tc_gemm_tn_full(const void* a, int M, const void* bm, int N, float* dw, int ldd, long long rows, cudaStream_t s) {
   ADP_CHECK_ARG(M > 0 && M % 64 == 0 && N > 0 && N % 64 == 0 && rows > 0 && rows < (1LL << 31) && ldd >= N,
                 "tc_gemm_tn_full: unsupported shape M=%d N=%d rows=%lld", M, N, rows);
@@ -376,24 +381,17 @@ int tc_gemm_tn_full(const void* a, int M, const void* bm, int N, float* dw, int 
   }
   const int NT = N % 128 == 0 ? 128 : 64;
   p.kblocks = (int)((rows + WG_P - 1) / WG_P);
-  const int blocks = adp_cdiv(M, 128) * (N / NT);
-  int splits = adp_cdiv(2 * sm_count(), blocks);
+  const int mblocks = adp_cdiv(M, 128), nblocks = N / NT;
+  ADP_CHECK_ARG(mblocks <= 65535 && nblocks <= 65535, "tc_gemm_tn_full: result too large");
+  int splits = adp_cdiv(2 * sm_count(), mblocks * nblocks);
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits < 1) splits = 1;
   p.kb_per_split = adp_cdiv(p.kblocks, splits);
   splits = adp_cdiv(p.kblocks, p.kb_per_split);
-  p.ldd = ldd;
-  for (int m0 = 0; m0 < M; m0 += 128) {
-    p.ca0 = m0; p.ca1 = m0 + 64;                   // (a half past M is outside the tensor: zero-filled, not stored)
-    p.m_valid = M - m0 < 128 ? M - m0 : 128;
-    for (int n0 = 0; n0 < N; n0 += NT) {
-      p.cb = n0;
-      p.D = dw + (size_t)m0 * ldd + n0;
-      if (NT == 128) ADP_TRY(launch_gemm_tn<128>(p, splits, s));
-      else ADP_TRY(launch_gemm_tn<64>(p, splits, s));
-    }
-  }
-  return ADP_OK;
+  p.ldd = ldd; p.D = dw; p.m_total = M;
+  p.ca0 = 0; p.ca1 = 64; p.cb = 0;                 // (a 64-column half past M is outside the tensor: zero-filled, not stored)
+  if (NT == 128) return launch_gemm_tn<128>(p, splits, s, mblocks, nblocks);
+  return launch_gemm_tn<64>(p, splits, s, mblocks, nblocks);
 }
 
 bool tc_supported_wgrad(int B, int Hs, int Ws, int M0, int M1, int N) {
@@ -440,8 +438,8 @@ int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int 
   p.kb_per_split = adp_cdiv(p.kblocks, splits);
   splits = adp_cdiv(p.kblocks, p.kb_per_split);
   dim3 grid(m_tiles, n_tiles, 4 * splits);
-  if (NT == 128) return launch_wgrad<128>(p, grid, s);
-  return launch_wgrad<64>(p, grid, s);
+  if (NT == 128) return launch_wgrad<128, false>(p, grid, s);
+  return launch_wgrad<64, false>(p, grid, s);
 }
 
 // Weight gradient of the 3x3 / stride 1 / pad 1 convolution:
@@ -486,8 +484,8 @@ int tc_wgrad3x3(const void* sgrad, int M, const void* g, int N, int ldn, int n_o
   p.kb_per_split = adp_cdiv(p.kblocks, splits);
   splits = adp_cdiv(p.kblocks, p.kb_per_split);
   dim3 grid(m_tiles, n_tiles, 3 * splits);
-  if (NT == 128) return launch_wgrad<128>(p, grid, s);
-  return launch_wgrad<64>(p, grid, s);
+  if (NT == 128) return launch_wgrad<128, true>(p, grid, s);
+  return launch_wgrad<64, true>(p, grid, s);
 }
 
 }  // namespace adp

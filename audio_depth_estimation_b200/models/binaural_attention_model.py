@@ -10,9 +10,10 @@ through the C ABI:
   BatchNorm + ReLU (:30-34)         adp_bn_act_{forward,backward}
   MaxPool2d / Upsample (:48,:62)    adp_maxpool2_*, adp_upsample2x_*; torch.cat (:75,:306) is never materialised
   1x1 convolutions (:97-103,:241)   adp_gemm_rows_bf16 / adp_gemm_tn_bf16 (+ adp_rows_op / adp_rows_reduce for biases)
-  cross attention (:106-153)        adp_gemm_rows_bf16 + adp_softmax_{rows,apply,backward}: like the reference the
-                                    [HW x HW] score matrix is materialised (one sample and direction at a time, fp32),
-                                    the backward pass recomputes it in both orientations instead of transposing
+  cross attention (:106-153)        adp_gemm_rows_softmax (score GEMM with the softmax / softmax-backward in its epilogue)
+                                    + adp_gemm_rows_bf16: the [HW x HW] matrices exist only in bf16, one sample and
+                                    direction at a time; the backward pass recomputes them in both orientations
+                                    instead of transposing
   head (:262-265, :318-332)         adp_depth_head_{forward,backward}
 
 Restrictions of this first version: bilinear=True, bf16 only, H = W = a power of two with H/16 >= 8 (every attention
@@ -250,7 +251,12 @@ class _Conv1x1(torch.autograd.Function):
 
 
 class _Attend(torch.autograd.Function):
-    """softmax(Q K^T / sqrt(C)) V per sample (:118-127).  q, k: [B,T,64p] (zero-padded projections), v: [B,T,C]."""
+    """softmax(Q K^T / sqrt(C)) V per sample (:118-127).  q, k: [B,T,64p] (zero-padded projections), v: [B,T,C].
+
+    The [T x T] matrices exist only in bf16: the score GEMM is run three times in the forward pass (row max, row sum,
+    probabilities -- its K dimension is 64, so it is cheap next to P V) with the softmax in its epilogue; the backward
+    pass recomputes P the same way, folds dS = scale * P * (dP - delta) into the epilogue of the dP GEMM, and forms the
+    transposed products dV = P^T dO, dK = dS^T Q with the MN-major x MN-major GEMM of the weight gradients."""
 
     @staticmethod
     def forward(ctx, q, k, v, scale):
@@ -258,13 +264,14 @@ class _Attend(torch.autograd.Function):
         C = v.shape[-1]
         lib = _lib.load()
         o = torch.empty_like(v)
-        m = torch.empty((B, T), device=q.device, dtype=torch.float32)
+        m = torch.empty((B, T), device=q.device, dtype=torch.int32)       # order-preserving int image of the row max
         l = torch.empty((B, T), device=q.device, dtype=torch.float32)
-        S = torch.empty((T, T), device=q.device, dtype=torch.float32)
         P = torch.empty((T, T), device=q.device, dtype=_BF16)
+        _lib.check(lib.adp_softmax_stats_init(m.data_ptr(), l.data_ptr(), B * T, _sp()))
         for b in range(B):
-            _lib.check(lib.adp_gemm_rows_bf16(q[b].data_ptr(), Dq, None, 0, k[b].data_ptr(), 0, None, T, None, 0, S.data_ptr(), T, _sp()))
-            _lib.check(lib.adp_softmax_rows(S.data_ptr(), T, T, scale, P.data_ptr(), m[b].data_ptr(), l[b].data_ptr(), _sp()))
+            for mode in (1, 2, 3):
+                _lib.check(lib.adp_gemm_rows_softmax(q[b].data_ptr(), Dq, k[b].data_ptr(), T, T, mode, 0, scale, m[b].data_ptr(),
+                                                     l[b].data_ptr(), None, None, P.data_ptr() if mode == 3 else None, _sp()))
             _lib.check(lib.adp_gemm_rows_bf16(P.data_ptr(), T, None, 0, v[b].data_ptr(), 1, o[b].data_ptr(), C, None, 0, None, T, _sp()))
         ctx.save_for_backward(q, k, v, o, m, l)
         ctx.scale = scale
@@ -280,30 +287,29 @@ class _Attend(torch.autograd.Function):
         lib = _lib.load()
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         dev = q.device
-        S = torch.empty((T, T), device=dev, dtype=torch.float32)
-        G = torch.empty((T, T), device=dev, dtype=torch.float32)
         P = torch.empty((T, T), device=dev, dtype=_BF16)
         D = torch.empty((T, T), device=dev, dtype=_BF16)
         delta = torch.empty(T, device=dev, dtype=torch.float32)
 
-        def gemm(a, ka, bmat, b_kn, c16, n, c32):
-            _lib.check(lib.adp_gemm_rows_bf16(a.data_ptr(), ka, None, 0, bmat.data_ptr(), b_kn, _ptr(c16), n, None, 0, _ptr(c32), T, _sp()))
+        dvf = torch.empty((T, C), device=dev, dtype=torch.float32)
+        dkf = torch.empty((T, Dq), device=dev, dtype=torch.float32)
+
+        def tn(a, bmat, n, acc, out):       # out[j][n] = sum_i a[i][j] * bmat[i][n]: both operands row-major, no transpose
+            acc.zero_()
+            _lib.check(lib.adp_gemm_tn_bf16(a.data_ptr(), T, bmat.data_ptr(), n, acc.data_ptr(), n, T, _sp()))
+            _lib.check(lib.adp_cast_bf16(acc.data_ptr(), out.data_ptr(), T * n, _sp()))
 
         for b in range(B):
             _lib.check(lib.adp_rows_reduce(1, do[b].data_ptr(), o[b].data_ptr(), T, C, delta.data_ptr(), None, _sp()))
-            # query-major: P, dP -> dS -> dQ
-            gemm(q[b], Dq, k[b], 0, None, T, S)
-            _lib.check(lib.adp_softmax_apply(S.data_ptr(), T, T, scale, m[b].data_ptr(), l[b].data_ptr(), 0, P.data_ptr(), _sp()))
-            gemm(do[b], C, v[b], 0, None, T, G)
-            _lib.check(lib.adp_softmax_backward(P.data_ptr(), G.data_ptr(), T, T, scale, delta.data_ptr(), 0, D.data_ptr(), _sp()))
-            gemm(D, T, k[b], 1, dq[b], Dq, None)
-            # key-major (the transposed matrices are recomputed with the operand roles swapped): P^T -> dV, dS^T -> dK
-            gemm(k[b], Dq, q[b], 0, None, T, S)
-            _lib.check(lib.adp_softmax_apply(S.data_ptr(), T, T, scale, m[b].data_ptr(), l[b].data_ptr(), 1, P.data_ptr(), _sp()))
-            gemm(P, T, do[b], 1, dv[b], C, None)
-            gemm(v[b], C, do[b], 0, None, T, G)
-            _lib.check(lib.adp_softmax_backward(P.data_ptr(), G.data_ptr(), T, T, scale, delta.data_ptr(), 1, D.data_ptr(), _sp()))
-            gemm(D, T, q[b], 1, dk[b], Dq, None)
+            # P [i][j] (score GEMM + softmax epilogue) -> dV = P^T dO
+            _lib.check(lib.adp_gemm_rows_softmax(q[b].data_ptr(), Dq, k[b].data_ptr(), T, T, 3, 0, scale, m[b].data_ptr(),
+                                                 l[b].data_ptr(), None, None, P.data_ptr(), _sp()))
+            tn(P, do[b], C, dvf, dv[b])
+            # dS = scale * P * (dO V^T - delta) in the epilogue of the dP GEMM -> dQ = dS K, dK = dS^T Q
+            _lib.check(lib.adp_gemm_rows_softmax(do[b].data_ptr(), C, v[b].data_ptr(), T, T, 4, 0, scale, None, None,
+                                                 delta.data_ptr(), P.data_ptr(), D.data_ptr(), _sp()))
+            _lib.check(lib.adp_gemm_rows_bf16(D.data_ptr(), T, None, 0, k[b].data_ptr(), 1, dq[b].data_ptr(), Dq, None, 0, None, T, _sp()))
+            tn(D, q[b], Dq, dkf, dk[b])
         return dq, dk, dv, None
 
 

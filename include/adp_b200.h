@@ -266,6 +266,15 @@ int adp_softmax_apply(const float* S, int64_t R, int N, float scale, const float
                       void* P, void* stream);
 int adp_softmax_backward(const void* P, const float* dP, int64_t R, int N, float scale, const float* delta,
                          int by_col, void* dS, void* stream);
+/* The same softmax folded into the epilogue of the score GEMM D[m][n] = sum_k a[m][k]*b[n][k], so the fp32 score matrix
+ * is never written: mode 1 running row max of scale*D into stat_m (order-preserving int images, see
+ * adp_softmax_stats_init), mode 2 row sums of exp(scale*D - max) into stat_l, mode 3 out = exp(scale*D - m[i]) / l[i]
+ * (bf16), mode 4 out = scale * pmat[m][n] * (D - delta[i]) (softmax backward with D = dP).  i = m, or n when by_col
+ * (D is the transposed score matrix K Q^T; the statistics stay per query). */
+int adp_softmax_stats_init(int* stat_m, float* stat_l, int64_t n, void* stream);
+int adp_gemm_rows_softmax(const void* a, int K, const void* b, int N, int64_t M, int mode, int by_col, float scale,
+                          int* stat_m, float* stat_l, const float* delta, const void* pmat, void* out_bf16,
+                          void* stream);
 /* dw[m][n] += sum_r a[r][m]*b[r][n] (fp32 [M][ldd], caller zeroes): 1x1-convolution weight gradients. */
 int adp_gemm_tn_bf16(const void* a, int M, const void* b, int N, float* dw, int ldd, int64_t rows, void* stream);
 /* Output head (:262-265, :318-332): y = clamp(max_depth * sigmoid(x . w + bias), 0, max_depth), fp32 [rows];
