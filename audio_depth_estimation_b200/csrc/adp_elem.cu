@@ -5,6 +5,7 @@
 // nn.LeakyReLU(0.2, inplace) (:189), nn.ReLU(inplace) (:191), torch.cat (:235, eliminated:
 // the decoder reads the two halves of the concat as two tensors) and nn.Sigmoid/ReLU head
 // (:201-206).  All activation tensors are NHWC, viewed as [rows = B*H*W, C].
+#include <stdlib.h>
 #include "adp_common.cuh"
 
 namespace {
@@ -616,7 +617,8 @@ ColLaunch col_launch8(long long rows, int C) {
   const int ty = 256 / tx;
   const int gx = adp_cdiv(C, tx * 8);
   long long gy = (rows + (long long)ty * 8 - 1) / ((long long)ty * 8);   // >= 8 rows per thread
-  long long cap = (long long)adp::sm_count() * 4 / gx;
+  static const int per_sm = getenv("ADP_COL_BLOCKS_PER_SM") ? atoi(getenv("ADP_COL_BLOCKS_PER_SM")) : 2;   // fewer blocks = fewer fp64 atomics per channel cell (4 -> 2: -33 us / step)
+  long long cap = (long long)adp::sm_count() * per_sm / gx;
   if (gy > cap) gy = cap;
   if (gy < 1) gy = 1;
   return ColLaunch{dim3(gx, (unsigned)gy), dim3(tx, ty)};
