@@ -866,8 +866,10 @@ struct StagesEnvInit {
   }
 } g_stages_env_init;
 
-float* g_scratch = nullptr;
-size_t g_scratch_bytes = 0;
+// set and consumed within one C-ABI call on the calling host thread (thread_local: calls from several host threads,
+// e.g. one per device, do not see each other's workspace)
+thread_local float* g_scratch = nullptr;
+thread_local size_t g_scratch_bytes = 0;
 
 }  // namespace
 
