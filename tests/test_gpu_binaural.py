@@ -331,3 +331,46 @@ def test_residual_gamma_op_exact():
     y.backward(dy)
     assert abs(float(gm.grad) - float((dy.float() * b.detach().float()).sum())) <= 1e-3 * float((dy.float() * b.detach().float()).abs().sum()) ** 0.5
     assert torch.equal(a.grad, dy) and rel(b.grad.float(), 0.5 * dy.float()) <= 3e-3
+
+
+@pytest.mark.parametrize("levels,training", [((), True), ((5,), True), ((4, 5), False)])
+def test_binaural_net_vs_oracle_other_configs(levels, training):
+    """Other attention_levels, non-trivial BN affine / conv biases loaded through load_state_dict, eval mode with given
+    running statistics -- against oracle/binaural_oracle.py (pinned to the reference in tests/test_oracle_golden.py)."""
+    from audio_depth_estimation_b200 import synthetic
+    from audio_depth_estimation_b200.models.binaural_attention_model import BinauralAttentionDepthNet
+    from oracle import binaural_oracle as bo
+    sd = bo.init_state_dict(64, levels, seed=7)
+    if not training:
+        gen = torch.Generator().manual_seed(8)
+        for k in sd:
+            if k.endswith("running_mean"):
+                sd[k] = 0.2 * torch.randn(sd[k].shape, generator=gen)
+            if k.endswith("running_var"):
+                sd[k] = 0.5 + torch.rand(sd[k].shape, generator=gen)
+    x = torch.from_numpy(synthetic.feature_like(2, 128, seed=311))
+    ref_sd = {k: v.clone() for k, v in sd.items()}
+    for k, v in ref_sd.items():
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(True)
+    torch.set_num_threads(8)
+    want = bo.forward(ref_sd, x, levels, 30.0, training=training, update_running=True)
+    net = BinauralAttentionDepthNet(64, True, 128, 30.0, list(levels))
+    net.load_state_dict(sd)
+    net = net.cuda().train(training)
+    y = net(x.cuda())
+    # these weights (BN gamma ~ N(1, 0.1), biases) are better conditioned than the kaiming/unit initialisation
+    assert rel(y.detach().cpu(), want.detach()) <= 3e-2
+    if training:
+        r = torch.from_numpy(np.random.default_rng(312).normal(0, 1, tuple(want.shape)).astype(np.float32))
+        (want * r).sum().backward()
+        (y * r.cuda()).sum().backward()
+        params = dict(net.named_parameters())
+        ref_max = max(float(ref_sd[k].grad.norm()) for k in params)
+        for k, p_ in params.items():
+            n, ref = float(p_.grad.double().norm()), float(ref_sd[k].grad.double().norm())
+            if k.endswith(".gamma") or ref < 1e-4 * ref_max:
+                continue
+            assert abs(n - ref) <= (0.35 if p_.dim() == 1 else 0.2) * ref, (k, n, ref)
+        rm = net.fusion_layers["fusion_2"][1].running_mean.cpu()
+        assert rel(rm, ref_sd["fusion_layers.fusion_2.1.running_mean"]) <= 2e-2

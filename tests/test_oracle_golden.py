@@ -212,3 +212,40 @@ def test_metrics_oracle_raw_branches(golden_dir):
         got = np.array(mo.compute_errors(a, b))
         ref = g[key + "_errors"]
         assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), key
+
+
+# ---- config 4: BinauralAttentionDepthNet -----------------------------------------------------------------------
+@pytest.mark.parametrize("name,levels", [("lv345_b2", (3, 4, 5))])
+def test_binaural_oracle_matches_reference(golden_dir, name, levels):
+    """oracle/binaural_oracle.forward on the reference's own initial weights (same seed, same module construction order
+    in the mirror) reproduces the reference's forward, gradients and eval forward."""
+    from audio_depth_estimation_b200.models.binaural_attention_model import BinauralAttentionDepthNet
+    from oracle import binaural_oracle as bo
+    g = np.load(os.path.join(golden_dir, "binaural.npz"))
+    torch.manual_seed(0)
+    net = BinauralAttentionDepthNet(64, True, 128, 30.0, list(levels))      # parameter container only (CPU)
+    with torch.no_grad():
+        for m in net.attention_modules.values():
+            m.gamma.fill_(0.5)
+        net.outc[0].weight.mul_(0.1)
+        net.outc[0].bias.fill_(-1.2)
+    sd = {k: v.detach().clone().contiguous() for k, v in net.state_dict().items()}
+    for k, v in sd.items():
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(True)
+    x = torch.from_numpy(synthetic.feature_like(2, 128, seed=301))
+    r = torch.from_numpy(np.random.default_rng(302).normal(0, 1, (2, 1, 128, 128)).astype(np.float32))
+    torch.set_num_threads(8)
+    y = bo.forward(sd, x, levels, 30.0, training=True, update_running=True)
+    assert rel_to_max(y.detach().numpy(), g[name + "_y"]) <= 1e-4
+    (y * r).sum().backward()
+    names = list(g[name + "_grad_names"])
+    for i, k in enumerate(names):
+        ref = g[name + "_grad_norms"][i]
+        if ref < 1e-4 * g[name + "_grad_norms"].max():
+            continue
+        assert abs(float(sd[k].grad.double().norm()) - ref) <= 2e-3 * ref, k
+    assert np.abs(sd["fusion_layers.fusion_3.1.running_mean"].numpy() - g[name + "_rm_fusion3"]).max() <= 1e-4
+    with torch.no_grad():
+        ye = bo.forward(sd, x, levels, 30.0, training=False)
+    assert rel_to_max(ye.numpy(), g[name + "_y_eval"]) <= 1e-4
