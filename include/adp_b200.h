@@ -311,6 +311,12 @@ long long adp_tc_launch_count(void);
 int adp_profile_enable(int on);
 int adp_profile_read(double* ms, double* work, long long* calls);
 
+/* Hardware probe, not on any product path (tools/probe_umma_offset.py): out[m][n] = sum_k X[m+shift][k]*W[n][k] with the
+ * UMMA A descriptor started `shift` rows into a SWIZZLE_128B tile; reports whether shifted windows into one shared-memory
+ * tile are usable as MMA operands (base_offset = descriptor bits 49-51, sbo_bytes = stride between 8-row groups). */
+int adp_selftest_umma_offset(const void* x, const void* w, int shift, int base_offset, int sbo_bytes, float* out,
+                             void* stream);
+
 /* adp_clip_adamw_step with the step counter on the device (int, incremented by the call; scratch = 2 floats):
  * capturable in a CUDA graph. */
 int adp_clip_adamw_step_graph(const adp_tensor_ref* refs_host, int n_tensors, const double* sumsq,
