@@ -89,6 +89,13 @@ extern "C" int adp_set_tensor_core(int on) {
   return prev;
 }
 
+// Tuning switches of the tensor-core kernels (the ADP_TC_* environment variables, at run time): "tc_halo" (halo-window
+// parity kernels), "tc_cluster" (2-CTA weight multicast), "tc_max_bn" (largest N tile).  Returns the previous value.
+extern "C" int adp_set_option(const char* name, int value) {
+  if (!name) return -1;
+  return adp::tc_set_option(name, value);
+}
+
 // Start (on = 1, clears the record) or stop (on = 0) timing the convolution kernel families.
 extern "C" int adp_profile_enable(int on) {
   adp::g_prof_on = on != 0;

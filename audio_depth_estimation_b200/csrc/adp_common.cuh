@@ -318,6 +318,8 @@ int tc_gemm_rows(const void* a0, int K0, const void* a1, int K1, const void* bm,
                  int N1, float* c32, long long M, cudaStream_t s, const GemmEpilogue* epi = nullptr);
 // fp32 scratch used to split the K range of deep, small-M layers across CTAs (NULL: never split)
 void tc_set_scratch(void* ptr, size_t bytes);
+// tuning switches ("tc_halo", "tc_cluster", "tc_max_bn"): returns the previous value, -1 for an unknown name
+int tc_set_option(const char* name, int value);
 bool tc_supported_gather(int B, int Hi, int Wi, int C, int N0, int N1);
 bool tc_supported_parity(int B, int Hi, int Wi, int C0, int C1, int N);
 bool tc_supported_wgrad(int B, int Hs, int Ws, int M0, int M1, int N);

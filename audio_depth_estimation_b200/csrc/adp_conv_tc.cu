@@ -99,6 +99,7 @@ struct IgemmParams {
   int epi, stat_by_col;
   float escale;
   int* stat_m; float* stat_l; const float* delta; const bf16* pmat;
+  int halo;                           // mode 1 only: HALO instantiation (16 x 8 pixel tiles, k-blocks = channel chunks)
   int wmode;                          // modes 2/4: 1 = weights through the MN-major 3-D map (N | taps | Ct), taps reversed
   int f32_rows;                       // modes 2/4: write fp32 [pixels][N] to out_f32 instead of bf16 (any BLOCK_N)
   long long rows_guard;               // > 0: output rows (opix) >= rows_guard are not stored (ragged GEMM M)
@@ -324,22 +325,31 @@ __device__ __forceinline__ TileCoord decode_pair_tile(const IgemmParams& p, int 
   return c;
 }
 
-template <int BLOCK_N>
+// HALO (parity mode, BLOCK_N <= 128): a k-block is one 64-channel chunk -- the (17 x 9)-pixel input window of a 16 x 8
+// pixel tile is loaded ONCE and the four taps read it through shifted descriptors (the SWIZZLE_128B pattern is a
+// function of the shared-memory address, so an operand may start at any 128-byte row and use any group pitch:
+// tools/probe_umma_offset.py), next to the four taps' weight tiles.
+constexpr int HALO_W = 9, HALO_H = 17;
+constexpr int HALO_BOX_BYTES = HALO_W * HALO_H * TILE_K * 2;     // 19584
+template <int BLOCK_N, bool HALO = false>
 struct PersistSmem {
-  using S = IgemmSmem<BLOCK_N>;
-  static constexpr int STAGES = (196 * 1024) / S::STAGE_BYTES > 10 ? 10 : (196 * 1024) / S::STAGE_BYTES;
+  static constexpr int A_BYTES = HALO ? 20480 : A_STAGE_BYTES;
+  static constexpr int B_TILE = BLOCK_N * TILE_K * 2;
+  static constexpr int B_BYTES = HALO ? 4 * B_TILE : B_TILE;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 10 ? 10 : (196 * 1024) / STAGE_BYTES;
   static constexpr int STAGING = 4 * 4096;        // epilogue transpose buffers: 4 warps x (32 rows x 128 B)
-  static constexpr int BAR_BYTES = 512;           // pipeline barriers, TMEM slot, tile queue
-  static constexpr int BYTES = STAGES * S::STAGE_BYTES + 1024 + BAR_BYTES + STAGING;
+  static constexpr int BAR_BYTES = 512;           // pipeline barriers, TMEM slot
+  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + STAGING;
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
 // EG = number of epilogue warp groups (4 warps each): 1 for the convolutions, 2 for the math-heavy STFT epilogue
 // ATT = attention (softmax) epilogues of the row GEMM compiled in (kept out of the convolution instantiations)
-template <int BLOCK_N, bool CLUSTER, int EG, bool ATT = false>
+template <int BLOCK_N, bool CLUSTER, int EG, bool ATT = false, bool HALO = false>
 __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
   using S = IgemmSmem<BLOCK_N>;
-  using PS = PersistSmem<BLOCK_N>;
+  using PS = PersistSmem<BLOCK_N, HALO>;
   const int crank = CLUSTER ? (int)cluster_ctarank() : 0;
   const int worker = CLUSTER ? (int)cluster_id_x() : (int)blockIdx.x;      // index of this CTA (pair) in the tile walk
   const int nworkers = CLUSTER ? (int)cluster_count_x() : (int)gridDim.x;
@@ -349,7 +359,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
   constexpr int ACC = PS::ACC_COLS;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * PS::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready for the epilogue
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained by the 4 epilogue warps
@@ -383,10 +393,22 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
         int tap = c.kb_begin / nchunk, ch = (c.kb_begin - tap * nchunk) * TILE_K;
         for (int it = 0; it < c.nkb; ++it) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          unsigned char* a_dst = smem + s * S::STAGE_BYTES;
-          unsigned char* b_dst = a_dst + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-          if (p.mode == 0) {
+          unsigned char* a_dst = smem + s * PS::STAGE_BYTES;
+          unsigned char* b_dst = a_dst + PS::A_BYTES;
+          mbar_expect_tx(&full_bar[s], HALO ? HALO_BOX_BYTES + 4 * PS::B_TILE : PS::STAGE_BYTES);
+          if (HALO) {
+            // one 64-channel chunk: the tile's halo window once + the weight tiles of the four taps of this parity
+            const int cx = c.x0 + c.pb - 1, cy = c.y0c + c.pa - 1;
+            if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, cx, cy, c.b0);
+            else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, cx, cy, c.b0);
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+              const int wtap = (3 - c.pa - 2 * (t4 >> 1)) * 4 + (3 - c.pb - 2 * (t4 & 1));
+#pragma unroll
+              for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h)
+                tma_load_3d(b_dst + t4 * PS::B_TILE + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
+            }
+          } else if (p.mode == 0) {
             const int kh = tap >> 2, kw = tap & 3;
             const int di = (kh + 1) / 2 - 1, ra = (kh + 1) & 1;
             const int dj = (kw + 1) / 2 - 1, rb = (kw + 1) & 1;
@@ -452,9 +474,9 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
       const uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, 0, b_mn ? 1 : 0);
       // descriptors differ from stage to stage only in the 14-bit start-address field: build them once
       const uint32_t smem_base = smem_u32(smem);
-      const uint64_t a_desc0 = umma_smem_desc(smem_base, 16, 1024);
-      const uint64_t b_desc0 = b_mn ? umma_smem_desc(smem_base + A_STAGE_BYTES, TILE_K * 128, 1024)
-                                    : umma_smem_desc(smem_base + A_STAGE_BYTES, 16, 1024);
+      const uint64_t a_desc0 = umma_smem_desc(smem_base, 16, HALO ? HALO_W * 128 : 1024);   // HALO: 8-pixel groups one halo row apart
+      const uint64_t b_desc0 = b_mn ? umma_smem_desc(smem_base + PS::A_BYTES, TILE_K * 128, 1024)
+                                    : umma_smem_desc(smem_base + PS::A_BYTES, 16, 1024);
       const uint32_t b_kstep = b_mn ? (2048u >> 4) : (32u >> 4);
       int s = 0;
       uint32_t ph = 0, local = 0;
@@ -467,11 +489,22 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
         for (int it = 0; it < c.nkb; ++it) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint64_t stage_off = (uint64_t)((uint32_t)(s * S::STAGE_BYTES) >> 4);
+          const uint64_t stage_off = (uint64_t)((uint32_t)(s * PS::STAGE_BYTES) >> 4);
           const uint64_t ad0 = a_desc0 + stage_off, bd0 = b_desc0 + stage_off;
+          if (HALO) {
 #pragma unroll
-          for (int k = 0; k < TILE_K / 16; ++k)
-            umma_bf16(tacc, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * b_kstep), idesc, (it | k) != 0 ? 1u : 0u);
+            for (int t4 = 0; t4 < 4; ++t4) {
+              const uint64_t at = ad0 + (uint64_t)((((t4 >> 1) * HALO_W + (t4 & 1)) * 128) >> 4);   // window shifted by (th, tw)
+              const uint64_t bt4 = bd0 + (uint64_t)((t4 * PS::B_TILE) >> 4);
+#pragma unroll
+              for (int k = 0; k < TILE_K / 16; ++k)
+                umma_bf16(tacc, at + (uint64_t)(k * 2), bt4 + (uint64_t)(k * b_kstep), idesc, (it | t4 | k) != 0 ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < TILE_K / 16; ++k)
+              umma_bf16(tacc, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * b_kstep), idesc, (it | k) != 0 ? 1u : 0u);
+          }
           if (CLUSTER) umma_commit_mc(&empty_bar[s], 3);
           else umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -488,7 +521,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     const int r = q * 32 + lane;
     const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
     constexpr bool STAGED_OK = BLOCK_N >= 64 && EG == 1;
-    unsigned char* stg = smem + STAGES * S::STAGE_BYTES + PS::BAR_BYTES + (STAGED_OK ? (warp - 2) * 4096 : 0);
+    unsigned char* stg = smem + STAGES * PS::STAGE_BYTES + PS::BAR_BYTES + (STAGED_OK ? (warp - 2) * 4096 : 0);
     const bool staged = p.splits <= 1 && p.mode != 3 && !p.f32_rows && !(ATT && (p.epi == 1 || p.epi == 2)) &&
                         (p.act_dual || p.N1 == 0 || p.N0 % 64 == 0);
     uint32_t local = 0;
@@ -730,6 +763,7 @@ int g_force_stages = 0;   // ADP_TC_STAGES environment override (tuning)
 int g_persistent = 1;     // ADP_TC_PERSISTENT=0 selects the one-tile-per-CTA kernel
 int g_cluster = 0;        // ADP_TC_CLUSTER=1: 2-CTA clusters, weight tile halves multicast between the pair
 
+int g_halo = 1;            // ADP_TC_HALO=0: parity layers with N <= 128 fall back to one TMA box per tap
 int g_tc_sms = 0;          // ADP_TC_SMS=n: persistent kernels use at most n CTAs (measured: no gain next to NCCL)
 template <int BLOCK_N>
 int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
@@ -742,7 +776,7 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
   p.gx = grid.x; p.gy = grid.y; p.gz = grid.z;
   p.total_tiles = (int)(grid.x * grid.y * grid.z);
   if (g_persistent) {
-    using PS = PersistSmem<BLOCK_N>;
+    using PS = PersistSmem<BLOCK_N, false>;
     static bool pattr_set = false;
     if (!pattr_set) {
       ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
@@ -753,7 +787,7 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
       pattr_set = true;
     }
     const int m_groups = p.mode == 1 ? (int)grid.x / 4 : (int)grid.x;
-    if (g_cluster && p.has_half_map && m_groups >= 2 && p.mode != 3) {
+    if (g_cluster && p.has_half_map && m_groups >= 2 && p.mode != 3 && !p.halo) {
       const int gxp = p.mode == 1 ? ((m_groups + 1) / 2) * 4 : (m_groups + 1) / 2;
       p.total_pair_tiles = gxp * (int)grid.y * (int)grid.z;
       int pairs = sm_count() / 2;
@@ -780,7 +814,18 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
       if (BLOCK_N != 128) { adp_set_error("stft: BLOCK_N must be 128"); return ADP_ERR_ARG; }
       tc_igemm_persist_kernel<128, false, 2><<<ctas, PERSIST_THREADS, PersistSmem<128>::BYTES, s>>>(p);
     } else {
-      if (p.epi != 0) {
+      if (p.halo) {
+        constexpr int HB = BLOCK_N == 64 || BLOCK_N == 128 ? BLOCK_N : 64;
+        if (HB != BLOCK_N) { adp_set_error("halo mode needs BLOCK_N 64 or 128"); return ADP_ERR_ARG; }
+        using HS = PersistSmem<HB, true>;
+        static bool hattr_set = false;
+        if (!hattr_set) {
+          ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<HB, false, 1, false, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, HS::BYTES));
+          hattr_set = true;
+        }
+        tc_igemm_persist_kernel<HB, false, 1, false, true><<<ctas, IGEMM_THREADS, HS::BYTES, s>>>(p);
+      } else if (p.epi != 0) {
         if (BLOCK_N < 64) { adp_set_error("attention epilogues need BLOCK_N >= 64"); return ADP_ERR_ARG; }
         static bool aattr_set = false;
         if (!aattr_set) {
@@ -859,6 +904,8 @@ struct StagesEnvInit {
     if (pe) g_persistent = atoi(pe);
     const char* ce = getenv("ADP_TC_CLUSTER");
     if (ce) g_cluster = atoi(ce);
+    const char* he = getenv("ADP_TC_HALO");
+    if (he) g_halo = atoi(he);
     const char* se = getenv("ADP_TC_SMS");
     if (se) g_tc_sms = atoi(se);
     const char* be = getenv("ADP_TC_MAX_BN");
@@ -872,6 +919,17 @@ thread_local float* g_scratch = nullptr;
 thread_local size_t g_scratch_bytes = 0;
 
 }  // namespace
+
+int tc_set_option(const char* name, int value) {
+  int* slot = nullptr;
+  if (!strcmp(name, "tc_halo")) slot = &g_halo;
+  else if (!strcmp(name, "tc_cluster")) slot = &g_cluster;
+  else if (!strcmp(name, "tc_max_bn")) slot = &g_max_block_n;
+  if (!slot) return -1;
+  const int prev = *slot;
+  *slot = value;
+  return prev;
+}
 
 void tc_set_scratch(void* ptr, size_t bytes) {
   g_scratch = reinterpret_cast<float*>(ptr);
@@ -932,9 +990,13 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
   const int bn = pick_block_n(N, N, 0);
   ADP_CHECK_ARG(bn >= 64 && C0 % TILE_K == 0 && C1 % TILE_K == 0, "tc_parity_convT: unsupported channels");
   const int Ct = C0 + C1;
+  // narrow-N layers are bound by L2 -> SM operand traffic: load the tile's input window once per channel chunk (HALO)
+  const bool halo = g_halo && g_persistent && (bn == 64 || bn == 128) && Hi >= 16 && Wi >= 8 && Hi % 16 == 0 && Wi % 8 == 0 &&
+                    (long long)B * (Hi / 16) * (Wi / 8) * 4 * (N / bn) >= sm_count();
+  if (halo) { p.Wt = 8; p.Ht = 16; p.Bt = 1; p.halo = 1; }
   p.tiles_w = Wi / p.Wt; p.tiles_h = Hi / p.Ht;
   p.B = B; p.Hs = Hi; p.Ws = Wi; p.mode = 1; p.C0 = C0; p.C1 = C1; p.Ct = Ct; p.N = N; p.N0 = N; p.N1 = 0;
-  p.kblocks = 4 * (Ct / TILE_K);
+  p.kblocks = (halo ? 1 : 4) * (Ct / TILE_K);
   p.y0 = (bf16*)y; p.y1 = nullptr;
   for (int h = 0; h < 2; ++h) {
     const int C = h == 0 ? C0 : C1;
@@ -942,7 +1004,8 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)Wi * C * 2, (uint64_t)Hi * Wi * C * 2};
     uint32_t box[4] = {TILE_K, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
-    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, box));
+    uint32_t hbox[4] = {TILE_K, HALO_W, HALO_H, 1};
+    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, halo ? hbox : box));
   }
   {  // w_kn: bf16 [Ct][16][N] (the master layout, cast)
     uint64_t dims[3] = {(uint64_t)N, 16, (uint64_t)Ct};

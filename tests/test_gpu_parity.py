@@ -171,6 +171,7 @@ def op_weights(lib, w_master, R, C):
 CONV_SHAPES = [  # B, H, Cin, Cout
     (2, 16, 16, 32), (3, 8, 32, 16), (1, 32, 64, 128), (2, 4, 128, 128), (4, 2, 64, 64), (2, 64, 64, 64),
     (3, 2, 256, 256), (5, 16, 128, 256), (2, 128, 64, 128), (70, 2, 128, 128),
+    (6, 64, 128, 256),                       # dgrad on the halo-window kernel with a 128-wide N tile
 ]
 
 
@@ -226,7 +227,35 @@ def test_conv2d_k4s2_all_passes(mode, B, H, Cin, Cout):
 CONVT_SHAPES = [  # B, Hin, C0, C1, Cout
     (2, 8, 32, 32, 16), (3, 4, 64, 0, 64), (1, 16, 64, 64, 32), (2, 2, 128, 128, 128), (2, 1, 64, 0, 64),
     (2, 32, 64, 64, 64), (3, 1, 256, 0, 256), (5, 8, 128, 128, 128), (2, 64, 128, 128, 64), (70, 1, 128, 0, 128),
+    (20, 16, 64, 64, 128), (3, 64, 64, 0, 128), (5, 32, 192, 64, 64),     # halo-window kernel: one tile row, N = 128, 3+1 chunks
 ]
+
+
+def test_halo_window_kernel_is_used_and_matches_the_per_tap_kernel():
+    """The parity kernels with N <= 128 load the tile's (17 x 9)-pixel input window once per channel chunk and run the four
+    taps through shifted shared-memory descriptors ("tc_halo"); same result as one TMA box per tap, and as torch."""
+    lib = _lib.load()
+    B, H, C0, C1, Cout = 4, 64, 128, 64, 64
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(B, C0 + C1, H, H, generator=g).to(DEV)
+    w = (torch.randn(C0 + C1, Cout, 4, 4, generator=g) * 0.05).to(DEV)
+    x0r, x1r = nhwc(x[:, :C0], torch.bfloat16), nhwc(x[:, C0:], torch.bfloat16)
+    wm = w.permute(0, 2, 3, 1).contiguous()
+    w_f = op_weights(lib, wm, C0 + C1, Cout)
+    ref = F.conv_transpose2d(torch.cat([from_nhwc(x0r), from_nhwc(x1r)], 1), wm.to(torch.bfloat16).float().permute(0, 3, 1, 2),
+                             stride=2, padding=1)
+    outs = []
+    for halo in (1, 0):
+        prev = lib.adp_set_option(b"tc_halo", halo)
+        y = torch.empty(B, 2 * H, 2 * H, Cout, device=DEV, dtype=torch.bfloat16)
+        _lib.check(lib.adp_convT2d_k4s2_fprop(_lib.ADP_BF16, x0r.data_ptr(), C0, x1r.data_ptr(), C1, wm.data_ptr(), w_f.data_ptr(),
+                                              y.data_ptr(), B, H, H, Cout, None))
+        lib.adp_set_option(b"tc_halo", prev)
+        assert rel_to_max(from_nhwc(y).cpu(), ref.cpu()) <= 1.5e-2
+        outs.append(from_nhwc(y))
+    assert lib.adp_set_option(b"tc_halo", 1) == 1 and lib.adp_set_option(b"no_such_option", 1) == -1
+    # same products, different summation order (chunk-major instead of tap-major): equal up to bf16 rounding of the output
+    assert rel_to_max(outs[0].cpu(), outs[1].cpu()) <= 8e-3
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16_simt", "bf16_tc"])
