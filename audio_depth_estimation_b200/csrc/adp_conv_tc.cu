@@ -99,7 +99,7 @@ struct IgemmParams {
   int epi, stat_by_col;
   float escale;
   int* stat_m; float* stat_l; const float* delta; const bf16* pmat;
-  int halo;                           // mode 1 only: HALO instantiation (16 x 8 pixel tiles, k-blocks = channel chunks)
+  int halo;                           // 0, or the HALO instantiation: 4 = parity mode (mode 1), 3 = 3x3 rows (mode 4)
   int wmode;                          // modes 2/4: 1 = weights through the MN-major 3-D map (N | taps | Ct), taps reversed
   int f32_rows;                       // modes 2/4: write fp32 [pixels][N] to out_f32 instead of bf16 (any BLOCK_N)
   long long rows_guard;               // > 0: output rows (opix) >= rows_guard are not stored (ragged GEMM M)
@@ -325,28 +325,32 @@ __device__ __forceinline__ TileCoord decode_pair_tile(const IgemmParams& p, int 
   return c;
 }
 
-// HALO (parity mode, BLOCK_N <= 128): a k-block is one 64-channel chunk -- the (17 x 9)-pixel input window of a 16 x 8
-// pixel tile is loaded ONCE and the four taps read it through shifted descriptors (the SWIZZLE_128B pattern is a
-// function of the shared-memory address, so an operand may start at any 128-byte row and use any group pitch:
-// tools/probe_umma_offset.py), next to the four taps' weight tiles.
-constexpr int HALO_W = 9, HALO_H = 17;
-constexpr int HALO_BOX_BYTES = HALO_W * HALO_H * TILE_K * 2;     // 19584
-template <int BLOCK_N, bool HALO = false>
+// HALO (BLOCK_N <= 128): the input window of a 16 x 8 pixel tile is loaded ONCE per k-block and several filter taps read it
+// through shifted descriptors (the SWIZZLE_128B pattern is a function of the shared-memory address, so an operand may
+// start at any 128-byte row and use any group pitch: tools/probe_umma_offset.py), next to those taps' weight tiles.
+//   HALO = 4: parity (transposed-conv) mode, k-block = one 64-channel chunk, 2 x 2 taps, window 17 x 9 pixels
+//   HALO = 3: 3x3 / stride 1 mode, k-block = (kernel row, chunk), 3 taps of that row, window 16 x 10 pixels
+template <int HALO> struct HaloGeom {
+  static constexpr int W = HALO == 3 ? 10 : 9, H = HALO == 3 ? 16 : 17;
+  static constexpr int BOX_BYTES = W * H * TILE_K * 2;            // 20480 / 19584
+};
+template <int BLOCK_N, int HALO = 0>
 struct PersistSmem {
   static constexpr int A_BYTES = HALO ? 20480 : A_STAGE_BYTES;
   static constexpr int B_TILE = BLOCK_N * TILE_K * 2;
-  static constexpr int B_BYTES = HALO ? 4 * B_TILE : B_TILE;
+  static constexpr int B_BYTES = HALO ? HALO * B_TILE : B_TILE;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 10 ? 10 : (196 * 1024) / STAGE_BYTES;
   static constexpr int STAGING = 4 * 4096;        // epilogue transpose buffers: 4 warps x (32 rows x 128 B)
   static constexpr int BAR_BYTES = 512;           // pipeline barriers, TMEM slot
+  static constexpr int RING_BUDGET = HALO ? (227 * 1024 - 1024 - BAR_BYTES - STAGING - 1024) : 196 * 1024;
+  static constexpr int STAGES = RING_BUDGET / STAGE_BYTES > 10 ? 10 : RING_BUDGET / STAGE_BYTES;
   static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + STAGING;
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
 // EG = number of epilogue warp groups (4 warps each): 1 for the convolutions, 2 for the math-heavy STFT epilogue
 // ATT = attention (softmax) epilogues of the row GEMM compiled in (kept out of the convolution instantiations)
-template <int BLOCK_N, bool CLUSTER, int EG, bool ATT = false, bool HALO = false>
+template <int BLOCK_N, bool CLUSTER, int EG, bool ATT = false, int HALO = 0>
 __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
   using S = IgemmSmem<BLOCK_N>;
   using PS = PersistSmem<BLOCK_N, HALO>;
@@ -395,8 +399,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
           mbar_wait(&empty_bar[s], ph ^ 1);
           unsigned char* a_dst = smem + s * PS::STAGE_BYTES;
           unsigned char* b_dst = a_dst + PS::A_BYTES;
-          mbar_expect_tx(&full_bar[s], HALO ? HALO_BOX_BYTES + 4 * PS::B_TILE : PS::STAGE_BYTES);
-          if (HALO) {
+          mbar_expect_tx(&full_bar[s], HALO ? HaloGeom<HALO>::BOX_BYTES + HALO * PS::B_TILE : PS::STAGE_BYTES);
+          if (HALO == 4) {
             // one 64-channel chunk: the tile's halo window once + the weight tiles of the four taps of this parity
             const int cx = c.x0 + c.pb - 1, cy = c.y0c + c.pa - 1;
             if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, cx, cy, c.b0);
@@ -407,6 +411,22 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
 #pragma unroll
               for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h)
                 tma_load_3d(b_dst + t4 * PS::B_TILE + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
+            }
+          } else if (HALO == 3) {
+            // `tap` counts kernel rows here: rows y0+kh-1 .. +15, columns x0-1 .. x0+8, and the three taps of that row
+            const int kh = tap;
+            if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, c.x0 - 1, c.y0c + kh - 1, c.b0);
+            else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, c.x0 - 1, c.y0c + kh - 1, c.b0);
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const int t9 = kh * 3 + kw;
+              if (p.wmode) {
+#pragma unroll
+                for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h)
+                  tma_load_3d(b_dst + kw * PS::B_TILE + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, 8 - t9, ch);
+              } else {
+                tma_load_2d(b_dst + kw * PS::B_TILE, &p.tmW, &full_bar[s], t9 * p.Ct + ch, c.n0);
+              }
             }
           } else if (p.mode == 0) {
             const int kh = tap >> 2, kw = tap & 3;
@@ -474,7 +494,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
       const uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, 0, b_mn ? 1 : 0);
       // descriptors differ from stage to stage only in the 14-bit start-address field: build them once
       const uint32_t smem_base = smem_u32(smem);
-      const uint64_t a_desc0 = umma_smem_desc(smem_base, 16, HALO ? HALO_W * 128 : 1024);   // HALO: 8-pixel groups one halo row apart
+      const uint64_t a_desc0 = umma_smem_desc(smem_base, 16, HALO ? HaloGeom<HALO>::W * 128 : 1024);   // HALO: 8-pixel groups one window row apart
       const uint64_t b_desc0 = b_mn ? umma_smem_desc(smem_base + PS::A_BYTES, TILE_K * 128, 1024)
                                     : umma_smem_desc(smem_base + PS::A_BYTES, 16, 1024);
       const uint32_t b_kstep = b_mn ? (2048u >> 4) : (32u >> 4);
@@ -493,8 +513,10 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
           const uint64_t ad0 = a_desc0 + stage_off, bd0 = b_desc0 + stage_off;
           if (HALO) {
 #pragma unroll
-            for (int t4 = 0; t4 < 4; ++t4) {
-              const uint64_t at = ad0 + (uint64_t)((((t4 >> 1) * HALO_W + (t4 & 1)) * 128) >> 4);   // window shifted by (th, tw)
+            for (int t4 = 0; t4 < HALO; ++t4) {
+              // window shifted by (th, tw) [parity] or by tw [3x3 row] pixels
+              const int shift_rows = HALO == 4 ? (t4 >> 1) * HaloGeom<HALO>::W + (t4 & 1) : t4;
+              const uint64_t at = ad0 + (uint64_t)((shift_rows * 128) >> 4);
               const uint64_t bt4 = bd0 + (uint64_t)((t4 * PS::B_TILE) >> 4);
 #pragma unroll
               for (int k = 0; k < TILE_K / 16; ++k)
@@ -776,7 +798,7 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
   p.gx = grid.x; p.gy = grid.y; p.gz = grid.z;
   p.total_tiles = (int)(grid.x * grid.y * grid.z);
   if (g_persistent) {
-    using PS = PersistSmem<BLOCK_N, false>;
+    using PS = PersistSmem<BLOCK_N, 0>;
     static bool pattr_set = false;
     if (!pattr_set) {
       ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
@@ -817,14 +839,25 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
       if (p.halo) {
         constexpr int HB = BLOCK_N == 64 || BLOCK_N == 128 ? BLOCK_N : 64;
         if (HB != BLOCK_N) { adp_set_error("halo mode needs BLOCK_N 64 or 128"); return ADP_ERR_ARG; }
-        using HS = PersistSmem<HB, true>;
-        static bool hattr_set = false;
-        if (!hattr_set) {
-          ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<HB, false, 1, false, true>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, HS::BYTES));
-          hattr_set = true;
+        if (p.halo == 4) {
+          using HS = PersistSmem<HB, 4>;
+          static bool hattr_set = false;
+          if (!hattr_set) {
+            ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<HB, false, 1, false, 4>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, HS::BYTES));
+            hattr_set = true;
+          }
+          tc_igemm_persist_kernel<HB, false, 1, false, 4><<<ctas, IGEMM_THREADS, HS::BYTES, s>>>(p);
+        } else {
+          using HS = PersistSmem<HB, 3>;
+          static bool h3attr_set = false;
+          if (!h3attr_set) {
+            ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<HB, false, 1, false, 3>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, HS::BYTES));
+            h3attr_set = true;
+          }
+          tc_igemm_persist_kernel<HB, false, 1, false, 3><<<ctas, IGEMM_THREADS, HS::BYTES, s>>>(p);
         }
-        tc_igemm_persist_kernel<HB, false, 1, false, true><<<ctas, IGEMM_THREADS, HS::BYTES, s>>>(p);
       } else if (p.epi != 0) {
         if (BLOCK_N < 64) { adp_set_error("attention epilogues need BLOCK_N >= 64"); return ADP_ERR_ARG; }
         static bool aattr_set = false;
@@ -993,7 +1026,7 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
   // narrow-N layers are bound by L2 -> SM operand traffic: load the tile's input window once per channel chunk (HALO)
   const bool halo = g_halo && g_persistent && (bn == 64 || bn == 128) && Hi >= 16 && Wi >= 8 && Hi % 16 == 0 && Wi % 8 == 0 &&
                     (long long)B * (Hi / 16) * (Wi / 8) * 4 * (N / bn) >= sm_count();
-  if (halo) { p.Wt = 8; p.Ht = 16; p.Bt = 1; p.halo = 1; }
+  if (halo) { p.Wt = 8; p.Ht = 16; p.Bt = 1; p.halo = 4; }
   p.tiles_w = Wi / p.Wt; p.tiles_h = Hi / p.Ht;
   p.B = B; p.Hs = Hi; p.Ws = Wi; p.mode = 1; p.C0 = C0; p.C1 = C1; p.Ct = Ct; p.N = N; p.N0 = N; p.N1 = 0;
   p.kblocks = (halo ? 1 : 4) * (Ct / TILE_K);
@@ -1004,7 +1037,7 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)Wi * C * 2, (uint64_t)Hi * Wi * C * 2};
     uint32_t box[4] = {TILE_K, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
-    uint32_t hbox[4] = {TILE_K, HALO_W, HALO_H, 1};
+    uint32_t hbox[4] = {TILE_K, HaloGeom<4>::W, HaloGeom<4>::H, 1};
     ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, halo ? hbox : box));
   }
   {  // w_kn: bf16 [Ct][16][N] (the master layout, cast)
@@ -1113,9 +1146,13 @@ int tc_conv3x3(const void* x0, int C0, const void* x1, int C1, const void* w, in
   const int bn = pick_block_n(N, N0, N1);
   ADP_CHECK_ARG(bn >= 64 && C0 > 0 && C0 % TILE_K == 0 && C1 % TILE_K == 0, "tc_conv3x3: unsupported channels %d+%d -> %d+%d",
                 C0, C1, N0, N1);
+  // narrow-N layers: one (16 x 10)-pixel window per kernel row and channel chunk instead of one box per tap (HALO = 3)
+  const bool halo = g_halo && (bn == 64 || bn == 128) && H >= 16 && W >= 8 && H % 16 == 0 && W % 8 == 0 &&
+                    (long long)B * (H / 16) * (W / 8) * (N / bn) >= sm_count();
+  if (halo) { p.Wt = 8; p.Ht = 16; p.Bt = 1; p.halo = 3; }
   p.tiles_w = W / p.Wt; p.tiles_h = H / p.Ht;
   p.B = B; p.Hs = H; p.Ws = W; p.mode = 4; p.wmode = wmode; p.C0 = C0; p.C1 = C1; p.Ct = Ct; p.N = N; p.N0 = N0; p.N1 = N1;
-  p.kblocks = 9 * (Ct / TILE_K);
+  p.kblocks = (halo ? 3 : 9) * (Ct / TILE_K);
   p.y0 = (bf16*)y0; p.y1 = (bf16*)y1;
   for (int h = 0; h < 2; ++h) {
     const int C = h == 0 ? C0 : C1;
@@ -1123,7 +1160,8 @@ int tc_conv3x3(const void* x0, int C0, const void* x1, int C1, const void* w, in
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
     uint32_t box[4] = {TILE_K, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
-    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, box));
+    uint32_t hbox[4] = {TILE_K, HaloGeom<3>::W, HaloGeom<3>::H, 1};
+    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, halo ? hbox : box));
   }
   if (wmode) {   // w = [K = Ct][9][N]
     uint64_t dims[3] = {(uint64_t)N, 9, (uint64_t)Ct};

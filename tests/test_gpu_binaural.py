@@ -23,7 +23,9 @@ def nhwc_bf16(t):     # [B,C,H,W] fp32 -> bf16 NHWC storage, plus the rounded fp
 
 
 @pytest.mark.parametrize("B,H,W,C0,C1,N", [(2, 32, 32, 64, 0, 64), (1, 16, 16, 128, 128, 128), (3, 8, 8, 256, 0, 512),
-                                           (2, 4, 4, 512, 512, 256), (1, 64, 64, 64, 64, 64), (2, 2, 2, 512, 0, 512)])
+                                           (2, 4, 4, 512, 512, 256), (1, 64, 64, 64, 64, 64), (2, 2, 2, 512, 0, 512),
+                                           # large grids with N <= 128: the halo-window instantiation (one window per kernel row)
+                                           (8, 64, 64, 64, 0, 64), (5, 64, 64, 128, 128, 128), (3, 128, 128, 64, 64, 64)])
 def test_conv3x3_fprop_dgrad_wgrad(B, H, W, C0, C1, N):
     _lib, L = lib()
     torch.backends.cudnn.allow_tf32 = False
