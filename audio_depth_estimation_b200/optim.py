@@ -122,3 +122,57 @@ class FusedClipAdamW:
             raise ValueError("per-parameter step counts differ: %s" % sorted(steps))
         self.step_count = steps.pop()
         self._state["step_dev"].fill_(self.step_count)
+
+
+class FusedClipAdamWParams:
+    """The same fused clip_grad_norm_(max_norm) + AdamW step for an arbitrary list of CUDA fp32 parameters (e.g. the
+    config-4 BinauralAttentionDepthNet, whose parameters are ordinary separate tensors): two multi-tensor launches per
+    24 tensors (adp_grad_sumsq, adp_clip_adamw_step).  Parameters must be dense (any memory format); a gradient whose
+    memory order differs from its parameter's is re-laid-out first."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=1.0):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no parameters")
+        for p in self.params:
+            _lib.require_cuda(p, "parameter", torch.float32)
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
+        self.max_norm = float(max_norm) if max_norm is not None else 0.0
+        self.step_count = 0
+        self.exp_avg = [torch.zeros_like(p) for p in self.params]          # preserve_format: same memory order as p
+        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        dev = self.params[0].device
+        self._sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self._norm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.last_norm = None
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            p.grad = None
+
+    def step(self):
+        lib = _lib.load()
+        live = [(p, m, v) for p, m, v in zip(self.params, self.exp_avg, self.exp_avg_sq) if p.grad is not None]
+        if not live:
+            return None
+        refs = (_lib.TensorRef * len(live))()
+        keep = []
+        for i, (p, m, v) in enumerate(live):
+            g = p.grad
+            # same element order in memory?  (1x1 kernels: channels_last and contiguous strides describe the same order)
+            same = g.dtype == torch.float32 and (g.stride() == p.stride() or
+                                                 (p.dim() == 4 and tuple(p.shape[2:]) == (1, 1) and g.is_contiguous()))
+            if not same:
+                g = torch.empty_like(p).copy_(g)
+            keep.append(g)
+            refs[i].p, refs[i].g, refs[i].m, refs[i].v, refs[i].n = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()
+            refs[i].p_bf16 = None
+        self.step_count += 1
+        with torch.cuda.device(self.params[0].device):
+            s = _lib.stream_ptr()
+            self._sumsq.zero_()
+            _lib.check(lib.adp_grad_sumsq(refs, len(live), self._sumsq.data_ptr(), s))
+            _lib.check(lib.adp_clip_adamw_step(refs, len(live), self._sumsq.data_ptr(), self.max_norm, self.lr, self.betas[0],
+                                               self.betas[1], self.eps, self.weight_decay, self.step_count, self._norm.data_ptr(), s))
+        self.last_norm = self._norm
+        return self._norm

@@ -376,3 +376,40 @@ def test_binaural_net_vs_oracle_other_configs(levels, training):
             assert abs(n - ref) <= (0.35 if p_.dim() == 1 else 0.2) * ref, (k, n, ref)
         rm = net.fusion_layers["fusion_2"][1].running_mean.cpu()
         assert rel(rm, ref_sd["fusion_layers.fusion_2.1.running_mean"]) <= 2e-2
+
+
+def test_binaural_train_steps_with_fused_optimizer_match_torch():
+    """Config 4 end to end on the library: forward, masked Combined loss (DepthCriterion), backward, fused clip + AdamW over
+    the network's separate parameter tensors -- against clip_grad_norm_ + torch.optim.AdamW fed with the same gradients."""
+    from audio_depth_estimation_b200 import synthetic
+    from audio_depth_estimation_b200.config_loader import load_config
+    from audio_depth_estimation_b200.models.binaural_attention_model import BinauralAttentionDepthNet
+    from audio_depth_estimation_b200.optim import FusedClipAdamWParams
+    from audio_depth_estimation_b200.utils_loss import DepthCriterion
+    cfg = load_config()
+    torch.manual_seed(3)
+    net = BinauralAttentionDepthNet(64, True, 128, 30.0, [4, 5]).cuda().train()
+    with torch.no_grad():
+        net.outc[0].weight.mul_(0.1)
+    crit = DepthCriterion.from_cfg(cfg)
+    opt = FusedClipAdamWParams(net.parameters(), lr=1e-3, max_norm=1.0)
+    shadow = [torch.nn.Parameter(p.detach().clone()) for p in net.parameters()]
+    topt = torch.optim.AdamW(shadow, lr=1e-3)
+    x = torch.from_numpy(synthetic.feature_like(2, 128, seed=321)).cuda()
+    gt = torch.from_numpy(synthetic.gt_depth(2, 128, 30.0, seed=322, normalised=False)).cuda()
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = crit(net(x), gt)
+        loss.backward()
+        for sp_, p_ in zip(shadow, net.parameters()):
+            sp_.grad = p_.grad.detach().clone().contiguous().view_as(sp_) if p_.grad.is_contiguous() else \
+                torch.empty_like(sp_).copy_(p_.grad)
+        tn = torch.nn.utils.clip_grad_norm_(shadow, 1.0)
+        topt.step()
+        n = opt.step()
+        assert abs(float(n) - float(tn)) <= 1e-4 * float(tn)
+        for sp_, p_ in zip(shadow, net.parameters()):
+            assert torch.allclose(p_.detach(), sp_.detach(), rtol=1e-5, atol=2e-7)
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
