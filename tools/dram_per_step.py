@@ -43,14 +43,23 @@ def main(src, dst):
         name = e["kernel"].split("(")[0].replace("void adp::<unnamed>::", "")
         per.append({"kernel": name, "grid": e["grid"], "read_MB": round(e.get("read", 0) / 1e6, 1),
                     "write_MB": round(e.get("write", 0) / 1e6, 1), "us": round(e.get("us", 0), 1)})
+    import re
+
+    def targs(k):      # template arguments of tc_igemm_persist_kernel<BLOCK_N, CLUSTER, EG, ATT, HALO>
+        m = re.search(r"tc_igemm_persist_kernel<([^>]*)>", k)
+        return [int(re.sub(r"\([a-z]+\)", "", a).strip()) for a in m.group(1).split(",")] if m else None
+
+    def is_stft(e):
+        a = targs(e["kernel"])
+        return bool(a) and len(a) >= 3 and a[2] == 2
+
     def is_thin(e):
-        k = e["kernel"]
-        return "gemm_tn" in k or "<16," in k or "(int)16" in k or ", 2>" in k or "(int)2>" in k
+        a = targs(e["kernel"])
+        return "gemm_tn" in e["kernel"] or is_stft(e) or (bool(a) and a[0] == 16)
     thin = [i for i, e in enumerate(per) if is_thin(e)]
     # the E1 pointwise GEMM is the launch right after the STFT GEMM, the last-layer dgrad the one right after gemm_tn<64>
     for i, e in enumerate(per[:-1]):
-        if (", 2>" in e["kernel"] or "(int)2>" in e["kernel"] or "gemm_tn_kernel<64>" in e["kernel"]
-                or "gemm_tn_kernel<(int)64>" in e["kernel"]):
+        if is_stft(e) or "gemm_tn_kernel<64>" in e["kernel"] or "gemm_tn_kernel<(int)64>" in e["kernel"]:
             thin.append(i + 1)
     conv = [i for i in range(len(per)) if i not in thin]
     tot = sum((launches[i].get("read", 0) + launches[i].get("write", 0)) for i in conv)
