@@ -93,7 +93,8 @@ extern "C" int adp_set_tensor_core(int on) {
 // parity kernels), "tc_cluster" (2-CTA weight multicast), "tc_max_bn" (largest N tile).  Returns the previous value.
 extern "C" int adp_set_option(const char* name, int value) {
   if (!name) return -1;
-  return adp::tc_set_option(name, value);
+  const int prev = adp::tc_set_option(name, value);
+  return prev >= 0 ? prev : adp::unet_set_option(name, value);   // "side_stream": weight gradients on a side stream
 }
 
 // Start (on = 1, clears the record) or stop (on = 0) timing the convolution kernel families.

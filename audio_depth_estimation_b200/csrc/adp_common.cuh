@@ -320,6 +320,7 @@ int tc_gemm_rows(const void* a0, int K0, const void* a1, int K1, const void* bm,
 void tc_set_scratch(void* ptr, size_t bytes);
 // tuning switches ("tc_halo", "tc_cluster", "tc_max_bn"): returns the previous value, -1 for an unknown name
 int tc_set_option(const char* name, int value);
+int unet_set_option(const char* name, int value);      // "side_stream"
 bool tc_supported_gather(int B, int Hi, int Wi, int C, int N0, int N1);
 bool tc_supported_parity(int B, int Hi, int Wi, int C0, int C1, int N);
 bool tc_supported_wgrad(int B, int Hs, int Ws, int M0, int M1, int N);

@@ -9,6 +9,7 @@
 //   y = act(ConvT(r[0] | q[0]) + bias)
 // torch.cat never materialises: the transposed convolutions read the two halves as two tensors.
 #include <string.h>
+#include <stdlib.h>
 #include "adp_common.cuh"
 
 namespace {
@@ -264,6 +265,46 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   return ADP_OK;
 }
 
+// Weight gradients run on a library-owned side stream, concurrently with the data-gradient chain of the same stage
+// group: dw(l) only feeds the optimiser, while dx(l) is on the critical path to level l-1, and the deep levels'
+// kernels use a fraction of the SMs each.  Forked with an event after the upstream gradient exists, joined before the
+// call returns (so callers -- the all-reduce hook, the optimiser, a CUDA-graph capture -- see one stream).
+namespace {
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork[32];
+  cudaEvent_t join = nullptr;
+};
+int g_side_stream = -1;    // ADP_SIDE_STREAM=0 keeps everything on the caller's stream
+int side_stream_for_device(SideStream** out) {
+  static SideStream tab[64];
+  *out = nullptr;
+  if (g_side_stream < 0) g_side_stream = getenv("ADP_SIDE_STREAM") ? atoi(getenv("ADP_SIDE_STREAM")) : 1;
+  if (!g_side_stream) return ADP_OK;
+  int dev = 0;
+  ADP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return ADP_OK;
+  SideStream& t = tab[dev];
+  if (!t.stream) {     // (first backward of a process is an eager step, never inside a capture)
+    ADP_CUDA(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking));
+    for (auto& e : t.fork) ADP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ADP_CUDA(cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming));
+  }
+  *out = &t;
+  return ADP_OK;
+}
+}  // namespace
+
+namespace adp {
+int unet_set_option(const char* name, int value) {
+  if (strcmp(name, "side_stream")) return -1;
+  if (g_side_stream < 0) g_side_stream = getenv("ADP_SIDE_STREAM") ? atoi(getenv("ADP_SIDE_STREAM")) : 1;
+  const int prev = g_side_stream;
+  g_side_stream = value ? 1 : 0;
+  return prev;
+}
+}  // namespace adp
+
 extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, const float* y, const float* dy,
                                         const adp_unet_level* params, const adp_unet_level* grads, void* ws,
                                         size_t ws_bytes, int stage_begin, int stage_end, void* stream) {
@@ -295,6 +336,20 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
     return ADP_OK;
   };
 
+  SideStream* side = nullptr;
+  if (tc) ADP_TRY(side_stream_for_device(&side));
+  bool forked = false;
+  // returns the stream the weight gradient of stage `st` should use (forks the side stream behind everything queued on s)
+  auto wgrad_stream = [&](int st) -> cudaStream_t {
+    if (!side) return s;
+    if (cudaEventRecord(side->fork[st & 31], s) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork[st & 31], 0) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return s;
+    }
+    forked = true;
+    return side->stream;
+  };
+
   for (int st = stage_begin; st < stage_end; ++st) {
     if (st == 0) {
       const LevelPlan& L = p.lv[0];
@@ -324,9 +379,12 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       const LevelPlan& L = p.lv[l];
       const LevelPlan& O = p.lv[l - 1];
       const int Ct = L.cout + L.t_c1;
-      ADP_CUDA(cudaMemsetAsync(grads[l].convT_w, 0, sizeof(float) * 16 * (size_t)Ct * L.t_cout, s));
-      ADP_TRY(conv_wgrad(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, at(ws, O.g_t), L.t_cout,
-                         grads[l].convT_w, B, L.hout, L.hout, s));
+      {
+        cudaStream_t sw = wgrad_stream(st);
+        ADP_CUDA(cudaMemsetAsync(grads[l].convT_w, 0, sizeof(float) * 16 * (size_t)Ct * L.t_cout, sw));
+        ADP_TRY(conv_wgrad(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, at(ws, O.g_t), L.t_cout,
+                           grads[l].convT_w, B, L.hout, L.hout, sw));
+      }
       ADP_TRY(conv_gather(dt, at(ws, O.g_t), params[l].convT_w, tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, L.g_r),
                           L.cout, L.t_c1 ? at(ws, L.g_q) : nullptr, L.t_c1, B, O.hout, O.hout, L.t_cout, s));
       if (l < D - 1) ADP_TRY(up_norm_bwd(l));
@@ -349,7 +407,8 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.a), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_a), 0.2f,
                                  at(ws, L.g_r), 0.f, nullptr, 0, at(ws, L.g_e), nullptr, nullptr, s));
       }
-      ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, s));
+      cudaStream_t sw = l > 0 ? wgrad_stream(st) : s;
+      ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, sw));
       if (l == 0 && thin_tc_bwd) {
         ProfScope prof(PROF_THIN, s, 2.0 * B * L.hout * L.hout * 16.0 * L.cin * L.cout);
         float* Dt = reinterpret_cast<float*>(at(ws, p.dthin));
@@ -362,11 +421,15 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       } else {
         const LevelPlan& I = p.lv[l - 1];
         ADP_TRY(conv_wgrad(dt, at(ws, L.g_e), L.cout, nullptr, 0, at(ws, I.a), L.cin, grads[l].conv_w, B, L.hout,
-                           L.hout, s));
+                           L.hout, sw));
         ADP_TRY(conv_parity(dt, at(ws, L.g_e), L.cout, nullptr, 0, params[l].conv_w, tc ? w16(params[l].conv_w_bf16, L.wb_conv) : nullptr,
                             at(ws, I.g_a), B, L.hout, L.hout, L.cin, s));
       }
     }
+  }
+  if (forked) {      // join: everything the side stream did is ordered before whatever the caller enqueues next on s
+    ADP_CUDA(cudaEventRecord(side->join, side->stream));
+    ADP_CUDA(cudaStreamWaitEvent(s, side->join, 0));
   }
   return ADP_OK;
 }

@@ -226,15 +226,18 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         resident_step()
     if not use_graph:
+        lib.adp_set_option(b"side_stream", 0)                  # the timed steps are also the profiled ones (see below)
         lib.adp_profile_enable(1)
     ms_total = timed(resident_step, args.steps)
     lib.adp_profile_enable(0)
     launches = launches_per_step * args.steps
     if use_graph:
         # the per-family CUDA events cannot live inside a replayed graph: the same K steps once more, eagerly
+        prev_side = lib.adp_set_option(b"side_stream", 0)       # family event brackets must not overlap each other
         lib.adp_profile_enable(1)
         ms_eager = timed(lambda: step._eager_step(wave_d, gt_d), args.steps)
         lib.adp_profile_enable(0)
+        lib.adp_set_option(b"side_stream", prev_side)
     else:
         ms_eager = ms_total
     pms, pwork, pcalls = (ctypes.c_double * 5)(), (ctypes.c_double * 5)(), (ctypes.c_longlong * 5)()

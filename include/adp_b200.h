@@ -312,7 +312,8 @@ int adp_profile_enable(int on);
 int adp_profile_read(double* ms, double* work, long long* calls);
 
 /* Run-time form of the ADP_TC_* tuning variables: "tc_halo" (parity kernels load the tile's input window once per
- * channel chunk), "tc_cluster", "tc_max_bn".  Returns the previous value, -1 for an unknown name. */
+ * channel chunk), "tc_cluster", "tc_max_bn", "side_stream" (U-Net weight gradients run on a library-owned side stream
+ * next to the data-gradient chain).  Returns the previous value, -1 for an unknown name. */
 int adp_set_option(const char* name, int value);
 /* Hardware probe, not on any product path (tools/probe_umma_offset.py): out[m][n] = sum_k X[m+shift][k]*W[n][k] with the
  * UMMA A descriptor started `shift` rows into a SWIZZLE_128B tile; reports whether shifted windows into one shared-memory
