@@ -339,6 +339,14 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
   SideStream* side = nullptr;
   if (tc) ADP_TRY(side_stream_for_device(&side));
   bool forked = false;
+  // join on every exit path (also the error returns): everything the side stream did is ordered before whatever the
+  // caller enqueues next on s, and a stream capture never ends with an un-joined branch
+  struct Join {
+    SideStream*& side; bool& forked; cudaStream_t s;
+    ~Join() {
+      if (forked && side && cudaEventRecord(side->join, side->stream) == cudaSuccess) (void)cudaStreamWaitEvent(s, side->join, 0);
+    }
+  } join_guard{side, forked, s};
   // returns the stream the weight gradient of stage `st` should use (forks the side stream behind everything queued on s)
   auto wgrad_stream = [&](int st) -> cudaStream_t {
     if (!side) return s;
@@ -427,11 +435,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       }
     }
   }
-  if (forked) {      // join: everything the side stream did is ordered before whatever the caller enqueues next on s
-    ADP_CUDA(cudaEventRecord(side->join, side->stream));
-    ADP_CUDA(cudaStreamWaitEvent(s, side->join, 0));
-  }
-  return ADP_OK;
+  return ADP_OK;      // (join_guard joins the side stream)
 }
 
 extern "C" int adp_unet_backward(const adp_unet_desc* d, const float* x, const float* y, const float* dy,
