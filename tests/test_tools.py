@@ -1,0 +1,40 @@
+"""The profile tooling parses the committed ncu captures (bench.py reports roofline.traffic from its output)."""
+import json
+import os
+import subprocess
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_dram_per_step_tool_reproduces_the_committed_json(tmp_path):
+    out = tmp_path / "dram.json"
+    subprocess.run([sys.executable, os.path.join(REPO, "tools", "dram_per_step.py"),
+                    os.path.join(REPO, "profiles", "r1_tc_dram_launches.csv"), str(out)], check=True, capture_output=True)
+    got = json.load(open(out))
+    ref = json.load(open(os.path.join(REPO, "profiles", "r1_tc_dram_per_step.json")))
+    assert got["launches"] == ref["launches"] == 42           # gather + parity + wgrad of E2-E8 / D8-D2, three passes each
+    assert abs(got["dram_bytes_per_launch"] - ref["dram_bytes_per_launch"]) <= 1e-6 * ref["dram_bytes_per_launch"]
+    assert 2e9 < got["dram_bytes_per_step"] < 4e9
+    thin = [e for e in got["per_launch"] if "gemm_tn" in e["kernel"]]
+    assert len(got["per_launch"]) == 48 and len(thin) == 2
+
+
+def test_launch_summary_tool_finds_one_step():
+    res = subprocess.run([sys.executable, os.path.join(REPO, "tools", "launch_summary.py"),
+                          os.path.join(REPO, "profiles", "r1q_launches_bench_b64.csv"), "--md", "--tc"], check=True,
+                         capture_output=True, text=True).stdout
+    assert "launches per step: 140" in res and "tc_wgrad_kernel" in res and "clip_adamw_kernel" in res
+
+
+def test_bench_lines_of_the_round_are_well_formed():
+    need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"}
+    for n in (1, 2, 8):
+        d = json.load(open(os.path.join(REPO, "profiles", "r1_bench_%dgpu.json" % n)))
+        assert need <= set(d), (n, need - set(d))
+        assert d["n_gpus"] == n and d["unit"] == "samples/s" and d["scaling"] == "weak" and d["dtype"] == "bf16"
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert "workload" in d["config"] and d["gpu_launches"] > 0
+    assert "cpu_baseline" in json.load(open(os.path.join(REPO, "profiles", "r1_bench_1gpu.json")))
