@@ -409,8 +409,13 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
             for (int t4 = 0; t4 < 4; ++t4) {
               const int wtap = (3 - c.pa - 2 * (t4 >> 1)) * 4 + (3 - c.pb - 2 * (t4 & 1));
 #pragma unroll
-              for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h)
-                tma_load_3d(b_dst + t4 * PS::B_TILE + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
+              for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h) {
+                if (CLUSTER)   // the pair works on the same parity / chunk: each CTA fetches half of every weight box for both
+                  tma_load_3d_mc(b_dst + t4 * PS::B_TILE + h * (TILE_K * 128) + crank * (TILE_K * 64), &p.tmWh, &full_bar[s], 3,
+                                 c.n0 + h * 64, wtap, ch + crank * (TILE_K / 2));
+                else
+                  tma_load_3d(b_dst + t4 * PS::B_TILE + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
+              }
             }
           } else if (HALO == 3) {
             // `tap` counts kernel rows here: rows y0+kh-1 .. +15, columns x0-1 .. x0+8, and the three taps of that row
@@ -785,6 +790,7 @@ int g_force_stages = 0;   // ADP_TC_STAGES environment override (tuning)
 int g_persistent = 1;     // ADP_TC_PERSISTENT=0 selects the one-tile-per-CTA kernel
 int g_cluster = 0;        // ADP_TC_CLUSTER=1: 2-CTA clusters, weight tile halves multicast between the pair
 
+int g_halo_cluster = 0;    // ADP_TC_HALO_CLUSTER=n: halo-window parity kernels with N tile <= n run as 2-CTA clusters (weight multicast)
 int g_halo = 1;            // ADP_TC_HALO=0: parity layers with N <= 128 fall back to one TMA box per tap
 int g_tc_sms = 0;          // ADP_TC_SMS=n: persistent kernels use at most n CTAs (measured: no gain next to NCCL)
 template <int BLOCK_N>
@@ -845,9 +851,32 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
           if (!hattr_set) {
             ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<HB, false, 1, false, 4>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, HS::BYTES));
+            ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<HB, true, 1, false, 4>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, HS::BYTES));
             hattr_set = true;
           }
-          tc_igemm_persist_kernel<HB, false, 1, false, 4><<<ctas, IGEMM_THREADS, HS::BYTES, s>>>(p);
+          if (g_halo_cluster && p.has_half_map && m_groups >= 2 && HB <= g_halo_cluster) {
+            // with the window loaded once, the weight tiles are most of the L2 -> SM bytes: CTA pairs on adjacent pixel tiles
+            // fetch half of every weight box each and multicast it to the other
+            const int gxp = ((m_groups + 1) / 2) * 4;
+            p.total_pair_tiles = gxp * (int)grid.y * (int)grid.z;
+            int pairs = sm_count() / 2;
+            if (pairs > p.total_pair_tiles) pairs = p.total_pair_tiles;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(2 * pairs);
+            cfg.blockDim = dim3(IGEMM_THREADS);
+            cfg.dynamicSmemBytes = HS::BYTES;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            ADP_CUDA(cudaLaunchKernelEx(&cfg, (tc_igemm_persist_kernel<HB, true, 1, false, 4>), p));
+          } else {
+            tc_igemm_persist_kernel<HB, false, 1, false, 4><<<ctas, IGEMM_THREADS, HS::BYTES, s>>>(p);
+          }
         } else {
           using HS = PersistSmem<HB, 3>;
           static bool h3attr_set = false;
@@ -937,6 +966,8 @@ struct StagesEnvInit {
     if (pe) g_persistent = atoi(pe);
     const char* ce = getenv("ADP_TC_CLUSTER");
     if (ce) g_cluster = atoi(ce);
+    const char* hce = getenv("ADP_TC_HALO_CLUSTER");
+    if (hce) g_halo_cluster = atoi(hce);
     const char* he = getenv("ADP_TC_HALO");
     if (he) g_halo = atoi(he);
     const char* se = getenv("ADP_TC_SMS");
@@ -956,6 +987,7 @@ thread_local size_t g_scratch_bytes = 0;
 int tc_set_option(const char* name, int value) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_halo;
+  else if (!strcmp(name, "tc_halo_cluster")) slot = &g_halo_cluster;
   else if (!strcmp(name, "tc_cluster")) slot = &g_cluster;
   else if (!strcmp(name, "tc_max_bn")) slot = &g_max_block_n;
   if (!slot) return -1;

@@ -245,14 +245,17 @@ def test_halo_window_kernel_is_used_and_matches_the_per_tap_kernel():
     ref = F.conv_transpose2d(torch.cat([from_nhwc(x0r), from_nhwc(x1r)], 1), wm.to(torch.bfloat16).float().permute(0, 3, 1, 2),
                              stride=2, padding=1)
     outs = []
-    for halo in (1, 0):
+    for halo, pair in ((1, 0), (0, 0), (1, 128)):       # pair: 2-CTA clusters multicasting the weight tiles between two pixel tiles
         prev = lib.adp_set_option(b"tc_halo", halo)
+        prevc = lib.adp_set_option(b"tc_halo_cluster", pair)
         y = torch.empty(B, 2 * H, 2 * H, Cout, device=DEV, dtype=torch.bfloat16)
         _lib.check(lib.adp_convT2d_k4s2_fprop(_lib.ADP_BF16, x0r.data_ptr(), C0, x1r.data_ptr(), C1, wm.data_ptr(), w_f.data_ptr(),
                                               y.data_ptr(), B, H, H, Cout, None))
         lib.adp_set_option(b"tc_halo", prev)
+        lib.adp_set_option(b"tc_halo_cluster", prevc)
         assert rel_to_max(from_nhwc(y).cpu(), ref.cpu()) <= 1.5e-2
         outs.append(from_nhwc(y))
+    assert torch.equal(outs[0], outs[2])                 # same arithmetic, only the weight delivery differs
     assert lib.adp_set_option(b"tc_halo", 1) == 1 and lib.adp_set_option(b"no_such_option", 1) == -1
     # same products, different summation order (chunk-major instead of tap-major): equal up to bf16 rounding of the output
     assert rel_to_max(outs[0].cpu(), outs[1].cpu()) <= 8e-3
