@@ -99,7 +99,7 @@ struct IgemmParams {
   int epi, stat_by_col;
   float escale;
   int* stat_m; float* stat_l; const float* delta; const bf16* pmat;
-  int halo;                           // 0, or the HALO instantiation: 4 = parity mode (mode 1), 3 = 3x3 rows (mode 4)
+  int halo;                           // 0, or the HALO instantiation: 4 / 8 = parity mode (one / two tiles), 3 = 3x3 rows
   int wmode;                          // modes 2/4: 1 = weights through the MN-major 3-D map (N | taps | Ct), taps reversed
   int f32_rows;                       // modes 2/4: write fp32 [pixels][N] to out_f32 instead of bf16 (any BLOCK_N)
   long long rows_guard;               // > 0: output rows (opix) >= rows_guard are not stored (ragged GEMM M)
@@ -330,22 +330,27 @@ __device__ __forceinline__ TileCoord decode_pair_tile(const IgemmParams& p, int 
 // start at any 128-byte row and use any group pitch: tools/probe_umma_offset.py), next to those taps' weight tiles.
 //   HALO = 4: parity (transposed-conv) mode, k-block = one 64-channel chunk, 2 x 2 taps, window 17 x 9 pixels
 //   HALO = 3: 3x3 / stride 1 mode, k-block = (kernel row, chunk), 3 taps of that row, window 16 x 10 pixels
+//   HALO = 8: parity mode with TWO 16 x 8 tiles side by side (M = 256, two accumulators) sharing the four weight tiles:
+//             window 17 x 17 pixels, second tile = the same window 8 pixels (1024 B) further -- the N = 64 layers are
+//             bound by what the SM ingests, and the weight tiles are most of it once the window is shared
 template <int HALO> struct HaloGeom {
-  static constexpr int W = HALO == 3 ? 10 : 9, H = HALO == 3 ? 16 : 17;
-  static constexpr int BOX_BYTES = W * H * TILE_K * 2;            // 20480 / 19584
+  static constexpr int W = HALO == 3 ? 10 : (HALO == 8 ? 17 : 9), H = HALO == 3 ? 16 : 17;
+  static constexpr int BOX_BYTES = W * H * TILE_K * 2;            // 20480 / 19584 / 36992
+  static constexpr int TAPS = HALO == 3 ? 3 : 4;
+  static constexpr int HALVES = HALO == 8 ? 2 : 1;
 };
 template <int BLOCK_N, int HALO = 0>
 struct PersistSmem {
-  static constexpr int A_BYTES = HALO ? 20480 : A_STAGE_BYTES;
+  static constexpr int A_BYTES = HALO == 8 ? 37888 : (HALO ? 20480 : A_STAGE_BYTES);
   static constexpr int B_TILE = BLOCK_N * TILE_K * 2;
-  static constexpr int B_BYTES = HALO ? HALO * B_TILE : B_TILE;
+  static constexpr int B_BYTES = HALO ? HaloGeom<HALO>::TAPS * B_TILE : B_TILE;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING = 4 * 4096;        // epilogue transpose buffers: 4 warps x (32 rows x 128 B)
   static constexpr int BAR_BYTES = 512;           // pipeline barriers, TMEM slot
   static constexpr int RING_BUDGET = HALO ? (227 * 1024 - 1024 - BAR_BYTES - STAGING - 1024) : 196 * 1024;
   static constexpr int STAGES = RING_BUDGET / STAGE_BYTES > 10 ? 10 : RING_BUDGET / STAGE_BYTES;
   static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + STAGING;
-  static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int ACC_COLS = (HALO == 8 ? 2 : 1) * (BLOCK_N < 32 ? 32 : BLOCK_N);
 };
 
 // EG = number of epilogue warp groups (4 warps each): 1 for the convolutions, 2 for the math-heavy STFT epilogue
@@ -399,8 +404,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
           mbar_wait(&empty_bar[s], ph ^ 1);
           unsigned char* a_dst = smem + s * PS::STAGE_BYTES;
           unsigned char* b_dst = a_dst + PS::A_BYTES;
-          mbar_expect_tx(&full_bar[s], HALO ? HaloGeom<HALO>::BOX_BYTES + HALO * PS::B_TILE : PS::STAGE_BYTES);
-          if (HALO == 4) {
+          mbar_expect_tx(&full_bar[s], HALO ? HaloGeom<HALO>::BOX_BYTES + HaloGeom<HALO>::TAPS * PS::B_TILE : PS::STAGE_BYTES);
+          if (HALO == 4 || HALO == 8) {
             // one 64-channel chunk: the tile's halo window once + the weight tiles of the four taps of this parity
             const int cx = c.x0 + c.pb - 1, cy = c.y0c + c.pa - 1;
             if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, cx, cy, c.b0);
@@ -518,14 +523,18 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
           const uint64_t ad0 = a_desc0 + stage_off, bd0 = b_desc0 + stage_off;
           if (HALO) {
 #pragma unroll
-            for (int t4 = 0; t4 < HALO; ++t4) {
+            for (int t4 = 0; t4 < HaloGeom<HALO>::TAPS; ++t4) {
               // window shifted by (th, tw) [parity] or by tw [3x3 row] pixels
-              const int shift_rows = HALO == 4 ? (t4 >> 1) * HaloGeom<HALO>::W + (t4 & 1) : t4;
-              const uint64_t at = ad0 + (uint64_t)((shift_rows * 128) >> 4);
+              const int shift_rows = HALO != 3 ? (t4 >> 1) * HaloGeom<HALO>::W + (t4 & 1) : t4;
               const uint64_t bt4 = bd0 + (uint64_t)((t4 * PS::B_TILE) >> 4);
 #pragma unroll
-              for (int k = 0; k < TILE_K / 16; ++k)
-                umma_bf16(tacc, at + (uint64_t)(k * 2), bt4 + (uint64_t)(k * b_kstep), idesc, (it | t4 | k) != 0 ? 1u : 0u);
+              for (int half = 0; half < HaloGeom<HALO>::HALVES; ++half) {      // HALO = 8: second tile 8 pixels to the right
+                const uint64_t at = ad0 + (uint64_t)(((shift_rows + 8 * half) * 128) >> 4);
+#pragma unroll
+                for (int k = 0; k < TILE_K / 16; ++k)
+                  umma_bf16(tacc + (uint32_t)(half * BLOCK_N), at + (uint64_t)(k * 2), bt4 + (uint64_t)(k * b_kstep), idesc,
+                            (it | t4 | k) != 0 ? 1u : 0u);
+              }
             }
           } else {
 #pragma unroll
@@ -546,7 +555,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     const int q = warp & 3;
     const int egroup = (warp - 2) >> 2;
     const int r = q * 32 + lane;
-    const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
+    const int ewt = HALO == 8 ? 8 : p.Wt;             // HALO = 8: the tile is two 16 x 8 halves, one accumulator each
+    const int wt = r % ewt, ht = (r / ewt) % p.Ht, bt = r / (ewt * p.Ht);
     constexpr bool STAGED_OK = BLOCK_N >= 64 && EG == 1;
     unsigned char* stg = smem + STAGES * PS::STAGE_BYTES + PS::BAR_BYTES + (STAGED_OK ? (warp - 2) * 4096 : 0);
     const bool staged = p.splits <= 1 && p.mode != 3 && !p.f32_rows && !(ATT && (p.epi == 1 || p.epi == 2)) &&
@@ -555,14 +565,16 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     for (int t = worker; t < ntiles; t += nworkers, ++local) {
       const TileCoord c = tile_at(t);
       const uint32_t buf = local & 1u, use = local >> 1;
-      const int b = c.b0 + bt, py = c.y0c + ht, px = c.x0 + wt;
+      mbar_wait(&tfull_bar[buf], use & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < HaloGeom<HALO>::HALVES; ++half) {
+      const int b = c.b0 + bt, py = c.y0c + ht, px = c.x0 + 8 * half + wt;
       size_t opix;
       if (p.mode != 1) opix = ((size_t)b * p.Hs + py) * p.Ws + px;
       else opix = ((size_t)b * 2 * p.Hs + 2 * py + c.pa) * (2 * p.Ws) + 2 * px + c.pb;
       const bool valid = b < p.B && c.nkb > 0 && (p.rows_guard <= 0 || (long long)opix < p.rows_guard);
-      mbar_wait(&tfull_bar[buf], use & 1u);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + buf * ACC + ((uint32_t)(q * 32) << 16);
+      const uint32_t tacc = tmem_base + buf * ACC + (uint32_t)(half * BLOCK_N) + ((uint32_t)(q * 32) << 16);
       float vmin = INFINITY, vmax = -INFINITY;
       if (STAGED_OK && staged) {
         // bf16 outputs, 64 columns at a time: every lane packs its own pixel row (128 B) into the warp's swizzled
@@ -736,6 +748,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
           atomicMax(&p.minmax[2 * b + 1], float_to_ordered(vmax));
         }
       }
+      }    // half
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);      // this warp's quarter of the accumulator is free again
@@ -791,7 +804,8 @@ int g_persistent = 1;     // ADP_TC_PERSISTENT=0 selects the one-tile-per-CTA ke
 int g_cluster = 0;        // ADP_TC_CLUSTER=1: 2-CTA clusters, weight tile halves multicast between the pair
 
 int g_halo_cluster = 0;    // ADP_TC_HALO_CLUSTER=n: halo-window parity kernels with N tile <= n run as 2-CTA clusters (weight multicast)
-int g_halo = 1;            // ADP_TC_HALO=0: parity layers with N <= 128 fall back to one TMA box per tap
+int g_halo = 1;            // ADP_TC_HALO: 0 = one TMA box per tap, 1 = halo windows, 2 = + double tiles for N = 64 (no gain: those
+                           // launches already sit at the smem-read ceiling of the M128 x N64 MMA shape, ~990 TFLOP/s)
 int g_tc_sms = 0;          // ADP_TC_SMS=n: persistent kernels use at most n CTAs (measured: no gain next to NCCL)
 template <int BLOCK_N>
 int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
@@ -877,6 +891,16 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
           } else {
             tc_igemm_persist_kernel<HB, false, 1, false, 4><<<ctas, IGEMM_THREADS, HS::BYTES, s>>>(p);
           }
+        } else if (p.halo == 8) {
+          if (BLOCK_N != 64) { adp_set_error("double-tile halo mode needs BLOCK_N 64"); return ADP_ERR_ARG; }
+          using HS = PersistSmem<64, 8>;
+          static bool h8attr_set = false;
+          if (!h8attr_set) {
+            ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<64, false, 1, false, 8>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, HS::BYTES));
+            h8attr_set = true;
+          }
+          tc_igemm_persist_kernel<64, false, 1, false, 8><<<ctas, IGEMM_THREADS, HS::BYTES, s>>>(p);
         } else {
           using HS = PersistSmem<HB, 3>;
           static bool h3attr_set = false;
@@ -1058,7 +1082,9 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
   // narrow-N layers are bound by L2 -> SM operand traffic: load the tile's input window once per channel chunk (HALO)
   const bool halo = g_halo && g_persistent && (bn == 64 || bn == 128) && Hi >= 16 && Wi >= 8 && Hi % 16 == 0 && Wi % 8 == 0 &&
                     (long long)B * (Hi / 16) * (Wi / 8) * 4 * (N / bn) >= sm_count();
-  if (halo) { p.Wt = 8; p.Ht = 16; p.Bt = 1; p.halo = 4; }
+  // N = 64: two tiles side by side share the weight tiles (HALO = 8) when the grid is still large enough
+  const bool halo2 = halo && g_halo >= 2 && bn == 64 && Wi % 16 == 0 && (long long)B * (Hi / 16) * (Wi / 16) * 4 * (N / bn) >= sm_count();
+  if (halo) { p.Wt = halo2 ? 16 : 8; p.Ht = 16; p.Bt = 1; p.halo = halo2 ? 8 : 4; }
   p.tiles_w = Wi / p.Wt; p.tiles_h = Hi / p.Ht;
   p.B = B; p.Hs = Hi; p.Ws = Wi; p.mode = 1; p.C0 = C0; p.C1 = C1; p.Ct = Ct; p.N = N; p.N0 = N; p.N1 = 0;
   p.kblocks = (halo ? 1 : 4) * (Ct / TILE_K);
@@ -1069,7 +1095,7 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)Wi * C * 2, (uint64_t)Hi * Wi * C * 2};
     uint32_t box[4] = {TILE_K, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
-    uint32_t hbox[4] = {TILE_K, HaloGeom<4>::W, HaloGeom<4>::H, 1};
+    uint32_t hbox[4] = {TILE_K, (uint32_t)(halo2 ? HaloGeom<8>::W : HaloGeom<4>::W), HaloGeom<4>::H, 1};
     ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, halo ? hbox : box));
   }
   {  // w_kn: bf16 [Ct][16][N] (the master layout, cast)

@@ -245,7 +245,8 @@ def test_halo_window_kernel_is_used_and_matches_the_per_tap_kernel():
     ref = F.conv_transpose2d(torch.cat([from_nhwc(x0r), from_nhwc(x1r)], 1), wm.to(torch.bfloat16).float().permute(0, 3, 1, 2),
                              stride=2, padding=1)
     outs = []
-    for halo, pair in ((1, 0), (0, 0), (1, 128)):       # pair: 2-CTA clusters multicasting the weight tiles between two pixel tiles
+    # halo 2: two tiles share the weight tiles (N = 64); pair: 2-CTA clusters multicasting the weight tiles
+    for halo, pair in ((1, 0), (0, 0), (1, 128), (2, 0)):
         prev = lib.adp_set_option(b"tc_halo", halo)
         prevc = lib.adp_set_option(b"tc_halo_cluster", pair)
         y = torch.empty(B, 2 * H, 2 * H, Cout, device=DEV, dtype=torch.bfloat16)
@@ -256,6 +257,7 @@ def test_halo_window_kernel_is_used_and_matches_the_per_tap_kernel():
         assert rel_to_max(from_nhwc(y).cpu(), ref.cpu()) <= 1.5e-2
         outs.append(from_nhwc(y))
     assert torch.equal(outs[0], outs[2])                 # same arithmetic, only the weight delivery differs
+    assert torch.equal(outs[0], outs[3])                 # ... or the tile pairing
     assert lib.adp_set_option(b"tc_halo", 1) == 1 and lib.adp_set_option(b"no_such_option", 1) == -1
     # same products, different summation order (chunk-major instead of tap-major): equal up to bf16 rounding of the output
     assert rel_to_max(outs[0].cpu(), outs[1].cpu()) <= 8e-3
