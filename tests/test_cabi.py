@@ -122,3 +122,31 @@ def test_binaural_mirror_state_dict_and_init_match_reference_layout(golden_dir):
     net.load_state_dict({"module." + k: v for k, v in sd.items()})
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 2, 128, 128))                     # no CPU fallback
+
+
+def test_new_host_entry_points_refuse_cpu_and_unsupported_configs(tmp_path):
+    """No CPU fallbacks anywhere on the product path, and the config-4 mirror states its limits instead of degrading."""
+    import torch
+    from audio_depth_estimation_b200 import feature, utils_criterion
+    from audio_depth_estimation_b200.checkpoint import checkpoint_path
+    from audio_depth_estimation_b200.models.binaural_attention_model import BinauralAttentionDepthNet, Up
+    from audio_depth_estimation_b200.optim import FusedClipAdamWParams
+    with pytest.raises(RuntimeError):
+        feature.DepthTransform(64, 30.0)(torch.zeros(1, 8, 8))
+    with pytest.raises(RuntimeError):
+        feature.melspectrogram(torch.zeros(2, 4000), n_fft=512, win_length=64)
+    with pytest.raises(RuntimeError):
+        utils_criterion.batch_errors(torch.ones(1, 1, 4, 4), torch.ones(1, 1, 4, 4), depth_norm=False, max_depth=30.0)
+    with pytest.raises(ValueError):
+        utils_criterion.batch_errors(torch.ones(1, 1, 4, 4), torch.ones(1, 1, 4, 4), depth_norm=False, max_depth=30.0, protocol="x")
+    with pytest.raises(RuntimeError):
+        FusedClipAdamWParams([torch.nn.Parameter(torch.zeros(4))])
+    with pytest.raises(NotImplementedError):
+        BinauralAttentionDepthNet(base_channels=32)
+    with pytest.raises(NotImplementedError):
+        Up(128, 64, bilinear=False)
+    assert checkpoint_path("exp", 3, root=str(tmp_path)).endswith(os.path.join("exp", "checkpoint_3.pth"))
+    # every conv weight of the mirror lives in channels_last memory (the layout the kernels read), also after .to()/.float()
+    net = BinauralAttentionDepthNet(64, True, 128, 30.0, [5]).float()
+    w = net.up1.conv.double_conv[0].weight
+    assert w.shape == (512, 1024, 3, 3) and w.stride() == (9 * 1024, 1, 3 * 1024, 1024)
