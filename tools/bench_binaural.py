@@ -3,6 +3,10 @@ attention_levels [3,4,5] and [2,3,4,5]).  Prints one JSON line per case (CUDA-ev
 
     PYTHONPATH=. python tools/bench_binaural.py [--steps 5] [--warmup 2] [--size 256]
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import argparse
 import json
 

@@ -1,5 +1,8 @@
 """Time the building blocks of one (sample, direction) of level-2 cross attention: T tokens, Dq = 64 (padded), C channels."""
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 

@@ -1,4 +1,8 @@
 """Time the 3x3 convolution family of config 4 per layer shape (B = 8, 256 x 256 input)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from audio_depth_estimation_b200 import _lib

@@ -1,4 +1,8 @@
 """How well-conditioned is d(gamma) of the cross-attention residual?  Prints |sum dy*att| / sum |dy*att| per call."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 

@@ -1,5 +1,9 @@
 """Can a SWIZZLE_128B UMMA A operand start at an arbitrary 128-byte row of a larger shared-memory tile?
 Prints, for every row shift 0..15 and descriptor base_offset in {0, shift & 7}, whether out == X[shift:shift+128] @ W^T."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from audio_depth_estimation_b200 import _lib
