@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 from .feature import SpectrogramTransform
-from .optim import FusedClipAdamW
+from .optim import FusedClipAdamW, FusedClipAdamWParams
 from .utils_criterion import METRIC_NAMES, batch_errors
 from .utils_loss import DepthCriterion
 
@@ -211,3 +211,36 @@ def evaluate_loader(step, batches, protocol="test"):
         raise ValueError("evaluate_loader: no batches")
     row = torch.cat([torch.cat(losses).mean().reshape(1), torch.cat(tables).mean(0)]).tolist()
     return dict(zip(("loss",) + METRIC_NAMES, row))
+
+
+class ModuleTrainStep:
+    """The same step body (train_binaural_attention.py: forward -> masked criterion -> backward -> clip_grad_norm_ ->
+    AdamW) for a model whose parameters are ordinary separate tensors, e.g. the config-4 BinauralAttentionDepthNet:
+    `DepthCriterion` + `FusedClipAdamWParams`.  `features` (optional) is applied to the batch first, e.g.
+    `SpectrogramTransform.for_cfg(cfg)`.  Single process; returns the loss as a 0-dim device tensor."""
+
+    def __init__(self, cfg, model, lr=None, max_norm=1.0, features=None):
+        self.cfg = cfg
+        self.model = model
+        self.features = features
+        self.criterion = DepthCriterion.from_cfg(cfg)
+        lr = lr if lr is not None else getattr(cfg.mode, "learning_rate", 1e-3)
+        self.optimizer = FusedClipAdamWParams(model.parameters(), lr=lr, max_norm=max_norm)
+
+    def __call__(self, batch, gtdepth):
+        self.model.train()
+        x = self.features(batch) if self.features is not None else batch
+        self.optimizer.zero_grad()
+        loss = self.criterion(self.model(x), gtdepth)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    @torch.no_grad()
+    def evaluate(self, batch, gtdepth, metrics=False, protocol="train"):
+        self.model.eval()
+        pred = self.model(self.features(batch) if self.features is not None else batch)
+        loss = self.criterion(pred, gtdepth)
+        if metrics:
+            return pred, loss, batch_errors(gtdepth, pred, self.cfg, protocol=protocol)
+        return pred, loss

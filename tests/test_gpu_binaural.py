@@ -413,3 +413,26 @@ def test_binaural_train_steps_with_fused_optimizer_match_torch():
             assert torch.allclose(p_.detach(), sp_.detach(), rtol=1e-5, atol=2e-7)
         losses.append(float(loss))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_module_train_step_on_config4_from_waveforms():
+    """ModuleTrainStep: waveform -> (GPU feature) -> BinauralAttentionDepthNet -> Combined loss -> fused clip + AdamW; the
+    loss goes down and evaluate() returns the metric table."""
+    from audio_depth_estimation_b200 import synthetic
+    from audio_depth_estimation_b200.config_loader import load_config
+    from audio_depth_estimation_b200.feature import SpectrogramTransform
+    from audio_depth_estimation_b200.models.binaural_attention_model import BinauralAttentionDepthNet
+    from audio_depth_estimation_b200.training import ModuleTrainStep
+    cfg = load_config()
+    cfg.dataset.images_size = 128
+    torch.manual_seed(5)
+    net = BinauralAttentionDepthNet(64, True, 128, cfg.dataset.max_depth, [4, 5]).cuda()
+    with torch.no_grad():
+        net.outc[0].weight.mul_(0.1)
+    step = ModuleTrainStep(cfg, net, lr=1e-3, features=SpectrogramTransform.for_cfg(cfg))
+    wave = torch.from_numpy(synthetic.waveform(2, synthetic.V2_LEN, seed=331)).cuda()
+    gt = torch.from_numpy(synthetic.gt_depth(2, 128, 30.0, seed=332, normalised=False)).cuda()
+    losses = [float(step(wave, gt)) for _ in range(4)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    pred, loss, errs = step.evaluate(wave, gt, metrics=True, protocol="test")
+    assert pred.shape == (2, 1, 128, 128) and errs.shape == (2, 7) and bool(torch.isfinite(errs).all()) and np.isfinite(float(loss))
