@@ -215,7 +215,7 @@ def test_metrics_oracle_raw_branches(golden_dir):
 
 
 # ---- config 4: BinauralAttentionDepthNet -----------------------------------------------------------------------
-@pytest.mark.parametrize("name,levels", [("lv345_b2", (3, 4, 5))])
+@pytest.mark.parametrize("name,levels", [("lv345_b2", (3, 4, 5)), ("lv2345_b2", (2, 3, 4, 5))])
 def test_binaural_oracle_matches_reference(golden_dir, name, levels):
     """oracle/binaural_oracle.forward on the reference's own initial weights (same seed, same module construction order
     in the mirror) reproduces the reference's forward, gradients and eval forward."""
