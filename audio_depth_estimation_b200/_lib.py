@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libadp_b200.so")
+# ADP_LIB_PATH: load another build of the same C ABI (A/B measurements against an earlier build)
+LIB_PATH = os.environ.get("ADP_LIB_PATH") or os.path.join(_PKG, "libadp_b200.so")
 
 ADP_F32 = 0
 ADP_BF16 = 1

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include "adp_common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -25,12 +26,13 @@ extern "C" int adp_device_is_sm100(void) {
   return (major == 10 && minor == 0) ? 1 : 0;
 }
 
-static long long g_launches = 0;
-void adp_count_launch() { ++g_launches; }
-extern "C" long long adp_launch_count(void) { return g_launches; }
-static long long g_tc_launches = 0;
-void adp_count_tc_launch() { ++g_tc_launches; }
-extern "C" long long adp_tc_launch_count(void) { return g_tc_launches; }
+// (relaxed atomics: several host threads, e.g. one per device, may launch concurrently)
+static std::atomic<long long> g_launches{0};
+void adp_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long adp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+static std::atomic<long long> g_tc_launches{0};
+void adp_count_tc_launch() { g_tc_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long adp_tc_launch_count(void) { return g_tc_launches.load(std::memory_order_relaxed); }
 
 namespace adp {
 
@@ -61,14 +63,31 @@ ProfScope::~ProfScope() {
   if (slot >= 0) cudaEventRecord(g_prof_ev[slot][1], stream);
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev;
+}
+
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> tab[ADP_MAX_DEVICES];
+  const int dev = current_device() % ADP_MAX_DEVICES;
+  int n = tab[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    tab[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): `done` is the call site's bitmap of devices
+int ensure_smem_attr(const void* func, int bytes, std::atomic<unsigned long long>* done) {
+  const int dev = current_device() % ADP_MAX_DEVICES;
+  if ((done->load(std::memory_order_relaxed) >> dev) & 1ull) return ADP_OK;
+  ADP_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done->fetch_or(1ull << dev, std::memory_order_relaxed);
+  return ADP_OK;
 }
 
 static int g_tc = -1;
@@ -89,8 +108,9 @@ extern "C" int adp_set_tensor_core(int on) {
   return prev;
 }
 
-// Tuning switches of the tensor-core kernels (the ADP_TC_* environment variables, at run time): "tc_halo" (halo-window
-// parity kernels), "tc_cluster" (2-CTA weight multicast), "tc_max_bn" (largest N tile).  Returns the previous value.
+// Switches of the tensor-core kernels: "tc_halo" (halo-window parity / 3x3 kernels; 0 = one TMA box per tap, the
+// A/B partner the parity tests compare against), "tc_max_bn" (largest N tile), "tc_stats" (BatchNorm statistics from
+// the convolution epilogue).  Returns the previous value.
 extern "C" int adp_set_option(const char* name, int value) {
   if (!name) return -1;
   const int prev = adp::tc_set_option(name, value);

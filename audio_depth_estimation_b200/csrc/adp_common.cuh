@@ -170,9 +170,20 @@ __device__ __forceinline__ float ordered_to_float(int i) {
 }
 
 // ---- internal cross-file entry points (host) -------------------------------
+#include <atomic>
+#define ADP_MAX_DEVICES 64
+
 namespace adp {
 
+int current_device();
 int sm_count();
+int ensure_smem_attr(const void* func, int bytes, std::atomic<unsigned long long>* done);
+// opt a kernel into > 48 KB of dynamic shared memory once per device (not once per process)
+#define ADP_SMEM_ATTR(func, bytes)                                                  \
+  do {                                                                              \
+    static std::atomic<unsigned long long> done_{0};                                \
+    ADP_TRY(adp::ensure_smem_attr(reinterpret_cast<const void*>(func), (bytes), &done_)); \
+  } while (0)
 
 // Optional per-family device timing (CUDA events on the launching stream), read by bench.py.
 enum ProfKind { PROF_GATHER = 0, PROF_PARITY, PROF_WGRAD, PROF_THIN, PROF_ELEM, PROF_KINDS };
@@ -196,6 +207,9 @@ struct BnFin {
   int training;
   float eps, momentum;
   float *scale, *shift, *mean, *invstd;   // outputs, kept for the backward pass
+  // x is stored as (true value - mean_offset[c]) (first-level centring, adp_unet.cu); NULL = no offset.  Batch statistics
+  // of the stored tensor are used as they are; the running mean and the eval-mode shift refer to the true value.
+  const float* mean_offset;
 };
 int bn_finalize(const BnFin& f, int C, cudaStream_t s);
 // finalize + (z = x*scale+shift; out0 = lrelu(z, slope0); out1 (optional) = lrelu(z, slope1)) in one launch
@@ -263,11 +277,28 @@ int thin_last_convT_wgrad(int dtype, const void* x0, int C0, const void* x1, int
                           int Hi, int Wi, cudaStream_t s);
 // tensor-core route for the thin layers: bf16 patch rows [pixels][64], padded weights, result folding
 int thin_patch_rows(const float* img, void* out, int B, int Cin, int H, int W, int split, cudaStream_t s);
+// first-level centring (adp_unet.cu: use_center).  xsum[ci] += sum of plane ci over the batch (x NCHW fp32)
+int center_input_sums(const float* x, int B, int Cin, long long HW, double* xsum, cudaStream_t s);
+// m[n] = bf16(LeakyReLU_0.2(sum_{tap,ci} w1[n][tap][ci] * mean_x[ci]))  (n < 64, w1 fp32 [64][16][Cin]);
+// T[n2] = sum_{tap,c} w2b[n2][tap][c] * m[c]  (w2b bf16 [N2][16][64]);  border ring of a0pad bf16 [B, H+2, W+2, 64] = -m
+int center_tables(const double* xsum, double inv_count, const float* w1, int Cin, const void* w2b, int N2, float* m,
+                  float* T, void* a0pad, int B, int H, int W, cudaStream_t s);
+// dw[n][tap][c] += m[c] * scale[n] * gsum[n]   (dw fp32 [N2][16][C])
+int center_wgrad_fix(float* dw, const float* m, const float* scale, const double* gsum, int N2, int C, cudaStream_t s);
 int thin_pad_rows(const float* src, void* dst, int R, int K, int dup, cudaStream_t s);
 int thin_fold_wgrad(const float* D, float* dw, int mode, int K, cudaStream_t s);
 // y[pix][n] = sum_c (x0|x1)[pix][c] * w_nk[n][c] over NHWC pixels (adp_conv_tc.cu)
+// Optional extras of the tensor-core convolutions (all zero / NULL = none):
+struct ConvExtras {
+  double* stats;        // gather / parity: [2N] sum and sum of squares of the stored output per channel, ACCUMULATED by the
+  int* stats_done;      //   epilogue when the launch qualifies (un-split, staged bf16 output); *stats_done = 1 then, else untouched
+  int pad_in;           // gather: the input is [B, Hi+2, Wi+2, C] with an explicit one-pixel border
+  int pad_out;          // pointwise act_dual: y0 is the interior of a [B, Hi+2, Wi+2, N] tensor
+  const float* center;  // pointwise act_dual: y0 = lrelu(D, slope0) - center[n]
+};
 int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_nk, void* y0, int N0, void* y1, int N1,
-                 int act_dual, float slope0, float slope1, int B, int Hi, int Wi, cudaStream_t s);
+                 int act_dual, float slope0, float slope1, int B, int Hi, int Wi, cudaStream_t s,
+                 const ConvExtras* ex = nullptr);
 // D[128][NT] (fp32, zeroed by the callee) = sum_rows A[row][0:128] * Bm[row][0:NT]; A = two 64-column halves
 // (a0: [rows][lda0] at column ca0, a1: [rows][lda1] at column ca1), Bm: [rows][ldb], all bf16 row-major (adp_wgrad_tc.cu)
 int tc_gemm_tn(const void* a0, int lda0, int ca0, const void* a1, int lda1, int ca1, const void* bm, int ldb, int NT,
@@ -290,12 +321,13 @@ int tc_stft_mag(const float* wave, int rows, int L, int pitch, int n_fft, int ho
 // tcgen05 paths (adp_conv_tc.cu), bf16 operands, fp32 accumulate in TMEM.
 // w_nk: bf16 [N][16][C] (K-major B operand)
 int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, int N1,
-                   int B, int Hi, int Wi, int C, cudaStream_t s);
+                   int B, int Hi, int Wi, int C, cudaStream_t s, const ConvExtras* ex = nullptr);
 // w_kn: bf16 [C0+C1][16][N] (N-major B operand: the master layout of the weight, cast)
 int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* w_kn, void* y,
-                    int B, int Hi, int Wi, int N, cudaStream_t s);
+                    int B, int Hi, int Wi, int N, cudaStream_t s, const ConvExtras* ex = nullptr);
+// g_pad = 1: G is [B, 2Hs+2, 2Ws+2, N] with an explicit one-pixel border (its values enter the sums)
 int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int N,
-             float* dw, int B, int Hs, int Ws, cudaStream_t s);
+             float* dw, int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0);
 // 3x3 / stride 1 / pad 1 on the same kernel (binaural_attention_model.py DoubleConv).  wmode 0: w = bf16 [N][9][Ct]
 // (forward); wmode 1: w = bf16 [Ct][9][N] read MN-major with reversed taps (data gradient through the forward weight).
 // scratch: fp32 [pixels][N] for split-K on small grids, or NULL.
@@ -318,7 +350,7 @@ int tc_gemm_rows(const void* a0, int K0, const void* a1, int K1, const void* bm,
                  int N1, float* c32, long long M, cudaStream_t s, const GemmEpilogue* epi = nullptr);
 // fp32 scratch used to split the K range of deep, small-M layers across CTAs (NULL: never split)
 void tc_set_scratch(void* ptr, size_t bytes);
-// tuning switches ("tc_halo", "tc_cluster", "tc_max_bn"): returns the previous value, -1 for an unknown name
+// switches ("tc_halo", "tc_max_bn", "tc_stats"): returns the previous value, -1 for an unknown name
 int tc_set_option(const char* name, int value);
 int unet_set_option(const char* name, int value);      // "side_stream"
 bool tc_supported_gather(int B, int Hi, int Wi, int C, int N0, int N1);

@@ -70,12 +70,10 @@ using namespace tc;
 constexpr int TILE_M = 128;
 constexpr int TILE_K = 64;            // bf16 elements = one 128-byte swizzled row
 constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;
-constexpr int IGEMM_THREADS = 192;    // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
-constexpr int PERSIST_THREADS = 320;  // persistent kernel: warps 2-9 = two epilogue groups (alternate 32-column chunks)
+// threads: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocation, then 4 (convolutions) or 8 (STFT) epilogue warps
 
 struct IgemmParams {
   CUtensorMap tmA0, tmA1, tmW;
-  CUtensorMap tmWh;                   // cluster mode: half-height weight boxes (each CTA of a pair multicasts one half)
   CUtensorMap tmA2;                   // mode 3: third bf16 slice of the frames
   // tile geometry over the "small" pixel grid (conv outputs for F1, convT inputs for F2)
   int Wt, Ht, Bt, tiles_w, tiles_h;
@@ -87,10 +85,7 @@ struct IgemmParams {
   bf16* y0; bf16* y1;
   float* partial;                     // fp32 [out pixels][N] when splits > 1
   float* out_f32;                     // mode 2: fp32 [pixels][BLOCK_N] result
-  int stages;                         // smem ring depth actually used (<= IgemmSmem::STAGES)
   int gx, gy, gz, total_tiles;        // logical grid (x fastest) walked by the persistent kernel
-  int total_pair_tiles;               // cluster mode: tiles of two adjacent m-tiles
-  int has_half_map;                   // tmWh encoded
   // Attention epilogues of the row GEMM (mode 2): D = A * B^T is a tile of the score matrix (row = opix, column = n)
   //   epi 1: stat_m[row] = max(stat_m[row], max_n scale*D)                     (ordered-int atomicMax)
   //   epi 2: stat_l[row] += sum_n exp(scale*D - m[row])
@@ -99,193 +94,26 @@ struct IgemmParams {
   int epi, stat_by_col;
   float escale;
   int* stat_m; float* stat_l; const float* delta; const bf16* pmat;
-  int halo;                           // 0, or the HALO instantiation: 4 / 8 = parity mode (one / two tiles), 3 = 3x3 rows
+  int halo;                           // 0, or the HALO instantiation: 4 = parity mode, 3 = 3x3 rows
   int wmode;                          // modes 2/4: 1 = weights through the MN-major 3-D map (N | taps | Ct), taps reversed
   int f32_rows;                       // modes 2/4: write fp32 [pixels][N] to out_f32 instead of bf16 (any BLOCK_N)
   long long rows_guard;               // > 0: output rows (opix) >= rows_guard are not stored (ragged GEMM M)
-  int act_dual;                       // mode 2: y0 = lrelu(D, slope0), y1 = lrelu(D, slope1), both [pixels][N]
+  int act_dual;                       // mode 2: y0 = lrelu(D, slope0) [- center], y1 = lrelu(D, slope1), both [pixels][N]
   float slope0, slope1;
   // mode 3 (STFT as a split-bf16 DFT GEMM): rows = frames, columns = (re, im) pairs of the bins
   float* spec; int F, T, log_mode; int* minmax;
+  // first-level centring (adp_unet.cu): the activation with the large per-channel DC component is stored as a - center[n]
+  // inside a tensor with an explicit one-pixel border holding -center[n], so that the next convolution sees exact zeros
+  // where the reference pads (bf16 keeps its 8 mantissa bits for the signal instead of the DC)
+  int pad_in;                         // mode 0: the input is [B, Hi+2, Wi+2, C] with that border; no tap is out of bounds
+  int pad_out;                        // act_dual: y0 is the interior of a [B, Hs+2, Ws+2, N] tensor
+  const float* center;                // act_dual: subtracted from y0 after the activation (NULL: nothing)
+  // BatchNorm statistics of the stored (bf16-rounded) output: stats[n] += sum, stats[N + n] += sum of squares (staged
+  // bf16 epilogue only; NULL: not wanted)
+  double* stats;
 };
 
-template <int BLOCK_N>
-struct IgemmSmem {
-  static constexpr int B_STAGE_BYTES = BLOCK_N * TILE_K * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BLOCK_N <= 16 ? 2 : (BLOCK_N <= 64 ? 6 : (BLOCK_N <= 128 ? 5 : 4));
-  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-};
-
-template <int BLOCK_N>
-__global__ void __launch_bounds__(IGEMM_THREADS, 1) tc_igemm_kernel(const __grid_constant__ IgemmParams p) {
-  using S = IgemmSmem<BLOCK_N>;
-  const int STAGES = p.stages;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // ---- tile coordinates
-  // parity mode: the four output-parity classes of one pixel tile read the same input pixels (different taps);
-  // they are adjacent in launch order so that the tile is fetched from HBM once and hit in L2 three times
-  const int tm = p.mode == 1 ? (int)(blockIdx.x >> 2) : (int)blockIdx.x;
-  const int tw_i = tm % p.tiles_w, th_i = (tm / p.tiles_w) % p.tiles_h, tb_i = tm / (p.tiles_w * p.tiles_h);
-  const int x0 = tw_i * p.Wt, y0c = th_i * p.Ht, b0 = tb_i * p.Bt;
-  const int n0 = blockIdx.y * BLOCK_N;
-  const int zpar = p.mode == 1 ? (int)(blockIdx.x & 3) : 0;
-  const int split = (int)blockIdx.z;
-  const int pa = zpar >> 1, pb = zpar & 1;
-  const int kb_begin = split * p.kb_per_split;
-  const int kb_end = min(kb_begin + p.kb_per_split, p.kblocks);
-  const int nkb = kb_end - kb_begin;
-
-  if (threadIdx.x == 0) {
-    prefetch_tmap(&p.tmA0);
-    if (p.C1 > 0) prefetch_tmap(&p.tmA1);
-    prefetch_tmap(&p.tmW);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(accum_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N < 32 ? 32 : BLOCK_N);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      const int nchunk = p.Ct / TILE_K;
-      for (int it = 0; it < nkb; ++it) {
-        const int kb = kb_begin + it;
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        unsigned char* a_dst = smem + s * S::STAGE_BYTES;
-        unsigned char* b_dst = a_dst + A_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        const int tap = kb / nchunk;
-        const int c = (kb - tap * nchunk) * TILE_K;
-        if (p.mode == 0) {
-          // 4x4 stride-2 window: tap row kh -> (row offset, row parity) = kh:0 (-1,1) 1 (0,0) 2 (0,1) 3 (+1,0)
-          const int kh = tap >> 2, kw = tap & 3;
-          const int di = (kh + 1) / 2 - 1, ra = (kh + 1) & 1;
-          const int dj = (kw + 1) / 2 - 1, rb = (kw + 1) & 1;
-          tma_load_5d(a_dst, &p.tmA0, &full_bar[s], rb * p.Ct + c, x0 + dj, ra, y0c + di, b0);
-          tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + c, n0);
-        } else if (p.mode == 2) {
-          if (c < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], c, x0, y0c, b0);
-          else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], c - p.C0, x0, y0c, b0);
-          tma_load_2d(b_dst, &p.tmW, &full_bar[s], c, n0);
-        } else {
-          const int th = tap >> 1, tw = tap & 1;
-          const int cx = x0 + pb - 1 + tw, cy = y0c + pa - 1 + th;
-          if (c < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], c, cx, cy, b0);
-          else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], c - p.C0, cx, cy, b0);
-          // weights stay in their master layout [c][tap][n]: the B tile is fetched N-major (64-row boxes of
-          // 64 output channels) and handed to the MMA through an MN-major descriptor -- no transposed copy
-          const int wtap = (3 - pa - 2 * th) * 4 + (3 - pb - 2 * tw);
-#pragma unroll
-          for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h)
-            tma_load_3d(b_dst + h * (TILE_K * 128), &p.tmW, &full_bar[s], n0 + h * 64, wtap, c);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      const bool b_mn = p.mode == 1;
-      const uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, 0, b_mn ? 1 : 0);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < TILE_K / 16; ++k) {
-          const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t bd = b_mn ? umma_smem_desc(b_addr + k * 2048, TILE_K * 128, 1024)
-                                   : umma_smem_desc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&empty_bar[s]);
-      }
-      umma_commit(accum_bar);
-    }
-  } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;                  // accumulator row = pixel within the tile
-    const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
-    const int b = b0 + bt, py = y0c + ht, px = x0 + wt;
-    const bool valid = b < p.B && nkb > 0;
-    size_t opix;
-    if (p.mode != 1) opix = ((size_t)b * p.Hs + py) * p.Ws + px;
-    else opix = ((size_t)b * 2 * p.Hs + 2 * py + pa) * (2 * p.Ws) + 2 * px + pb;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int cc = 0; cc < BLOCK_N; cc += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
-      if (!valid) continue;
-      const int n = n0 + cc;
-      if (BLOCK_N == 16) {
-        float* dst = p.out_f32 + opix * 16;
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-      } else if (p.act_dual) {
-        bf16* d0 = p.y0 + opix * p.N + n;
-        bf16* d1 = p.y1 + opix * p.N + n;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 u, w;
-          u.x = pack_bf16x2(lrelu(v[i + 0], p.slope0), lrelu(v[i + 1], p.slope0));
-          u.y = pack_bf16x2(lrelu(v[i + 2], p.slope0), lrelu(v[i + 3], p.slope0));
-          u.z = pack_bf16x2(lrelu(v[i + 4], p.slope0), lrelu(v[i + 5], p.slope0));
-          u.w = pack_bf16x2(lrelu(v[i + 6], p.slope0), lrelu(v[i + 7], p.slope0));
-          w.x = pack_bf16x2(lrelu(v[i + 0], p.slope1), lrelu(v[i + 1], p.slope1));
-          w.y = pack_bf16x2(lrelu(v[i + 2], p.slope1), lrelu(v[i + 3], p.slope1));
-          w.z = pack_bf16x2(lrelu(v[i + 4], p.slope1), lrelu(v[i + 5], p.slope1));
-          w.w = pack_bf16x2(lrelu(v[i + 6], p.slope1), lrelu(v[i + 7], p.slope1));
-          *reinterpret_cast<uint4*>(d0 + i) = u;
-          *reinterpret_cast<uint4*>(d1 + i) = w;
-        }
-      } else if (p.splits > 1) {
-        float* dst = p.partial + opix * p.N + n;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
-                       "f"(v[i + 2]), "f"(v[i + 3]) : "memory");
-      } else {
-        bf16* dst = n < p.N0 ? p.y0 + opix * p.N0 + n : p.y1 + opix * p.N1 + (n - p.N0);
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(v[i + 0], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
-          u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
-          *reinterpret_cast<uint4*>(dst + i) = u;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, BLOCK_N < 32 ? 32 : BLOCK_N);
-  }
-}
-
-// ------------------------------------------------------------------ persistent variant
+// ------------------------------------------------------------------ persistent implicit-GEMM kernel
 // One CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x).  The smem ring and its phases run
 // continuously across tiles, the accumulator is double-buffered in tensor memory (2 x BLOCK_N columns), so the
 // epilogue of tile i (TMEM -> registers -> global) overlaps the TMA/MMA main loop of tile i+1, and TMEM allocation,
@@ -296,6 +124,8 @@ template <int BLOCK_N>
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t) {
   const int bx = t % p.gx, r = t / p.gx, by = r % p.gy, bz = r / p.gy;
   TileCoord c;
+  // parity mode: the four output-parity classes of one pixel tile read the same input pixels (different taps);
+  // they are adjacent in the walk so that the tile is fetched from HBM once and hit in L2 three times
   const int tm = p.mode == 1 ? (bx >> 2) : bx;
   const int tw_i = tm % p.tiles_w, th_i = (tm / p.tiles_w) % p.tiles_h, tb_i = tm / (p.tiles_w * p.tiles_h);
   c.x0 = tw_i * p.Wt; c.y0c = th_i * p.Ht; c.b0 = tb_i * p.Bt;
@@ -307,63 +137,46 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t) {
   return c;
 }
 
-// Pair tiles for the 2-CTA cluster variant: both CTAs take the same (n-tile, split, parity) and adjacent m-tiles,
-// so the weight tile is identical and each CTA fetches (and multicasts) only half of it.
-template <int BLOCK_N>
-__device__ __forceinline__ TileCoord decode_pair_tile(const IgemmParams& p, int u, int rank) {
-  const int gxp = p.mode == 1 ? ((p.gx / 4 + 1) / 2) * 4 : (p.gx + 1) / 2;
-  const int bxp = u % gxp, r = u / gxp, by = r % p.gy, bz = r / p.gy;
-  TileCoord c;
-  const int zpar = p.mode == 1 ? (bxp & 3) : 0;
-  const int tm = (p.mode == 1 ? (bxp >> 2) : bxp) * 2 + rank;
-  const int tw_i = tm % p.tiles_w, th_i = (tm / p.tiles_w) % p.tiles_h, tb_i = tm / (p.tiles_w * p.tiles_h);
-  c.x0 = tw_i * p.Wt; c.y0c = th_i * p.Ht; c.b0 = tb_i * p.Bt;     // tb_i past the batch: zero-filled, nothing stored
-  c.n0 = by * BLOCK_N;
-  c.pa = zpar >> 1; c.pb = zpar & 1;
-  c.kb_begin = bz * p.kb_per_split;
-  c.nkb = min(c.kb_begin + p.kb_per_split, p.kblocks) - c.kb_begin;
-  return c;
-}
-
 // HALO (BLOCK_N <= 128): the input window of a 16 x 8 pixel tile is loaded ONCE per k-block and several filter taps read it
 // through shifted descriptors (the SWIZZLE_128B pattern is a function of the shared-memory address, so an operand may
 // start at any 128-byte row and use any group pitch: tools/probe_umma_offset.py), next to those taps' weight tiles.
 //   HALO = 4: parity (transposed-conv) mode, k-block = one 64-channel chunk, 2 x 2 taps, window 17 x 9 pixels
 //   HALO = 3: 3x3 / stride 1 mode, k-block = (kernel row, chunk), 3 taps of that row, window 16 x 10 pixels
-//   HALO = 8: parity mode with TWO 16 x 8 tiles side by side (M = 256, two accumulators) sharing the four weight tiles:
-//             window 17 x 17 pixels, second tile = the same window 8 pixels (1024 B) further -- the N = 64 layers are
-//             bound by what the SM ingests, and the weight tiles are most of it once the window is shared
 template <int HALO> struct HaloGeom {
-  static constexpr int W = HALO == 3 ? 10 : (HALO == 8 ? 17 : 9), H = HALO == 3 ? 16 : 17;
-  static constexpr int BOX_BYTES = W * H * TILE_K * 2;            // 20480 / 19584 / 36992
+  static constexpr int W = HALO == 3 ? 10 : 9, H = HALO == 3 ? 16 : 17;
+  static constexpr int BOX_BYTES = W * H * TILE_K * 2;            // 20480 / 19584
   static constexpr int TAPS = HALO == 3 ? 3 : 4;
-  static constexpr int HALVES = HALO == 8 ? 2 : 1;
 };
 template <int BLOCK_N, int HALO = 0>
 struct PersistSmem {
-  static constexpr int A_BYTES = HALO == 8 ? 37888 : (HALO ? 20480 : A_STAGE_BYTES);
+  static constexpr int A_BYTES = HALO ? 20480 : A_STAGE_BYTES;
   static constexpr int B_TILE = BLOCK_N * TILE_K * 2;
   static constexpr int B_BYTES = HALO ? HaloGeom<HALO>::TAPS * B_TILE : B_TILE;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING = 4 * 4096;        // epilogue transpose buffers: 4 warps x (32 rows x 128 B)
   static constexpr int BAR_BYTES = 512;           // pipeline barriers, TMEM slot
-  static constexpr int RING_BUDGET = HALO ? (227 * 1024 - 1024 - BAR_BYTES - STAGING - 1024) : 196 * 1024;
+  // BatchNorm partial sums, private to each of the 4 epilogue warps: [4][2][STATS_N] floats.  The 64-wide parity halo
+  // kernel (N = 64 only) keeps them in the 896 unused bytes behind each stage's 17 x 9 window instead, so that its
+  // 4th pipeline stage survives; the 3x3 halo kernels (config 4) never fuse statistics.
+  static constexpr bool STATS_IN_SLACK = HALO == 4 && BLOCK_N == 64;
+  static constexpr int STATS_N = HALO == 3 ? 0 : (STATS_IN_SLACK ? 64 : 512);
+  static constexpr int STATS_BYTES = STATS_IN_SLACK ? 0 : 4 * 2 * STATS_N * 4;
+  static constexpr int RING_BUDGET = HALO ? (227 * 1024 - 1024 - BAR_BYTES - STAGING - STATS_BYTES - 256) : 192 * 1024;
   static constexpr int STAGES = RING_BUDGET / STAGE_BYTES > 10 ? 10 : RING_BUDGET / STAGE_BYTES;
-  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + STAGING;
-  static constexpr int ACC_COLS = (HALO == 8 ? 2 : 1) * (BLOCK_N < 32 ? 32 : BLOCK_N);
+  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + STAGING + STATS_BYTES;
+  static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static_assert(BYTES <= 227 * 1024, "shared-memory budget");
+  static_assert(!STATS_IN_SLACK || (STAGES >= 4 && A_BYTES - HaloGeom<HALO ? HALO : 4>::BOX_BYTES >= 2 * STATS_N * 4), "statistics slack");
 };
 
 // EG = number of epilogue warp groups (4 warps each): 1 for the convolutions, 2 for the math-heavy STFT epilogue
 // ATT = attention (softmax) epilogues of the row GEMM compiled in (kept out of the convolution instantiations)
-template <int BLOCK_N, bool CLUSTER, int EG, bool ATT = false, int HALO = 0>
+template <int BLOCK_N, int EG, bool ATT = false, int HALO = 0>
 __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
-  using S = IgemmSmem<BLOCK_N>;
   using PS = PersistSmem<BLOCK_N, HALO>;
-  const int crank = CLUSTER ? (int)cluster_ctarank() : 0;
-  const int worker = CLUSTER ? (int)cluster_id_x() : (int)blockIdx.x;      // index of this CTA (pair) in the tile walk
-  const int nworkers = CLUSTER ? (int)cluster_count_x() : (int)gridDim.x;
-  const int ntiles = CLUSTER ? p.total_pair_tiles : p.total_tiles;
-  auto tile_at = [&](int t) { return CLUSTER ? decode_pair_tile<BLOCK_N>(p, t, crank) : decode_tile<BLOCK_N>(p, t); };
+  const int worker = (int)blockIdx.x;                     // index of this CTA in the tile walk
+  const int nworkers = (int)gridDim.x;
+  const int ntiles = p.total_tiles;
   constexpr int STAGES = PS::STAGES;
   constexpr int ACC = PS::ACC_COLS;
   extern __shared__ unsigned char smem_raw[];
@@ -374,20 +187,28 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained by the 4 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool want_stats = EG == 1 && BLOCK_N >= 64 && PS::STATS_N > 0 && p.stats != nullptr;
+  // BN partial sums of epilogue warp e: [2][N] floats
+  auto stats_of = [&](int e) -> float* {
+    if (PS::STATS_IN_SLACK) return reinterpret_cast<float*>(smem + e * PS::STAGE_BYTES + HaloGeom<HALO ? HALO : 4>::BOX_BYTES);
+    return reinterpret_cast<float*>(smem + STAGES * PS::STAGE_BYTES + PS::BAR_BYTES + PS::STAGING) + e * 2 * p.N;
+  };
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&p.tmA0);
     if (p.C1 > 0) prefetch_tmap(&p.tmA1);
     prefetch_tmap(&p.tmW);
-    // cluster mode: a stage may be refilled only when BOTH CTAs have consumed it (each multicasts into the other)
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER ? 2 : 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4 * EG); }
     fence_barrier_init();
+  }
+  if (want_stats) {
+    for (int e = 0; e < 4; ++e)
+      for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) stats_of(e)[i] = 0.f;
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC);
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER) cluster_sync_all();                        // peer barriers are initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -398,14 +219,14 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
       int s = 0;                                          // ring position and its phase bit
       uint32_t ph = 0;
       for (int t = worker; t < ntiles; t += nworkers) {
-        const TileCoord c = tile_at(t);
+        const TileCoord c = decode_tile<BLOCK_N>(p, t);
         int tap = c.kb_begin / nchunk, ch = (c.kb_begin - tap * nchunk) * TILE_K;
         for (int it = 0; it < c.nkb; ++it) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           unsigned char* a_dst = smem + s * PS::STAGE_BYTES;
           unsigned char* b_dst = a_dst + PS::A_BYTES;
           mbar_expect_tx(&full_bar[s], HALO ? HaloGeom<HALO>::BOX_BYTES + HaloGeom<HALO>::TAPS * PS::B_TILE : PS::STAGE_BYTES);
-          if (HALO == 4 || HALO == 8) {
+          if (HALO == 4) {
             // one 64-channel chunk: the tile's halo window once + the weight tiles of the four taps of this parity
             const int cx = c.x0 + c.pb - 1, cy = c.y0c + c.pa - 1;
             if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, cx, cy, c.b0);
@@ -414,13 +235,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
             for (int t4 = 0; t4 < 4; ++t4) {
               const int wtap = (3 - c.pa - 2 * (t4 >> 1)) * 4 + (3 - c.pb - 2 * (t4 & 1));
 #pragma unroll
-              for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h) {
-                if (CLUSTER)   // the pair works on the same parity / chunk: each CTA fetches half of every weight box for both
-                  tma_load_3d_mc(b_dst + t4 * PS::B_TILE + h * (TILE_K * 128) + crank * (TILE_K * 64), &p.tmWh, &full_bar[s], 3,
-                                 c.n0 + h * 64, wtap, ch + crank * (TILE_K / 2));
-                else
-                  tma_load_3d(b_dst + t4 * PS::B_TILE + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
-              }
+              for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h)
+                tma_load_3d(b_dst + t4 * PS::B_TILE + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
             }
           } else if (HALO == 3) {
             // `tap` counts kernel rows here: rows y0+kh-1 .. +15, columns x0-1 .. x0+8, and the three taps of that row
@@ -439,30 +255,24 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
               }
             }
           } else if (p.mode == 0) {
+            // 4x4 stride-2 window over the (2C | W/2 | row parity | H/2 | B) view: tap row kh -> (row offset, row parity)
+            // = kh:0 (-1,1) 1 (0,0) 2 (0,1) 3 (+1,0); with an explicit border (pad_in) row 2oy+kh -> (kh >> 1, kh & 1)
             const int kh = tap >> 2, kw = tap & 3;
-            const int di = (kh + 1) / 2 - 1, ra = (kh + 1) & 1;
-            const int dj = (kw + 1) / 2 - 1, rb = (kw + 1) & 1;
+            const int di = p.pad_in ? (kh >> 1) : (kh + 1) / 2 - 1, ra = p.pad_in ? (kh & 1) : (kh + 1) & 1;
+            const int dj = p.pad_in ? (kw >> 1) : (kw + 1) / 2 - 1, rb = p.pad_in ? (kw & 1) : (kw + 1) & 1;
             tma_load_5d(a_dst, &p.tmA0, &full_bar[s], rb * p.Ct + ch, c.x0 + dj, ra, c.y0c + di, c.b0);
-            if (CLUSTER)
-              tma_load_2d_mc(b_dst + crank * (S::B_STAGE_BYTES / 2), &p.tmWh, &full_bar[s], 3, tap * p.Ct + ch,
-                             c.n0 + crank * (BLOCK_N / 2));
-            else
-              tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + ch, c.n0);
+            tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + ch, c.n0);
           } else if (p.mode == 1) {
             const int th = tap >> 1, tw = tap & 1;
             const int cx = c.x0 + c.pb - 1 + tw, cy = c.y0c + c.pa - 1 + th;
             if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, cx, cy, c.b0);
             else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, cx, cy, c.b0);
+            // weights stay in their master layout [c][tap][n]: the B tile is fetched N-major (64-row boxes of
+            // 64 output channels) and handed to the MMA through an MN-major descriptor -- no transposed copy
             const int wtap = (3 - c.pa - 2 * th) * 4 + (3 - c.pb - 2 * tw);
 #pragma unroll
-            for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h) {
-              if (CLUSTER)   // every 64-row box is fetched as two 32-row halves, one per CTA
-                tma_load_3d_mc(b_dst + h * (TILE_K * 128) + crank * (TILE_K * 64), &p.tmWh, &full_bar[s], 3, c.n0 + h * 64,
-                               wtap, ch + crank * (TILE_K / 2));
-              else
-                tma_load_3d(b_dst + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
-            }
-          
+            for (int h = 0; h < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++h)
+              tma_load_3d(b_dst + h * (TILE_K * 128), &p.tmW, &full_bar[s], c.n0 + h * 64, wtap, ch);
           } else if (p.mode == 3) {
             // six K blocks x0*W0, x0*W1, x1*W0, x0*W2, x1*W1, x2*W0 of the three-way bf16 split (A slice 0,0,1,0,1,2)
             const int kbi = ch / TILE_K;
@@ -486,10 +296,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
           } else if (p.mode == 2) {
             if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, c.x0, c.y0c, c.b0);
             else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, c.x0, c.y0c, c.b0);
-            if (CLUSTER)
-              tma_load_2d_mc(b_dst + crank * (S::B_STAGE_BYTES / 2), &p.tmWh, &full_bar[s], 3, ch, c.n0 + crank * (BLOCK_N / 2));
-            else
-              tma_load_2d(b_dst, &p.tmW, &full_bar[s], ch, c.n0);
+            tma_load_2d(b_dst, &p.tmW, &full_bar[s], ch, c.n0);
           }
           ch += TILE_K;
           if (ch == p.Ct) { ch = 0; ++tap; }
@@ -511,7 +318,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
       int s = 0;
       uint32_t ph = 0, local = 0;
       for (int t = worker; t < ntiles; t += nworkers, ++local) {
-        const TileCoord c = tile_at(t);
+        const TileCoord c = decode_tile<BLOCK_N>(p, t);
         const uint32_t buf = local & 1u, use = local >> 1;
         mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);    // epilogue has drained this accumulator
         tc_fence_after();
@@ -522,27 +329,24 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
           const uint64_t stage_off = (uint64_t)((uint32_t)(s * PS::STAGE_BYTES) >> 4);
           const uint64_t ad0 = a_desc0 + stage_off, bd0 = b_desc0 + stage_off;
           if (HALO) {
-#pragma unroll
+            // (not unrolled over the taps: the fully unrolled form keeps 32 descriptors = 64+ uniform registers live and
+            // was observed to raise "illegal instruction" on the UTCHMMA sequence depending on the surrounding code)
+#pragma unroll 1
             for (int t4 = 0; t4 < HaloGeom<HALO>::TAPS; ++t4) {
               // window shifted by (th, tw) [parity] or by tw [3x3 row] pixels
               const int shift_rows = HALO != 3 ? (t4 >> 1) * HaloGeom<HALO>::W + (t4 & 1) : t4;
               const uint64_t bt4 = bd0 + (uint64_t)((t4 * PS::B_TILE) >> 4);
+              const uint64_t at = ad0 + (uint64_t)((shift_rows * 128) >> 4);
 #pragma unroll
-              for (int half = 0; half < HaloGeom<HALO>::HALVES; ++half) {      // HALO = 8: second tile 8 pixels to the right
-                const uint64_t at = ad0 + (uint64_t)(((shift_rows + 8 * half) * 128) >> 4);
-#pragma unroll
-                for (int k = 0; k < TILE_K / 16; ++k)
-                  umma_bf16(tacc + (uint32_t)(half * BLOCK_N), at + (uint64_t)(k * 2), bt4 + (uint64_t)(k * b_kstep), idesc,
-                            (it | t4 | k) != 0 ? 1u : 0u);
-              }
+              for (int k = 0; k < TILE_K / 16; ++k)
+                umma_bf16(tacc, at + (uint64_t)(k * 2), bt4 + (uint64_t)(k * b_kstep), idesc, (it | t4 | k) != 0 ? 1u : 0u);
             }
           } else {
 #pragma unroll
             for (int k = 0; k < TILE_K / 16; ++k)
               umma_bf16(tacc, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * b_kstep), idesc, (it | k) != 0 ? 1u : 0u);
           }
-          if (CLUSTER) umma_commit_mc(&empty_bar[s], 3);
-          else umma_commit(&empty_bar[s]);
+          umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         umma_commit(&tfull_bar[buf]);
@@ -555,41 +359,49 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     const int q = warp & 3;
     const int egroup = (warp - 2) >> 2;
     const int r = q * 32 + lane;
-    const int ewt = HALO == 8 ? 8 : p.Wt;             // HALO = 8: the tile is two 16 x 8 halves, one accumulator each
-    const int wt = r % ewt, ht = (r / ewt) % p.Ht, bt = r / (ewt * p.Ht);
+    const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
     constexpr bool STAGED_OK = BLOCK_N >= 64 && EG == 1;
     unsigned char* stg = smem + STAGES * PS::STAGE_BYTES + PS::BAR_BYTES + (STAGED_OK ? (warp - 2) * 4096 : 0);
     const bool staged = p.splits <= 1 && p.mode != 3 && !p.f32_rows && !(ATT && (p.epi == 1 || p.epi == 2)) &&
                         (p.act_dual || p.N1 == 0 || p.N0 % 64 == 0);
     uint32_t local = 0;
     for (int t = worker; t < ntiles; t += nworkers, ++local) {
-      const TileCoord c = tile_at(t);
+      const TileCoord c = decode_tile<BLOCK_N>(p, t);
       const uint32_t buf = local & 1u, use = local >> 1;
       mbar_wait(&tfull_bar[buf], use & 1u);
       tc_fence_after();
-#pragma unroll 1
-      for (int half = 0; half < HaloGeom<HALO>::HALVES; ++half) {
-      const int b = c.b0 + bt, py = c.y0c + ht, px = c.x0 + 8 * half + wt;
+      const int b = c.b0 + bt, py = c.y0c + ht, px = c.x0 + wt;
       size_t opix;
       if (p.mode != 1) opix = ((size_t)b * p.Hs + py) * p.Ws + px;
       else opix = ((size_t)b * 2 * p.Hs + 2 * py + c.pa) * (2 * p.Ws) + 2 * px + c.pb;
       const bool valid = b < p.B && c.nkb > 0 && (p.rows_guard <= 0 || (long long)opix < p.rows_guard);
-      const uint32_t tacc = tmem_base + buf * ACC + (uint32_t)(half * BLOCK_N) + ((uint32_t)(q * 32) << 16);
+      const uint32_t tacc = tmem_base + buf * ACC + ((uint32_t)(q * 32) << 16);
       float vmin = INFINITY, vmax = -INFINITY;
       if (STAGED_OK && staged) {
         // bf16 outputs, 64 columns at a time: every lane packs its own pixel row (128 B) into the warp's swizzled
         // staging buffer, then 8 lanes write one row -- full 128-byte lines per store instead of 32 scattered
         // 16-byte pieces (the L1 tag stage processes one line per cycle, which bounded the thin layers).
         const uint32_t okm = __ballot_sync(0xffffffffu, valid);
-        unsigned long long orow[8];
+        unsigned orow[8];                                 // (run_igemm refuses problems with 2^32 or more output pixels)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) orow[i] = __shfl_sync(0xffffffffu, (unsigned long long)opix, 4 * i + (lane >> 3));
-        auto emit = [&](const float (&v)[64], bf16* base, int ldn, float slope, bool act) {
+        for (int i = 0; i < 8; ++i) orow[i] = __shfl_sync(0xffffffffu, (unsigned)opix, 4 * i + (lane >> 3));
+        // pad_out: this pixel's row index inside the bordered tensor, as an offset from opix (fetched by shuffle at the store)
+        const unsigned dpad = p.pad_out ? (unsigned)((((size_t)b * (p.Hs + 2) + py + 1) * (p.Ws + 2) + px + 1) - opix) : 0u;
+        const bool dpad_uniform = (p.Wt & 31) == 0;      // a warp's 32 pixels then lie in one image row: one offset for all of them
+        float* const my_stats = stats_of(warp - 2);
+        // padded: rows of the bordered tensor; cen: per-column constants subtracted after the activation (NULL: none);
+        // col0 >= 0: accumulate the BatchNorm partial sums of the stored values for columns col0 .. col0 + 63
+        auto emit = [&](const float (&v)[64], bf16* base, int ldn, float slope, bool act, bool padded, const float* cen, int col0) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float w[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) w[k] = act ? lrelu(v[8 * j + k], slope) : v[8 * j + k];
+            if (cen) {
+              const float4 c0 = __ldg(reinterpret_cast<const float4*>(cen + 8 * j));
+              const float4 c1 = __ldg(reinterpret_cast<const float4*>(cen + 8 * j + 4));
+              w[0] -= c0.x; w[1] -= c0.y; w[2] -= c0.z; w[3] -= c0.w; w[4] -= c1.x; w[5] -= c1.y; w[6] -= c1.z; w[7] -= c1.w;
+            }
             uint4 u;
             u.x = pack_bf16x2(w[0], w[1]); u.y = pack_bf16x2(w[2], w[3]);
             u.z = pack_bf16x2(w[4], w[5]); u.w = pack_bf16x2(w[6], w[7]);
@@ -600,7 +412,29 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + (lane >> 3);
             const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
-            if ((okm >> rr) & 1u) *reinterpret_cast<uint4*>(base + orow[i] * (unsigned long long)ldn + (lane & 7) * 8) = u;
+            unsigned row = orow[i];
+            if (padded) row += dpad_uniform ? dpad : __shfl_sync(0xffffffffu, dpad, rr);
+            if ((okm >> rr) & 1u) *reinterpret_cast<uint4*>(base + row * (unsigned long long)ldn + (lane & 7) * 8) = u;
+          }
+          if (col0 >= 0) {
+            // BatchNorm partial sums of the stored (rounded) values: lane = (16-byte chunk j, word w) owns columns
+            // 8j + 2w, 8j + 2w + 1 and walks the 32 staged rows (one conflict-free 4-byte read per row); the sums go to
+            // this warp's private accumulators -- no shuffles, no atomics
+            const int j = lane >> 2, w = lane & 3;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(stg + r * 128 + ((j ^ (r & 7)) << 4) + w * 4);
+              const float lo = ((okm >> r) & 1u) ? __uint_as_float(u << 16) : 0.f;
+              const float hi = ((okm >> r) & 1u) ? __uint_as_float(u & 0xffff0000u) : 0.f;
+              s0 += lo; q0 = fmaf(lo, lo, q0);
+              s1 += hi; q1 = fmaf(hi, hi, q1);
+            }
+            float2* ps = reinterpret_cast<float2*>(my_stats + col0 + 8 * j + 2 * w);
+            float2* pq = reinterpret_cast<float2*>(my_stats + p.N + col0 + 8 * j + 2 * w);
+            float2 a = *ps, b2 = *pq;
+            a.x += s0; a.y += s1; b2.x += q0; b2.y += q1;
+            *ps = a; *pq = b2;
           }
           __syncwarp();
         };
@@ -636,7 +470,6 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float8 pv = ld8(prow + 8 * j);
-#pragma unroll
                 float dl[8];
                 if (p.stat_by_col) {
                   const float4 d0 = ld4(p.delta + n + 8 * j), d1 = ld4(p.delta + n + 8 * j + 4);
@@ -651,12 +484,12 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
             }
           }
           if (p.act_dual) {
-            emit(v, p.y0 + n, p.N, p.slope0, true);
-            emit(v, p.y1 + n, p.N, p.slope1, true);
+            emit(v, p.y0 + n, p.N, p.slope0, true, p.pad_out != 0, p.center ? p.center + n : nullptr, -1);
+            emit(v, p.y1 + n, p.N, p.slope1, true, false, nullptr, -1);
           } else if (n < p.N0) {
-            emit(v, p.y0 + n, p.N0, 0.f, false);
+            emit(v, p.y0 + n, p.N0, 0.f, false, false, nullptr, want_stats ? n : -1);
           } else {
-            emit(v, p.y1 + (n - p.N0), p.N1, 0.f, false);
+            emit(v, p.y1 + (n - p.N0), p.N1, 0.f, false, false, nullptr, want_stats ? n : -1);
           }
         }
       } else {
@@ -702,15 +535,17 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
 #pragma unroll
           for (int i = 0; i < 16; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
         } else if (p.act_dual) {
-          bf16* d0 = p.y0 + opix * p.N + n;
+          const size_t opad = p.pad_out ? ((size_t)b * (p.Hs + 2) + py + 1) * (p.Ws + 2) + px + 1 : opix;
+          bf16* d0 = p.y0 + opad * p.N + n;
           bf16* d1 = p.y1 + opix * p.N + n;
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
+            float a[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = lrelu(v[i + k], p.slope0) - (p.center ? p.center[n + i + k] : 0.f);
             uint4 u, w;
-            u.x = pack_bf16x2(lrelu(v[i + 0], p.slope0), lrelu(v[i + 1], p.slope0));
-            u.y = pack_bf16x2(lrelu(v[i + 2], p.slope0), lrelu(v[i + 3], p.slope0));
-            u.z = pack_bf16x2(lrelu(v[i + 4], p.slope0), lrelu(v[i + 5], p.slope0));
-            u.w = pack_bf16x2(lrelu(v[i + 6], p.slope0), lrelu(v[i + 7], p.slope0));
+            u.x = pack_bf16x2(a[0], a[1]); u.y = pack_bf16x2(a[2], a[3]);
+            u.z = pack_bf16x2(a[4], a[5]); u.w = pack_bf16x2(a[6], a[7]);
             w.x = pack_bf16x2(lrelu(v[i + 0], p.slope1), lrelu(v[i + 1], p.slope1));
             w.y = pack_bf16x2(lrelu(v[i + 2], p.slope1), lrelu(v[i + 3], p.slope1));
             w.z = pack_bf16x2(lrelu(v[i + 4], p.slope1), lrelu(v[i + 5], p.slope1));
@@ -748,7 +583,6 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
           atomicMax(&p.minmax[2 * b + 1], float_to_ordered(vmax));
         }
       }
-      }    // half
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);      // this warp's quarter of the accumulator is free again
@@ -756,7 +590,17 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
   }
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER) cluster_sync_all();                        // no multicast / remote arrive may target a CTA that has left
+  if (want_stats) {
+    // one fp64 atomic per (CTA, channel, moment); CTAs start at different channels so that they do not queue on one cell
+    const int n2 = 2 * p.N;
+    const int start = (int)(((unsigned)worker * 67u) % (unsigned)n2);
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      int c = i + start;
+      if (c >= n2) c -= n2;
+      const float v = (stats_of(0)[c] + stats_of(1)[c]) + (stats_of(2)[c] + stats_of(3)[c]);
+      if (v != 0.f) atomicAdd(&p.stats[c], (double)v);
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * ACC);
@@ -780,7 +624,7 @@ finish_partial_kernel(const float* __restrict__ partial, long long pixels, int N
 
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-int g_max_block_n = 256;   // ADP_TC_MAX_BN environment override (tuning)
+int g_max_block_n = 256;   // "tc_max_bn" / ADP_TC_MAX_BN: largest N tile
 
 int pick_block_n(int N, int N0, int N1) {
   const int cands[4] = {256, 128, 64, 32};
@@ -799,158 +643,56 @@ bool tile_geometry(int B, int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
   return *Bt <= 256;
 }
 
-int g_force_stages = 0;   // ADP_TC_STAGES environment override (tuning)
-int g_persistent = 1;     // ADP_TC_PERSISTENT=0 selects the one-tile-per-CTA kernel
-int g_cluster = 0;        // ADP_TC_CLUSTER=1: 2-CTA clusters, weight tile halves multicast between the pair
+int g_halo = 1;            // "tc_halo" / ADP_TC_HALO: 0 = one TMA box per tap, 1 = halo windows (narrow-N parity and 3x3 layers)
+int g_stats = 1;           // "tc_stats" / ADP_TC_STATS: BatchNorm statistics accumulated by the convolution epilogue
 
-int g_halo_cluster = 0;    // ADP_TC_HALO_CLUSTER=n: halo-window parity kernels with N tile <= n run as 2-CTA clusters (weight multicast)
-int g_halo = 1;            // ADP_TC_HALO: 0 = one TMA box per tap, 1 = halo windows, 2 = + double tiles for N = 64 (no gain: those
-                           // launches already sit at the smem-read ceiling of the M128 x N64 MMA shape, ~990 TFLOP/s)
-int g_tc_sms = 0;          // ADP_TC_SMS=n: persistent kernels use at most n CTAs (measured: no gain next to NCCL)
+template <int BLOCK_N, int EG, bool ATT, int HALO>
+int launch_persist(const IgemmParams& p, int ctas, cudaStream_t s) {
+  using PS = PersistSmem<BLOCK_N, HALO>;
+  if (p.stats && (p.N > PS::STATS_N || EG != 1 || BLOCK_N < 64)) {
+    adp_set_error("tc igemm: fused statistics need 64 <= N <= %d here", PS::STATS_N);
+    return ADP_ERR_ARG;
+  }
+  ADP_SMEM_ATTR((tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO>), PS::BYTES);
+  tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO><<<ctas, 64 + 128 * EG, PS::BYTES, s>>>(p);
+  return ADP_OK;
+}
+
 template <int BLOCK_N>
 int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
-  using S = IgemmSmem<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ADP_CUDA(cudaFuncSetAttribute(tc_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
-    attr_set = true;
-  }
   p.gx = grid.x; p.gy = grid.y; p.gz = grid.z;
   p.total_tiles = (int)(grid.x * grid.y * grid.z);
-  if (g_persistent) {
-    using PS = PersistSmem<BLOCK_N, 0>;
-    static bool pattr_set = false;
-    if (!pattr_set) {
-      ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
-      ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<BLOCK_N, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS::BYTES));
-      if (BLOCK_N == 128)
-        ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<128, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      PersistSmem<128>::BYTES));
-      pattr_set = true;
-    }
-    const int m_groups = p.mode == 1 ? (int)grid.x / 4 : (int)grid.x;
-    if (g_cluster && p.has_half_map && m_groups >= 2 && p.mode != 3 && !p.halo) {
-      const int gxp = p.mode == 1 ? ((m_groups + 1) / 2) * 4 : (m_groups + 1) / 2;
-      p.total_pair_tiles = gxp * (int)grid.y * (int)grid.z;
-      int pairs = sm_count() / 2;
-      if (pairs > p.total_pair_tiles) pairs = p.total_pair_tiles;
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(2 * pairs);
-      cfg.blockDim = dim3(IGEMM_THREADS);
-      cfg.dynamicSmemBytes = PS::BYTES;
-      cfg.stream = s;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      ADP_CUDA(cudaLaunchKernelEx(&cfg, (tc_igemm_persist_kernel<BLOCK_N, true, 1>), p));
-      adp_count_tc_launch();
-      ADP_LAUNCH_CHECK();
-      return ADP_OK;
-    }
-    const int sms = g_tc_sms > 0 && g_tc_sms < sm_count() ? g_tc_sms : sm_count();
-    const int ctas = p.total_tiles < sms ? p.total_tiles : sms;
-    if (p.mode == 3) {
-      if (BLOCK_N != 128) { adp_set_error("stft: BLOCK_N must be 128"); return ADP_ERR_ARG; }
-      tc_igemm_persist_kernel<128, false, 2><<<ctas, PERSIST_THREADS, PersistSmem<128>::BYTES, s>>>(p);
-    } else {
-      if (p.halo) {
-        constexpr int HB = BLOCK_N == 64 || BLOCK_N == 128 ? BLOCK_N : 64;
-        if (HB != BLOCK_N) { adp_set_error("halo mode needs BLOCK_N 64 or 128"); return ADP_ERR_ARG; }
-        if (p.halo == 4) {
-          using HS = PersistSmem<HB, 4>;
-          static bool hattr_set = false;
-          if (!hattr_set) {
-            ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<HB, false, 1, false, 4>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, HS::BYTES));
-            ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<HB, true, 1, false, 4>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, HS::BYTES));
-            hattr_set = true;
-          }
-          if (g_halo_cluster && p.has_half_map && m_groups >= 2 && HB <= g_halo_cluster) {
-            // with the window loaded once, the weight tiles are most of the L2 -> SM bytes: CTA pairs on adjacent pixel tiles
-            // fetch half of every weight box each and multicast it to the other
-            const int gxp = ((m_groups + 1) / 2) * 4;
-            p.total_pair_tiles = gxp * (int)grid.y * (int)grid.z;
-            int pairs = sm_count() / 2;
-            if (pairs > p.total_pair_tiles) pairs = p.total_pair_tiles;
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof(cfg));
-            cfg.gridDim = dim3(2 * pairs);
-            cfg.blockDim = dim3(IGEMM_THREADS);
-            cfg.dynamicSmemBytes = HS::BYTES;
-            cfg.stream = s;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            ADP_CUDA(cudaLaunchKernelEx(&cfg, (tc_igemm_persist_kernel<HB, true, 1, false, 4>), p));
-          } else {
-            tc_igemm_persist_kernel<HB, false, 1, false, 4><<<ctas, IGEMM_THREADS, HS::BYTES, s>>>(p);
-          }
-        } else if (p.halo == 8) {
-          if (BLOCK_N != 64) { adp_set_error("double-tile halo mode needs BLOCK_N 64"); return ADP_ERR_ARG; }
-          using HS = PersistSmem<64, 8>;
-          static bool h8attr_set = false;
-          if (!h8attr_set) {
-            ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<64, false, 1, false, 8>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, HS::BYTES));
-            h8attr_set = true;
-          }
-          tc_igemm_persist_kernel<64, false, 1, false, 8><<<ctas, IGEMM_THREADS, HS::BYTES, s>>>(p);
-        } else {
-          using HS = PersistSmem<HB, 3>;
-          static bool h3attr_set = false;
-          if (!h3attr_set) {
-            ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<HB, false, 1, false, 3>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, HS::BYTES));
-            h3attr_set = true;
-          }
-          tc_igemm_persist_kernel<HB, false, 1, false, 3><<<ctas, IGEMM_THREADS, HS::BYTES, s>>>(p);
-        }
-      } else if (p.epi != 0) {
-        if (BLOCK_N < 64) { adp_set_error("attention epilogues need BLOCK_N >= 64"); return ADP_ERR_ARG; }
-        static bool aattr_set = false;
-        if (!aattr_set) {
-          ADP_CUDA(cudaFuncSetAttribute(tc_igemm_persist_kernel<(BLOCK_N < 64 ? 64 : BLOCK_N), false, 1, true>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, PersistSmem<(BLOCK_N < 64 ? 64 : BLOCK_N)>::BYTES));
-          aattr_set = true;
-        }
-        tc_igemm_persist_kernel<(BLOCK_N < 64 ? 64 : BLOCK_N), false, 1, true><<<ctas, IGEMM_THREADS, PS::BYTES, s>>>(p);
-      } else {
-        tc_igemm_persist_kernel<BLOCK_N, false, 1><<<ctas, IGEMM_THREADS, PS::BYTES, s>>>(p);
-      }
-    }
-    adp_count_tc_launch();
-    ADP_LAUNCH_CHECK();
-    return ADP_OK;
+  const int sms = sm_count();
+  const int ctas = p.total_tiles < sms ? p.total_tiles : sms;
+  if (p.mode == 3) {
+    if (BLOCK_N != 128) { adp_set_error("stft: BLOCK_N must be 128"); return ADP_ERR_ARG; }
+    ADP_TRY((launch_persist<128, 2, false, 0>(p, ctas, s)));
+  } else if (p.halo) {
+    constexpr int HB = BLOCK_N == 128 ? 128 : 64;
+    if (HB != BLOCK_N) { adp_set_error("halo mode needs BLOCK_N 64 or 128"); return ADP_ERR_ARG; }
+    if (p.halo == 4) ADP_TRY((launch_persist<HB, 1, false, 4>(p, ctas, s)));
+    else ADP_TRY((launch_persist<HB, 1, false, 3>(p, ctas, s)));
+  } else if (p.epi != 0) {
+    constexpr int AB = BLOCK_N < 64 ? 64 : BLOCK_N;
+    if (AB != BLOCK_N) { adp_set_error("attention epilogues need BLOCK_N >= 64"); return ADP_ERR_ARG; }
+    ADP_TRY((launch_persist<AB, 1, true, 0>(p, ctas, s)));
+  } else {
+    ADP_TRY((launch_persist<BLOCK_N, 1, false, 0>(p, ctas, s)));
   }
-  // Ring depth: at most what fits twice into an SM's shared memory, so that two CTAs are co-resident and one
-  // CTA's epilogue (TMEM -> global) overlaps the other's TMA/MMA main loop; never deeper than the K loop.
-  int max_stages = (108 * 1024) / S::STAGE_BYTES;
-  if (max_stages > S::STAGES) max_stages = S::STAGES;
-  if (max_stages < 2) max_stages = 2;
-  if (g_force_stages > 0) max_stages = g_force_stages < S::STAGES ? g_force_stages : S::STAGES;
-  p.stages = p.kb_per_split < max_stages ? (p.kb_per_split < 1 ? 1 : p.kb_per_split) : max_stages;
-  const int smem_bytes = p.stages * S::STAGE_BYTES + 1024 + 256;
-  tc_igemm_kernel<BLOCK_N><<<grid, IGEMM_THREADS, smem_bytes, s>>>(p);
   adp_count_tc_launch();
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }
 
-int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes, cudaStream_t s) {
+// true when run_igemm would split the K range of this problem (fused statistics are then unavailable)
+int pick_splits(const IgemmParams& p, int block_n, bool have_scratch, size_t scratch_bytes) {
   const int m_tiles = p.tiles_w * p.tiles_h * adp_cdiv(p.B, p.Bt);
   const int n_tiles = p.N / block_n;
   const int par = p.mode == 1 ? 4 : 1;
   const long long out_pixels = (long long)p.B * p.Hs * p.Ws * par;
-  // split the K range when the tile count cannot fill the machine (deep layers: small M, huge K)
   int splits = 1;
   const long long ctas = (long long)m_tiles * n_tiles * par;
-  if ((scratch || p.f32_rows) && ctas < sm_count()) {
+  if ((have_scratch || p.f32_rows) && ctas < sm_count()) {
     splits = (int)((sm_count() + ctas - 1) / ctas);
     const int max_by_k = p.kblocks / 4 > 0 ? p.kblocks / 4 : 1;
     if (splits > max_by_k) splits = max_by_k;
@@ -958,9 +700,21 @@ int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes,
     if (!p.f32_rows && (size_t)out_pixels * p.N * sizeof(float) > scratch_bytes) splits = 1;
     if (p.rows_guard > 0) splits = 1;      // (ragged row counts: keep the guarded direct store)
   }
+  return splits;
+}
+
+int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes, cudaStream_t s) {
+  const int m_tiles = p.tiles_w * p.tiles_h * adp_cdiv(p.B, p.Bt);
+  const int n_tiles = p.N / block_n;
+  const int par = p.mode == 1 ? 4 : 1;
+  const long long out_pixels = (long long)p.B * p.Hs * p.Ws * par;
+  ADP_CHECK_ARG(out_pixels + 4LL * p.B * (p.Hs + p.Ws + 4) < (1LL << 32), "tc igemm: too many output pixels (%lld)", out_pixels);
+  // split the K range when the tile count cannot fill the machine (deep layers: small M, huge K)
+  int splits = pick_splits(p, block_n, scratch != nullptr, scratch_bytes);
   p.kb_per_split = adp_cdiv(p.kblocks, splits);
   splits = adp_cdiv(p.kblocks, p.kb_per_split);
   p.splits = splits;
+  if (splits > 1 && p.stats) { adp_set_error("tc igemm: fused statistics with a split K range"); return ADP_ERR_ARG; }
   if (p.f32_rows && splits > 1) scratch = p.out_f32;      // fp32 result: the split-K partial sums ARE the output
   p.partial = splits > 1 ? scratch : nullptr;
   if (splits > 1) ADP_CUDA(cudaMemsetAsync(scratch, 0, (size_t)out_pixels * p.N * sizeof(float), s));
@@ -982,37 +736,36 @@ int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes,
   return ADP_OK;
 }
 
-struct StagesEnvInit {
-  StagesEnvInit() {
-    const char* e = getenv("ADP_TC_STAGES");
-    if (e) g_force_stages = atoi(e);
-    const char* pe = getenv("ADP_TC_PERSISTENT");
-    if (pe) g_persistent = atoi(pe);
-    const char* ce = getenv("ADP_TC_CLUSTER");
-    if (ce) g_cluster = atoi(ce);
-    const char* hce = getenv("ADP_TC_HALO_CLUSTER");
-    if (hce) g_halo_cluster = atoi(hce);
+struct TcEnvInit {
+  TcEnvInit() {
     const char* he = getenv("ADP_TC_HALO");
     if (he) g_halo = atoi(he);
-    const char* se = getenv("ADP_TC_SMS");
-    if (se) g_tc_sms = atoi(se);
     const char* be = getenv("ADP_TC_MAX_BN");
     if (be) g_max_block_n = atoi(be);
+    const char* se = getenv("ADP_TC_STATS");
+    if (se) g_stats = atoi(se);
   }
-} g_stages_env_init;
+} g_tc_env_init;
 
 // set and consumed within one C-ABI call on the calling host thread (thread_local: calls from several host threads,
 // e.g. one per device, do not see each other's workspace)
 thread_local float* g_scratch = nullptr;
 thread_local size_t g_scratch_bytes = 0;
 
+// BatchNorm statistics can ride in the epilogue when the output goes through the staged bf16 path of one un-split launch
+bool stats_fusable(const IgemmParams& p, int block_n, bool have_scratch, size_t scratch_bytes) {
+  if (!g_stats || block_n < 64 || p.N1 != 0) return false;
+  const int cap = p.halo == 3 ? 0 : ((p.halo && block_n == 64) ? PersistSmem<64, 4>::STATS_N : PersistSmem<256>::STATS_N);
+  if (p.N > cap) return false;
+  return pick_splits(p, block_n, have_scratch, scratch_bytes) <= 1;
+}
+
 }  // namespace
 
 int tc_set_option(const char* name, int value) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_halo;
-  else if (!strcmp(name, "tc_halo_cluster")) slot = &g_halo_cluster;
-  else if (!strcmp(name, "tc_cluster")) slot = &g_cluster;
+  else if (!strcmp(name, "tc_stats")) slot = &g_stats;
   else if (!strcmp(name, "tc_max_bn")) slot = &g_max_block_n;
   if (!slot) return -1;
   const int prev = *slot;
@@ -1042,7 +795,7 @@ bool tc_supported_parity(int B, int Hi, int Wi, int C0, int C1, int N) {
 }
 
 int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, int N1, int B, int Hi, int Wi, int C,
-                   cudaStream_t s) {
+                   cudaStream_t s, const ConvExtras* ex) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   const int Ho = Hi / 2, Wo = Wi / 2, N = N0 + N1;
@@ -1053,9 +806,11 @@ int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, 
   p.B = B; p.Hs = Ho; p.Ws = Wo; p.mode = 0; p.C0 = C; p.C1 = 0; p.Ct = C; p.N = N; p.N0 = N0; p.N1 = N1;
   p.kblocks = 16 * (C / TILE_K);
   p.y0 = (bf16*)y0; p.y1 = (bf16*)y1;
-  {  // x viewed as (2C | Wi/2 | 2 | Hi/2 | B)
-    uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)Wo, 2, (uint64_t)Ho, (uint64_t)B};
-    uint64_t str[4] = {(uint64_t)2 * C * 2, (uint64_t)Wi * C * 2, (uint64_t)2 * Wi * C * 2, (uint64_t)Hi * Wi * C * 2};
+  p.pad_in = ex && ex->pad_in ? 1 : 0;
+  {  // x viewed as (2C | Wi/2 | 2 | Hi/2 | B); with an explicit border the tensor is [B, Hi+2, Wi+2, C]
+    const int Hp = Hi + 2 * p.pad_in, Wp = Wi + 2 * p.pad_in;
+    uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)Wp / 2, 2, (uint64_t)Hp / 2, (uint64_t)B};
+    uint64_t str[4] = {(uint64_t)2 * C * 2, (uint64_t)Wp * C * 2, (uint64_t)2 * Wp * C * 2, (uint64_t)Hp * Wp * C * 2};
     uint32_t box[5] = {TILE_K, (uint32_t)p.Wt, 1, (uint32_t)p.Ht, (uint32_t)p.Bt};
     ADP_TRY(make_tmap_bf16(&p.tmA0, x, 5, dims, str, box));
   }
@@ -1064,15 +819,16 @@ int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, 
     uint64_t str[1] = {(uint64_t)16 * C * 2};
     uint32_t box[2] = {TILE_K, (uint32_t)bn};
     ADP_TRY(make_tmap_bf16(&p.tmW, w_nk, 2, dims, str, box));
-    uint32_t hbox[2] = {TILE_K, (uint32_t)bn / 2};
-    ADP_TRY(make_tmap_bf16(&p.tmWh, w_nk, 2, dims, str, hbox));
-    p.has_half_map = 1;
+  }
+  if (ex && ex->stats && stats_fusable(p, bn, g_scratch != nullptr, g_scratch_bytes)) {
+    p.stats = ex->stats;
+    if (ex->stats_done) *ex->stats_done = 1;
   }
   return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
 }
 
 int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* w_kn, void* y, int B, int Hi, int Wi, int N,
-                    cudaStream_t s) {
+                    cudaStream_t s, const ConvExtras* ex) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   ADP_CHECK_ARG(tile_geometry(B, Hi, Wi, &p.Wt, &p.Ht, &p.Bt), "tc_parity_convT: unsupported spatial size %dx%d", Hi, Wi);
@@ -1080,11 +836,9 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
   ADP_CHECK_ARG(bn >= 64 && C0 % TILE_K == 0 && C1 % TILE_K == 0, "tc_parity_convT: unsupported channels");
   const int Ct = C0 + C1;
   // narrow-N layers are bound by L2 -> SM operand traffic: load the tile's input window once per channel chunk (HALO)
-  const bool halo = g_halo && g_persistent && (bn == 64 || bn == 128) && Hi >= 16 && Wi >= 8 && Hi % 16 == 0 && Wi % 8 == 0 &&
+  const bool halo = g_halo && (bn == 64 || bn == 128) && Hi >= 16 && Wi >= 8 && Hi % 16 == 0 && Wi % 8 == 0 &&
                     (long long)B * (Hi / 16) * (Wi / 8) * 4 * (N / bn) >= sm_count();
-  // N = 64: two tiles side by side share the weight tiles (HALO = 8) when the grid is still large enough
-  const bool halo2 = halo && g_halo >= 2 && bn == 64 && Wi % 16 == 0 && (long long)B * (Hi / 16) * (Wi / 16) * 4 * (N / bn) >= sm_count();
-  if (halo) { p.Wt = halo2 ? 16 : 8; p.Ht = 16; p.Bt = 1; p.halo = halo2 ? 8 : 4; }
+  if (halo) { p.Wt = 8; p.Ht = 16; p.Bt = 1; p.halo = 4; }
   p.tiles_w = Wi / p.Wt; p.tiles_h = Hi / p.Ht;
   p.B = B; p.Hs = Hi; p.Ws = Wi; p.mode = 1; p.C0 = C0; p.C1 = C1; p.Ct = Ct; p.N = N; p.N0 = N; p.N1 = 0;
   p.kblocks = (halo ? 1 : 4) * (Ct / TILE_K);
@@ -1095,7 +849,7 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)Wi * C * 2, (uint64_t)Hi * Wi * C * 2};
     uint32_t box[4] = {TILE_K, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
-    uint32_t hbox[4] = {TILE_K, (uint32_t)(halo2 ? HaloGeom<8>::W : HaloGeom<4>::W), HaloGeom<4>::H, 1};
+    uint32_t hbox[4] = {TILE_K, (uint32_t)HaloGeom<4>::W, HaloGeom<4>::H, 1};
     ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmA0 : &p.tmA1, h == 0 ? x0 : x1, 4, dims, str, halo ? hbox : box));
   }
   {  // w_kn: bf16 [Ct][16][N] (the master layout, cast)
@@ -1103,9 +857,10 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
     uint64_t str[2] = {(uint64_t)N * 2, (uint64_t)16 * N * 2};
     uint32_t box[3] = {64, 1, TILE_K};
     ADP_TRY(make_tmap_bf16(&p.tmW, w_kn, 3, dims, str, box));
-    uint32_t hbox[3] = {64, 1, TILE_K / 2};
-    ADP_TRY(make_tmap_bf16(&p.tmWh, w_kn, 3, dims, str, hbox));
-    p.has_half_map = 1;
+  }
+  if (ex && ex->stats && stats_fusable(p, bn, g_scratch != nullptr, g_scratch_bytes)) {
+    p.stats = ex->stats;
+    if (ex->stats_done) *ex->stats_done = 1;
   }
   return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
 }
@@ -1149,7 +904,7 @@ int tc_pointwise16(const void* x0, int C0, const void* x1, int C1, const void* w
 //   y[pix][n] = sum_c (x0|x1)[pix][c] * w_nk[n][c]
 // act_dual = 0: bf16 output split (y0: n < N0 | y1: rest);  act_dual = 1: y0 = lrelu(., slope0), y1 = lrelu(., slope1).
 int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_nk, void* y0, int N0, void* y1, int N1,
-                 int act_dual, float slope0, float slope1, int B, int Hi, int Wi, cudaStream_t s) {
+                 int act_dual, float slope0, float slope1, int B, int Hi, int Wi, cudaStream_t s, const ConvExtras* ex) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   ADP_CHECK_ARG(tile_geometry(B, Hi, Wi, &p.Wt, &p.Ht, &p.Bt), "tc_pointwise: unsupported spatial size %dx%d", Hi, Wi);
@@ -1162,6 +917,7 @@ int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_n
   p.kblocks = Ct / TILE_K;
   p.y0 = (bf16*)y0; p.y1 = (bf16*)y1;
   p.act_dual = act_dual; p.slope0 = slope0; p.slope1 = slope1;
+  if (ex && act_dual) { p.center = ex->center; p.pad_out = ex->pad_out ? 1 : 0; }
   for (int h = 0; h < 2; ++h) {
     const int C = h == 0 ? C0 : C1;
     if (C == 0) continue;
@@ -1175,9 +931,6 @@ int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_n
     uint64_t str[1] = {(uint64_t)Ct * 2};
     uint32_t box[2] = {TILE_K, (uint32_t)bn};
     ADP_TRY(make_tmap_bf16(&p.tmW, w_nk, 2, dims, str, box));
-    uint32_t hbox[2] = {TILE_K, (uint32_t)bn / 2};
-    ADP_TRY(make_tmap_bf16(&p.tmWh, w_nk, 2, dims, str, hbox));
-    p.has_half_map = 1;
   }
   return run_igemm(p, bn, nullptr, 0, s);
 }
@@ -1188,7 +941,7 @@ int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_n
 // MN-major (N = Cin | tap | K = Cout) map with the taps reversed (wmode 1), dy as the input, dx split N0 | N1.
 bool tc_supported_conv3x3(int B, int H, int W, int C0, int C1, int N0, int N1) {
   int Wt, Ht, Bt;
-  if (!g_persistent || !adp_device_is_sm100() || !encode_tiled_fn()) return false;
+  if (!adp_device_is_sm100() || !encode_tiled_fn()) return false;
   if (C0 <= 0 || C0 % TILE_K || C1 % TILE_K || B < 1) return false;
   if (!tile_geometry(B, H, W, &Wt, &Ht, &Bt)) return false;
   return pick_block_n(N0 + N1, N0, N1) >= 64;
@@ -1198,7 +951,6 @@ int tc_conv3x3(const void* x0, int C0, const void* x1, int C1, const void* w, in
                int B, int H, int W, void* scratch, size_t scratch_bytes, cudaStream_t s) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  ADP_CHECK_ARG(g_persistent, "tc_conv3x3 needs the persistent kernel (ADP_TC_PERSISTENT=0 is set)");
   ADP_CHECK_ARG(tile_geometry(B, H, W, &p.Wt, &p.Ht, &p.Bt), "tc_conv3x3: unsupported spatial size %dx%d", H, W);
   const int N = N0 + N1, Ct = C0 + C1;
   const int bn = pick_block_n(N, N0, N1);
@@ -1248,7 +1000,7 @@ int tc_gemm_rows(const void* a0, int K0, const void* a1, int K1, const void* bm,
     p.epi = epi->mode; p.stat_by_col = epi->by_col; p.escale = epi->scale;
     p.stat_m = epi->stat_m; p.stat_l = epi->stat_l; p.delta = epi->delta; p.pmat = reinterpret_cast<const bf16*>(epi->pmat);
   }
-  ADP_CHECK_ARG(g_persistent && adp_device_is_sm100() && encode_tiled_fn(), "tc_gemm_rows: tcgen05 path unavailable");
+  ADP_CHECK_ARG(adp_device_is_sm100() && encode_tiled_fn(), "tc_gemm_rows: tcgen05 path unavailable");
   const int N = N0 + N1, Kt = K0 + K1;
   const int bn = pick_block_n(N, N0, N1);
   ADP_CHECK_ARG(bn >= 64 && K0 > 0 && K0 % TILE_K == 0 && K1 % TILE_K == 0 && M >= 1 && M < (1LL << 31),
@@ -1367,7 +1119,7 @@ size_t tc_stft_workspace_bytes(int rows, int L, int n_fft, int hop) {
 }
 
 bool tc_supported_stft(int rows, int L, int n_fft, int win, int hop) {
-  if (!g_persistent || !adp_device_is_sm100() || !encode_tiled_fn()) return false;
+  if (!adp_device_is_sm100() || !encode_tiled_fn()) return false;
   return win == 64 && hop > 0 && n_fft >= 64 && n_fft <= 2048 && rows >= 1 && L > 32 && (1 + L / hop) <= 32768;
 }
 

@@ -62,7 +62,7 @@ __device__ __forceinline__ BnCoef bn_coef(const adp::BnFin& f, int C, int c) {
     o.invstd = 1.f / sqrtf((float)var + f.eps);
     o.unbiased = (float)var * f.unbias;
   } else {
-    o.mean = f.rm[c];
+    o.mean = f.rm[c] - (f.mean_offset ? f.mean_offset[c] : 0.f);     // statistics of the stored (offset) tensor
     o.invstd = 1.f / sqrtf(f.rv[c] + f.eps);
     o.unbiased = 0.f;
   }
@@ -72,7 +72,7 @@ __device__ __forceinline__ BnCoef bn_coef(const adp::BnFin& f, int C, int c) {
 }
 __device__ __forceinline__ void bn_store(const adp::BnFin& f, int c, const BnCoef& o) {
   if (f.training && f.rm) {
-    f.rm[c] = (1.f - f.momentum) * f.rm[c] + f.momentum * o.mean;
+    f.rm[c] = (1.f - f.momentum) * f.rm[c] + f.momentum * (o.mean + (f.mean_offset ? f.mean_offset[c] : 0.f));
     f.rv[c] = (1.f - f.momentum) * f.rv[c] + f.momentum * o.unbiased;
   }
   f.scale[c] = o.scale;
@@ -81,6 +81,7 @@ __device__ __forceinline__ void bn_store(const adp::BnFin& f, int c, const BnCoe
   f.invstd[c] = o.invstd;
 }
 
+// (fallback for channel counts the fused 8-wide kernels do not cover: 2048 % C != 0)
 __global__ void bn_finalize_kernel(const adp::BnFin f, int C) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) bn_store(f, c, bn_coef(f, C, c));
@@ -710,16 +711,8 @@ int act_bn_bwd_reduce(int dtype, const void* x, long long rows, int C, const flo
   if (C % 8 == 0) {
     ColLaunch L = col_launch8(rows, C);
     const size_t smem = (size_t)RED_STAGES * RED_ROWS * 3 * 256 * (dtype == ADP_F32 ? 32 : 16);
-    {
-      static bool attr_set = false;
-      if (!attr_set) {
-        ADP_CUDA(cudaFuncSetAttribute(act_bn_bwd_reduce8_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      RED_STAGES * RED_ROWS * 3 * 256 * 32));
-        ADP_CUDA(cudaFuncSetAttribute(act_bn_bwd_reduce8_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      RED_STAGES * RED_ROWS * 3 * 256 * 16));
-        attr_set = true;
-      }
-    }
+    ADP_SMEM_ATTR(act_bn_bwd_reduce8_kernel<float>, RED_STAGES * RED_ROWS * 3 * 256 * 32);
+    ADP_SMEM_ATTR(act_bn_bwd_reduce8_kernel<bf16>, RED_STAGES * RED_ROWS * 3 * 256 * 16);
     ADP_DISPATCH_T(dtype, act_bn_bwd_reduce8_kernel<T><<<L.grid, L.block, smem, s>>>(
                               (const T*)x, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0, (const T*)gB,
                               slope1, sums);)
@@ -742,14 +735,8 @@ int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const floa
     long long n8 = rows * C / 8;
     if (2048 % C == 0) {
       const size_t smem = (size_t)RED_STAGES * RED_ROWS * 3 * 256 * (dtype == ADP_F32 ? 32 : 16);
-      static bool attr_set = false;
-      if (!attr_set) {
-        ADP_CUDA(cudaFuncSetAttribute(act_bn_bwd_apply8_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      RED_STAGES * RED_ROWS * 3 * 256 * 32));
-        ADP_CUDA(cudaFuncSetAttribute(act_bn_bwd_apply8_kernel<bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      RED_STAGES * RED_ROWS * 3 * 256 * 16));
-        attr_set = true;
-      }
+      ADP_SMEM_ATTR((act_bn_bwd_apply8_kernel<float, true>), RED_STAGES * RED_ROWS * 3 * 256 * 32);
+      ADP_SMEM_ATTR((act_bn_bwd_apply8_kernel<bf16, true>), RED_STAGES * RED_ROWS * 3 * 256 * 16);
       ADP_DISPATCH_T(dtype, (act_bn_bwd_apply8_kernel<T, true><<<ew_grid(n8), EW_THREADS, smem, s>>>(
                                 (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
                                 (const T*)gB, slope1, sums, mode, (T*)dx, dgamma, dbeta));)

@@ -389,6 +389,91 @@ __global__ void fold_thin_wgrad_kernel(const float* __restrict__ D, float* __res
   }
 }
 
+
+// ------------------------------------------------------------------ first-level centring (adp_unet.cu: use_center)
+// xsum[ci] += sum over the batch of plane ci; x NCHW fp32 [B][Cin][HW]; grid (blocks, B * Cin)
+__global__ void __launch_bounds__(256)
+center_input_sums_kernel(const float* __restrict__ x, int Cin, long long HW, double* __restrict__ xsum) {
+  const int plane = blockIdx.y, ci = plane % Cin;
+  const float4* src = reinterpret_cast<const float4*>(x + (size_t)plane * HW);
+  const long long n4 = HW / 4;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(src + i);
+    acc += (v.x + v.y) + (v.z + v.w);
+  }
+  if (blockIdx.x == 0)
+    for (long long i = 4 * n4 + threadIdx.x; i < HW; i += blockDim.x) acc += x[(size_t)plane * HW + i];
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += (double)red[w];
+    atomicAdd(&xsum[ci], t);
+  }
+}
+
+// blocks [0, N2): T[n2] = sum_{tap,c} w2b[n2][tap][c] * m[c];  blocks >= N2: border ring of a0pad = -m.
+// Every block derives m itself (64 x 16*Cin multiply-adds): m[n] = bf16(LeakyReLU_0.2(sum_t w1[n][t] * mean_x[t % Cin])),
+// rounded to bf16 so that -m is stored exactly in the ring.  Block 0 publishes m.
+__global__ void __launch_bounds__(256)
+center_tables_kernel(const double* __restrict__ xsum, double inv_count, const float* __restrict__ w1, int Cin,
+                     const bf16* __restrict__ w2b, int N2, float* __restrict__ m_out, float* __restrict__ T,
+                     bf16* __restrict__ a0pad, int B, int H, int W) {
+  __shared__ float m_s[64];
+  __shared__ float red[8];
+  if (threadIdx.x < 64) {
+    const int n = threadIdx.x, K = 16 * Cin;
+    float acc = 0.f;
+    for (int t = 0; t < K; ++t) acc = fmaf(w1[n * K + t], (float)(xsum[t % Cin] * inv_count), acc);
+    const float mv = __bfloat162float(__float2bfloat16_rn(lrelu(acc, 0.2f)));
+    m_s[n] = mv;
+    if (blockIdx.x == 0) m_out[n] = mv;
+  }
+  __syncthreads();
+  if ((int)blockIdx.x < N2) {
+    const bf16* row = w2b + (size_t)blockIdx.x * 16 * 64;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) acc = fmaf(__bfloat162float(row[i]), m_s[i & 63], acc);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      T[blockIdx.x] = t;
+    }
+    return;
+  }
+  // ring: 2 (W+2) + 2 H pixels per sample, 8 chunks of 8 channels per pixel
+  const int Hp = H + 2, Wp = W + 2, ring = 2 * Wp + 2 * H;
+  const long long total = (long long)B * ring * 8;
+  const int rblocks = gridDim.x - N2;
+  for (long long idx = (long long)(blockIdx.x - N2) * blockDim.x + threadIdx.x; idx < total; idx += (long long)rblocks * blockDim.x) {
+    const int ch8 = (int)(idx & 7);
+    const long long rp = idx >> 3;
+    const int r = (int)(rp % ring), b = (int)(rp / ring);
+    int yy, xx;
+    if (r < Wp) { yy = 0; xx = r; }
+    else if (r < 2 * Wp) { yy = Hp - 1; xx = r - Wp; }
+    else { const int k = r - 2 * Wp; yy = 1 + (k >> 1); xx = (k & 1) ? Wp - 1 : 0; }
+    uint4 u;
+    u.x = pack_bf16x2(-m_s[ch8 * 8 + 0], -m_s[ch8 * 8 + 1]); u.y = pack_bf16x2(-m_s[ch8 * 8 + 2], -m_s[ch8 * 8 + 3]);
+    u.z = pack_bf16x2(-m_s[ch8 * 8 + 4], -m_s[ch8 * 8 + 5]); u.w = pack_bf16x2(-m_s[ch8 * 8 + 6], -m_s[ch8 * 8 + 7]);
+    *reinterpret_cast<uint4*>(a0pad + (((size_t)b * Hp + yy) * Wp + xx) * 64 + ch8 * 8) = u;
+  }
+}
+
+__global__ void center_wgrad_fix_kernel(float* __restrict__ dw, const float* __restrict__ m, const float* __restrict__ scale,
+                                        const double* __restrict__ gsum, int N2, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N2 * 16 * C) return;
+  const int c = (int)(i % C), n = (int)(i / (16LL * C));
+  dw[i] += m[c] * scale[n] * (float)gsum[n];
+}
+
 int tile_grid(int B, int Hs, int Ws, int per_sm) {
   long long tiles = (long long)B * ((Hs + TT_H - 1) / TT_H) * ((Ws + TT_W - 1) / TT_W);
   long long cap = (long long)adp::sm_count() * per_sm;
@@ -485,6 +570,37 @@ int thin_patch_rows(const float* img, void* out, int B, int Cin, int H, int W, i
     case 8: patch_rows_kernel<4, false><<<(int)blocks, 256, 0, s>>>(img, (bf16*)out, B, H, W, lw, lh); break;
     default: adp_set_error("patch_rows: Cin %d unsupported", Cin); return ADP_ERR_UNSUPPORTED;
   }
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+
+int center_input_sums(const float* x, int B, int Cin, long long HW, double* xsum, cudaStream_t s) {
+  ADP_CHECK_ARG(Cin >= 1 && Cin <= 16 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && HW % 4 == 0,
+                "center_input_sums: unsupported input");
+  long long bx = (HW / 4 + 255) / 256;
+  if (bx > 8) bx = 8;
+  if (bx < 1) bx = 1;
+  center_input_sums_kernel<<<dim3((unsigned)bx, (unsigned)(B * Cin)), 256, 0, s>>>(x, Cin, HW, xsum);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int center_tables(const double* xsum, double inv_count, const float* w1, int Cin, const void* w2b, int N2, float* m,
+                  float* T, void* a0pad, int B, int H, int W, cudaStream_t s) {
+  const long long ring_items = (long long)B * (2 * (W + 2) + 2 * H) * 8;
+  long long rblocks = (ring_items + 255) / 256;
+  const long long cap = (long long)sm_count() * 4;
+  if (rblocks > cap) rblocks = cap;
+  center_tables_kernel<<<(unsigned)(N2 + rblocks), 256, 0, s>>>(xsum, inv_count, w1, Cin, (const bf16*)w2b, N2, m, T,
+                                                                 (bf16*)a0pad, B, H, W);
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int center_wgrad_fix(float* dw, const float* m, const float* scale, const double* gsum, int N2, int C, cudaStream_t s) {
+  const long long n = (long long)N2 * 16 * C;
+  center_wgrad_fix_kernel<<<adp_cdiv(n, 256), 256, 0, s>>>(dw, m, scale, gsum, N2, C);
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }

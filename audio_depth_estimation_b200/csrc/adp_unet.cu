@@ -35,6 +35,8 @@ struct Plan {
   size_t p_last, w16_last;       // tensor-core head: P fp32 [B,H/2,W/2,16], bf16 weights [16][Ct]
   size_t xp0, dp0, w1pad, wLpad, dthin;  // tensor-core thin layers: patch rows [pix][64] bf16, padded weights, D fp32 [128][128]
   bool thin_tc;
+  // first-level centring (see use_center): per-input-channel sums of x, the constants m[cout0] / T[cout1]
+  size_t xsum, center_m, center_T;
   size_t tc_scratch, tc_scratch_bytes;  // fp32 split-K partial sums of the tensor-core convolutions
   size_t sums_begin, sums_end;   // forward BN sums region (zeroed every forward)
   size_t bsums_begin, bsums_end; // backward sums region
@@ -67,6 +69,7 @@ int make_plan(const adp_unet_desc* d, Plan* p) {
     L.bn_up = l > 0;
   }
   p->sums_begin = off;
+  p->xsum = take(sizeof(double) * 16);
   for (int l = 0; l < D; ++l) {
     LevelPlan& L = p->lv[l];
     L.sums_down = take(sizeof(double) * 2 * L.cout);
@@ -85,7 +88,8 @@ int make_plan(const adp_unet_desc* d, Plan* p) {
     const size_t act = (size_t)d->batch * L.hout * L.hout * L.cout * p->esz;
     L.bn_down_f = take(sizeof(float) * 4 * L.cout);
     L.bn_up_f = take(sizeof(float) * 4 * (L.t_cout > 4 ? L.t_cout : 4));
-    L.e = take(act); L.a = take(act); L.r = take(act);
+    // (level 0: room for the explicit one-pixel border of the centred activation)
+    L.e = take(act); L.a = take(l == 0 ? (size_t)d->batch * (L.hout + 2) * (L.hout + 2) * L.cout * p->esz : act); L.r = take(act);
     L.g_a = take(act); L.g_r = take(act); L.g_e = take(act);
     if (l < D - 1) { L.t = take(act); L.q = take(act); L.g_q = take(act); L.g_t = take(act); }
     else { L.t = L.q = L.g_q = L.g_t = 0; }
@@ -109,6 +113,8 @@ int make_plan(const adp_unet_desc* d, Plan* p) {
     p->w1pad = take(64 * 64 * 2);
     p->wLpad = take(128 * 64 * 2);
     p->dthin = take(128 * 128 * sizeof(float));
+    p->center_m = take(sizeof(float) * L0.cout);
+    p->center_T = take(sizeof(float) * (D > 1 ? p->lv[1].cout : 4));
   }
   p->total = off;
   return ADP_OK;
@@ -124,26 +130,56 @@ inline BnBuf bnbuf(void* ws, size_t off, int C) {
 
 bool use_tc(int dtype) { return dtype == ADP_BF16 && tc_enabled(); }
 
+int g_center = -1;    // "center" / ADP_CENTER=0 switches the first-level centring off
+bool center_enabled() {
+  if (g_center < 0) g_center = getenv("ADP_CENTER") ? atoi(getenv("ADP_CENTER")) : 1;
+  return g_center != 0;
+}
+
+// First-level centring (bf16 tensor-core path).  With min-max-normalised log-spectrogram inputs (mean ~0.8, std ~0.05) the
+// first activation a[0] = LeakyReLU(Conv(x)) is a large per-channel constant plus a small signal, and the first
+// BatchNorm (level 1) divides by the standard deviation of the signal alone: bf16 storage of a[0] and of the raw
+// Conv(a[0]) then costs ~2.4e-2 of the depth map (emulated on the CPU oracle and measured on the GPU), above the
+// 2e-2 the path promises.  The network function is kept EXACTLY, only the storage changes:
+//   * a[0] is stored as a[0] - m[n] (m = bf16(LeakyReLU(W1 . mean(x))), any constant is exact) inside a tensor with an
+//     explicit one-pixel border holding -m[n], so the level-1 convolution sees zeros where the reference pads;
+//   * its accumulators are then e[1] - T[n'], T = sum_{taps,c} W2[n'][tap][c] m[c]: a per-channel constant the level-1
+//     BatchNorm removes (train: the batch mean shifts by -T; running_mean and the eval-mode shift add T back);
+//   * the level-1 weight gradient sums over the border too (-m * dL/de[1]), which adds m[c] * sum_pixels dL/de[1][n']:
+//     zero with batch statistics (BatchNorm's backward output sums to zero per channel), scale * sum gz in eval mode.
+bool use_center(const adp_unet_desc* d, const Plan& p, bool tc) {
+  if (!tc || !p.thin_tc || p.D < 3 || !center_enabled()) return false;
+  const LevelPlan& L0 = p.lv[0];
+  const LevelPlan& L1 = p.lv[1];
+  return L1.bn_down && L0.cout == 64 && tc_supported_pointwise16(p.B, L0.hout, L0.hout, L0.cout, L0.t_c1) &&
+         tc_supported_gather(p.B, L1.hin, L1.hin, L1.cin, L1.cout, 0) &&
+         tc_supported_wgrad(p.B, L1.hout, L1.hout, L1.cout, 0, L1.cin) && d->out_ch == 1;
+}
+
 // ---- family dispatch: tensor cores when the operands are bf16 and the shape is supported
+// (ex: tensor-core extras -- fused BatchNorm statistics, padded input; ignored by the SIMT kernels, whose callers check
+// *ex->stats_done and never request padding)
 int conv_gather(int dtype, const void* x, const float* w, const void* wb, void* y0, int N0, void* y1, int N1,
-                int B, int Hi, int Wi, int C, cudaStream_t s) {
+                int B, int Hi, int Wi, int C, cudaStream_t s, const ConvExtras* ex = nullptr) {
   ProfScope prof(PROF_GATHER, s, 2.0 * B * (Hi / 2) * (Wi / 2) * (double)(N0 + N1) * 16.0 * C);
   if (use_tc(dtype) && wb && tc_supported_gather(B, Hi, Wi, C, N0, N1))
-    return tc_gather_conv(x, wb, y0, N0, y1, N1, B, Hi, Wi, C, s);
+    return tc_gather_conv(x, wb, y0, N0, y1, N1, B, Hi, Wi, C, s, ex);
+  ADP_CHECK_ARG(!ex || !ex->pad_in, "conv_gather: padded input needs the tensor-core path");
   return simt_gather_conv(dtype, x, w, y0, N0, y1, N1, B, Hi, Wi, C, s);
 }
 int conv_parity(int dtype, const void* x0, int C0, const void* x1, int C1, const float* w, const void* wb, void* y,
-                int B, int Hi, int Wi, int N, cudaStream_t s) {
+                int B, int Hi, int Wi, int N, cudaStream_t s, const ConvExtras* ex = nullptr) {
   ProfScope prof(PROF_PARITY, s, 2.0 * B * Hi * Wi * 4.0 * (double)N * 4.0 * (C0 + C1));
   if (use_tc(dtype) && wb && tc_supported_parity(B, Hi, Wi, C0, C1, N))
-    return tc_parity_convT(x0, C0, x1, C1, wb, y, B, Hi, Wi, N, s);
+    return tc_parity_convT(x0, C0, x1, C1, wb, y, B, Hi, Wi, N, s, ex);
   return simt_parity_convT(dtype, x0, C0, x1, C1, w, y, B, Hi, Wi, N, s);
 }
 int conv_wgrad(int dtype, const void* s0, int M0, const void* s1, int M1, const void* g, int N, float* dw,
-               int B, int Hs, int Ws, cudaStream_t s) {
+               int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0) {
   ProfScope prof(PROF_WGRAD, s, 2.0 * B * Hs * Ws * 16.0 * (double)N * (M0 + M1));
   if (use_tc(dtype) && tc_supported_wgrad(B, Hs, Ws, M0, M1, N))
-    return tc_wgrad(s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s);
+    return tc_wgrad(s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s, g_pad);
+  ADP_CHECK_ARG(!g_pad, "conv_wgrad: padded operand needs the tensor-core path");
   return simt_wgrad(dtype, s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s);
 }
 
@@ -204,17 +240,30 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
       }
     }
   }
-  if (d->training)
-    ADP_CUDA(cudaMemsetAsync(at(ws, p.sums_begin), 0, p.sums_end - p.sums_begin, s));
+  ADP_CUDA(cudaMemsetAsync(at(ws, p.sums_begin), 0, p.sums_end - p.sums_begin, s));
+  const bool center = thin_tc && use_center(d, p, tc);
+  float* cen_m = reinterpret_cast<float*>(at(ws, p.center_m));
+  float* cen_T = reinterpret_cast<float*>(at(ws, p.center_T));
 
   // ---- encoder
   {
     const LevelPlan& L = p.lv[0];
     ProfScope prof(PROF_THIN, s, 2.0 * B * L.hout * L.hout * 16.0 * L.cin * L.cout);
     if (thin_tc) {  // im2col rows (bf16, padded to 64) + pointwise tensor-core GEMM with both activations in the epilogue
+      ConvExtras ex;
+      memset(&ex, 0, sizeof(ex));
+      if (center) {
+        double* xsum = reinterpret_cast<double*>(at(ws, p.xsum));
+        ADP_TRY(center_input_sums(x, B, L.cin, (long long)L.hin * L.hin, xsum, s));
+        ADP_TRY(center_tables(xsum, 1.0 / ((double)B * L.hin * L.hin), params[0].conv_w, L.cin,
+                              w16(params[1].conv_w_bf16, p.lv[1].wb_conv), p.lv[1].cout, cen_m, cen_T, at(ws, L.a), B, L.hout,
+                              L.hout, s));
+        ex.center = cen_m;
+        ex.pad_out = 1;
+      }
       ADP_TRY(thin_patch_rows(x, at(ws, p.xp0), B, L.cin, L.hin, L.hin, L.cin <= 2, s));
       ADP_TRY(tc_pointwise(at(ws, p.xp0), 64, nullptr, 0, at(ws, p.w1pad), at(ws, L.a), 64, at(ws, L.r), 0, 1, 0.2f, 0.f, B,
-                           L.hout, L.hout, s));
+                           L.hout, L.hout, s, &ex));
     } else {
       ADP_TRY(first_conv_fprop(dt, x, params[0].conv_w, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), B, L.hin, L.hin, L.cin,
                                L.cout, s));
@@ -223,14 +272,20 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   for (int l = 1; l < D; ++l) {
     const LevelPlan& L = p.lv[l];
     const long long rows = (long long)B * L.hout * L.hout;
+    double* sums = reinterpret_cast<double*>(at(ws, L.sums_down));
+    int fused = 0;
+    ConvExtras ex;
+    memset(&ex, 0, sizeof(ex));
+    if (L.bn_down && d->training) { ex.stats = sums; ex.stats_done = &fused; }
+    ex.pad_in = (l == 1 && center) ? 1 : 0;
     ADP_TRY(conv_gather(dt, at(ws, p.lv[l - 1].a), params[l].conv_w, tc ? w16(params[l].conv_w_bf16, L.wb_conv) : nullptr,
-                        at(ws, L.e), L.cout, nullptr, 0, B, L.hin, L.hin, L.cin, s));
+                        at(ws, L.e), L.cout, nullptr, 0, B, L.hin, L.hin, L.cin, s, &ex));
     if (L.bn_down) {
       BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
-      double* sums = reinterpret_cast<double*>(at(ws, L.sums_down));
-      if (d->training) ADP_TRY(bn_stats(dt, at(ws, L.e), rows, L.cout, sums, s));
+      if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, L.e), rows, L.cout, sums, s));
       const BnFin fin{sums, 1.0 / (double)rows, rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f, params[l].bn_down_w, params[l].bn_down_b, params[l].bn_down_rm, params[l].bn_down_rv,
-                      d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd};
+                      d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd,
+                      (l == 1 && center) ? cen_T : nullptr};
       ADP_TRY(bn_affine_act(dt, at(ws, L.e), rows, L.cout, fin, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), s));
     } else {
       ADP_TRY(affine_act(dt, at(ws, L.e), rows, L.cout, nullptr, nullptr, 0.f, at(ws, L.r), 0.f, nullptr, s));
@@ -241,13 +296,17 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     const LevelPlan& L = p.lv[l];
     const LevelPlan& O = p.lv[l - 1];  // output lives at level l-1's resolution
     const long long rows = (long long)B * O.hout * O.hout;
-    ADP_TRY(conv_parity(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, params[l].convT_w,
-                        tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, O.t), B, L.hout, L.hout, L.t_cout, s));
-    BnBuf bn = bnbuf(ws, L.bn_up_f, L.t_cout);
     double* sums = reinterpret_cast<double*>(at(ws, L.sums_up));
-    if (d->training) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));
+    int fused = 0;
+    ConvExtras ex;
+    memset(&ex, 0, sizeof(ex));
+    if (d->training) { ex.stats = sums; ex.stats_done = &fused; }
+    ADP_TRY(conv_parity(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, params[l].convT_w,
+                        tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, O.t), B, L.hout, L.hout, L.t_cout, s, &ex));
+    BnBuf bn = bnbuf(ws, L.bn_up_f, L.t_cout);
+    if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));
     const BnFin fin{sums, 1.0 / (double)rows, rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f, params[l].bn_up_w, params[l].bn_up_b, params[l].bn_up_rm, params[l].bn_up_rv,
-                    d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd};
+                    d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd, nullptr};
     ADP_TRY(bn_affine_act(dt, at(ws, O.t), rows, L.t_cout, fin, 0.f, at(ws, O.q), 0.f, nullptr, s));
   }
   {
@@ -297,6 +356,11 @@ int side_stream_for_device(SideStream** out) {
 
 namespace adp {
 int unet_set_option(const char* name, int value) {
+  if (!strcmp(name, "center")) {
+    const int prev = center_enabled() ? 1 : 0;
+    g_center = value ? 1 : 0;
+    return prev;
+  }
   if (strcmp(name, "side_stream")) return -1;
   if (g_side_stream < 0) g_side_stream = getenv("ADP_SIDE_STREAM") ? atoi(getenv("ADP_SIDE_STREAM")) : 1;
   const int prev = g_side_stream;
@@ -320,6 +384,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
   const bool thin_tc_bwd = tc && p.thin_tc && tc_supported_pointwise16(B, p.lv[0].hout, p.lv[0].hout, p.lv[0].cout, p.lv[0].t_c1);
   const int bn_mode = d->training ? 2 : 1;
   tc_set_scratch(p.tc_scratch_bytes ? at(ws, p.tc_scratch) : nullptr, p.tc_scratch_bytes);
+  const bool center = thin_tc_bwd && use_center(d, p, tc);     // (same decision as the forward pass that filled the workspace)
 
   // BatchNorm + ReLU backward of q[l] (up-norm of level l+1): g_q[l] -> g_t[l]
   auto up_norm_bwd = [&](int l) -> int {
@@ -411,8 +476,8 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_a),
                                  0.2f, at(ws, L.g_r), 0.f, bs, bn_mode, at(ws, L.g_e), grads[l].bn_down_w,
                                  grads[l].bn_down_b, s));
-      } else {  // level 0: no norm; sign(e) == sign(a)
-        ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.a), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_a), 0.2f,
+      } else {  // level 0: no norm; e > 0 <=> r = ReLU(e) > 0 (a[0] may be stored centred, r[0] never is)
+        ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.r), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_a), 0.2f,
                                  at(ws, L.g_r), 0.f, nullptr, 0, at(ws, L.g_e), nullptr, nullptr, s));
       }
       cudaStream_t sw = l > 0 ? wgrad_stream(st) : s;
@@ -428,8 +493,14 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         ADP_TRY(first_conv_wgrad(dt, x, at(ws, L.g_e), grads[0].conv_w, B, L.hin, L.hin, L.cin, L.cout, s));
       } else {
         const LevelPlan& I = p.lv[l - 1];
+        const bool cen = l == 1 && center;
         ADP_TRY(conv_wgrad(dt, at(ws, L.g_e), L.cout, nullptr, 0, at(ws, I.a), L.cin, grads[l].conv_w, B, L.hout,
-                           L.hout, sw));
+                           L.hout, sw, cen ? 1 : 0));
+        if (cen && !d->training) {   // eval-mode BatchNorm: sum_pixels dL/de = scale * sum gz is not zero
+          BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
+          ADP_TRY(center_wgrad_fix(grads[l].conv_w, reinterpret_cast<const float*>(at(ws, p.center_m)), bn.scale,
+                                   reinterpret_cast<const double*>(at(ws, L.bsums_down)), L.cout, L.cin, sw));
+        }
         ADP_TRY(conv_parity(dt, at(ws, L.g_e), L.cout, nullptr, 0, params[l].conv_w, tc ? w16(params[l].conv_w_bf16, L.wb_conv) : nullptr,
                             at(ws, I.g_a), B, L.hout, L.hout, L.cin, s));
       }

@@ -36,6 +36,7 @@ struct WgradParams {
   int ntaps;          // taps per CTA (= per kernel row): 4 or 3
   int taps_total;     // 16 or 9
   int ldn, n_off;     // dw row pitch per tap (total input channels) and column offset of this G tensor
+  int g_pad;          // 4x4 mode: G carries an explicit one-pixel border (row 2i+kh of the padded tensor, never out of bounds)
 };
 
 template <int NT>
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
       const bool second = m0 >= p.M0;
       const CUtensorMap* tmS = second ? &p.tmS1 : &p.tmS0;
       const int mc = second ? m0 - p.M0 : m0;
-      const int di = (kh + 1) / 2 - 1, ra = (kh + 1) & 1;
+      const int di = p.g_pad ? (kh >> 1) : (kh + 1) / 2 - 1, ra = p.g_pad ? (kh & 1) : (kh + 1) & 1;
       int s = 0;
       uint32_t ph = 0;
       for (int it = 0; it < nkb; ++it) {
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         tma_load_4d(a_dst + WG_BOX_BYTES, tmS, &full_bar[s], mc + 64, x0, y0, b0);   // (rows past M: zero-filled)
 #pragma unroll
         for (int kw = 0; kw < NTAPS; ++kw) {
-          const int dj = (kw + 1) / 2 - 1, rb = (kw + 1) & 1;
+          const int dj = p.g_pad ? (kw >> 1) : (kw + 1) / 2 - 1, rb = p.g_pad ? (kw & 1) : (kw + 1) & 1;
 #pragma unroll
           for (int h = 0; h < NT / 64; ++h) {
             unsigned char* dst = b_dst + kw * S::B_TAP_BYTES + h * WG_BOX_BYTES;
@@ -291,11 +292,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_gemm_tn_kernel(const __grid_
 template <int NT>
 int launch_gemm_tn(const GemmTnParams& p, int splits, cudaStream_t s, int mblocks = 1, int nblocks = 1) {
   using S = GemmTnSmem<NT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ADP_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
-    attr_set = true;
-  }
+  ADP_SMEM_ATTR(tc_gemm_tn_kernel<NT>, S::BYTES);
   tc_gemm_tn_kernel<NT><<<dim3(splits, mblocks, nblocks), WG_THREADS, S::BYTES, s>>>(p);
   adp_count_tc_launch();
   ADP_LAUNCH_CHECK();
@@ -316,11 +313,7 @@ bool wg_geometry(int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
 template <int NT, bool K3>
 int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t s) {
   using S = WgradSmem<NT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ADP_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<NT, K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
-    attr_set = true;
-  }
+  ADP_SMEM_ATTR((tc_wgrad_kernel<NT, K3>), S::BYTES);
   tc_wgrad_kernel<NT, K3><<<grid, WG_THREADS, S::BYTES, s>>>(p);
   adp_count_tc_launch();
   ADP_LAUNCH_CHECK();
@@ -402,7 +395,7 @@ bool tc_supported_wgrad(int B, int Hs, int Ws, int M0, int M1, int N) {
 }
 
 int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int N, float* dw, int B, int Hs, int Ws,
-             cudaStream_t s) {
+             cudaStream_t s, int g_pad) {
   WgradParams p;
   memset(&p, 0, sizeof(p));
   ADP_CHECK_ARG(wg_geometry(Hs, Ws, &p.Wt, &p.Ht, &p.Bt), "tc_wgrad: unsupported spatial size %dx%d", Hs, Ws);
@@ -420,9 +413,10 @@ int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int 
     uint32_t box[4] = {64, (uint32_t)p.Wt, (uint32_t)p.Ht, (uint32_t)p.Bt};
     ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmS0 : &p.tmS1, h == 0 ? s0 : s1, 4, dims, str, box));
   }
-  {  // G [B, 2Hs, 2Ws, N] viewed as (2N | Ws | 2 | Hs | B)
-    const int Hg = 2 * Hs, Wg = 2 * Ws;
-    uint64_t dims[5] = {(uint64_t)2 * N, (uint64_t)Ws, 2, (uint64_t)Hs, (uint64_t)B};
+  p.g_pad = g_pad ? 1 : 0;
+  {  // G [B, 2Hs, 2Ws, N] viewed as (2N | Ws | 2 | Hs | B); with a border: [B, 2Hs+2, 2Ws+2, N] as (2N | Ws+1 | 2 | Hs+1 | B)
+    const int Hg = 2 * Hs + 2 * p.g_pad, Wg = 2 * Ws + 2 * p.g_pad;
+    uint64_t dims[5] = {(uint64_t)2 * N, (uint64_t)Wg / 2, 2, (uint64_t)Hg / 2, (uint64_t)B};
     uint64_t str[4] = {(uint64_t)2 * N * 2, (uint64_t)Wg * N * 2, (uint64_t)2 * Wg * N * 2, (uint64_t)Hg * Wg * N * 2};
     uint32_t box[5] = {64, (uint32_t)p.Wt, 1, (uint32_t)p.Ht, (uint32_t)p.Bt};
     ADP_TRY(make_tmap_bf16(&p.tmG, g, 5, dims, str, box));

@@ -381,6 +381,8 @@ class UnetGenerator(nn.Module):
             if need == 0:
                 raise _lib.AdpError(lib.adp_last_error().decode())
             self._ws = torch.empty(need, device=x.device, dtype=torch.uint8)
+            if os.environ.get("ADP_DEBUG_POISON", "0") == "1":      # every byte 0xFF: bf16 / fp32 / fp64 NaN patterns, so a
+                self._ws.fill_(255)                                 # read of never-written workspace shows up as NaN
             self._ws_key = key
             reuse = False
             desc.reuse_weight_cache = 0

@@ -245,19 +245,14 @@ def test_halo_window_kernel_is_used_and_matches_the_per_tap_kernel():
     ref = F.conv_transpose2d(torch.cat([from_nhwc(x0r), from_nhwc(x1r)], 1), wm.to(torch.bfloat16).float().permute(0, 3, 1, 2),
                              stride=2, padding=1)
     outs = []
-    # halo 2: two tiles share the weight tiles (N = 64); pair: 2-CTA clusters multicasting the weight tiles
-    for halo, pair in ((1, 0), (0, 0), (1, 128), (2, 0)):
+    for halo in (1, 0):
         prev = lib.adp_set_option(b"tc_halo", halo)
-        prevc = lib.adp_set_option(b"tc_halo_cluster", pair)
         y = torch.empty(B, 2 * H, 2 * H, Cout, device=DEV, dtype=torch.bfloat16)
         _lib.check(lib.adp_convT2d_k4s2_fprop(_lib.ADP_BF16, x0r.data_ptr(), C0, x1r.data_ptr(), C1, wm.data_ptr(), w_f.data_ptr(),
                                               y.data_ptr(), B, H, H, Cout, None))
         lib.adp_set_option(b"tc_halo", prev)
-        lib.adp_set_option(b"tc_halo_cluster", prevc)
         assert rel_to_max(from_nhwc(y).cpu(), ref.cpu()) <= 1.5e-2
         outs.append(from_nhwc(y))
-    assert torch.equal(outs[0], outs[2])                 # same arithmetic, only the weight delivery differs
-    assert torch.equal(outs[0], outs[3])                 # ... or the tile pairing
     assert lib.adp_set_option(b"tc_halo", 1) == 1 and lib.adp_set_option(b"no_such_option", 1) == -1
     # same products, different summation order (chunk-major instead of tap-major): equal up to bf16 rounding of the output
     assert rel_to_max(outs[0].cpu(), outs[1].cpu()) <= 8e-3
@@ -470,6 +465,167 @@ def test_unet_bf16_matches_fp32_path_at_b200_shapes():
     with torch.no_grad():
         y32, y16 = net32(x), net16(x)
     assert rel_to_max(y16.cpu().numpy(), y32.cpu().numpy()) <= 2e-2
+
+
+# ----------------------------------------------------------------------------- BASELINE config 2 against the oracle
+def _waveform_case(B, size, ngf, nd, seed):
+    wave = synthetic.waveform(B, synthetic.V2_LEN, seed=seed)
+    gt = synthetic.gt_depth(B, size, 30.0, seed=seed + 1)
+    sd = uo.make_state_dict(ngf, nd, seed=seed + 2)
+    ref_x = np.stack([fo.feature_v2(wave[b], 30.0, size) for b in range(B)])
+    return wave, gt, sd, ref_x
+
+
+def _oracle_step(ref_x, gt, sd, nd, dy_inj):
+    """fp32 CPU oracle: training-mode forward, Combined loss, and parameter gradients for an injected upstream gradient."""
+    torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
+    sdg = {k: v.clone() for k, v in sd.items()}
+    names = [k for k in uo.ordered_state_dict(sdg, nd) if k.endswith((".weight", ".bias"))]
+    for n in names:
+        sdg[n].requires_grad_(True)
+    y = uo.unet_forward(torch.from_numpy(ref_x), sdg, nd, False, training=True)
+    loss = uo.depth_loss(y.detach(), torch.from_numpy(gt)).item()
+    y.backward(torch.from_numpy(dy_inj))
+    return y.detach().numpy(), loss, {n: sdg[n].grad for n in names}
+
+
+def _grad_report(net, og):
+    rows = []
+    for n, prm in net.named_parameters():
+        ref = og[n if n.startswith("model.") else "model." + n].double()
+        got = prm.grad.detach().cpu().double().reshape(ref.shape)
+        rn, gn = float(ref.norm()), float(got.norm())
+        rows.append((n, rn, gn / max(rn, 1e-30), float((got - ref).norm() / max(rn, 1e-30)),
+                     float((got * ref).sum() / max(gn * rn, 1e-30))))
+    print("\n".join("%-58s |g|=%.3e  norm ratio %.4f  relerr %.3e  cos %.5f" % r for r in rows))
+    return rows
+
+
+def test_config2_b64_bf16_step_from_waveforms_vs_oracle():
+    """BASELINE config 2 as benchmarked: unet_256 / ngf 64 / batch 64 / bf16, features computed on the GPU from
+    waveforms (train.py:633-693), against the fp32 CPU oracle: depth map and loss <= 2e-2 (north_star), and every
+    parameter gradient (injected upstream gradient, see test_unet_step_vs_reference_golden) by direction AND norm."""
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    from audio_depth_estimation_b200.training import TrainStep
+    B, S, ngf, nd = 64, 256, 64, 8
+    wave, gt, sd, ref_x = _waveform_case(B, S, ngf, nd, seed=640)
+    rng = np.random.default_rng(649)
+    dy_inj = (rng.standard_normal((B, 1, S, S)) * 1e-3).astype(np.float32)
+    ref_y, ref_loss, og = _oracle_step(ref_x, gt, sd, nd, dy_inj)
+    cfg = make_cfg(False, 30.0, S, "bf16")
+    net = define_G(cfg, 2, 1, ngf, "unet_256", "batch", False, gpu_ids=[0])
+    net.load_state_dict(uo.ordered_state_dict({k: v.clone() for k, v in sd.items()}, nd))
+    step = TrainStep(cfg, net, lr=0.002)
+    x = step.features(cuda(wave))
+    assert np.abs(x.cpu().numpy() - ref_x).max() <= 5e-4
+    net.train()
+    y = net(x)
+    loss = step.criterion(y, cuda(gt)).item()
+    yv = y.detach().cpu().numpy()
+    rel = float(np.linalg.norm(yv - ref_y) / np.linalg.norm(ref_y))
+    print("config 2: depth map rel L2 %.3e, max/max %.3e, loss %.6f vs %.6f" % (rel, rel_to_max(yv, ref_y), loss, ref_loss))
+    assert rel <= 2e-2 and rel_to_max(yv, ref_y) <= 2e-2
+    assert abs(loss - ref_loss) <= 2e-2 * abs(ref_loss)
+    y.backward(cuda(dy_inj))
+    rows = _grad_report(net, og)
+    big = [r for r in rows if r[1] >= 1e-3 * max(r[1] for r in rows)]
+    # Measured (r2): cosine 0.967 .. 0.997, norm ratio 0.98 .. 1.05, relative error 5 .. 26 %.  The error is the ReLU /
+    # LeakyReLU mask: with a 0.9 % forward error ~1 % of the activations change sign w.r.t. the fp32 oracle, and for a
+    # random upstream gradient a fraction f of flipped terms moves a weight gradient by ~sqrt(2 f) -- any bf16 forward
+    # pass (the reference's own autocast path included) shows it; the fp32 mode below has none of it.
+    assert min(r[4] for r in big) >= 0.96, rows                  # direction of every (non-vanishing) parameter gradient
+    assert max(abs(r[2] - 1.0) for r in big) <= 0.06, rows       # ... and its norm
+    assert max(r[3] for r in big) <= 0.28, rows
+    # one optimiser step from waveforms through the public step, loss finite and equal to the forward's
+    net.load_state_dict(uo.ordered_state_dict({k: v.clone() for k, v in sd.items()}, nd))
+    l0 = step(cuda(wave), cuda(gt)).item()
+    assert abs(l0 - ref_loss) <= 2e-2 * abs(ref_loss)
+    # the same network in fp32 mode on the first 8 samples' features (per-sample statistics differ from the B = 64 oracle
+    # run, so it gets its own): structure exact, <= 1e-3 / gradient cosine >= 0.9995 (measured 0.99987)
+    Bs = 8
+    ys, ls, ogs = _oracle_step(ref_x[:Bs], gt[:Bs], sd, nd, dy_inj[:Bs])
+    net32 = define_G(make_cfg(False, 30.0, S, "fp32"), 2, 1, ngf, "unet_256", "batch", False, gpu_ids=[0])
+    net32.load_state_dict(uo.ordered_state_dict({k: v.clone() for k, v in sd.items()}, nd))
+    net32.train()
+    y32 = net32(x[:Bs].contiguous())
+    assert rel_to_max(y32.detach().cpu().numpy(), ys) <= 1e-3
+    y32.backward(cuda(dy_inj[:Bs]))
+    rows32 = _grad_report(net32, ogs)
+    big32 = [r for r in rows32 if r[1] >= 1e-3 * max(r[1] for r in rows32)]
+    assert min(r[4] for r in big32) >= 0.9995 and max(r[3] for r in big32) <= 3e-2, rows32
+
+
+def test_first_level_centring_is_exact_and_restores_bf16_accuracy():
+    """a[0] is stored centred (adp_unet.cu use_center).  With real log-spectrogram features the bf16 depth map
+    must stay <= 2e-2 of the fp32 oracle (2.4e-2 without centring), in train AND eval mode, and the eval-mode backward
+    (where sum dL/de != 0) must agree with the uncentred path."""
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    lib = _lib.load()
+    B, S, ngf, nd = 4, 128, 64, 7
+    wave, gt, sd, ref_x = _waveform_case(B, S, ngf, nd, seed=5)
+    x = cuda(ref_x)
+    with torch.no_grad():
+        ref_train = uo.unet_forward(torch.from_numpy(ref_x), {k: v.clone() for k, v in sd.items()}, nd, False, training=True).numpy()
+        sde = {k: v.clone() for k, v in sd.items()}
+        for k in sde:                                   # non-trivial running statistics for the eval pass
+            if k.endswith("running_mean"):
+                sde[k] = sde[k] + 0.05
+            if k.endswith("running_var"):
+                sde[k] = sde[k] * 0.5 + 0.1
+        ref_eval = uo.unet_forward(torch.from_numpy(ref_x), {k: v.clone() for k, v in sde.items()}, nd, False, training=False).numpy()
+    cfg = make_cfg(False, 30.0, S, "bf16")
+    errs, grads, rms = {}, {}, {}
+    for center in (1, 0):
+        prev = lib.adp_set_option(b"center", center)
+        try:
+            net = define_G(cfg, 2, 1, ngf, "unet_128", "batch", False, gpu_ids=[0])
+            net.load_state_dict(uo.ordered_state_dict({k: v.clone() for k, v in sde.items()}, nd))
+            net.train()
+            with torch.no_grad():
+                yt = net(x).cpu().numpy()
+            rms[center] = net.state_dict()["model.model.1.model.2.running_mean"].cpu().numpy().copy()
+            net.load_state_dict(uo.ordered_state_dict({k: v.clone() for k, v in sde.items()}, nd))
+            net.eval()
+            ye = net(x)
+            ye.backward(torch.ones_like(ye) * 1e-3)
+            grads[center] = {n: prm.grad.detach().cpu().double().clone() for n, prm in net.named_parameters()}
+            ye = ye.detach().cpu().numpy()
+            errs[center] = (float(np.linalg.norm(yt - ref_train) / np.linalg.norm(ref_train)),
+                            float(np.linalg.norm(ye - ref_eval) / np.linalg.norm(ref_eval)))
+        finally:
+            lib.adp_set_option(b"center", prev)
+    print("rel L2 error (train, eval): centred %s, plain %s" % (errs[1], errs[0]))
+    assert errs[1][0] <= 1.2e-2 and errs[1][1] <= 1.5e-2
+    assert errs[1][0] < errs[0][0]
+    # the level-1 running mean refers to the true (uncentred) activation
+    assert np.abs(rms[1] - rms[0]).max() <= 2e-2 * max(np.abs(rms[0]).max(), 1e-3)
+    for n in grads[1]:
+        a, b = grads[1][n], grads[0][n]
+        if float(b.norm()) > 0:
+            cos = float((a * b).sum() / max(float(a.norm() * b.norm()), 1e-30))
+            assert cos >= 0.97 and abs(float(a.norm() / b.norm()) - 1.0) <= 0.08, (n, cos, float(a.norm()), float(b.norm()))
+
+
+def test_fused_bn_statistics_match_the_standalone_pass():
+    """The convolution epilogues accumulate the BatchNorm sums ("tc_stats"); same depth map and running statistics as the
+    separate bn_stats pass, up to the summation order."""
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    lib = _lib.load()
+    case = ("unet_256", 64, 8, 256, False, 30.0, 910, True, False)
+    outs, stats = [], []
+    for fused in (1, 0):
+        prev = lib.adp_set_option(b"tc_stats", fused)
+        try:
+            _, net, x, _ = build_case(case, "bf16")
+            net.train()
+            with torch.no_grad():
+                outs.append(net(x).cpu().numpy())
+            sdo = net.state_dict()
+            stats.append(np.concatenate([sdo[k].cpu().numpy().ravel() for k in sdo if k.endswith(("running_mean", "running_var"))]))
+        finally:
+            lib.adp_set_option(b"tc_stats", prev)
+    assert float(np.linalg.norm(outs[0] - outs[1]) / np.linalg.norm(outs[1])) <= 5e-3 and rel_to_max(outs[0], outs[1]) <= 1.5e-2
+    assert np.abs(stats[0] - stats[1]).max() <= 2e-3 * max(1.0, np.abs(stats[1]).max())   # (bf16 activations downstream)
 
 
 def test_optimizer_vs_oracle_multi_step():
