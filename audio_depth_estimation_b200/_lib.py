@@ -92,6 +92,7 @@ SIGNATURES = {
     "adp_depth_head_forward": (_i, [_vp, _vp, _vp, _f, _i64, _i, _vp, _vp]),
     "adp_depth_head_backward": (_i, [_vp, _vp, _vp, _f, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
     "adp_set_option": (_i, [C.c_char_p, _i]),
+    "adp_profile_read_n": (_i, [_i, _vp, _vp, _vp]),
     "adp_selftest_umma_offset": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "adp_unet_workspace_bytes": (_sz, [C.POINTER(UnetDesc)]),
     "adp_unet_forward": (_i, [C.POINTER(UnetDesc), _vp, C.POINTER(UnetLevel), _vp, _sz, _vp, _vp]),

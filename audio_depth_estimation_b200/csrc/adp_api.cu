@@ -123,19 +123,25 @@ extern "C" int adp_profile_enable(int on) {
   if (on) adp::g_prof_n = 0;
   return ADP_OK;
 }
-// After the stream has been synchronised: per family (ADP_PROF_* order: gather, parity, wgrad,
-// thin first/last layers, elementwise) total milliseconds, total algorithmic work (FLOP, or bytes
-// for elementwise) and number of timed calls.  Arrays have 5 entries.
-extern "C" int adp_profile_read(double* ms, double* work, long long* calls) {
-  ADP_CHECK_ARG(ms && work && calls, "profile_read: null pointer");
-  for (int k = 0; k < adp::PROF_KINDS; ++k) { ms[k] = 0.0; work[k] = 0.0; calls[k] = 0; }
+// After the stream has been synchronised: per family total milliseconds, total algorithmic work (FLOP for the
+// convolution families, bytes for the BatchNorm / activation passes) and number of timed calls.  n entries, in the order
+// {gather conv, parity convT, wgrad, thin first/last layers, BatchNorm + activation passes,
+//  gather conv (deep levels), parity convT (deep levels), wgrad (deep levels), feature stage, loss, clip + AdamW}; the first
+// three hold the LARGE layers when n > 5 and large + deep when n == 5 (the round-1 layout).
+extern "C" int adp_profile_read_n(int n, double* ms, double* work, long long* calls) {
+  ADP_CHECK_ARG(ms && work && calls && (n == 5 || n == adp::PROF_KINDS), "profile_read: null pointer or bad entry count");
+  for (int k = 0; k < n; ++k) { ms[k] = 0.0; work[k] = 0.0; calls[k] = 0; }
   for (int i = 0; i < adp::g_prof_n; ++i) {
     float t = 0.f;
     ADP_CUDA(cudaEventSynchronize(adp::g_prof_ev[i][1]));
     ADP_CUDA(cudaEventElapsedTime(&t, adp::g_prof_ev[i][0], adp::g_prof_ev[i][1]));
-    ms[adp::g_prof_kind[i]] += t;
-    work[adp::g_prof_kind[i]] += adp::g_prof_work[i];
-    calls[adp::g_prof_kind[i]] += 1;
+    int k = adp::g_prof_kind[i];
+    if (n == 5 && k >= adp::PROF_FEATURE) continue;
+    if (n == 5 && k >= adp::PROF_GATHER_DEEP) k -= adp::PROF_GATHER_DEEP;
+    ms[k] += t;
+    work[k] += adp::g_prof_work[i];
+    calls[k] += 1;
   }
   return ADP_OK;
 }
+extern "C" int adp_profile_read(double* ms, double* work, long long* calls) { return adp_profile_read_n(5, ms, work, calls); }

@@ -186,7 +186,10 @@ int ensure_smem_attr(const void* func, int bytes, std::atomic<unsigned long long
   } while (0)
 
 // Optional per-family device timing (CUDA events on the launching stream), read by bench.py.
-enum ProfKind { PROF_GATHER = 0, PROF_PARITY, PROF_WGRAD, PROF_THIN, PROF_ELEM, PROF_KINDS };
+// (PROF_*_DEEP: the small-M weight-streaming levels E5-E8 / D8-D6, reported next to the large layers that carry 90 % of the
+// FLOPs; work = algorithmic FLOP for the convolution kinds, algorithmic bytes for PROF_THIN_BYTES-free PROF_ELEM)
+enum ProfKind { PROF_GATHER = 0, PROF_PARITY, PROF_WGRAD, PROF_THIN, PROF_ELEM, PROF_GATHER_DEEP, PROF_PARITY_DEEP,
+                PROF_WGRAD_DEEP, PROF_FEATURE, PROF_LOSS, PROF_OPTIM, PROF_KINDS };   // (the last three: work = bytes)
 struct ProfScope {
   int slot;
   cudaStream_t stream;

@@ -373,6 +373,7 @@ extern "C" int adp_feature_forward(const float* wave, int rows, int L, int wave_
   ADP_TRY(check_stft_args(rows, L, wave_pitch, n_fft, win_length, hop));
   ADP_CHECK_ARG(wave && out && workspace, "feature: null pointer");
   ADP_CHECK_ARG(out_size > 0 && out_size <= 65535 && rows <= 65535, "feature: bad out_size/rows");
+  adp::ProfScope prof(adp::PROF_FEATURE, s, (double)rows * ((double)L + (double)out_size * out_size) * 4.0);   // waveform in, feature out
   ADP_CHECK_ARG(workspace_bytes >= adp_feature_workspace_bytes(rows, L, n_fft, hop),
                 "feature: workspace too small (%zu)", workspace_bytes);
   const int T = 1 + L / hop, F = n_fft / 2 + 1;

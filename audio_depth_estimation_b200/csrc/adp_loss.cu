@@ -140,6 +140,7 @@ extern "C" int adp_depth_loss_sums(const float* pred, const float* gt, int64_t n
                                    int use_mask, double* sums, void* stream) {
   ADP_CHECK_ARG(pred && gt && sums && n >= 0, "loss_sums: bad arguments");
   ADP_CHECK_ARG(((uintptr_t)pred % 16 == 0) && ((uintptr_t)gt % 16 == 0), "loss_sums: pointers must be 16-byte aligned");
+  adp::ProfScope prof(adp::PROF_LOSS, (cudaStream_t)stream, (double)n * 8.0);            // pred, gt in
   loss_sums_kernel<<<loss_grid(n), LOSS_THREADS, 0, (cudaStream_t)stream>>>(pred, gt, n, scale, eps, use_mask, sums);
   ADP_LAUNCH_CHECK();
   return ADP_OK;
@@ -157,6 +158,7 @@ extern "C" int adp_depth_loss_backward(const float* pred, const float* gt, int64
                                        int use_mask, const double* sums, float l1_w, float silog_w, float lam,
                                        const float* grad_scale, float* dpred, void* stream) {
   ADP_CHECK_ARG(pred && gt && sums && dpred && n >= 0, "loss_backward: bad arguments");
+  adp::ProfScope prof(adp::PROF_LOSS, (cudaStream_t)stream, (double)n * 4.0);            // dpred out (pred, gt counted by loss_sums)
   ADP_CHECK_ARG(((uintptr_t)pred % 16 == 0) && ((uintptr_t)gt % 16 == 0) && ((uintptr_t)dpred % 16 == 0),
                 "loss_backward: pointers must be 16-byte aligned");
   loss_backward_kernel<<<loss_grid(n), LOSS_THREADS, 0, (cudaStream_t)stream>>>(

@@ -146,6 +146,9 @@ int for_each_table(const adp_tensor_ref* refs, int n_tensors, F&& launch) {
 extern "C" int adp_grad_sumsq(const adp_tensor_ref* refs_host, int n_tensors, double* sumsq, void* stream) {
   ADP_CHECK_ARG(refs_host && n_tensors > 0 && sumsq, "grad_sumsq: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
+  double elems = 0.0;
+  for (int i = 0; i < n_tensors; ++i) elems += (double)refs_host[i].n;
+  adp::ProfScope prof(adp::PROF_OPTIM, s, elems * 4.0);                                  // g in
   return for_each_table(refs_host, n_tensors, [&](const TensorTable& tab, int blocks) -> int {
     grad_sumsq_kernel<<<blocks, OPT_THREADS, 0, s>>>(tab, sumsq);
     ADP_LAUNCH_CHECK();
@@ -158,6 +161,9 @@ extern "C" int adp_clip_adamw_step(const adp_tensor_ref* refs_host, int n_tensor
                                    float weight_decay, int step, float* norm_out, void* stream) {
   ADP_CHECK_ARG(refs_host && n_tensors > 0 && sumsq && step >= 1, "clip_adamw_step: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
+  double elems = 0.0;
+  for (int i = 0; i < n_tensors; ++i) elems += (double)refs_host[i].n;
+  adp::ProfScope prof(adp::PROF_OPTIM, s, elems * 4.0 * 7.0);                            // p, g, m, v in; p, m, v out
   AdamArgs a;
   a.max_norm = max_norm; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
   a.decay_mul = 1.f - lr * weight_decay;
@@ -180,6 +186,9 @@ extern "C" int adp_clip_adamw_step_graph(const adp_tensor_ref* refs_host, int n_
                                          void* stream) {
   ADP_CHECK_ARG(refs_host && n_tensors > 0 && sumsq && step_dev && scratch, "clip_adamw_step_graph: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
+  double elems = 0.0;
+  for (int i = 0; i < n_tensors; ++i) elems += (double)refs_host[i].n;
+  adp::ProfScope prof(adp::PROF_OPTIM, s, elems * 4.0 * 7.0);                            // p, g, m, v in; p, m, v out
   AdamArgs a;
   a.max_norm = max_norm; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
   a.decay_mul = 1.f - lr * weight_decay;

@@ -130,6 +130,10 @@ inline BnBuf bnbuf(void* ws, size_t off, int C) {
 
 bool use_tc(int dtype) { return dtype == ADP_BF16 && tc_enabled(); }
 
+// the small-M, weight-streaming levels (at B = 64: E5-E8 / D8-D6, conv outputs of 8 x 8 pixels and below) are reported
+// separately by the per-family timers
+inline bool deep_level(int conv_out_side) { return conv_out_side <= 8; }
+
 int g_center = -1;    // "center" / ADP_CENTER=0 switches the first-level centring off
 bool center_enabled() {
   if (g_center < 0) g_center = getenv("ADP_CENTER") ? atoi(getenv("ADP_CENTER")) : 1;
@@ -160,23 +164,23 @@ bool use_center(const adp_unet_desc* d, const Plan& p, bool tc) {
 // (ex: tensor-core extras -- fused BatchNorm statistics, padded input; ignored by the SIMT kernels, whose callers check
 // *ex->stats_done and never request padding)
 int conv_gather(int dtype, const void* x, const float* w, const void* wb, void* y0, int N0, void* y1, int N1,
-                int B, int Hi, int Wi, int C, cudaStream_t s, const ConvExtras* ex = nullptr) {
-  ProfScope prof(PROF_GATHER, s, 2.0 * B * (Hi / 2) * (Wi / 2) * (double)(N0 + N1) * 16.0 * C);
+                int B, int Hi, int Wi, int C, cudaStream_t s, const ConvExtras* ex = nullptr, bool deep = false) {
+  ProfScope prof(deep ? PROF_GATHER_DEEP : PROF_GATHER, s, 2.0 * B * (Hi / 2) * (Wi / 2) * (double)(N0 + N1) * 16.0 * C);
   if (use_tc(dtype) && wb && tc_supported_gather(B, Hi, Wi, C, N0, N1))
     return tc_gather_conv(x, wb, y0, N0, y1, N1, B, Hi, Wi, C, s, ex);
   ADP_CHECK_ARG(!ex || !ex->pad_in, "conv_gather: padded input needs the tensor-core path");
   return simt_gather_conv(dtype, x, w, y0, N0, y1, N1, B, Hi, Wi, C, s);
 }
 int conv_parity(int dtype, const void* x0, int C0, const void* x1, int C1, const float* w, const void* wb, void* y,
-                int B, int Hi, int Wi, int N, cudaStream_t s, const ConvExtras* ex = nullptr) {
-  ProfScope prof(PROF_PARITY, s, 2.0 * B * Hi * Wi * 4.0 * (double)N * 4.0 * (C0 + C1));
+                int B, int Hi, int Wi, int N, cudaStream_t s, const ConvExtras* ex = nullptr, bool deep = false) {
+  ProfScope prof(deep ? PROF_PARITY_DEEP : PROF_PARITY, s, 2.0 * B * Hi * Wi * 4.0 * (double)N * 4.0 * (C0 + C1));
   if (use_tc(dtype) && wb && tc_supported_parity(B, Hi, Wi, C0, C1, N))
     return tc_parity_convT(x0, C0, x1, C1, wb, y, B, Hi, Wi, N, s, ex);
   return simt_parity_convT(dtype, x0, C0, x1, C1, w, y, B, Hi, Wi, N, s);
 }
 int conv_wgrad(int dtype, const void* s0, int M0, const void* s1, int M1, const void* g, int N, float* dw,
-               int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0) {
-  ProfScope prof(PROF_WGRAD, s, 2.0 * B * Hs * Ws * 16.0 * (double)N * (M0 + M1));
+               int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0, bool deep = false) {
+  ProfScope prof(deep ? PROF_WGRAD_DEEP : PROF_WGRAD, s, 2.0 * B * Hs * Ws * 16.0 * (double)N * (M0 + M1));
   if (use_tc(dtype) && tc_supported_wgrad(B, Hs, Ws, M0, M1, N))
     return tc_wgrad(s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s, g_pad);
   ADP_CHECK_ARG(!g_pad, "conv_wgrad: padded operand needs the tensor-core path");
@@ -279,7 +283,9 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     if (L.bn_down && d->training) { ex.stats = sums; ex.stats_done = &fused; }
     ex.pad_in = (l == 1 && center) ? 1 : 0;
     ADP_TRY(conv_gather(dt, at(ws, p.lv[l - 1].a), params[l].conv_w, tc ? w16(params[l].conv_w_bf16, L.wb_conv) : nullptr,
-                        at(ws, L.e), L.cout, nullptr, 0, B, L.hin, L.hin, L.cin, s, &ex));
+                        at(ws, L.e), L.cout, nullptr, 0, B, L.hin, L.hin, L.cin, s, &ex, deep_level(L.hout)));
+    // (work of the BatchNorm / activation passes = ALGORITHMIC bytes: every input once, every output once)
+    ProfScope eprof(PROF_ELEM, s, (double)rows * L.cout * p.esz * (L.bn_down ? 3.0 : 2.0));
     if (L.bn_down) {
       BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
       if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, L.e), rows, L.cout, sums, s));
@@ -302,7 +308,9 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     memset(&ex, 0, sizeof(ex));
     if (d->training) { ex.stats = sums; ex.stats_done = &fused; }
     ADP_TRY(conv_parity(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, params[l].convT_w,
-                        tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, O.t), B, L.hout, L.hout, L.t_cout, s, &ex));
+                        tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, O.t), B, L.hout, L.hout, L.t_cout, s, &ex,
+                        deep_level(O.hout)));
+    ProfScope eprof(PROF_ELEM, s, (double)rows * L.t_cout * p.esz * 2.0);
     BnBuf bn = bnbuf(ws, L.bn_up_f, L.t_cout);
     if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));
     const BnFin fin{sums, 1.0 / (double)rows, rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f, params[l].bn_up_w, params[l].bn_up_b, params[l].bn_up_rm, params[l].bn_up_rv,
@@ -394,6 +402,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
     const int C = U.t_cout;
     BnBuf bn = bnbuf(ws, U.bn_up_f, C);
     double* bs = reinterpret_cast<double*>(at(ws, U.bsums_up));
+    ProfScope eprof(PROF_ELEM, s, (double)rows * C * p.esz * 3.0);      // x, g -> dx
     ADP_TRY(act_bn_bwd_reduce(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f,
                               nullptr, 0.f, bs, s));
     ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f,
@@ -456,15 +465,18 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         cudaStream_t sw = wgrad_stream(st);
         ADP_CUDA(cudaMemsetAsync(grads[l].convT_w, 0, sizeof(float) * 16 * (size_t)Ct * L.t_cout, sw));
         ADP_TRY(conv_wgrad(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, at(ws, O.g_t), L.t_cout,
-                           grads[l].convT_w, B, L.hout, L.hout, sw));
+                           grads[l].convT_w, B, L.hout, L.hout, sw, 0, deep_level(O.hout)));
       }
       ADP_TRY(conv_gather(dt, at(ws, O.g_t), params[l].convT_w, tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, L.g_r),
-                          L.cout, L.t_c1 ? at(ws, L.g_q) : nullptr, L.t_c1, B, O.hout, O.hout, L.t_cout, s));
+                          L.cout, L.t_c1 ? at(ws, L.g_q) : nullptr, L.t_c1, B, O.hout, O.hout, L.t_cout, s, nullptr,
+                          deep_level(O.hout)));
       if (l < D - 1) ADP_TRY(up_norm_bwd(l));
     } else {
       const int l = 2 * D - 1 - st;
       const LevelPlan& L = p.lv[l];
       const long long rows = (long long)B * L.hout * L.hout;
+      {
+      ProfScope eprof(PROF_ELEM, s, (double)rows * L.cout * p.esz * (l == D - 1 ? 3.0 : 4.0));   // x, gA[, gB] -> dx
       if (l == D - 1) {
         ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.e), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_r), 0.f,
                                  nullptr, 0.f, nullptr, 0, at(ws, L.g_e), nullptr, nullptr, s));
@@ -479,6 +491,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       } else {  // level 0: no norm; e > 0 <=> r = ReLU(e) > 0 (a[0] may be stored centred, r[0] never is)
         ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.r), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_a), 0.2f,
                                  at(ws, L.g_r), 0.f, nullptr, 0, at(ws, L.g_e), nullptr, nullptr, s));
+      }
       }
       cudaStream_t sw = l > 0 ? wgrad_stream(st) : s;
       ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, sw));
@@ -495,14 +508,14 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         const LevelPlan& I = p.lv[l - 1];
         const bool cen = l == 1 && center;
         ADP_TRY(conv_wgrad(dt, at(ws, L.g_e), L.cout, nullptr, 0, at(ws, I.a), L.cin, grads[l].conv_w, B, L.hout,
-                           L.hout, sw, cen ? 1 : 0));
+                           L.hout, sw, cen ? 1 : 0, deep_level(L.hout)));
         if (cen && !d->training) {   // eval-mode BatchNorm: sum_pixels dL/de = scale * sum gz is not zero
           BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
           ADP_TRY(center_wgrad_fix(grads[l].conv_w, reinterpret_cast<const float*>(at(ws, p.center_m)), bn.scale,
                                    reinterpret_cast<const double*>(at(ws, L.bsums_down)), L.cout, L.cin, sw));
         }
         ADP_TRY(conv_parity(dt, at(ws, L.g_e), L.cout, nullptr, 0, params[l].conv_w, tc ? w16(params[l].conv_w_bf16, L.wb_conv) : nullptr,
-                            at(ws, I.g_a), B, L.hout, L.hout, L.cin, s));
+                            at(ws, I.g_a), B, L.hout, L.hout, L.cin, s, nullptr, deep_level(L.hout)));
       }
     }
   }

@@ -179,6 +179,7 @@ class UnetGenerator(nn.Module):
         self._mirror = None           # bf16 copy of the flat parameters kept current by FusedClipAdamW
         self._fwd_mirror = False
         self._anchor = None
+        self._master_sync = None      # callable: bring the fp32 master weights up to date (sharded optimiser)
         self.grad_ready_hook = None   # callable(stage_group_index) used by the data-parallel trainer
         self.stage_groups = None      # list of (stage_begin, stage_end)
         for w in self._conv_weights():
@@ -269,18 +270,34 @@ class UnetGenerator(nn.Module):
             return False
         return all(p.data_ptr() == ptr for p, ptr in zip(f["params"], f["ptrs"]))
 
+    @staticmethod
+    def _is_bulk(p):
+        """The hidden layers' convolution weights (99.97 % of the parameters): what a sharded optimiser splits."""
+        return p.dim() == 4 and p.numel() >= 65536
+
     def _flatten(self, device):
         stages = self.staged_parameters()
         params = [p for st in stages for p in st]
         if len(params) != len(list(self.parameters())):
             raise RuntimeError("internal error: staged parameter list does not cover the module")
-        offs, off, stage_slices = [], 0, []
+        # Layout: [bulk convolution weights in backward-stage order | tail: every small tensor (BatchNorm affine
+        # parameters, the bias, the two thin layers' weights)].  The stage slices tile the bulk region, so a data-parallel
+        # trainer reduces (or reduce-scatters) one contiguous slice per stage group and all-reduces the few-KB tail once.
+        off_of, off, stage_slices = {}, 0, []
+        pad = lambda n: (n + _ALIGN - 1) // _ALIGN * _ALIGN
         for st in stages:
             begin = off
             for p in st:
-                offs.append(off)
-                off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+                if self._is_bulk(p):
+                    off_of[id(p)] = off
+                    off += pad(p.numel())
             stage_slices.append((begin, off))
+        tail_begin = off
+        for p in params:
+            if not self._is_bulk(p):
+                off_of[id(p)] = off
+                off += pad(p.numel())
+        offs = [off_of[id(p)] for p in params]
         flat_p = torch.zeros(off, device=device, dtype=torch.float32)
         flat_g = torch.zeros(off, device=device, dtype=torch.float32)
         with torch.no_grad():
@@ -291,7 +308,7 @@ class UnetGenerator(nn.Module):
                 p.grad = None
         self._flat = dict(p=flat_p, g=flat_g, params=params, offs=offs, ptrs=[p.data_ptr() for p in params],
                           gviews=[self._view_like(flat_g, o, p) for p, o in zip(params, offs)],
-                          stage_slices=stage_slices, m=None, v=None, step=0)
+                          stage_slices=stage_slices, tail=(tail_begin, off), m=None, v=None, step=0)
         for lv in self.levels():
             for bn in (lv["bn_down"], lv["bn_up"]):
                 if bn is not None:
@@ -305,8 +322,18 @@ class UnetGenerator(nn.Module):
         self._dirty = True
         self._mirror = None
 
+    def tail_slice(self):
+        """(begin, end) element offsets of the small-tensor region behind the stage slices."""
+        self.flat_buffers()
+        return self._flat["tail"]
+
+    def state_dict(self, *args, **kwargs):
+        if self._master_sync is not None:       # a sharded optimiser leaves other ranks' fp32 master shards stale
+            self._master_sync()
+        return super().state_dict(*args, **kwargs)
+
     def flat_buffers(self):
-        """(flat parameters, flat gradients, per-stage (begin, end) element offsets)."""
+        """(flat parameters, flat gradients, per-stage (begin, end) element offsets of the bulk region; see tail_slice)."""
         if self._flat is None:
             dev = next(self.parameters()).device
             if dev.type != "cuda":

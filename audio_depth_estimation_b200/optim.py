@@ -13,9 +13,17 @@ from . import _lib
 
 class FusedClipAdamW:
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=1.0,
-                 capturable=False):
-        """capturable=True keeps the step counter on the device so that step() can be recorded in a CUDA graph."""
+                 capturable=False, reducer=None):
+        """capturable=True keeps the step counter on the device so that step() can be recorded in a CUDA graph.
+        reducer: a training.GradientReducer in shard mode -- the gradients arrive reduce-scattered, this rank updates the
+        1/world of every bucket it owns (plus the replicated tail of small tensors) and the new weights are all-gathered
+        (bf16 mirror; fp32 masters in fp32 mode).  The other ranks' fp32 master shards and moments stay stale until
+        sync_shards(), which state_dict() of the model and of the optimiser call."""
         self.model = model
+        self.reducer = reducer
+        self._stale = False
+        if reducer is not None:
+            model._master_sync = self.sync_shards
         self.capturable = bool(capturable)
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
         self.max_norm = float(max_norm) if max_norm is not None else 0.0
@@ -37,50 +45,83 @@ class FusedClipAdamW:
                 st["m"].copy_(old["m"])
                 st["v"].copy_(old["v"])
             self._state = st
-        ref = (_lib.TensorRef * 1)()
-        ref[0].p, ref[0].g, ref[0].m, ref[0].v, ref[0].n = (p.data_ptr(), g.data_ptr(), st["m"].data_ptr(),
-                                                           st["v"].data_ptr(), p.numel())
         # bf16 models: the update also writes bf16(p) into the model's mirror, which replaces the per-forward casts
         self._mirrored = getattr(self.model, "precision", None) == "bf16" and hasattr(self.model, "bf16_mirror")
-        ref[0].p_bf16 = self.model.bf16_mirror().data_ptr() if self._mirrored else None
-        return p, st, ref
+        mirror = self.model.bf16_mirror() if self._mirrored else None
+
+        def refs(ranges):
+            arr = (_lib.TensorRef * len(ranges))()
+            for i, (lo, hi) in enumerate(ranges):
+                arr[i].p, arr[i].g = p.data_ptr() + 4 * lo, g.data_ptr() + 4 * lo
+                arr[i].m, arr[i].v, arr[i].n = st["m"].data_ptr() + 4 * lo, st["v"].data_ptr() + 4 * lo, hi - lo
+                arr[i].p_bf16 = (mirror.data_ptr() + 2 * lo) if mirror is not None else None
+            return arr, len(ranges)
+        return p, st, refs, mirror
 
     def zero_grad(self, set_to_none=True):
         pass  # gradients are overwritten by every backward pass
 
-    def step(self):
+    def step(self, local_only=False):
+        """local_only: (measurement) skip the cross-rank work of the sharded mode and just update what this rank owns."""
         lib = _lib.load()
-        p, st, ref = self._buffers()
+        p, st, refs, mirror = self._buffers()
         self.step_count += 1
+        red = self.reducer
         with torch.cuda.device(p.device):
             s = _lib.stream_ptr()
             st["sumsq"].zero_()
-            _lib.check(lib.adp_grad_sumsq(ref, 1, st["sumsq"].data_ptr(), s))
+            if red is None:
+                every, n = refs([(0, p.numel())])
+                _lib.check(lib.adp_grad_sumsq(every, n, st["sumsq"].data_ptr(), s))
+            else:
+                # global norm: this rank's pieces summed over the ranks, plus the (replicated) tail once
+                own, n_own = refs(red.owned_pieces())
+                _lib.check(lib.adp_grad_sumsq(own, n_own, st["sumsq"].data_ptr(), s))
+                if not local_only:
+                    red.all_reduce_scalar(st["sumsq"])
+                tail, n_tail = refs([self.model.tail_slice()])
+                _lib.check(lib.adp_grad_sumsq(tail, n_tail, st["sumsq"].data_ptr(), s))
+                every, n = refs(red.owned_pieces() + [self.model.tail_slice()])
             if self.capturable:
-                _lib.check(lib.adp_clip_adamw_step_graph(ref, 1, st["sumsq"].data_ptr(), self.max_norm, self.lr,
+                _lib.check(lib.adp_clip_adamw_step_graph(every, n, st["sumsq"].data_ptr(), self.max_norm, self.lr,
                                                          self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                                          st["step_dev"].data_ptr(), st["scratch"].data_ptr(),
                                                          st["norm"].data_ptr(), s))
             else:
-                _lib.check(lib.adp_clip_adamw_step(ref, 1, st["sumsq"].data_ptr(), self.max_norm, self.lr,
+                _lib.check(lib.adp_clip_adamw_step(every, n, st["sumsq"].data_ptr(), self.max_norm, self.lr,
                                                    self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                                    self.step_count, st["norm"].data_ptr(), s))
+            if red is not None and not local_only:
+                red.gather(mirror if mirror is not None else p)        # the new weights, as the forward pass reads them
+                self._stale = mirror is not None                       # (fp32 masters of the other ranks' pieces, m, v)
         self.model.mark_weights_dirty(by_optimizer=True)
         if self._mirrored:
             self.model.mirror_written()
         self.last_norm = st["norm"]
         return st["norm"]
 
+    def sync_shards(self):
+        """Sharded mode: all-gather the fp32 master weights and both AdamW moments (checkpoints, state_dict())."""
+        if self.reducer is None or self._state is None:
+            return
+        p = self.model.flat_buffers()[0]
+        if self._stale:
+            self.reducer.gather(p)
+            self._stale = False
+        self.reducer.gather(self._state["m"])
+        self.reducer.gather(self._state["v"])
+
     # ---- checkpointing: the layout torch.optim.AdamW.state_dict() has in the reference's checkpoints
     # (train.py:1006-1011 saves 'optimizer': optimizer.state_dict()), parameters in model.parameters() order.
     def _moment_views(self):
-        _, st, _ = self._buffers()
+        _, st, _, _ = self._buffers()
         flat = self.model._flat
         off_of = {id(q): o for q, o in zip(flat["params"], flat["offs"])}
         return [(self.model._view_like(st["m"], off_of[id(q)], q), self.model._view_like(st["v"], off_of[id(q)], q))
                 for q in self.model.parameters()]
 
     def state_dict(self):
+        self.sync_shards()
         n = len(list(self.model.parameters()))
         state = {}
         if self._state is not None or self.model._flat is not None:

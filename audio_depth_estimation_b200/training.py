@@ -37,26 +37,73 @@ def default_stage_groups(num_downs, stages_per_group=2):
 
 
 class GradientReducer:
-    """Bucketed gradient all-reduce driven by UnetGenerator's backward stage groups."""
+    """Bucketed gradient reduction driven by UnetGenerator's backward stage groups.
 
-    def __init__(self, model, process_group=None, stages_per_group=2):
+    shard=False: SUM all-reduce of each stage group's slice of the flat gradient buffer (every rank then runs the whole
+    optimiser step).  shard=True (ZeRO-1 style): SUM reduce-scatter of each slice -- rank r keeps the r-th 1/world of
+    every bucket --, the optimiser updates only what the rank owns, and the updated weights come back with an
+    all-gather of the bf16 mirror (half the bytes of the fp32 masters; fp32 mode gathers the masters).  The few-KB tail
+    of small tensors is all-reduced and updated on every rank in both modes."""
+
+    def __init__(self, model, process_group=None, stages_per_group=2, shard=False):
         self.model = model
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        self.shard = bool(shard) and self.world > 1 and 64 % self.world == 0      # (every slice is a multiple of 64 elements)
         self.pending = []
         model.stage_groups = default_stage_groups(model.num_downs, stages_per_group)
         model.grad_ready_hook = self._on_group_done if self.world > 1 else None
+
+    def buckets(self):
+        """[(lo, hi)] element ranges of the stage groups' slices (empty ones dropped)."""
+        slices = self.model.flat_buffers()[2]
+        out = []
+        for b, e in self.model.stage_groups:
+            lo, hi = slices[b][0], slices[e - 1][1]
+            if hi > lo:
+                out.append((lo, hi))
+        return out
+
+    def owned(self, lo, hi):
+        piece = (hi - lo) // self.world
+        return lo + self.rank * piece, lo + (self.rank + 1) * piece
+
+    def owned_pieces(self):
+        return [self.owned(lo, hi) for lo, hi in self.buckets()]
 
     def _on_group_done(self, gi):
         _, flat_g, slices = self.model.flat_buffers()
         b, e = self.model.stage_groups[gi]
         lo, hi = slices[b][0], slices[e - 1][1]
         if hi > lo and not _SKIP_GRAD_ALLREDUCE:
-            self.pending.append(dist.all_reduce(flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if self.shard:
+                olo, ohi = self.owned(lo, hi)
+                self.pending.append(dist.reduce_scatter_tensor(flat_g[olo:ohi], flat_g[lo:hi], op=dist.ReduceOp.SUM,
+                                                               group=self.group, async_op=True))
+            else:
+                self.pending.append(dist.all_reduce(flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if gi == len(self.model.stage_groups) - 1 and not _SKIP_GRAD_ALLREDUCE:
+            tlo, thi = self.model.tail_slice()
+            if thi > tlo:
+                self.pending.append(dist.all_reduce(flat_g[tlo:thi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def reduce_loss_sums(self, sums):
         if self.world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+
+    def all_reduce_scalar(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def gather(self, flat):
+        """All-gather every rank's owned piece of each bucket of `flat` (any flat buffer with the parameter layout)."""
+        works = []
+        for lo, hi in self.buckets():
+            olo, ohi = self.owned(lo, hi)
+            works.append(dist.all_gather_into_tensor(flat[lo:hi], flat[olo:ohi], group=self.group, async_op=True))
+        for w in works:
+            w.wait()
 
     def wait(self):
         for w in self.pending:
@@ -122,26 +169,34 @@ class DevicePrefetcher:
 
 class TrainStep:
     def __init__(self, cfg, model, lr=None, max_norm=1.0, process_group=None, stages_per_group=2,
-                 waveform_input=True, cuda_graph=False):
+                 waveform_input=True, cuda_graph=False, shard_optimizer=False):
         """cuda_graph=True records the whole step (feature -> forward -> loss -> backward -> clip+AdamW) once, after
         two eager warm-up steps, and replays it for every later batch of the same shape.  With several ranks the NCCL
         all-reduces are recorded into the graph as well (every rank must record and replay in lock-step)."""
         self.cfg = cfg
         self.cuda_graph = bool(cuda_graph)
+        self.shard_optimizer = bool(shard_optimizer)
         self._graph = None
         self._static = None
         self._eager_calls = 0
         self._epoch = None
         self.model = model
         self.transform = SpectrogramTransform.for_cfg(cfg) if waveform_input else None
-        self.reducer = GradientReducer(model, process_group, stages_per_group)
+        self.reducer = GradientReducer(model, process_group, stages_per_group, shard=shard_optimizer)
+        self.shard_optimizer = self.reducer.shard
         self.criterion = DepthCriterion.from_cfg(cfg, reduce_fn=self.reducer.reduce_loss_sums
                                                  if self.reducer.world > 1 else None)
         lr = lr if lr is not None else getattr(cfg.mode, "learning_rate", 1e-3)
-        self.optimizer = FusedClipAdamW(model, lr=lr, max_norm=max_norm, capturable=self.cuda_graph)
+        self.optimizer = FusedClipAdamW(model, lr=lr, max_norm=max_norm, capturable=self.cuda_graph,
+                                        reducer=self.reducer if self.reducer.shard else None)
 
     def features(self, batch):
         return self.transform(batch) if self.transform is not None else batch
+
+    def sync_master_weights(self):
+        """Sharded optimiser: all-gather the fp32 master weights (and the AdamW moments) every rank updated for the others.
+        Called before state_dict() / checkpoints automatically; a no-op otherwise."""
+        self.optimizer.sync_shards()
 
     def __call__(self, batch, gtdepth):
         """batch: waveform [B,2,L] (or features [B,2,S,S] when waveform_input=False), gtdepth [B,1,S,S];

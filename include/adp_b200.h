@@ -310,6 +310,10 @@ long long adp_tc_launch_count(void);
  * elementwise}: total ms, total algorithmic FLOP, timed calls. */
 int adp_profile_enable(int on);
 int adp_profile_read(double* ms, double* work, long long* calls);
+/* n = 11 entries: {gather conv, parity convT, wgrad} of the LARGE layers, thin first/last layers (FLOP), BatchNorm +
+ * activation passes (work = algorithmic BYTES), {gather, parity, wgrad} of the deep small-M levels (E5-E8, D8-D6), then
+ * the feature stage, the loss and clip + AdamW (work = algorithmic bytes).  n = 5 is adp_profile_read. */
+int adp_profile_read_n(int n, double* ms, double* work, long long* calls);
 
 /* Run-time form of the ADP_TC_* tuning variables: "tc_halo" (parity kernels load the tile's input window once per
  * channel chunk), "tc_cluster", "tc_max_bn", "side_stream" (U-Net weight gradients run on a library-owned side stream

@@ -45,11 +45,16 @@ def _worker(rank, world, port, out):
         red = GradientReducer(net, stages_per_group=2)
         assert red.world == world and net.grad_ready_hook is not None
         assert net.stage_groups == default_stage_groups(7, 2)
-        # every parameter lives in exactly one stage slice, slices tile the flat buffer
-        assert slices[0][0] == 0 and slices[-1][1] == flat_p.numel()
+        # the stage slices tile the bulk region (hidden-layer convolution weights), the tail holds every small tensor
+        tlo, thi = net.tail_slice()
+        assert slices[0][0] == 0 and slices[-1][1] == tlo and thi == flat_p.numel()
         assert all(slices[i][1] == slices[i + 1][0] for i in range(len(slices) - 1))
         n_in_slices = sum(p.numel() for st in net.staged_parameters() for p in st)
         assert n_in_slices == sum(p.numel() for p in net.parameters())
+        offs = dict(zip(map(id, net._flat["params"]), net._flat["offs"]))
+        for q in net.parameters():
+            assert (offs[id(q)] < tlo) == net._is_bulk(q)
+        assert all((e - b) % 64 == 0 for b, e in slices)
         # parameters are views of the flat buffer, 4-D weights in channels_last ([Cout][kh][kw][Cin]) order
         w = net.levels()[1]["conv"].weight
         assert w.data_ptr() >= flat_p.data_ptr() and w.stride() == (16 * w.shape[1], 1, 4 * w.shape[1], w.shape[1])
@@ -69,6 +74,21 @@ def _worker(rank, world, port, out):
         red.wait()
         both = [torch.randn(flat_g.numel(), generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
         assert torch.allclose(flat_g, both[0] + both[1], atol=1e-6)
+        # shard mode: reduce-scatter leaves the sum in the piece of every bucket this rank owns (and in the tail, which is
+        # all-reduced); gathering the pieces restores the whole buffer on every rank
+        sred = GradientReducer(net, stages_per_group=2, shard=True)
+        assert sred.shard
+        flat_g.copy_(local)
+        for gi in range(len(net.stage_groups)):
+            net.grad_ready_hook(gi)
+        sred.wait()
+        total = both[0] + both[1]
+        for b, e in sred.owned_pieces() + [net.tail_slice()]:
+            assert torch.allclose(flat_g[b:e], total[b:e], atol=1e-6)
+        pieces = sred.owned_pieces()
+        assert sum(e - b for b, e in pieces) * world == tlo
+        sred.gather(flat_g)
+        assert torch.allclose(flat_g, total, atol=1e-6)
         # global-batch loss from all-reduced statistics
         B = 2
         gt = synthetic.gt_depth(world * B, 64, 30.0, seed=9)

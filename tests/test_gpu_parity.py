@@ -671,9 +671,11 @@ def test_cuda_graph_step_matches_eager_steps():
     (same weights, same batches), including the device-side AdamW step counter."""
     from audio_depth_estimation_b200.models.unetbaseline_model import define_G
     from audio_depth_estimation_b200.training import TrainStep
-    cfg = make_cfg(False, 30.0, 128, "fp32")
+    # Sigmoid head (depth_norm): with the ReLU head the SIlog gradient ~1/p of predictions within rounding of 0 makes
+    # the trajectory bimodal from run to run (fp32 atomics order), in eager and in graph mode alike
+    cfg = make_cfg(True, 12.0, 128, "fp32")
     sd = uo.ordered_state_dict(uo.make_state_dict(16, 7, seed=42), 7)
-    batches = [(cuda(synthetic.waveform(2, synthetic.V2_LEN, seed=50 + i)), cuda(synthetic.gt_depth(2, 128, 30.0, seed=60 + i)))
+    batches = [(cuda(synthetic.waveform(2, synthetic.V2_LEN, seed=50 + i)), cuda(synthetic.gt_depth(2, 128, 12.0, seed=60 + i, normalised=True)))
                for i in range(6)]
     losses = {}
     for graph in (False, True):
