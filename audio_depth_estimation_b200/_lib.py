@@ -139,6 +139,13 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+def on_device(t):
+    """Context manager: make `t`'s GPU the current device for the library call (launches, per-device kernel attributes and
+    `stream_ptr()` all refer to the CURRENT device; a process may drive several GPUs, e.g. gpu_ids=[1])."""
+    import torch
+    return torch.cuda.device(t.device)
+
+
 def require_cuda(t, name="tensor", dtype=None):
     """The product path is CUDA only: refuse CPU tensors instead of falling back."""
     if not t.is_cuda:

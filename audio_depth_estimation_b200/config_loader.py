@@ -52,7 +52,10 @@ def load_config(dataset_name="batvisionv2", mode="train", experiment_name="defau
     conf_dir = conf_dir or CONF_DIR
     groups = {}
     for group, name in (("dataset", dataset_name), ("mode", mode), ("model", model_name)):
-        groups[group] = SimpleNamespace(**_read(os.path.join(conf_dir, group, name + ".yaml")))
-    if experiment_name is not None:
-        groups["mode"].experiment_name = experiment_name
+        path = os.path.join(conf_dir, group, name + ".yaml")
+        if group == "model" and not os.path.exists(path):       # reference :73-76: unknown model -> unet_baseline.yaml
+            path = os.path.join(conf_dir, "model", "unet_baseline.yaml")
+        groups[group] = SimpleNamespace(**_read(path))
+    groups["mode"].mode = mode                                  # reference :93
+    groups["mode"].experiment_name = experiment_name
     return SimpleNamespace(**groups)

@@ -27,9 +27,10 @@ class BatvisionV2Dataset(Dataset):
         self.device = torch.device("cuda") if torch.cuda.is_available() else None
         if use_image:
             raise NotImplementedError("use_image=True (camera branch, reference :199-210) is outside the audio hot path")
-        locations = sorted(d for d in os.listdir(self.root_dir)
-                           if os.path.isdir(os.path.join(self.root_dir, d))
-                           and not d.startswith((".", "__")) and not d.endswith("_unzipped"))
+        # (os.listdir order, as the reference :22-26 -- the row order of .instances follows it)
+        locations = [d for d in os.listdir(self.root_dir)
+                     if os.path.isdir(os.path.join(self.root_dir, d))
+                     and not d.startswith((".", "__")) and not d.endswith("_unzipped")]
         if location_blacklist:
             locations = [d for d in locations if d not in location_blacklist]
         frames = []
@@ -69,15 +70,24 @@ class BatvisionV2Dataset(Dataset):
             # STFT + log + per-channel min-max + Resize (reference :117-135) as one fused library call
             # ('mel_spectrogram': the mel bank sits between magnitude and log, hop = win_length // 2, :111-114)
             mel = "mel" in self.audio_format
-            fused = feature.SpectrogramTransform(self.cfg.dataset.images_size, self.cfg.dataset.max_depth,
-                                                 log_minmax=True, cut=False, mel={} if mel else None,
-                                                 stft=(n_fft, win_length, win_length // 2 if mel else hop_length))
-            return fused(self._to_device(waveform)), gt_depth
+            key = (n_fft, win_length, hop_length, mel)
+            if getattr(self, "_fused_key", None) != key:          # one transform (and workspace) for the whole dataset
+                self._fused = feature.SpectrogramTransform(self.cfg.dataset.images_size, self.cfg.dataset.max_depth,
+                                                           log_minmax=True, cut=False, mel={} if mel else None,
+                                                           stft=(n_fft, win_length, win_length // 2 if mel else hop_length))
+                self._fused_key = key
+            return self._fused(self._to_device(waveform)), gt_depth
         if "waveform" in self.audio_format:
             return waveform, gt_depth
         raise ValueError("unknown audio_format %r" % (self.audio_format,))
 
     def _to_device(self, waveform):
+        from ._common import in_worker_process
+        if in_worker_process():
+            raise RuntimeError("audio_format=%r computes the feature on the GPU inside __getitem__, which cannot run in a "
+                               "DataLoader worker process (num_workers > 0): use audio_format='waveform' and apply "
+                               "feature.SpectrogramTransform.for_cfg(cfg) to the collated batch (TrainStep does), or "
+                               "num_workers=0" % (self.audio_format,))
         if self.device is None:
             raise RuntimeError("BatvisionV2Dataset needs a CUDA device for the spectrogram transform "
                                "(no CPU fallback); use audio_format='waveform' in CPU worker processes")

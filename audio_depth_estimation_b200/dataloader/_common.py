@@ -14,8 +14,15 @@ def nearest_resize(depth, size):
     return depth[iy][:, ix]
 
 
+def in_worker_process():
+    """True inside a torch DataLoader worker (a forked process must not touch CUDA)."""
+    from torch.utils.data import get_worker_info
+    return get_worker_info() is not None
+
+
 def load_audio(path):
-    """Returns (waveform [C,L] float32 tensor, sample_rate).  .npy and PCM .wav are read directly."""
+    """Returns (waveform [C,L] float32 tensor, sample_rate).  .npy and 8/16/32-bit PCM .wav are read directly, anything
+    else goes through torchaudio.load as in the reference (BatvisionV2_Dataset.py:92-95)."""
     ext = os.path.splitext(path)[1].lower()
     if ext == ".npy":
         arr = np.load(path).astype(np.float32)
@@ -23,9 +30,16 @@ def load_audio(path):
             arr = arr[None]
         return torch.from_numpy(arr), 44100
     if ext == ".wav":
-        with _wave.open(path, "rb") as f:
-            sr, ch, width, n = f.getframerate(), f.getnchannels(), f.getsampwidth(), f.getnframes()
-            raw = f.readframes(n)
+        try:
+            with _wave.open(path, "rb") as f:
+                sr, ch, width, n = f.getframerate(), f.getnchannels(), f.getsampwidth(), f.getnframes()
+                raw = f.readframes(n)
+        except _wave.Error:                       # float / extensible wav files: what the reference uses throughout
+            import torchaudio
+            return torchaudio.load(path)
+        if width == 3:
+            import torchaudio
+            return torchaudio.load(path)
         if width == 2:
             data = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
         elif width == 4:

@@ -47,8 +47,9 @@ def spectrogram(waveform, n_fft=400, power=1.0, win_length=400, hop_length=100, 
     T = 1 + L // hop_length
     spec = torch.empty((rows, n_fft // 2 + 1, T), device=flat.device, dtype=torch.float32)
     lib = _lib.load()
-    _lib.check(lib.adp_stft_mag(flat.data_ptr(), rows, L, pitch, n_fft, win_length, hop_length,
-                                spec.data_ptr(), _lib.stream_ptr()))
+    with _lib.on_device(flat):
+        _lib.check(lib.adp_stft_mag(flat.data_ptr(), rows, L, pitch, n_fft, win_length, hop_length,
+                                    spec.data_ptr(), _lib.stream_ptr()))
     return spec.reshape(*lead, n_fft // 2 + 1, T)
 
 
@@ -71,9 +72,10 @@ def melspectrogram(waveform, n_fft=400, power=1.0, win_length=400, f_min=20.0, f
     lib = _lib.load()
     ws = torch.empty(lib.adp_feature_workspace_bytes(rows, L, n_fft, hop), device=flat.device, dtype=torch.uint8)
     mel = torch.empty((rows, n_mels, T), device=flat.device, dtype=torch.float32)
-    _lib.check(lib.adp_mel_spectrogram(flat.data_ptr(), rows, L, pitch, n_fft, win_length, hop, n_mels,
-                                       float(sample_rate), float(f_min), float(f_max), mel.data_ptr(),
-                                       ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    with _lib.on_device(flat):
+        _lib.check(lib.adp_mel_spectrogram(flat.data_ptr(), rows, L, pitch, n_fft, win_length, hop, n_mels,
+                                           float(sample_rate), float(f_min), float(f_max), mel.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
     return mel.reshape(*lead, n_mels, T)
 
 
@@ -85,7 +87,8 @@ def resize(spec, size):
     lead = spec.shape[:-2]
     rows = int(spec.numel() // (H * W))
     out = torch.empty((rows, size, size), device=spec.device, dtype=torch.float32)
-    _lib.check(_lib.load().adp_resize_aa(spec.data_ptr(), rows, H, W, size, out.data_ptr(), _lib.stream_ptr()))
+    with _lib.on_device(spec):
+        _lib.check(_lib.load().adp_resize_aa(spec.data_ptr(), rows, H, W, size, out.data_ptr(), _lib.stream_ptr()))
     return out.reshape(*lead, size, size)
 
 
@@ -132,17 +135,18 @@ class SpectrogramTransform:
         if self._ws is None or self._ws.numel() < need or self._ws.device != flat.device:
             self._ws = torch.empty(need, device=flat.device, dtype=torch.uint8)
         out = torch.empty((rows, self.size, self.size), device=flat.device, dtype=torch.float32)
-        if self.mel is not None:
-            m = self.mel
-            _lib.check(lib.adp_feature_forward_mel(flat.data_ptr(), rows, L, pitch, self.n_fft, self.win, self.hop,
-                                                   int(m["n_mels"]), float(m["sample_rate"]), float(m["f_min"]),
-                                                   float(m["f_max"]), 1 if self.log_minmax else 0, self.size,
-                                                   out.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
-                                                   _lib.stream_ptr()))
-        else:
-            _lib.check(lib.adp_feature_forward(flat.data_ptr(), rows, L, pitch, self.n_fft, self.win, self.hop,
-                                               1 if self.log_minmax else 0, self.size, out.data_ptr(),
-                                               self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()))
+        with _lib.on_device(flat):
+            if self.mel is not None:
+                m = self.mel
+                _lib.check(lib.adp_feature_forward_mel(flat.data_ptr(), rows, L, pitch, self.n_fft, self.win, self.hop,
+                                                       int(m["n_mels"]), float(m["sample_rate"]), float(m["f_min"]),
+                                                       float(m["f_max"]), 1 if self.log_minmax else 0, self.size,
+                                                       out.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                                       _lib.stream_ptr()))
+            else:
+                _lib.check(lib.adp_feature_forward(flat.data_ptr(), rows, L, pitch, self.n_fft, self.win, self.hop,
+                                                   1 if self.log_minmax else 0, self.size, out.data_ptr(),
+                                                   self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()))
         return out.reshape(*lead, self.size, self.size)
 
 
@@ -177,7 +181,8 @@ class DepthTransform:
         H, W = raw.shape[-2:]
         rows = raw.numel() // (H * W)
         out = torch.empty((rows, 1, self.size, self.size), device=raw.device, dtype=torch.float32)
-        _lib.check(_lib.load().adp_depth_prepare(raw.data_ptr(), code, rows, H, W, self.size, self.max_depth,
-                                                 1 if self.nan_to_num else 0, self.norm_div, out.data_ptr(),
-                                                 _lib.stream_ptr()))
+        with _lib.on_device(raw):
+            _lib.check(_lib.load().adp_depth_prepare(raw.data_ptr(), code, rows, H, W, self.size, self.max_depth,
+                                                     1 if self.nan_to_num else 0, self.norm_div, out.data_ptr(),
+                                                     _lib.stream_ptr()))
         return out

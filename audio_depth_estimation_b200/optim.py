@@ -10,8 +10,24 @@ import torch
 
 from . import _lib
 
+class _LrShim:
+    """What torch.optim.lr_scheduler needs from an optimiser: `param_groups` whose 'lr' it reads and writes."""
 
-class FusedClipAdamW:
+    def _init_groups(self):
+        self.param_groups = [dict(lr=self.lr, initial_lr=self.lr, betas=tuple(self.betas), eps=self.eps,
+                                  weight_decay=self.weight_decay, params=[])]
+        self.defaults = dict(lr=self.lr)
+        self._opt_called = True
+
+    def _pull_lr(self):
+        self.lr = float(self.param_groups[0]["lr"])
+
+    def set_lr(self, lr):
+        self.lr = float(lr)
+        self.param_groups[0]["lr"] = self.lr
+
+
+class FusedClipAdamW(_LrShim):
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=1.0,
                  capturable=False, reducer=None):
         """capturable=True keeps the step counter on the device so that step() can be recorded in a CUDA graph.
@@ -30,6 +46,7 @@ class FusedClipAdamW:
         self.step_count = 0
         self._state = None
         self.last_norm = None
+        self._init_groups()
 
     def _buffers(self):
         p, g, _ = self.model.flat_buffers()
@@ -64,6 +81,7 @@ class FusedClipAdamW:
     def step(self, local_only=False):
         """local_only: (measurement) skip the cross-rank work of the sharded mode and just update what this rank owns."""
         lib = _lib.load()
+        self._pull_lr()
         p, st, refs, mirror = self._buffers()
         self.step_count += 1
         red = self.reducer
@@ -139,7 +157,7 @@ class FusedClipAdamW:
     def load_state_dict(self, sd):
         """Accepts the dictionary above, i.e. also a stock torch.optim.AdamW state_dict saved by the reference."""
         group = sd["param_groups"][0]
-        self.lr = float(group.get("lr", self.lr))
+        self.set_lr(float(group.get("lr", self.lr)))
         self.betas = tuple(group.get("betas", self.betas))
         self.eps = float(group.get("eps", self.eps))
         self.weight_decay = float(group.get("weight_decay", self.weight_decay))
@@ -165,7 +183,7 @@ class FusedClipAdamW:
         self._state["step_dev"].fill_(self.step_count)
 
 
-class FusedClipAdamWParams:
+class FusedClipAdamWParams(_LrShim):
     """The same fused clip_grad_norm_(max_norm) + AdamW step for an arbitrary list of CUDA fp32 parameters (e.g. the
     config-4 BinauralAttentionDepthNet, whose parameters are ordinary separate tensors): two multi-tensor launches per
     24 tensors (adp_grad_sumsq, adp_clip_adamw_step).  Parameters must be dense (any memory format); a gradient whose
@@ -186,6 +204,7 @@ class FusedClipAdamWParams:
         self._sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
         self._norm = torch.zeros(1, device=dev, dtype=torch.float32)
         self.last_norm = None
+        self._init_groups()
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -193,6 +212,7 @@ class FusedClipAdamWParams:
 
     def step(self):
         lib = _lib.load()
+        self._pull_lr()
         live = [(p, m, v) for p, m, v in zip(self.params, self.exp_avg, self.exp_avg_sq) if p.grad is not None]
         if not live:
             return None

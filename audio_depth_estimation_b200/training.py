@@ -180,6 +180,7 @@ class TrainStep:
         self._static = None
         self._eager_calls = 0
         self._epoch = None
+        self._graph_lr = None
         self.model = model
         self.transform = SpectrogramTransform.for_cfg(cfg) if waveform_input else None
         self.reducer = GradientReducer(model, process_group, stages_per_group, shard=shard_optimizer)
@@ -187,6 +188,9 @@ class TrainStep:
         self.criterion = DepthCriterion.from_cfg(cfg, reduce_fn=self.reducer.reduce_loss_sums
                                                  if self.reducer.world > 1 else None)
         lr = lr if lr is not None else getattr(cfg.mode, "learning_rate", 1e-3)
+        opt_name = str(getattr(cfg.mode, "optimizer", "AdamW"))
+        if opt_name != "AdamW":             # train.py:471-476 also offers Adam / SGD; only the default is fused here
+            raise NotImplementedError("cfg.mode.optimizer=%r: only 'AdamW' (the reference default) is implemented" % opt_name)
         self.optimizer = FusedClipAdamW(model, lr=lr, max_norm=max_norm, capturable=self.cuda_graph,
                                         reducer=self.reducer if self.reducer.shard else None)
 
@@ -217,9 +221,10 @@ class TrainStep:
 
     def _graphed_step(self, batch, gtdepth):
         key = (tuple(batch.shape), tuple(gtdepth.shape), batch.device)
-        if self._static is not None and (self._static[0] != key or self._epoch != self.model._external_epoch):
-            # new shape, or the parameters were replaced behind the graph's back (load_state_dict, broadcast):
-            # the recorded step reads the optimiser-maintained bf16 weight mirror, so record again
+        if self._static is not None and (self._static[0] != key or self._epoch != self.model._external_epoch
+                                         or self._graph_lr != self.optimizer.lr):
+            # new shape, a new learning rate (set_lr / a scheduler: lr is a captured kernel argument), or the parameters
+            # were replaced behind the graph's back (load_state_dict, broadcast): record again
             self._graph, self._static, self._eager_calls = None, None, 0
         if self._graph is None:
             if self._eager_calls < 2:                  # workspaces, tensor maps, func attributes: all set up eagerly
@@ -229,16 +234,19 @@ class TrainStep:
             sb, sg = batch.clone(), gtdepth.clone()
             torch.cuda.synchronize(batch.device)
             graph = torch.cuda.CUDAGraph()
+            count = self.optimizer.step_count
             with torch.cuda.graph(graph):
                 sloss = self._eager_step(sb, sg)
+            self.optimizer.step_count = count          # recording is not a step (the device-side counter did not move)
             self._graph, self._static = graph, (key, sb, sg, sloss)
+            self._graph_lr = self.optimizer.lr
             self._epoch = self.model._external_epoch
         _, sb, sg, sloss = self._static
         sb.copy_(batch, non_blocking=True)
         sg.copy_(gtdepth, non_blocking=True)
         self._graph.replay()
         self.optimizer.step_count += 1
-        return sloss
+        return sloss.clone()           # (the static tensor is overwritten by the next replay)
 
     @torch.no_grad()
     def evaluate(self, batch, gtdepth, metrics=False, protocol="train"):
@@ -269,18 +277,20 @@ def evaluate_loader(step, batches, protocol="test"):
 
 
 class ModuleTrainStep:
-    """The same step body (train_binaural_attention.py: forward -> masked criterion -> backward -> clip_grad_norm_ ->
-    AdamW) for a model whose parameters are ordinary separate tensors, e.g. the config-4 BinauralAttentionDepthNet:
-    `DepthCriterion` + `FusedClipAdamWParams`.  `features` (optional) is applied to the batch first, e.g.
-    `SpectrogramTransform.for_cfg(cfg)`.  Single process; returns the loss as a 0-dim device tensor."""
+    """The step body of train_binaural_attention.py:430-438 (zero_grad -> forward -> masked criterion -> backward -> AdamW;
+    that trainer does NOT clip gradients, so max_norm defaults to None) for a model whose parameters are ordinary separate
+    tensors, e.g. the config-4 BinauralAttentionDepthNet: `DepthCriterion` + `FusedClipAdamWParams`.  `features`
+    (optional) is applied to the batch first, e.g. `SpectrogramTransform.for_cfg(cfg)`.  A torch LR scheduler can drive
+    the step through `optimizer.param_groups` (CosineAnnealingLR / StepLR as in :300-312) or `optimizer.set_lr()`.
+    Single process; returns the loss as a 0-dim device tensor."""
 
-    def __init__(self, cfg, model, lr=None, max_norm=1.0, features=None):
+    def __init__(self, cfg, model, lr=None, max_norm=None, features=None, weight_decay=1e-2):
         self.cfg = cfg
         self.model = model
         self.features = features
         self.criterion = DepthCriterion.from_cfg(cfg)
         lr = lr if lr is not None else getattr(cfg.mode, "learning_rate", 1e-3)
-        self.optimizer = FusedClipAdamWParams(model.parameters(), lr=lr, max_norm=max_norm)
+        self.optimizer = FusedClipAdamWParams(model.parameters(), lr=lr, max_norm=max_norm, weight_decay=weight_decay)
 
     def __call__(self, batch, gtdepth):
         self.model.train()

@@ -22,9 +22,10 @@ def _run(gt, pred, batch, scale, prepare, lo, hi):
     lib = _lib.load()
     ws = torch.empty(lib.adp_depth_metrics_workspace_bytes(batch), dtype=torch.uint8, device=pred.device)
     out = torch.empty((batch, 7), dtype=torch.float64, device=pred.device)
-    _lib.check(lib.adp_depth_metrics(pred.data_ptr(), gt.data_ptr(), batch, pred.numel() // batch, float(scale),
-                                     int(prepare), float(lo), float(hi), out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                     _lib.stream_ptr()))
+    with _lib.on_device(pred):
+        _lib.check(lib.adp_depth_metrics(pred.data_ptr(), gt.data_ptr(), batch, pred.numel() // batch, float(scale),
+                                         int(prepare), float(lo), float(hi), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         _lib.stream_ptr()))
     return out
 
 

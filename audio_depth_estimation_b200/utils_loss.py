@@ -83,6 +83,8 @@ class DepthCriterion(nn.Module):
             self.l1_w, self.silog_w = 0.0, 1.0
         elif criterion == "Combined":
             self.l1_w, self.silog_w = float(l1_weight), float(silog_weight)
+            if self.silog_w == 0.0:            # train.py:446-459: SIlog disabled -> "L1 only" with weight 1.0
+                self.l1_w = 1.0
         else:
             raise ValueError("Unknown criterion: %s" % criterion)
         self.criterion = criterion

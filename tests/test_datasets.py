@@ -75,7 +75,8 @@ def test_v2_dataset_waveform_and_depth(v2_tree):
     cut = int((2 * 30.0 / 340) * 44100)
     assert w.shape == (2, cut) and w.dtype == torch.float32
     # depth: the reference's steps (BatvisionV2_Dataset.py:65-78) with cv2 itself
-    first_loc = sorted(["office_a", "hall_b"])[0]
+    import os
+    first_loc = [d for d in os.listdir(root) if (root / d).is_dir()][0]      # os.listdir order, as the reference (:22-26)
     d = np.load(root / first_loc / "depth" / "d0.npy").astype(np.float32) / 1000.0
     d[d > 30.0] = 30.0
     d[d < 0] = 0
@@ -126,7 +127,8 @@ def test_v2_and_v1_spectrogram_getitem_on_gpu(v2_tree, tmp_path):
     root, waves = v2_tree
     ds = BatvisionV2Dataset(cfg_v2(root, "spectrogram", size=256), "train.csv")
     x, gt = ds[1]
-    first_loc = sorted(["office_a", "hall_b"])[0]
+    import os
+    first_loc = [d for d in os.listdir(root) if (root / d).is_dir()][0]      # os.listdir order, as the reference (:22-26)
     ref = fo.feature_v2(waves[(first_loc, 1)], 30.0, 256)
     assert x.is_cuda and x.shape == (2, 256, 256) and gt.shape == (1, 256, 256)
     assert np.abs(x.cpu().numpy() - ref).max() <= 5e-4
