@@ -298,6 +298,13 @@ struct ConvExtras {
   int pad_in;           // gather: the input is [B, Hi+2, Wi+2, C] with an explicit one-pixel border
   int pad_out;          // pointwise act_dual: y0 is the interior of a [B, Hi+2, Wi+2, N] tensor
   const float* center;  // pointwise act_dual: y0 = lrelu(D, slope0) - center[n]
+  // gather / parity, inference: eval-mode BatchNorm and the activation(s) in the epilogue -- instead of the raw output,
+  // y_act0 = lrelu(D * bn_scale[n] + bn_shift[n], slope0) and (optional) y_act1 = lrelu(., slope1) are written, and
+  // *fold_done = 1; a launch that does not qualify (split K range, narrow N) writes the raw output as usual
+  const float* bn_scale; const float* bn_shift;
+  float slope0, slope1;
+  void* y_act0; void* y_act1;
+  int* fold_done;
 };
 int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_nk, void* y0, int N0, void* y1, int N1,
                  int act_dual, float slope0, float slope1, int B, int Hi, int Wi, cudaStream_t s,

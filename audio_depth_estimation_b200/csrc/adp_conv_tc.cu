@@ -98,8 +98,9 @@ struct IgemmParams {
   int wmode;                          // modes 2/4: 1 = weights through the MN-major 3-D map (N | taps | Ct), taps reversed
   int f32_rows;                       // modes 2/4: write fp32 [pixels][N] to out_f32 instead of bf16 (any BLOCK_N)
   long long rows_guard;               // > 0: output rows (opix) >= rows_guard are not stored (ragged GEMM M)
-  int act_dual;                       // mode 2: y0 = lrelu(D, slope0) [- center], y1 = lrelu(D, slope1), both [pixels][N]
-  float slope0, slope1;
+  int act_dual;                       // y0 = lrelu(z, slope0) [- center], y1 (optional) = lrelu(z, slope1), both [pixels][N];
+  float slope0, slope1;               //   z = D, or D * aff_scale[n] + aff_shift[n] (eval-mode BatchNorm folded in)
+  const float* aff_scale; const float* aff_shift;
   // mode 3 (STFT as a split-bf16 DFT GEMM): rows = frames, columns = (re, im) pairs of the bins
   float* spec; int F, T, log_mode; int* minmax;
   // first-level centring (adp_unet.cu): the activation with the large per-channel DC component is stored as a - center[n]
@@ -147,19 +148,21 @@ template <int HALO> struct HaloGeom {
   static constexpr int BOX_BYTES = W * H * TILE_K * 2;            // 20480 / 19584
   static constexpr int TAPS = HALO == 3 ? 3 : 4;
 };
-template <int BLOCK_N, int HALO = 0>
+// ALT: two epilogue warp groups that take alternate TILES (one TMEM accumulator buffer each) -- the thin pointwise layers
+// have a 4-MMA main loop and are bound by the latency of one epilogue group; no fused statistics in that variant
+template <int BLOCK_N, int HALO = 0, bool ALT = false>
 struct PersistSmem {
   static constexpr int A_BYTES = HALO ? 20480 : A_STAGE_BYTES;
   static constexpr int B_TILE = BLOCK_N * TILE_K * 2;
   static constexpr int B_BYTES = HALO ? HaloGeom<HALO>::TAPS * B_TILE : B_TILE;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING = 4 * 4096;        // epilogue transpose buffers: 4 warps x (32 rows x 128 B)
+  static constexpr int STAGING = (ALT ? 8 : 4) * 4096;   // epilogue transpose buffers: one (32 rows x 128 B) per epilogue warp
   static constexpr int BAR_BYTES = 512;           // pipeline barriers, TMEM slot
   // BatchNorm partial sums, private to each of the 4 epilogue warps: [4][2][STATS_N] floats.  The 64-wide parity halo
   // kernel (N = 64 only) keeps them in the 896 unused bytes behind each stage's 17 x 9 window instead, so that its
   // 4th pipeline stage survives; the 3x3 halo kernels (config 4) never fuse statistics.
   static constexpr bool STATS_IN_SLACK = HALO == 4 && BLOCK_N == 64;
-  static constexpr int STATS_N = HALO == 3 ? 0 : (STATS_IN_SLACK ? 64 : 512);
+  static constexpr int STATS_N = (HALO == 3 || ALT) ? 0 : (STATS_IN_SLACK ? 64 : 512);
   static constexpr int STATS_BYTES = STATS_IN_SLACK ? 0 : 4 * 2 * STATS_N * 4;
   static constexpr int RING_BUDGET = HALO ? (227 * 1024 - 1024 - BAR_BYTES - STAGING - STATS_BYTES - 256) : 192 * 1024;
   static constexpr int STAGES = RING_BUDGET / STAGE_BYTES > 10 ? 10 : RING_BUDGET / STAGE_BYTES;
@@ -171,9 +174,10 @@ struct PersistSmem {
 
 // EG = number of epilogue warp groups (4 warps each): 1 for the convolutions, 2 for the math-heavy STFT epilogue
 // ATT = attention (softmax) epilogues of the row GEMM compiled in (kept out of the convolution instantiations)
-template <int BLOCK_N, int EG, bool ATT = false, int HALO = 0>
+template <int BLOCK_N, int EG, bool ATT = false, int HALO = 0, bool ALT = false>
 __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
-  using PS = PersistSmem<BLOCK_N, HALO>;
+  static_assert(!ALT || (EG == 2 && HALO == 0 && !ATT), "alternating epilogue groups: two groups, plain staged epilogue");
+  using PS = PersistSmem<BLOCK_N, HALO, ALT>;
   const int worker = (int)blockIdx.x;                     // index of this CTA in the tile walk
   const int nworkers = (int)gridDim.x;
   const int ntiles = p.total_tiles;
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained by the 4 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool want_stats = EG == 1 && BLOCK_N >= 64 && PS::STATS_N > 0 && p.stats != nullptr;
+  const bool want_stats = EG == 1 && !ALT && BLOCK_N >= 64 && PS::STATS_N > 0 && p.stats != nullptr;
   // BN partial sums of epilogue warp e: [2][N] floats
   auto stats_of = [&](int e) -> float* {
     if (PS::STATS_IN_SLACK) return reinterpret_cast<float*>(smem + e * PS::STAGE_BYTES + HaloGeom<HALO ? HALO : 4>::BOX_BYTES);
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     if (p.C1 > 0) prefetch_tmap(&p.tmA1);
     prefetch_tmap(&p.tmW);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4 * EG); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], ALT ? 4 : 4 * EG); }
     fence_barrier_init();
   }
   if (want_stats) {
@@ -360,12 +364,13 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
     const int egroup = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int wt = r % p.Wt, ht = (r / p.Wt) % p.Ht, bt = r / (p.Wt * p.Ht);
-    constexpr bool STAGED_OK = BLOCK_N >= 64 && EG == 1;
+    constexpr bool STAGED_OK = BLOCK_N >= 64 && (EG == 1 || ALT);
     unsigned char* stg = smem + STAGES * PS::STAGE_BYTES + PS::BAR_BYTES + (STAGED_OK ? (warp - 2) * 4096 : 0);
     const bool staged = p.splits <= 1 && p.mode != 3 && !p.f32_rows && !(ATT && (p.epi == 1 || p.epi == 2)) &&
                         (p.act_dual || p.N1 == 0 || p.N0 % 64 == 0);
     uint32_t local = 0;
     for (int t = worker; t < ntiles; t += nworkers, ++local) {
+      if (ALT && (int)(local & 1u) != egroup) continue;     // the other group's tile (and accumulator buffer)
       const TileCoord c = decode_tile<BLOCK_N>(p, t);
       const uint32_t buf = local & 1u, use = local >> 1;
       mbar_wait(&tfull_bar[buf], use & 1u);
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
         // pad_out: this pixel's row index inside the bordered tensor, as an offset from opix (fetched by shuffle at the store)
         const unsigned dpad = p.pad_out ? (unsigned)((((size_t)b * (p.Hs + 2) + py + 1) * (p.Ws + 2) + px + 1) - opix) : 0u;
         const bool dpad_uniform = (p.Wt & 31) == 0;      // a warp's 32 pixels then lie in one image row: one offset for all of them
-        float* const my_stats = stats_of(warp - 2);
+        float* const my_stats = ALT ? nullptr : stats_of(warp - 2);
         // padded: rows of the bordered tensor; cen: per-column constants subtracted after the activation (NULL: none);
         // col0 >= 0: accumulate the BatchNorm partial sums of the stored values for columns col0 .. col0 + 63
         auto emit = [&](const float (&v)[64], bf16* base, int ldn, float slope, bool act, bool padded, const float* cen, int col0) {
@@ -484,8 +489,17 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
             }
           }
           if (p.act_dual) {
+            if (p.aff_scale) {           // eval-mode BatchNorm: per-channel scale / shift of the running statistics
+#pragma unroll
+              for (int k4 = 0; k4 < 64; k4 += 4) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(p.aff_scale + n + k4));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(p.aff_shift + n + k4));
+                v[k4] = fmaf(v[k4], sc.x, sh.x); v[k4 + 1] = fmaf(v[k4 + 1], sc.y, sh.y);
+                v[k4 + 2] = fmaf(v[k4 + 2], sc.z, sh.z); v[k4 + 3] = fmaf(v[k4 + 3], sc.w, sh.w);
+              }
+            }
             emit(v, p.y0 + n, p.N, p.slope0, true, p.pad_out != 0, p.center ? p.center + n : nullptr, -1);
-            emit(v, p.y1 + n, p.N, p.slope1, true, false, nullptr, -1);
+            if (p.y1) emit(v, p.y1 + n, p.N, p.slope1, true, false, nullptr, -1);
           } else if (n < p.N0) {
             emit(v, p.y0 + n, p.N0, 0.f, false, false, nullptr, want_stats ? n : -1);
           } else {
@@ -645,16 +659,17 @@ bool tile_geometry(int B, int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
 
 int g_halo = 1;            // "tc_halo" / ADP_TC_HALO: 0 = one TMA box per tap, 1 = halo windows (narrow-N parity and 3x3 layers)
 int g_stats = 1;           // "tc_stats" / ADP_TC_STATS: BatchNorm statistics accumulated by the convolution epilogue
+int g_alt = 1;             // "tc_alt" / ADP_TC_ALT: two alternating epilogue groups for the thin pointwise layers
 
-template <int BLOCK_N, int EG, bool ATT, int HALO>
+template <int BLOCK_N, int EG, bool ATT, int HALO, bool ALT = false>
 int launch_persist(const IgemmParams& p, int ctas, cudaStream_t s) {
-  using PS = PersistSmem<BLOCK_N, HALO>;
+  using PS = PersistSmem<BLOCK_N, HALO, ALT>;
   if (p.stats && (p.N > PS::STATS_N || EG != 1 || BLOCK_N < 64)) {
     adp_set_error("tc igemm: fused statistics need 64 <= N <= %d here", PS::STATS_N);
     return ADP_ERR_ARG;
   }
-  ADP_SMEM_ATTR((tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO>), PS::BYTES);
-  tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO><<<ctas, 64 + 128 * EG, PS::BYTES, s>>>(p);
+  ADP_SMEM_ATTR((tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO, ALT>), PS::BYTES);
+  tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO, ALT><<<ctas, 64 + 128 * EG, PS::BYTES, s>>>(p);
   return ADP_OK;
 }
 
@@ -676,6 +691,11 @@ int launch_igemm(IgemmParams& p, dim3 grid, cudaStream_t s) {
     constexpr int AB = BLOCK_N < 64 ? 64 : BLOCK_N;
     if (AB != BLOCK_N) { adp_set_error("attention epilogues need BLOCK_N >= 64"); return ADP_ERR_ARG; }
     ADP_TRY((launch_persist<AB, 1, true, 0>(p, ctas, s)));
+  } else if (g_alt && p.mode == 2 && (BLOCK_N == 64 || BLOCK_N == 128) && !p.f32_rows && !p.stats && p.splits <= 1 &&
+             p.rows_guard <= 0 && p.kblocks <= 2 && (p.act_dual || p.N1 == 0 || p.N0 % 64 == 0)) {
+    // thin pointwise layers (K <= 128): a 4-8 MMA main loop, the kernel is its epilogue -- two groups on alternate tiles
+    constexpr int AB = (BLOCK_N == 64 || BLOCK_N == 128) ? BLOCK_N : 64;
+    ADP_TRY((launch_persist<AB, 2, false, 0, true>(p, ctas, s)));
   } else {
     ADP_TRY((launch_persist<BLOCK_N, 1, false, 0>(p, ctas, s)));
   }
@@ -744,6 +764,8 @@ struct TcEnvInit {
     if (be) g_max_block_n = atoi(be);
     const char* se = getenv("ADP_TC_STATS");
     if (se) g_stats = atoi(se);
+    const char* ae = getenv("ADP_TC_ALT");
+    if (ae) g_alt = atoi(ae);
   }
 } g_tc_env_init;
 
@@ -751,6 +773,20 @@ struct TcEnvInit {
 // e.g. one per device, do not see each other's workspace)
 thread_local float* g_scratch = nullptr;
 thread_local size_t g_scratch_bytes = 0;
+
+// eval-mode BatchNorm + activation(s) in the epilogue: needs the staged bf16 path of one un-split launch
+bool fold_bn_act(IgemmParams& p, int block_n, const ConvExtras* ex) {
+  if (!ex || !ex->bn_scale || !ex->bn_shift || !ex->y_act0 || block_n < 64 || p.N1 != 0) return false;
+  if (pick_splits(p, block_n, g_scratch != nullptr, g_scratch_bytes) > 1) return false;
+  p.act_dual = 1;
+  p.aff_scale = ex->bn_scale; p.aff_shift = ex->bn_shift;
+  p.slope0 = ex->slope0; p.slope1 = ex->slope1;
+  p.y0 = reinterpret_cast<bf16*>(ex->y_act0);
+  p.y1 = reinterpret_cast<bf16*>(ex->y_act1);
+  p.N0 = p.N;
+  if (ex->fold_done) *ex->fold_done = 1;
+  return true;
+}
 
 // BatchNorm statistics can ride in the epilogue when the output goes through the staged bf16 path of one un-split launch
 bool stats_fusable(const IgemmParams& p, int block_n, bool have_scratch, size_t scratch_bytes) {
@@ -766,6 +802,7 @@ int tc_set_option(const char* name, int value) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_halo;
   else if (!strcmp(name, "tc_stats")) slot = &g_stats;
+  else if (!strcmp(name, "tc_alt")) slot = &g_alt;
   else if (!strcmp(name, "tc_max_bn")) slot = &g_max_block_n;
   if (!slot) return -1;
   const int prev = *slot;
@@ -824,6 +861,7 @@ int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, 
     p.stats = ex->stats;
     if (ex->stats_done) *ex->stats_done = 1;
   }
+  fold_bn_act(p, bn, ex);
   return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
 }
 
@@ -862,6 +900,7 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
     p.stats = ex->stats;
     if (ex->stats_done) *ex->stats_done = 1;
   }
+  fold_bn_act(p, bn, ex);
   return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
 }
 

@@ -246,6 +246,7 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   }
   ADP_CUDA(cudaMemsetAsync(at(ws, p.sums_begin), 0, p.sums_end - p.sums_begin, s));
   const bool center = thin_tc && use_center(d, p, tc);
+  const bool fold = tc && !d->training && d->inference_only;      // BatchNorm + activation in the conv epilogues
   float* cen_m = reinterpret_cast<float*>(at(ws, p.center_m));
   float* cen_T = reinterpret_cast<float*>(at(ws, p.center_T));
 
@@ -282,8 +283,22 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     memset(&ex, 0, sizeof(ex));
     if (L.bn_down && d->training) { ex.stats = sums; ex.stats_done = &fused; }
     ex.pad_in = (l == 1 && center) ? 1 : 0;
+    int folded = 0;
+    if (fold && L.bn_down) {
+      // inference: scale / shift from the running statistics (cached with the weight operands; level 1 depends on the
+      // batch through the centring offset), then BatchNorm + LeakyReLU / ReLU in the convolution epilogue
+      BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
+      if (!d->reuse_weight_cache || (l == 1 && center)) {
+        const BnFin fin{sums, 0.0, 1.f, params[l].bn_down_w, params[l].bn_down_b, params[l].bn_down_rm, params[l].bn_down_rv,
+                        0, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd, (l == 1 && center) ? cen_T : nullptr};
+        ADP_TRY(bn_finalize(fin, L.cout, s));
+      }
+      ex.bn_scale = bn.scale; ex.bn_shift = bn.shift; ex.slope0 = 0.2f; ex.slope1 = 0.f;
+      ex.y_act0 = at(ws, L.a); ex.y_act1 = at(ws, L.r); ex.fold_done = &folded;
+    }
     ADP_TRY(conv_gather(dt, at(ws, p.lv[l - 1].a), params[l].conv_w, tc ? w16(params[l].conv_w_bf16, L.wb_conv) : nullptr,
                         at(ws, L.e), L.cout, nullptr, 0, B, L.hin, L.hin, L.cin, s, &ex, deep_level(L.hout)));
+    if (folded) continue;
     // (work of the BatchNorm / activation passes = ALGORITHMIC bytes: every input once, every output once)
     ProfScope eprof(PROF_ELEM, s, (double)rows * L.cout * p.esz * (L.bn_down ? 3.0 : 2.0));
     if (L.bn_down) {
@@ -307,9 +322,21 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     ConvExtras ex;
     memset(&ex, 0, sizeof(ex));
     if (d->training) { ex.stats = sums; ex.stats_done = &fused; }
+    int folded = 0;
+    if (fold) {
+      BnBuf bnf = bnbuf(ws, L.bn_up_f, L.t_cout);
+      if (!d->reuse_weight_cache) {
+        const BnFin fin{sums, 0.0, 1.f, params[l].bn_up_w, params[l].bn_up_b, params[l].bn_up_rm, params[l].bn_up_rv,
+                        0, d->bn_eps, d->bn_momentum, bnf.scale, bnf.shift, bnf.mean, bnf.invstd, nullptr};
+        ADP_TRY(bn_finalize(fin, L.t_cout, s));
+      }
+      ex.bn_scale = bnf.scale; ex.bn_shift = bnf.shift; ex.slope0 = 0.f; ex.slope1 = 0.f;
+      ex.y_act0 = at(ws, O.q); ex.y_act1 = nullptr; ex.fold_done = &folded;
+    }
     ADP_TRY(conv_parity(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, params[l].convT_w,
                         tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, O.t), B, L.hout, L.hout, L.t_cout, s, &ex,
                         deep_level(O.hout)));
+    if (folded) continue;
     ProfScope eprof(PROF_ELEM, s, (double)rows * L.t_cout * p.esz * 2.0);
     BnBuf bn = bnbuf(ws, L.bn_up_f, L.t_cout);
     if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));

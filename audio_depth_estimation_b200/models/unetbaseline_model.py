@@ -374,7 +374,7 @@ class UnetGenerator(nn.Module):
                         setattr(a, tag + "_rv", bn.running_var.data_ptr())
         return arr
 
-    def _desc(self, batch, size, training, reuse):
+    def _desc(self, batch, size, training, reuse, inference=False):
         bns = [lv["bn_up"] for lv in self.levels() if lv["bn_up"] is not None]
         d = _lib.UnetDesc()
         d.batch, d.in_ch, d.out_ch, d.ngf = batch, self.input_nc, self.output_nc, self.ngf
@@ -382,6 +382,7 @@ class UnetGenerator(nn.Module):
         d.final_sigmoid, d.training = int(self.final_sigmoid), int(training)
         d.bn_eps, d.bn_momentum = bns[0].eps, (bns[0].momentum if bns[0].momentum is not None else 0.1)
         d.reuse_weight_cache = int(reuse)
+        d.inference_only = int(bool(inference) and not training)
         return d
 
     # ------------------------------------------------------------------ execution
@@ -402,7 +403,8 @@ class UnetGenerator(nn.Module):
         versions = tuple(p._version for p in self._flat["params"])
         key = (B, S, self._dtype, x.device)
         reuse = (not self.training) and (not self._dirty) and self._wcache_key == (key, versions)
-        desc = self._desc(B, S, self.training, reuse)
+        # eval mode under no_grad: nothing will be back-propagated, BatchNorm + activations fold into the conv epilogues
+        desc = self._desc(B, S, self.training, reuse, inference=not torch.is_grad_enabled())
         if self._ws is None or self._ws_key != key:
             need = lib.adp_unet_workspace_bytes(ctypes.byref(desc))
             if need == 0:

@@ -170,6 +170,9 @@ typedef struct adp_unet_desc {
   float bn_eps;     /* 1e-5 */
   float bn_momentum;/* 0.1 */
   int reuse_weight_cache; /* 1: the bf16 weight operands in the workspace are still valid (inference) */
+  int inference_only;     /* 1 (with training = 0): no backward pass will follow -- eval-mode BatchNorm scale/shift and the
+                           * activations are applied in the convolution epilogues (test.py:231-241) and the workspace
+                           * does not keep the raw convolution outputs the backward pass would need */
 } adp_unet_desc;
 
 typedef struct adp_unet_level {      /* level 0 = outermost block */
