@@ -232,6 +232,16 @@ int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const floa
                      const float* mean, const float* invstd, const void* gA, float slope0,
                      const void* gB, float slope1, const double* sums, int mode, void* dx, float* dgamma, float* dbeta,
                      cudaStream_t s);
+// Small tensors (deep levels): the whole BatchNorm layer in ONE launch, each tensor read once (an 8-channel slab per block
+// staged in shared memory).  tensors = 1 (forward) / 3 (backward) slabs must fit: bn_small_ok.
+bool bn_small_ok(int dtype, long long rows, int C, int tensors);
+// batch statistics (f.training must be 1) -> scale/shift/mean/invstd + running statistics -> out0 [, out1]
+int bn_small_fwd(int dtype, const void* x, long long rows, int C, const BnFin& f, float slope0, void* out0, float slope1,
+                 void* out1, cudaStream_t s);
+// act_bn_bwd_reduce + act_bn_bwd_apply (mode 1 or 2); sums (optional, double [2C]) receives sum gz / sum gz*xhat
+int bn_small_bwd(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift, const float* mean,
+                 const float* invstd, const void* gA, float slope0, const void* gB, float slope1, int mode, void* dx,
+                 float* dgamma, float* dbeta, double* sums, cudaStream_t s);
 // dgamma[c] = sums[C+c], dbeta[c] = sums[c]
 int bn_param_grads(const double* sums, int C, float* dgamma, float* dbeta, cudaStream_t s);
 // final head: y = act(u + bias); du = dy*act'(y) ; dbias[0] += sum du   (out_ch == 1)

@@ -232,31 +232,53 @@ resize_aa_kernel(const float* __restrict__ in, int rows, int H, int W, int S, fl
     ww[j] = j < aw.size ? aa_w(aw, j) * iw : 0.f;
     cw[j] = min(aw.lo + j, W - 1);          // clamped: taps beyond the footprint carry weight 0
   }
-  const int row_end = min(rows, (int)(blockIdx.z + 1) * RESIZE_PLANES);
-  for (int row = blockIdx.z * RESIZE_PLANES; row < row_end; ++row) {
-    const float* src = in + (size_t)row * H * W;
-    float acc = 0.f;
-    if (fast) {
+  const int row0 = blockIdx.z * RESIZE_PLANES;
+  if (fast) {
+    // all planes of this thread at once: RESIZE_PLANES x (<= 4 x 6) independent loads in flight before the first use
+    float acc[RESIZE_PLANES];
+#pragma unroll
+    for (int k = 0; k < RESIZE_PLANES; ++k) {
+      acc[k] = 0.f;
+      const int row = min(row0 + k, rows - 1);                     // (clamped: the surplus planes of the last block are not stored)
+      const float* src = in + (size_t)row * H * W;
 #pragma unroll
       for (int jh = 0; jh < RESIZE_VT; ++jh) {
         if (jh < ah.size) {
           const float* line = src + (size_t)(ah.lo + jh) * W;
           float hacc = 0.f;
 #pragma unroll
-          for (int jw = 0; jw < RESIZE_HT; ++jw) hacc = fmaf(line[cw[jw]], ww[jw], hacc);
-          acc = fmaf(hacc, wh[jh], acc);
+          for (int jw = 0; jw < RESIZE_HT; ++jw)
+            if (jw < aw.size) hacc = fmaf(__ldg(line + cw[jw]), ww[jw], hacc);
+          acc[k] = fmaf(hacc, wh[jh], acc[k]);
         }
       }
-    } else {
-      for (int jh = 0; jh < ah.size; ++jh) {
-        const float* line = src + (size_t)(ah.lo + jh) * W + aw.lo;
-        float hacc = 0.f;
-        for (int jw = 0; jw < aw.size; ++jw) hacc = fmaf(line[jw], aa_w(aw, jw) * iw, hacc);
-        acc = fmaf(hacc, aa_w(ah, jh) * ih, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < RESIZE_PLANES; ++k) {
+      const int row = row0 + k;
+      if (row < rows) {
+        float v = acc[k];
+        if (minmax) {
+          // the weights sum to one, so the per-channel min-max commutes with the resize
+          const float mn = ordered_to_float(minmax[2 * row]), mx = ordered_to_float(minmax[2 * row + 1]);
+          v = mx > mn ? (v - mn) / (mx - mn) : 0.f;
+        }
+        out[((size_t)row * S + p) * S + o] = v;
       }
     }
+    return;
+  }
+  const int row_end = min(rows, row0 + RESIZE_PLANES);
+  for (int row = row0; row < row_end; ++row) {
+    const float* src = in + (size_t)row * H * W;
+    float acc = 0.f;
+    for (int jh = 0; jh < ah.size; ++jh) {
+      const float* line = src + (size_t)(ah.lo + jh) * W + aw.lo;
+      float hacc = 0.f;
+      for (int jw = 0; jw < aw.size; ++jw) hacc = fmaf(line[jw], aa_w(aw, jw) * iw, hacc);
+      acc = fmaf(hacc, aa_w(ah, jh) * ih, acc);
+    }
     if (minmax) {
-      // the weights sum to one, so the per-channel min-max commutes with the resize
       const float mn = ordered_to_float(minmax[2 * row]), mx = ordered_to_float(minmax[2 * row + 1]);
       acc = mx > mn ? (acc - mn) / (mx - mn) : 0.f;
     }

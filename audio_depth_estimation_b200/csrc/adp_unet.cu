@@ -303,11 +303,15 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     ProfScope eprof(PROF_ELEM, s, (double)rows * L.cout * p.esz * (L.bn_down ? 3.0 : 2.0));
     if (L.bn_down) {
       BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
-      if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, L.e), rows, L.cout, sums, s));
       const BnFin fin{sums, 1.0 / (double)rows, rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f, params[l].bn_down_w, params[l].bn_down_b, params[l].bn_down_rm, params[l].bn_down_rv,
                       d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd,
                       (l == 1 && center) ? cen_T : nullptr};
-      ADP_TRY(bn_affine_act(dt, at(ws, L.e), rows, L.cout, fin, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), s));
+      if (d->training && !fused && bn_small_ok(dt, rows, L.cout, 1)) {
+        ADP_TRY(bn_small_fwd(dt, at(ws, L.e), rows, L.cout, fin, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), s));
+      } else {
+        if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, L.e), rows, L.cout, sums, s));
+        ADP_TRY(bn_affine_act(dt, at(ws, L.e), rows, L.cout, fin, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), s));
+      }
     } else {
       ADP_TRY(affine_act(dt, at(ws, L.e), rows, L.cout, nullptr, nullptr, 0.f, at(ws, L.r), 0.f, nullptr, s));
     }
@@ -339,10 +343,14 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     if (folded) continue;
     ProfScope eprof(PROF_ELEM, s, (double)rows * L.t_cout * p.esz * 2.0);
     BnBuf bn = bnbuf(ws, L.bn_up_f, L.t_cout);
-    if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));
     const BnFin fin{sums, 1.0 / (double)rows, rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f, params[l].bn_up_w, params[l].bn_up_b, params[l].bn_up_rm, params[l].bn_up_rv,
                     d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd, nullptr};
-    ADP_TRY(bn_affine_act(dt, at(ws, O.t), rows, L.t_cout, fin, 0.f, at(ws, O.q), 0.f, nullptr, s));
+    if (d->training && !fused && bn_small_ok(dt, rows, L.t_cout, 1)) {
+      ADP_TRY(bn_small_fwd(dt, at(ws, O.t), rows, L.t_cout, fin, 0.f, at(ws, O.q), 0.f, nullptr, s));
+    } else {
+      if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));
+      ADP_TRY(bn_affine_act(dt, at(ws, O.t), rows, L.t_cout, fin, 0.f, at(ws, O.q), 0.f, nullptr, s));
+    }
   }
   {
     const LevelPlan& L = p.lv[0];
@@ -430,6 +438,9 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
     BnBuf bn = bnbuf(ws, U.bn_up_f, C);
     double* bs = reinterpret_cast<double*>(at(ws, U.bsums_up));
     ProfScope eprof(PROF_ELEM, s, (double)rows * C * p.esz * 3.0);      // x, g -> dx
+    if (bn_small_ok(dt, rows, C, 3))
+      return bn_small_bwd(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f, nullptr, 0.f,
+                          bn_mode, at(ws, L.g_t), grads[l + 1].bn_up_w, grads[l + 1].bn_up_b, bs, s);
     ADP_TRY(act_bn_bwd_reduce(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f,
                               nullptr, 0.f, bs, s));
     ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f,
@@ -510,11 +521,16 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       } else if (L.bn_down) {
         BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
         double* bs = reinterpret_cast<double*>(at(ws, L.bsums_down));
-        ADP_TRY(act_bn_bwd_reduce(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd,
-                                  at(ws, L.g_a), 0.2f, at(ws, L.g_r), 0.f, bs, s));
-        ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_a),
-                                 0.2f, at(ws, L.g_r), 0.f, bs, bn_mode, at(ws, L.g_e), grads[l].bn_down_w,
-                                 grads[l].bn_down_b, s));
+        if (bn_small_ok(dt, rows, L.cout, 3)) {
+          ADP_TRY(bn_small_bwd(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_a), 0.2f,
+                               at(ws, L.g_r), 0.f, bn_mode, at(ws, L.g_e), grads[l].bn_down_w, grads[l].bn_down_b, bs, s));
+        } else {
+          ADP_TRY(act_bn_bwd_reduce(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd,
+                                    at(ws, L.g_a), 0.2f, at(ws, L.g_r), 0.f, bs, s));
+          ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_a),
+                                   0.2f, at(ws, L.g_r), 0.f, bs, bn_mode, at(ws, L.g_e), grads[l].bn_down_w,
+                                   grads[l].bn_down_b, s));
+        }
       } else {  // level 0: no norm; e > 0 <=> r = ReLU(e) > 0 (a[0] may be stored centred, r[0] never is)
         ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.r), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_a), 0.2f,
                                  at(ws, L.g_r), 0.f, nullptr, 0, at(ws, L.g_e), nullptr, nullptr, s));

@@ -628,6 +628,55 @@ def test_fused_bn_statistics_match_the_standalone_pass():
     assert np.abs(stats[0] - stats[1]).max() <= 2e-3 * max(1.0, np.abs(stats[1]).max())   # (bf16 activations downstream)
 
 
+def test_config5_eval_inference_b64_vs_oracle_and_b1024_batch_invariance():
+    """BASELINE config 5 (test.py:231-241): eval-mode prediction from waveforms.  Under no_grad the running-statistics
+    BatchNorm and the activations run in the conv epilogues (adp_unet_desc.inference_only): B = 64 against the fp32 CPU
+    oracle (<= 2e-2) and against the unfolded eval forward; B = 1024 through a size-independent property -- eval-mode
+    predictions do not depend on what else is in the batch."""
+    from audio_depth_estimation_b200.models.unetbaseline_model import define_G
+    from audio_depth_estimation_b200.training import TrainStep
+    B, S, ngf, nd = 64, 256, 64, 8
+    wave, gt, sd, ref_x = _waveform_case(B, S, ngf, nd, seed=550)
+    rng = np.random.default_rng(551)
+    for k in sd:                                        # a "trained" network: non-trivial running statistics
+        if k.endswith("running_mean"):
+            sd[k] = torch.from_numpy(rng.normal(0, 0.05, sd[k].shape).astype(np.float32))
+        if k.endswith("running_var"):
+            sd[k] = torch.from_numpy(rng.uniform(0.5, 1.5, sd[k].shape).astype(np.float32))
+    torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
+    with torch.no_grad():
+        ref = uo.unet_forward(torch.from_numpy(ref_x), {k: v.clone() for k, v in sd.items()}, nd, False, training=False).numpy()
+    cfg = make_cfg(False, 30.0, S, "bf16")
+    net = define_G(cfg, 2, 1, ngf, "unet_256", "batch", False, gpu_ids=[0])
+    net.load_state_dict(uo.ordered_state_dict({k: v.clone() for k, v in sd.items()}, nd))
+    step = TrainStep(cfg, net, lr=0.002)
+    net.eval()
+    wd = cuda(wave)
+    lib = _lib.load()
+    with torch.no_grad():
+        y = net(step.features(wd))                      # (first call: weight casts, BatchNorm coefficients)
+        l0 = lib.adp_launch_count()
+        y2 = net(step.features(wd))                     # cached weight operands and BatchNorm coefficients
+        n_fold = lib.adp_launch_count() - l0
+    l0 = lib.adp_launch_count()
+    y_plain = net(step.features(wd)).detach()           # grad mode: raw conv outputs kept, separate BatchNorm passes
+    n_plain = lib.adp_launch_count() - l0
+    yv = y.cpu().numpy()
+    rel = float(np.linalg.norm(yv - ref) / np.linalg.norm(ref))
+    print("config 5, B = 64: rel L2 %.3e, max/max %.3e; launches folded %d vs unfolded %d" % (rel, rel_to_max(yv, ref), n_fold, n_plain))
+    assert rel <= 2e-2 and rel_to_max(yv, ref) <= 2e-2
+    assert n_fold < n_plain                             # the BatchNorm passes of the un-split layers are gone
+    assert rel_to_max(y2.cpu().numpy(), yv) <= 1e-2
+    assert float((y_plain - y).norm() / y.norm()) <= 1e-2
+    # B = 1024: the same 64 waveforms 16 times over
+    big = wd.repeat(16, 1, 1)
+    with torch.no_grad():
+        yb = net(step.features(big))
+    assert yb.shape == (1024, 1, S, S)
+    for j in (0, 7, 15):
+        assert float((yb[64 * j:64 * (j + 1)] - y).norm() / y.norm()) <= 1e-2, j
+
+
 def test_optimizer_vs_oracle_multi_step():
     from audio_depth_estimation_b200.models.unetbaseline_model import define_G
     from audio_depth_estimation_b200.optim import FusedClipAdamW
