@@ -134,7 +134,7 @@ class UnetSkipConnectionBlock(nn.Module):
 class _UnetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, anchor, gen):
-        y = gen._engine_forward(x)
+        y = gen._engine_forward(x, inference=False)      # (grad mode is off inside Function.forward: say it explicitly)
         ctx.gen = gen
         ctx.token = gen._fwd_token
         ctx.save_for_backward(x, y)
@@ -395,16 +395,16 @@ class UnetGenerator(nn.Module):
         x = x.contiguous()
         if torch.is_grad_enabled() and any(p.requires_grad for p in self._flat["params"]):
             return _UnetFunction.apply(x, self._anchor, self)
-        return self._engine_forward(x)
+        return self._engine_forward(x, inference=True)
 
-    def _engine_forward(self, x):
+    def _engine_forward(self, x, inference):
         lib = _lib.load()
         B, _, S, _ = x.shape
         versions = tuple(p._version for p in self._flat["params"])
         key = (B, S, self._dtype, x.device)
         reuse = (not self.training) and (not self._dirty) and self._wcache_key == (key, versions)
-        # eval mode under no_grad: nothing will be back-propagated, BatchNorm + activations fold into the conv epilogues
-        desc = self._desc(B, S, self.training, reuse, inference=not torch.is_grad_enabled())
+        # eval mode with nothing to back-propagate: BatchNorm + activations fold into the conv epilogues
+        desc = self._desc(B, S, self.training, reuse, inference=inference)
         if self._ws is None or self._ws_key != key:
             need = lib.adp_unet_workspace_bytes(ctypes.byref(desc))
             if need == 0:
