@@ -298,6 +298,14 @@ int center_tables(const double* xsum, double inv_count, const float* w1, int Cin
                   float* T, void* a0pad, int B, int H, int W, cudaStream_t s);
 // dw[n][tap][c] += m[c] * scale[n] * gsum[n]   (dw fp32 [N2][16][C])
 int center_wgrad_fix(float* dw, const float* m, const float* scale, const double* gsum, int N2, int C, cudaStream_t s);
+// thin layers with the patch tile built in shared memory (adp_thin_tc.cu): Cin = 2 (network input, hi/lo split) and
+// Cin = 1 (dL/du of the head), power-of-two output grids >= 16 wide
+bool thin_tc_supported(int B, int Cin, int H, int W);
+int thin_tc_first_conv(const float* x, const void* w_pad, void* a, float slope0, void* r, float slope1, const float* center,
+                       int pad_out, int B, int H, int W, cudaStream_t s);
+int thin_tc_first_wgrad(const float* x, const void* g_e, float* dw, int B, int H, int W, cudaStream_t s);
+int thin_tc_last_dgrad(const float* du, const void* w_pad, void* g0, void* g1, int B, int Hi, int Wi, cudaStream_t s);
+int thin_tc_last_wgrad(const void* x0, const void* x1, const float* du, float* dw, int B, int Hi, int Wi, cudaStream_t s);
 int thin_pad_rows(const float* src, void* dst, int R, int K, int dup, cudaStream_t s);
 int thin_fold_wgrad(const float* D, float* dw, int mode, int K, cudaStream_t s);
 // y[pix][n] = sum_c (x0|x1)[pix][c] * w_nk[n][c] over NHWC pixels (adp_conv_tc.cu)

@@ -713,7 +713,7 @@ int pick_splits(const IgemmParams& p, int block_n, bool have_scratch, size_t scr
   int splits = 1;
   const long long ctas = (long long)m_tiles * n_tiles * par;
   if ((have_scratch || p.f32_rows) && ctas < sm_count()) {
-    splits = (int)((sm_count() + ctas - 1) / ctas);
+    splits = (int)(sm_count() / ctas);       // (rounded down: tiles x splits stays within one wave of the persistent grid)
     const int max_by_k = p.kblocks / 4 > 0 ? p.kblocks / 4 : 1;
     if (splits > max_by_k) splits = max_by_k;
     if (splits > 32) splits = 32;

@@ -134,6 +134,12 @@ bool use_tc(int dtype) { return dtype == ADP_BF16 && tc_enabled(); }
 // separately by the per-family timers
 inline bool deep_level(int conv_out_side) { return conv_out_side <= 8; }
 
+int g_thin_fused = -1;    // "thin_fused" / ADP_THIN_FUSED=0: patch matrices in HBM + pointwise GEMMs (the route for Cin != 2)
+bool thin_fused_enabled() {
+  if (g_thin_fused < 0) g_thin_fused = getenv("ADP_THIN_FUSED") ? atoi(getenv("ADP_THIN_FUSED")) : 1;
+  return g_thin_fused != 0;
+}
+
 int g_center = -1;    // "center" / ADP_CENTER=0 switches the first-level centring off
 bool center_enabled() {
   if (g_center < 0) g_center = getenv("ADP_CENTER") ? atoi(getenv("ADP_CENTER")) : 1;
@@ -266,9 +272,15 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
         ex.center = cen_m;
         ex.pad_out = 1;
       }
-      ADP_TRY(thin_patch_rows(x, at(ws, p.xp0), B, L.cin, L.hin, L.hin, L.cin <= 2, s));
-      ADP_TRY(tc_pointwise(at(ws, p.xp0), 64, nullptr, 0, at(ws, p.w1pad), at(ws, L.a), 64, at(ws, L.r), 0, 1, 0.2f, 0.f, B,
-                           L.hout, L.hout, s, &ex));
+      if (thin_fused_enabled() && L.cin == 2 && thin_tc_supported(B, 2, L.hin, L.hin)) {
+        // (patch tile built in shared memory from the fp32 planes: no im2col matrix in HBM)
+        ADP_TRY(thin_tc_first_conv(x, at(ws, p.w1pad), at(ws, L.a), 0.2f, at(ws, L.r), 0.f, ex.center, ex.pad_out, B, L.hin,
+                                   L.hin, s));
+      } else {
+        ADP_TRY(thin_patch_rows(x, at(ws, p.xp0), B, L.cin, L.hin, L.hin, L.cin <= 2, s));
+        ADP_TRY(tc_pointwise(at(ws, p.xp0), 64, nullptr, 0, at(ws, p.w1pad), at(ws, L.a), 64, at(ws, L.r), 0, 1, 0.2f, 0.f, B,
+                             L.hout, L.hout, s, &ex));
+      }
     } else {
       ADP_TRY(first_conv_fprop(dt, x, params[0].conv_w, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), B, L.hin, L.hin, L.cin,
                                L.cout, s));
@@ -404,6 +416,11 @@ int unet_set_option(const char* name, int value) {
     g_center = value ? 1 : 0;
     return prev;
   }
+  if (!strcmp(name, "thin_fused")) {
+    const int prev = thin_fused_enabled() ? 1 : 0;
+    g_thin_fused = value ? 1 : 0;
+    return prev;
+  }
   if (strcmp(name, "side_stream")) return -1;
   if (g_side_stream < 0) g_side_stream = getenv("ADP_SIDE_STREAM") ? atoi(getenv("ADP_SIDE_STREAM")) : 1;
   const int prev = g_side_stream;
@@ -481,12 +498,18 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       ADP_TRY(head_bwd(y, dy, (long long)B * d->size * d->size, d->final_sigmoid, du, grads[0].convT_bias, s));
       if (thin_tc_bwd) {
         ProfScope prof(PROF_THIN, s, 4.0 * B * L.hout * L.hout * 16.0 * Ct);
-        float* Dt = reinterpret_cast<float*>(at(ws, p.dthin));
-        ADP_TRY(thin_patch_rows(du, at(ws, p.dp0), B, 1, d->size, d->size, 0, s));
-        ADP_TRY(tc_gemm_tn(at(ws, L.r), 64, 0, at(ws, L.q), 64, 0, at(ws, p.dp0), 64, 64, (long long)B * L.hout * L.hout, Dt, s));
-        ADP_TRY(thin_fold_wgrad(Dt, grads[0].convT_w, 0, 16, s));
-        ADP_TRY(tc_pointwise(at(ws, p.dp0), 64, nullptr, 0, at(ws, p.wLpad), at(ws, L.g_r), 64, at(ws, L.g_q), 64, 0, 0.f,
-                             0.f, B, L.hout, L.hout, s));
+        if (thin_fused_enabled() && L.cout == 64 && L.t_c1 == 64 && thin_tc_supported(B, 1, d->size, d->size)) {
+          ADP_CUDA(cudaMemsetAsync(grads[0].convT_w, 0, sizeof(float) * 16 * Ct, s));
+          ADP_TRY(thin_tc_last_wgrad(at(ws, L.r), at(ws, L.q), du, grads[0].convT_w, B, L.hout, L.hout, s));
+          ADP_TRY(thin_tc_last_dgrad(du, at(ws, p.wLpad), at(ws, L.g_r), at(ws, L.g_q), B, L.hout, L.hout, s));
+        } else {
+          float* Dt = reinterpret_cast<float*>(at(ws, p.dthin));
+          ADP_TRY(thin_patch_rows(du, at(ws, p.dp0), B, 1, d->size, d->size, 0, s));
+          ADP_TRY(tc_gemm_tn(at(ws, L.r), 64, 0, at(ws, L.q), 64, 0, at(ws, p.dp0), 64, 64, (long long)B * L.hout * L.hout, Dt, s));
+          ADP_TRY(thin_fold_wgrad(Dt, grads[0].convT_w, 0, 16, s));
+          ADP_TRY(tc_pointwise(at(ws, p.dp0), 64, nullptr, 0, at(ws, p.wLpad), at(ws, L.g_r), 64, at(ws, L.g_q), 64, 0, 0.f,
+                               0.f, B, L.hout, L.hout, s));
+        }
       } else {
         ADP_CUDA(cudaMemsetAsync(grads[0].convT_w, 0, sizeof(float) * 16 * Ct, s));
         ADP_TRY(last_convT_wgrad(dt, at(ws, L.r), L.cout, at(ws, L.q), L.t_c1, du, grads[0].convT_w, B, L.hout, L.hout, s));
@@ -540,11 +563,15 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, sw));
       if (l == 0 && thin_tc_bwd) {
         ProfScope prof(PROF_THIN, s, 2.0 * B * L.hout * L.hout * 16.0 * L.cin * L.cout);
-        float* Dt = reinterpret_cast<float*>(at(ws, p.dthin));
-        // pixel pairs folded into 128 "channels": D[(h,n)][(h',t)], the two diagonal blocks are the gradient
-        ADP_TRY(tc_gemm_tn(at(ws, L.g_e), 128, 0, at(ws, L.g_e), 128, 64, at(ws, p.xp0), 128, 128,
-                           (long long)B * L.hout * L.hout / 2, Dt, s));
-        ADP_TRY(thin_fold_wgrad(Dt, grads[0].conv_w, L.cin <= 2 ? 2 : 1, 16 * L.cin, s));
+        if (thin_fused_enabled() && L.cin == 2 && thin_tc_supported(B, 2, L.hin, L.hin)) {
+          ADP_TRY(thin_tc_first_wgrad(x, at(ws, L.g_e), grads[0].conv_w, B, L.hin, L.hin, s));     // (dw zeroed above)
+        } else {
+          float* Dt = reinterpret_cast<float*>(at(ws, p.dthin));
+          // pixel pairs folded into 128 "channels": D[(h,n)][(h',t)], the two diagonal blocks are the gradient
+          ADP_TRY(tc_gemm_tn(at(ws, L.g_e), 128, 0, at(ws, L.g_e), 128, 64, at(ws, p.xp0), 128, 128,
+                             (long long)B * L.hout * L.hout / 2, Dt, s));
+          ADP_TRY(thin_fold_wgrad(Dt, grads[0].conv_w, L.cin <= 2 ? 2 : 1, 16 * L.cin, s));
+        }
       } else if (l == 0) {
         ADP_TRY(first_conv_wgrad(dt, x, at(ws, L.g_e), grads[0].conv_w, B, L.hin, L.hin, L.cin, L.cout, s));
       } else {
@@ -613,4 +640,33 @@ extern "C" int adp_convT2d_k4s2_wgrad(int dtype, const void* x0, int c0, const v
                                       float* dw, int B, int Hin, int Win, int Cout, void* stream) {
   ADP_CHECK_ARG(x0 && dy && dw && (c1 == 0 || x1), "convT2d_wgrad: null pointer");
   return conv_wgrad(dtype, x0, c0, x1, c1, dy, Cout, dw, B, Hin, Win, (cudaStream_t)stream);
+}
+
+// ---- thin layers (adp_thin_tc.cu)
+extern "C" int adp_first_conv_k4s2_fprop(const float* x, const float* w1, void* w_scratch, void* a, float slope0, void* r,
+                                         float slope1, int B, int H, int W, void* stream) {
+  ADP_CHECK_ARG(x && w1 && w_scratch && a && r, "first_conv_fprop: null pointer");
+  ADP_CHECK_ARG(thin_tc_supported(B, 2, H, W), "first_conv_fprop: unsupported shape %dx%dx%d (power-of-two grid >= 16 wide on sm_100)", B, H, W);
+  cudaStream_t s = (cudaStream_t)stream;
+  ADP_TRY(thin_pad_rows(w1, w_scratch, 64, 32, 1, s));
+  return thin_tc_first_conv(x, w_scratch, a, slope0, r, slope1, nullptr, 0, B, H, W, s);
+}
+extern "C" int adp_first_conv_k4s2_wgrad(const float* x, const void* g_e, float* dw, int B, int H, int W, void* stream) {
+  ADP_CHECK_ARG(x && g_e && dw, "first_conv_wgrad: null pointer");
+  ADP_CHECK_ARG(thin_tc_supported(B, 2, H, W), "first_conv_wgrad: unsupported shape %dx%dx%d", B, H, W);
+  return thin_tc_first_wgrad(x, g_e, dw, B, H, W, (cudaStream_t)stream);
+}
+extern "C" int adp_last_convT_k4s2_dgrad(const float* du, const float* wT, void* w_scratch, void* g0, void* g1, int B, int Hi,
+                                         int Wi, void* stream) {
+  ADP_CHECK_ARG(du && wT && w_scratch && g0 && g1, "last_convT_dgrad: null pointer");
+  ADP_CHECK_ARG(thin_tc_supported(B, 1, 2 * Hi, 2 * Wi), "last_convT_dgrad: unsupported shape %dx%dx%d", B, Hi, Wi);
+  cudaStream_t s = (cudaStream_t)stream;
+  ADP_TRY(thin_pad_rows(wT, w_scratch, 128, 16, 0, s));
+  return thin_tc_last_dgrad(du, w_scratch, g0, g1, B, Hi, Wi, s);
+}
+extern "C" int adp_last_convT_k4s2_wgrad(const void* x0, const void* x1, const float* du, float* dw, int B, int Hi, int Wi,
+                                         void* stream) {
+  ADP_CHECK_ARG(x0 && x1 && du && dw, "last_convT_wgrad: null pointer");
+  ADP_CHECK_ARG(thin_tc_supported(B, 1, 2 * Hi, 2 * Wi), "last_convT_wgrad: unsupported shape %dx%dx%d", B, Hi, Wi);
+  return thin_tc_last_wgrad(x0, x1, du, dw, B, Hi, Wi, (cudaStream_t)stream);
 }

@@ -426,7 +426,9 @@ int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int 
   // one resident CTA per SM (160 KB of smem, all 512 TMEM columns): aim at ADP_WG_WAVES (default 1) full waves
   static int waves = getenv("ADP_WG_WAVES") ? atoi(getenv("ADP_WG_WAVES")) : 1;
   const int eff_waves = NT == 64 ? 2 * waves : waves;      // the narrow-N tiles are short: two waves balance better
-  int splits = (int)(((long long)eff_waves * sm_count() + ctas / 2) / ctas);
+  // (rounded down: 152 or 160 CTAs on 148 SMs cost a second, nearly empty wave -- E3 / E4 at B = 64)
+  static int round_near = getenv("ADP_WG_ROUND") ? atoi(getenv("ADP_WG_ROUND")) : 0;
+  int splits = (int)(((long long)eff_waves * sm_count() + (round_near ? ctas / 2 : 0)) / ctas);
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits < 1) splits = 1;
   p.kb_per_split = adp_cdiv(p.kblocks, splits);
@@ -472,7 +474,7 @@ int tc_wgrad3x3(const void* sgrad, int M, const void* g, int N, int ldn, int n_o
   }
   const int m_tiles = adp_cdiv(M, WG_M), n_tiles = N / NT;
   const long long ctas = (long long)m_tiles * n_tiles * 3;
-  int splits = (int)(((long long)(NT == 64 ? 2 : 1) * sm_count() + ctas / 2) / ctas);
+  int splits = (int)(((long long)(NT == 64 ? 2 : 1) * sm_count()) / ctas);
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits < 1) splits = 1;
   p.kb_per_split = adp_cdiv(p.kblocks, splits);

@@ -151,6 +151,21 @@ int adp_convT2d_k4s2_dgrad(int dtype, const void* dy, const float* w, const void
                            void* stream);
 int adp_convT2d_k4s2_wgrad(int dtype, const void* x0, int c0, const void* x1, int c1,
                            const void* dy, float* dw, int B, int Hin, int Win, int Cout, void* stream);
+/* The two thin layers of the U-Net on tensor cores, the im2col tile built in shared memory (bf16 storage, Cin = 2 /
+ * Cout = 1, power-of-two grids at least 16 wide): the outermost nn.Conv2d(2 -> 64, k4 s2 p1) with both activations of its
+ * output (models/unetbaseline_model.py:187, :195, :215 -- `a` feeds the next conv, `r` the skip), and the backward of the
+ * outermost nn.ConvTranspose2d(128 -> 1, k4 s2 p1) (:196).
+ *   x      fp32 NCHW [B,2,H,W] (kept to ~16 mantissa bits: hi/lo bf16 split);   w1 fp32 [64][16][2]
+ *   a, r   bf16 NHWC [B,H/2,W/2,64]: a = lrelu(conv, slope0), r = lrelu(conv, slope1)
+ *   du     fp32 [B,1,2Hi,2Wi] (rounded to bf16);   wT fp32 [128][16];   g0 | g1, x0 | x1: bf16 [B,Hi,Wi,64] halves
+ *   w_scratch: 16 KB of device memory for the padded bf16 weight operand;  dw: ACCUMULATED into (zero it first). */
+int adp_first_conv_k4s2_fprop(const float* x, const float* w1, void* w_scratch, void* a, float slope0, void* r,
+                              float slope1, int B, int H, int W, void* stream);
+int adp_first_conv_k4s2_wgrad(const float* x, const void* g_e, float* dw, int B, int H, int W, void* stream);
+int adp_last_convT_k4s2_dgrad(const float* du, const float* wT, void* w_scratch, void* g0, void* g1, int B, int Hi,
+                              int Wi, void* stream);
+int adp_last_convT_k4s2_wgrad(const void* x0, const void* x1, const float* du, float* dw, int B, int Hi, int Wi,
+                              void* stream);
 /* 1 = use tcgen05 kernels for bf16 tensors where supported (default), 0 = SIMT only.
  * Returns the previous setting.  (Also: environment ADP_TC=0.) */
 int adp_set_tensor_core(int on);
