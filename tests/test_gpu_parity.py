@@ -699,35 +699,39 @@ def test_thin_layer_kernels_vs_torch(B, H):
 @pytest.mark.parametrize("netG,size,batch", [("unet_256", 256, 2), ("unet_128", 128, 3), ("unet_256", 512, 1)])
 def test_thin_layers_patch_tiles_built_in_shared_memory(netG, size, batch):
     """E1 (Conv2d 2 -> 64) and D1 (ConvTranspose2d 128 -> 1) with the im2col tile built in shared memory from the fp32
-    planes ("thin_fused", adp_thin_tc.cu) against the route through a patch matrix in HBM: same operands in the same K
-    order (adp_thin_tc.cu; the kernels themselves are held to torch in test_thin_layer_kernels_vs_torch).  Through the
-    whole network the two routes agree like two runs of one route do: the BatchNorm sums are fp64 atomics in arrival
-    order, so single bf16 roundings flip from run to run (same bounds as the fused-statistics A/B above)."""
+    planes ("thin_fused", adp_thin_tc.cu; held to torch in test_thin_layer_kernels_vs_torch) against the route through a
+    patch matrix in HBM, inside the whole network with the first-level centring and the bordered a[0] tensor.  Eval-mode
+    BatchNorm (running statistics), so that no batch statistic amplifies the order of fp32 atomics: same operands in the
+    same K order give the same depth map; the gradients differ by the order of the split-K / weight-gradient sums."""
     lib = _lib.load()
-    case = (netG, 64, batch, size, False, 30.0, 930 + size, True, False)
+    case = (netG, 64, batch, size, False, 30.0, 930 + size, True, True)
     ys, gs = [], []
     for fused in (1, 0):
         prev = lib.adp_set_option(b"thin_fused", fused)
         assert prev in (0, 1)
         try:
             _, net, x, gt = build_case(case, "bf16")
-            net.train()
+            net.eval()
             y = net(x)
             y.backward(torch.ones_like(y) * 1e-3)
             ys.append(y.detach().cpu().numpy())
             gs.append({n: prm.grad.detach().double().cpu() for n, prm in net.named_parameters()})
         finally:
             lib.adp_set_option(b"thin_fused", prev)
-    assert np.isfinite(ys[0]).all()
-    assert float(np.linalg.norm(ys[0] - ys[1]) / np.linalg.norm(ys[1])) <= 5e-3 and rel_to_max(ys[0], ys[1]) <= 1.5e-2
+    assert np.isfinite(ys[0]).all() and np.abs(ys[0]).max() > 0
+    # (not bit-identical: the centring constant comes from fp64 atomics and the deep layers split K over atomics)
+    assert rel_to_max(ys[0], ys[1]) <= 8e-3, rel_to_max(ys[0], ys[1])
     names = list(gs[0])
     last_w = [n for n in names if gs[0][n].dim() == 4][-1]
     for n in names:
         a, b = gs[0][n], gs[1][n]
         if float(b.norm()) == 0:
             continue
-        rel = float((a - b).norm() / b.norm())
-        assert rel <= (1e-2 if n == last_w else 6e-2), (n, rel)      # (everything below D1 sees re-rounded bf16 gradients)
+        if n in (names[0], last_w):      # the thin layers' own weight gradients: same inputs up to the upstream roundings
+            assert float((a - b).norm() / b.norm()) <= 2e-2, (n, float((a - b).norm() / b.norm()))
+        else:                            # (the bottleneck layers amplify single bf16 flips at these tiny batches)
+            cos = float((a * b).sum() / max(float(a.norm() * b.norm()), 1e-30))
+            assert cos >= 0.98 and abs(float(a.norm() / b.norm()) - 1.0) <= 0.1, (n, cos, float(a.norm() / b.norm()))
 
 
 def test_config5_eval_inference_b64_vs_oracle_and_b1024_batch_invariance():
