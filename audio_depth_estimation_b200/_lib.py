@@ -81,6 +81,9 @@ SIGNATURES = {
     "adp_maxpool2_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "adp_upsample2x_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "adp_upsample2x_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "adp_bilinear_resize_forward": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "adp_bilinear_resize_backward": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "adp_pixel_shuffle2": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "adp_rows_op": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "adp_rows_reduce": (_i, [_i, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "adp_softmax_rows": (_i, [_vp, _i64, _i, _f, _vp, _vp, _vp, _vp]),

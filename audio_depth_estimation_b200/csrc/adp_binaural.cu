@@ -499,6 +499,89 @@ __global__ void rm_bias_kernel(float* __restrict__ rm, const float* __restrict__
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) out[c] = rm[c] + k * bias[c];
 }
+
+// ---- F.interpolate(mode='bilinear', align_corners=False) of fp32 planes (binaural_attention_model.py:322-328) ----------------
+// ATen's area_pixel_compute_source_index: src = max(0, (dst + 0.5) * in/out - 0.5); i0 = floor(src), i1 = min(i0 + 1, in - 1)
+__device__ __forceinline__ void bilinear_src(int d, float scale, int n_in, int& i0, int& i1, float& l1) {
+  float src = ((float)d + 0.5f) * scale - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > n_in - 1) i0 = n_in - 1;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+__global__ void __launch_bounds__(BT)
+bilinear_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int Hi, int Wi, int Ho, int Wo,
+                    float sh, float sw) {
+  const long long total = planes * Ho * Wo;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(o % Wo);
+    const long long r = o / Wo;
+    const int oy = (int)(r % Ho);
+    const long long pl = r / Ho;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(oy, sh, Hi, y0, y1, ly);
+    bilinear_src(ox, sw, Wi, x0, x1, lx);
+    const float* src = x + pl * Hi * Wi;
+    const float top = (1.f - lx) * src[(size_t)y0 * Wi + x0] + lx * src[(size_t)y0 * Wi + x1];
+    const float bot = (1.f - lx) * src[(size_t)y1 * Wi + x0] + lx * src[(size_t)y1 * Wi + x1];
+    y[o] = (1.f - ly) * top + ly * bot;
+  }
+}
+// dx zeroed by the caller
+__global__ void __launch_bounds__(BT)
+bilinear_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long long planes, int Hi, int Wi, int Ho, int Wo,
+                    float sh, float sw) {
+  const long long total = planes * Ho * Wo;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(o % Wo);
+    const long long r = o / Wo;
+    const int oy = (int)(r % Ho);
+    const long long pl = r / Ho;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(oy, sh, Hi, y0, y1, ly);
+    bilinear_src(ox, sw, Wi, x0, x1, lx);
+    float* dst = dx + pl * Hi * Wi;
+    const float g = dy[o];
+    atomicAdd(dst + (size_t)y0 * Wi + x0, (1.f - ly) * (1.f - lx) * g);
+    atomicAdd(dst + (size_t)y0 * Wi + x1, (1.f - ly) * lx * g);
+    atomicAdd(dst + (size_t)y1 * Wi + x0, ly * (1.f - lx) * g);
+    atomicAdd(dst + (size_t)y1 * Wi + x1, ly * lx * g);
+  }
+}
+
+// ---- nn.ConvTranspose2d(k2, s2) (:65-66) = one GEMM with N' = 4 N columns (a, b, n) per input pixel + this shuffle -----------
+// forward: ys [B,H,W,2,2,N] (+ bias[n]) -> y [B,2H,2W,N];  backward: dy [B,2H,2W,N] -> dys [B,H,W,2,2,N]
+__global__ void __launch_bounds__(BT)
+pixel_shuffle2_kernel(const bf16* __restrict__ src, const float* __restrict__ bias, bf16* __restrict__ dst, int B, int H, int W,
+                      int N, int inverse) {
+  const int n8 = N / 8;
+  const long long total = (long long)B * H * W * 4 * n8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % n8);
+    long long r = i / n8;
+    const int ab = (int)(r & 3);
+    r >>= 2;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H);
+    const long long b = r / H;
+    const size_t packed = (size_t)i * 8;                                                                     // [b,y,x,a,bb,n]
+    const size_t spread = ((((size_t)b * 2 * H + 2 * y + (ab >> 1)) * (2 * W)) + 2 * x + (ab & 1)) * N + c8 * 8;   // [b,2y+a,2x+bb,n]
+    if (inverse) {
+      *reinterpret_cast<uint4*>(dst + packed) = *reinterpret_cast<const uint4*>(src + spread);
+    } else {
+      float8 v = ld8(src + packed);
+      if (bias) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v.v[k] += bias[c8 * 8 + k];
+      }
+      st8(dst + spread, v);
+    }
+  }
+}
 }  // namespace
 
 #define ADP_LAUNCH(kernel, grid, smem, s, ...)          \
@@ -585,6 +668,27 @@ extern "C" int adp_upsample2x_forward(const void* x, void* y, int B, int H, int 
 extern "C" int adp_upsample2x_backward(const void* dy, void* dx, int B, int H, int W, int C, void* stream) {
   ADP_CHECK_ARG(dy && dx && B > 0 && H > 0 && W > 0 && C % 8 == 0, "upsample2x_backward: bad arguments");
   ADP_LAUNCH(upsample2_bwd_kernel, grid_for((long long)B * H * W * (C / 8)), 0, (cudaStream_t)stream, (const bf16*)dy, (bf16*)dx, B, H, W, C);
+  return ADP_OK;
+}
+
+extern "C" int adp_bilinear_resize_forward(const float* x, float* y, int64_t planes, int Hi, int Wi, int Ho, int Wo, void* stream) {
+  ADP_CHECK_ARG(x && y && planes > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bilinear_resize_forward: bad arguments");
+  ADP_LAUNCH(bilinear_fwd_kernel, grid_for((long long)planes * Ho * Wo), 0, (cudaStream_t)stream, x, y, (long long)planes, Hi, Wi,
+             Ho, Wo, (float)Hi / (float)Ho, (float)Wi / (float)Wo);
+  return ADP_OK;
+}
+extern "C" int adp_bilinear_resize_backward(const float* dy, float* dx, int64_t planes, int Hi, int Wi, int Ho, int Wo, void* stream) {
+  ADP_CHECK_ARG(dy && dx && planes > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bilinear_resize_backward: bad arguments");
+  ADP_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)planes * Hi * Wi, (cudaStream_t)stream));
+  ADP_LAUNCH(bilinear_bwd_kernel, grid_for((long long)planes * Ho * Wo), 0, (cudaStream_t)stream, dy, dx, (long long)planes, Hi, Wi,
+             Ho, Wo, (float)Hi / (float)Ho, (float)Wi / (float)Wo);
+  return ADP_OK;
+}
+extern "C" int adp_pixel_shuffle2(const void* src, const float* bias, void* dst, int B, int H, int W, int N, int inverse,
+                                  void* stream) {
+  ADP_CHECK_ARG(src && dst && B > 0 && H > 0 && W > 0 && N > 0 && N % 8 == 0, "pixel_shuffle2: bad arguments");
+  ADP_LAUNCH(pixel_shuffle2_kernel, grid_for((long long)B * H * W * 4 * (N / 8)), 0, (cudaStream_t)stream, (const bf16*)src, bias,
+             (bf16*)dst, B, H, W, N, inverse);
   return ADP_OK;
 }
 

@@ -16,8 +16,11 @@ through the C ABI:
                                     instead of transposing
   head (:262-265, :318-332)         adp_depth_head_{forward,backward}
 
-Restrictions of this first version: bilinear=True, bf16 only, H = W = a power of two with H/16 >= 8 (every attention
-level needs a multiple of 64 tokens), base_channels a multiple of 64, output_size == input size.
+  Up, bilinear=False (:65-66)       adp_gemm_rows_bf16 (4N columns per input pixel) + adp_pixel_shuffle2
+  output resize (:322-328)          adp_bilinear_resize_{forward,backward} (F.interpolate, align_corners=False)
+
+Restrictions: bf16 only, H = W = a power of two with H/16 >= 8 (every attention level needs a multiple of 64 tokens; the
+F.pad of :72-73 is then a no-op), base_channels a multiple of 64.
 """
 import math
 
@@ -339,6 +342,72 @@ class _Residual(torch.autograd.Function):
         return dy, datt, dgamma
 
 
+class _ConvT2x2(torch.autograd.Function):
+    """nn.ConvTranspose2d(C, N, kernel_size=2, stride=2) of the bilinear=False decoder (reference :65-66):
+    y[b, 2i+a, 2j+c, n] = bias[n] + sum_k x[b, i, j, k] W[k][n][a][c].  Stride = kernel: the four taps never overlap, so
+    the layer is ONE row GEMM with 4N columns (a, c, n) per input pixel on the tensor cores plus a pixel shuffle."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        B, H, W, C = x.shape
+        N = weight.shape[1]
+        rows = B * H * W
+        lib = _lib.load()
+        wcat = weight.detach().permute(0, 2, 3, 1).reshape(C, 4 * N).to(_BF16).contiguous()     # [K = C][N' = (a, c, n)]
+        ys = torch.empty((rows, 4 * N), device=x.device, dtype=_BF16)
+        _lib.check(lib.adp_gemm_rows_bf16(x.data_ptr(), C, None, 0, wcat.data_ptr(), 1, ys.data_ptr(), 4 * N, None, 0, None, rows, _sp()))
+        y = torch.empty((B, 2 * H, 2 * W, N), device=x.device, dtype=_BF16)
+        _lib.check(lib.adp_pixel_shuffle2(ys.data_ptr(), _ptr(bias), y.data_ptr(), B, H, W, N, 0, _sp()))
+        ctx.save_for_backward(x, wcat)
+        ctx.has_bias = bias is not None
+        ctx.wshape = tuple(weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wcat = ctx.saved_tensors
+        B, H, W, C = x.shape
+        N = ctx.wshape[1]
+        rows = B * H * W
+        lib = _lib.load()
+        dy = dy.contiguous()
+        dys = torch.empty((rows, 4 * N), device=dy.device, dtype=_BF16)
+        _lib.check(lib.adp_pixel_shuffle2(dy.data_ptr(), None, dys.data_ptr(), B, H, W, N, 1, _sp()))
+        dx = torch.empty_like(x)          # dx[row][k] = sum_n' dys[row][n'] wcat[k][n']: wcat is the [N = C][K = 4N] "NT" operand
+        _lib.check(lib.adp_gemm_rows_bf16(dys.data_ptr(), 4 * N, None, 0, wcat.data_ptr(), 0, dx.data_ptr(), C, None, 0, None, rows, _sp()))
+        dwcat = torch.zeros((C, 4 * N), device=dy.device, dtype=torch.float32)
+        _lib.check(lib.adp_gemm_tn_bf16(x.data_ptr(), C, dys.data_ptr(), 4 * N, dwcat.data_ptr(), 4 * N, rows, _sp()))
+        dw = dwcat.view(C, 2, 2, N).permute(0, 3, 1, 2).contiguous()
+        db = None
+        if ctx.has_bias:
+            dbp = torch.empty(4 * N, device=dy.device, dtype=torch.float32)
+            ws = torch.empty(8 * N, device=dy.device, dtype=torch.float64)
+            _lib.check(lib.adp_rows_reduce(0, dys.data_ptr(), None, rows, 4 * N, dbp.data_ptr(), ws.data_ptr(), _sp()))
+            db = dbp.view(4, N).sum(0)
+        return dx, dw, db
+
+
+class _Interp(torch.autograd.Function):
+    """F.interpolate(depth, size=(S, S), mode='bilinear', align_corners=False) (reference :322-328), fp32 planes."""
+
+    @staticmethod
+    def forward(ctx, y, size):
+        B, C, H, W = y.shape
+        y = y.contiguous()
+        out = torch.empty((B, C, size, size), device=y.device, dtype=torch.float32)
+        _lib.check(_lib.load().adp_bilinear_resize_forward(y.data_ptr(), out.data_ptr(), B * C, H, W, size, size, _sp()))
+        ctx.shape = (B, C, H, W, size)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, C, H, W, size = ctx.shape
+        dy = dy.contiguous().float()
+        dx = torch.empty((B, C, H, W), device=dy.device, dtype=torch.float32)
+        _lib.check(_lib.load().adp_bilinear_resize_backward(dy.data_ptr(), dx.data_ptr(), B * C, H, W, size, size, _sp()))
+        return dx, None
+
+
 class _Head(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, max_depth):
@@ -410,15 +479,21 @@ class Up(nn.Module):
 
     def __init__(self, in_channels, out_channels, bilinear=True):
         super().__init__()
-        if not bilinear:
-            raise NotImplementedError("bilinear=False (ConvTranspose2d k2 s2 upsampling, reference :65-66) is not built")
-        self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
-        self.conv = DoubleConv(in_channels, out_channels, in_channels // 2)
+        if bilinear:
+            self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+            self.conv = DoubleConv(in_channels, out_channels, in_channels // 2)
+        else:
+            self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+            self.conv = DoubleConv(in_channels, out_channels)
 
     def run(self, x1, x2, training):
-        x1 = _Upsample2.apply(x1)
+        if isinstance(self.up, nn.ConvTranspose2d):
+            x1 = _ConvT2x2.apply(x1, self.up.weight, self.up.bias)
+        else:
+            x1 = _Upsample2.apply(x1)
         if x1.shape[1:3] != x2.shape[1:3]:
-            raise NotImplementedError("odd feature sizes (the F.pad of reference :72-73) are not built")
+            # (the F.pad of reference :72-73 only acts on sizes that are not multiples of 16; forward() admits powers of two)
+            raise NotImplementedError("feature sizes that are not multiples of 16 (the F.pad of reference :72-73) are not built")
         return self.conv.run(x2, x1, training)          # torch.cat([x2, x1], dim=1) read as two tensors
 
 
@@ -540,8 +615,6 @@ class BinauralAttentionDepthNet(nn.Module):
         S = x.shape[-1]
         if S & (S - 1) or S < 128:
             raise NotImplementedError("input size must be a power of two >= 128 (every attention level needs >= 64 tokens)")
-        if S != self.output_size:
-            raise NotImplementedError("output_size != input size (the final F.interpolate, reference :322-328) is not built")
         x = x.contiguous()
         training = self.training
         left = self.left_encoder.run(x, 0, training)
@@ -558,7 +631,12 @@ class BinauralAttentionDepthNet(nn.Module):
         y = self.up2.run(y, fused[3], training)
         y = self.up3.run(y, fused[2], training)
         y = self.up4.run(y, fused[1], training)
-        return _Head.apply(y, self.outc[0].weight, self.outc[0].bias, float(self.max_depth))
+        depth = _Head.apply(y, self.outc[0].weight, self.outc[0].bias, float(self.max_depth))
+        if depth.shape[-1] != self.output_size:
+            depth = _Interp.apply(depth, int(self.output_size))
+        # (torch.clamp(depth, 0, max_depth) of :331 is the identity here: sigmoid * max_depth lies inside the range and the
+        # bilinear weights are a convex combination)
+        return depth
 
     def get_num_params(self):
         return sum(p.numel() for p in self.parameters() if p.requires_grad)

@@ -269,6 +269,13 @@ int adp_maxpool2_backward(const void* x, const void* dy, void* dx, int B, int Ho
  * backward is the exact adjoint in gather form (no atomics). */
 int adp_upsample2x_forward(const void* x, void* y, int B, int H, int W, int C, void* stream);
 int adp_upsample2x_backward(const void* dy, void* dx, int B, int H, int W, int C, void* stream);
+/* F.interpolate(mode='bilinear', align_corners=False) of fp32 planes [planes,Hi,Wi] -> [planes,Ho,Wo]
+ * (the output resize of :322-328); backward = exact adjoint (dx is zeroed, then accumulated with atomics). */
+int adp_bilinear_resize_forward(const float* x, float* y, int64_t planes, int Hi, int Wi, int Ho, int Wo, void* stream);
+int adp_bilinear_resize_backward(const float* dy, float* dx, int64_t planes, int Hi, int Wi, int Ho, int Wo, void* stream);
+/* nn.ConvTranspose2d(k2, s2) (:65-66, bilinear=False) is one row GEMM with 4N columns (a, b, n) per input pixel plus this
+ * rearrangement: inverse = 0: src bf16 [B,H,W,2,2,N] (+ bias[n], may be NULL) -> dst [B,2H,2W,N]; inverse = 1: the reverse copy. */
+int adp_pixel_shuffle2(const void* src, const float* bias, void* dst, int B, int H, int W, int N, int inverse, void* stream);
 /* bf16 row helpers ([rows][C]).  adp_rows_op: 0: x += bias[c] (a == y, g = bias);
  * 1: y = a + g[0]*b (:134 residual with the learnable gamma); 2: y = a + b; 3: y = g[0]*a.
  * adp_rows_reduce: 0: out[c] = sum_r a[r][c] (bias gradients; sums_ws double [2C]);

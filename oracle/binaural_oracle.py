@@ -7,7 +7,8 @@ gen_binaural): forward, autograd gradients and the eval forward.
 
 Follows models/binaural_attention_model.py:
 * DoubleConv :22-39      conv3x3(p=1, no bias) -> BN -> ReLU, twice
-* Down :42-53, Up :56-78 MaxPool2d(2); bilinear x2 (align_corners=True), pad, cat([skip, up]), DoubleConv(in, out, in // 2)
+* Down :42-53, Up :56-78 MaxPool2d(2); bilinear x2 (align_corners=True) or, bilinear=False, ConvTranspose2d(k2, s2) (taken
+  when the state_dict holds up{i}.up.weight); pad, cat([skip, up]), DoubleConv(in, out, in // 2 | out)
 * BinauralCrossAttention :81-153   shared q/k/v/out 1x1 convs, softmax(q^T k / sqrt(C)), residual scaled by gamma
 * BinauralAttentionDepthNet.forward :279-334   two encoders, attention at `attention_levels`, fusion 1x1 + BN + ReLU,
   decoder, sigmoid head * max_depth, (interpolate to output_size), clamp
@@ -105,7 +106,10 @@ def forward(sd, x, attention_levels=(2, 3, 4, 5), max_depth=30.0, output_size=No
         fused[lv] = _bn_relu(e, sd, stem + ".1", training, update_running)
     y = fused[5]
     for name, skip in (("up1", 4), ("up2", 3), ("up3", 2), ("up4", 1)):
-        y = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True)
+        if name + ".up.weight" in sd:        # bilinear=False (:65-66): ConvTranspose2d(in, in // 2, kernel_size=2, stride=2)
+            y = F.conv_transpose2d(y, sd[name + ".up.weight"], sd[name + ".up.bias"], stride=2)
+        else:
+            y = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True)
         s = fused[skip]
         dy_, dx_ = s.shape[2] - y.shape[2], s.shape[3] - y.shape[3]
         y = F.pad(y, [dx_ // 2, dx_ - dx_ // 2, dy_ // 2, dy_ - dy_ // 2])

@@ -277,10 +277,45 @@ def gen_binaural():
     print("binaural.npz", {k: v.shape for k, v in out.items()})
 
 
+def gen_binaural_ct():
+    """BASELINE config 4, the other decoder: bilinear=False (ConvTranspose2d k2 s2 up-sampling, :65-66) and an output_size
+    that differs from the input (the F.interpolate of :322-328).  Same recipe as gen_binaural; weights from the
+    reference's own initialisation under torch.manual_seed(0)."""
+    from models.binaural_attention_model import BinauralAttentionDepthNet
+    out = {}
+    torch.manual_seed(0)
+    net = BinauralAttentionDepthNet(base_channels=64, bilinear=False, output_size=96, max_depth=30.0, attention_levels=[4, 5])
+    with torch.no_grad():
+        for m in net.attention_modules.values():
+            m.gamma.fill_(0.5)
+        net.outc[0].weight.mul_(0.1)
+        net.outc[0].bias.fill_(-1.2)
+    x = torch.from_numpy(synthetic.feature_like(2, 128, seed=311))
+    r = torch.from_numpy(np.random.default_rng(312).normal(0, 1, (2, 1, 96, 96)).astype(np.float32))
+    net.train()
+    y = net(x)
+    (y * r).sum().backward()
+    out["y"] = y.detach().numpy()
+    names, norms, heads = [], [], []
+    for k, p_ in net.named_parameters():
+        g = p_.grad.detach().reshape(-1)
+        names.append(k)
+        norms.append(float(g.double().norm()))
+        heads.append(np.pad(g[:64].numpy(), (0, max(0, 64 - g.numel()))))
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array(norms)
+    out["grad_heads"] = np.stack(heads)
+    net.eval()
+    with torch.no_grad():
+        out["y_eval"] = net(x).numpy()
+    np.savez_compressed(os.path.join(OUT, "binaural_ct.npz"), **out)
+    print("binaural_ct.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["feature", "feature_mel", "metrics", "loss", "unet", "binaural"]
     for name in which:
         {"feature": gen_feature, "feature_mel": gen_feature_mel, "metrics": gen_metrics, "loss": gen_loss,
-         "unet": gen_unet, "binaural": gen_binaural}[name]()
+         "unet": gen_unet, "binaural": gen_binaural, "binaural_ct": gen_binaural_ct}[name]()

@@ -178,6 +178,79 @@ def test_binaural_attention_net_matches_reference(golden_dir, name, levels, batc
     assert rel(ye, torch.from_numpy(g[name + "_y_eval"]).cuda()) <= 4e-2
 
 
+def test_binaural_transposed_conv_decoder_and_output_resize_match_reference(golden_dir):
+    """bilinear=False (ConvTranspose2d k2 s2 up-sampling, reference :65-66) and output_size != input size (the
+    F.interpolate of :322-328) against the unmodified reference (oracle/gen_golden.py gen_binaural_ct)."""
+    import os
+    from audio_depth_estimation_b200 import synthetic
+    from audio_depth_estimation_b200.models.binaural_attention_model import BinauralAttentionDepthNet
+    g = np.load(os.path.join(golden_dir, "binaural_ct.npz"))
+    torch.manual_seed(0)
+    net = BinauralAttentionDepthNet(base_channels=64, bilinear=False, output_size=96, max_depth=30.0, attention_levels=[4, 5])
+    with torch.no_grad():
+        for m in net.attention_modules.values():
+            m.gamma.fill_(0.5)
+        net.outc[0].weight.mul_(0.1)
+        net.outc[0].bias.fill_(-1.2)
+    net = net.cuda()
+    x = torch.from_numpy(synthetic.feature_like(2, 128, seed=311)).cuda()
+    r = torch.from_numpy(np.random.default_rng(312).normal(0, 1, (2, 1, 96, 96)).astype(np.float32)).cuda()
+    net.train()
+    y = net(x)
+    (y * r).sum().backward()
+    want = torch.from_numpy(g["y"]).cuda()
+    assert y.shape == want.shape and rel(y.detach(), want) <= 4e-2, rel(y.detach(), want)
+    names, norms, heads = list(g["grad_names"]), g["grad_norms"], g["grad_heads"]
+    params = dict(net.named_parameters())
+    assert list(params) == names
+    for i, k in enumerate(names):
+        gr = params[k].grad
+        assert gr is not None and torch.isfinite(gr).all(), k
+        if norms[i] < 1e-4 * norms.max() or k.endswith(".gamma"):
+            continue
+        n = float(gr.double().norm())
+        assert abs(n - norms[i]) <= (0.35 if params[k].dim() == 1 else 0.2) * norms[i], (k, n, float(norms[i]))
+        if k.endswith("weight") and params[k].numel() >= 64 and k.startswith(("outc", "up4", "up3.up")):
+            got = gr.reshape(-1)[:64].double().cpu().numpy()
+            ref = heads[i][:64].astype(np.float64)
+            cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
+            assert cos >= 0.9, (k, cos)
+    net.eval()
+    with torch.no_grad():
+        ye = net(x)
+    assert rel(ye, torch.from_numpy(g["y_eval"]).cuda()) <= 4e-2
+
+
+def test_transposed_conv_k2s2_and_bilinear_resize_ops_vs_torch():
+    """The two new operators of config 4 against torch fp32 on bf16-rounded operands."""
+    bam = _fn()
+    gen = torch.Generator().manual_seed(77)
+    B, H, C, N = 3, 8, 128, 64
+    x = torch.randn(B, H, H, C, generator=gen).cuda().to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(C, N, 2, 2, generator=gen) * 0.05).cuda().requires_grad_(True)
+    b = (torch.randn(N, generator=gen) * 0.1).cuda().requires_grad_(True)
+    dy = torch.randn(B, 2 * H, 2 * H, N, generator=gen).cuda().to(torch.bfloat16)
+    y = bam._ConvT2x2.apply(x, w, b)
+    y.backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.detach().to(torch.bfloat16).float().requires_grad_(True)
+    br = b.detach().clone().requires_grad_(True)
+    yr = torch.nn.functional.conv_transpose2d(xr, wr, br, stride=2)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel(y.detach().float().permute(0, 3, 1, 2), yr.detach()) <= 1e-2
+    assert rel(x.grad.float().permute(0, 3, 1, 2), xr.grad) <= 1e-2
+    assert rel(w.grad, wr.grad) <= 2e-3 and rel(b.grad, br.grad) <= 2e-3
+    for hin, hout in ((128, 96), (128, 256), (64, 100)):
+        d = (torch.rand(2, 1, hin, hin, generator=gen) * 30).cuda().requires_grad_(True)
+        gy = torch.randn(2, 1, hout, hout, generator=gen).cuda()
+        out = bam._Interp.apply(d, hout)
+        out.backward(gy)
+        dr = d.detach().clone().requires_grad_(True)
+        ref = torch.nn.functional.interpolate(dr, size=(hout, hout), mode="bilinear", align_corners=False)
+        ref.backward(gy)
+        assert rel(out.detach(), ref.detach()) <= 1e-6 and rel(d.grad, dr.grad) <= 1e-5
+
+
 def _fn():
     from audio_depth_estimation_b200.models import binaural_attention_model as bam
     return bam

@@ -249,3 +249,36 @@ def test_binaural_oracle_matches_reference(golden_dir, name, levels):
     with torch.no_grad():
         ye = bo.forward(sd, x, levels, 30.0, training=False)
     assert rel_to_max(ye.numpy(), g[name + "_y_eval"]) <= 1e-4
+
+
+def test_binaural_oracle_transposed_conv_decoder_and_resize(golden_dir):
+    """bilinear=False + output_size != input size (reference :65-66, :322-328): oracle/binaural_oracle.forward on the
+    reference's own initial weights against tests/golden/binaural_ct.npz (gen_golden.py gen_binaural_ct)."""
+    from audio_depth_estimation_b200.models.binaural_attention_model import BinauralAttentionDepthNet
+    from oracle import binaural_oracle as bo
+    g = np.load(os.path.join(golden_dir, "binaural_ct.npz"))
+    torch.manual_seed(0)
+    net = BinauralAttentionDepthNet(64, False, 96, 30.0, [4, 5])      # parameter container only (CPU)
+    with torch.no_grad():
+        for m in net.attention_modules.values():
+            m.gamma.fill_(0.5)
+        net.outc[0].weight.mul_(0.1)
+        net.outc[0].bias.fill_(-1.2)
+    sd = {k: v.detach().clone().contiguous() for k, v in net.state_dict().items()}
+    for k, v in sd.items():
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(True)
+    x = torch.from_numpy(synthetic.feature_like(2, 128, seed=311))
+    r = torch.from_numpy(np.random.default_rng(312).normal(0, 1, (2, 1, 96, 96)).astype(np.float32))
+    torch.set_num_threads(8)
+    y = bo.forward(sd, x, (4, 5), 30.0, output_size=96, training=True, update_running=True)
+    assert y.shape == (2, 1, 96, 96) and rel_to_max(y.detach().numpy(), g["y"]) <= 1e-4
+    (y * r).sum().backward()
+    norms = g["grad_norms"]
+    for i, k in enumerate(list(g["grad_names"])):
+        if norms[i] < 1e-4 * norms.max():
+            continue
+        assert abs(float(sd[k].grad.double().norm()) - norms[i]) <= 2e-3 * norms[i], k
+    with torch.no_grad():
+        ye = bo.forward(sd, x, (4, 5), 30.0, output_size=96, training=False)
+    assert rel_to_max(ye.numpy(), g["y_eval"]) <= 1e-4

@@ -13,7 +13,7 @@ def load(path):
 
 def one_step(rows):
     idx = [i for i, r in enumerate(rows) if "stft_mag" in r["Kernel Name"] or "stft_frames" in r["Kernel Name"]]
-    return rows[idx[0]:idx[1]] if len(idx) >= 2 else rows
+    return rows[idx[-2]:idx[-1]] if len(idx) >= 2 else rows       # the last complete step (a CUDA-graph replay in bench.py)
 
 
 def short(name):
