@@ -24,8 +24,7 @@ class UnetDesc(C.Structure):
     _fields_ = [("batch", C.c_int), ("in_ch", C.c_int), ("out_ch", C.c_int), ("ngf", C.c_int),
                 ("num_downs", C.c_int), ("size", C.c_int), ("dtype", C.c_int),
                 ("final_sigmoid", C.c_int), ("training", C.c_int), ("bn_eps", C.c_float),
-                ("bn_momentum", C.c_float), ("reuse_weight_cache", C.c_int), ("inference_only", C.c_int),
-                ("grad_sumsq", C.c_void_p)]
+                ("bn_momentum", C.c_float), ("reuse_weight_cache", C.c_int), ("inference_only", C.c_int)]
 
 
 _LEVEL_SLOTS = ("conv_w", "convT_w", "convT_bias", "bn_down_w", "bn_down_b", "bn_down_rm", "bn_down_rv",

@@ -193,16 +193,6 @@ int conv_wgrad(int dtype, const void* s0, int M0, const void* s1, int M1, const 
   return simt_wgrad(dtype, s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s);
 }
 
-// sum of squares of one freshly written weight gradient into the caller's accumulator (adp_unet_desc.grad_sumsq)
-int add_grad_sumsq(const adp_unet_desc* d, float* dw, size_t n, cudaStream_t s) {
-  if (!d->grad_sumsq) return ADP_OK;
-  adp_tensor_ref r;
-  memset(&r, 0, sizeof(r));
-  r.g = dw;
-  r.n = (long long)n;
-  return adp_grad_sumsq(&r, 1, d->grad_sumsq, s);
-}
-
 int check_params(const adp_unet_desc* d, const Plan& p, const adp_unet_level* params) {
   ADP_CHECK_ARG(params, "unet: null params");
   for (int l = 0; l < p.D; ++l) {
@@ -502,7 +492,6 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       const LevelPlan& L = p.lv[0];
       const int Ct = L.cout + L.t_c1;
       ADP_CUDA(cudaMemsetAsync(at(ws, p.bsums_begin), 0, p.bsums_end - p.bsums_begin, s));
-      if (d->grad_sumsq) ADP_CUDA(cudaMemsetAsync(d->grad_sumsq, 0, sizeof(double), s));
       float* du = reinterpret_cast<float*>(at(ws, p.du));
       ADP_CHECK_ARG(grads[0].convT_bias, "unet_backward: level 0 convT bias gradient missing");
       ADP_CUDA(cudaMemsetAsync(grads[0].convT_bias, 0, sizeof(float), s));
@@ -538,7 +527,6 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         ADP_CUDA(cudaMemsetAsync(grads[l].convT_w, 0, sizeof(float) * 16 * (size_t)Ct * L.t_cout, sw));
         ADP_TRY(conv_wgrad(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, at(ws, O.g_t), L.t_cout,
                            grads[l].convT_w, B, L.hout, L.hout, sw, 0, deep_level(O.hout)));
-        ADP_TRY(add_grad_sumsq(d, grads[l].convT_w, (size_t)16 * Ct * L.t_cout, sw));
       }
       ADP_TRY(conv_gather(dt, at(ws, O.g_t), params[l].convT_w, tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, L.g_r),
                           L.cout, L.t_c1 ? at(ws, L.g_q) : nullptr, L.t_c1, B, O.hout, O.hout, L.t_cout, s, nullptr,
@@ -596,7 +584,6 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
           ADP_TRY(center_wgrad_fix(grads[l].conv_w, reinterpret_cast<const float*>(at(ws, p.center_m)), bn.scale,
                                    reinterpret_cast<const double*>(at(ws, L.bsums_down)), L.cout, L.cin, sw));
         }
-        ADP_TRY(add_grad_sumsq(d, grads[l].conv_w, (size_t)16 * L.cout * L.cin, sw));
         ADP_TRY(conv_parity(dt, at(ws, L.g_e), L.cout, nullptr, 0, params[l].conv_w, tc ? w16(params[l].conv_w_bf16, L.wb_conv) : nullptr,
                             at(ws, I.g_a), B, L.hout, L.hout, L.cin, s, nullptr, deep_level(L.hout)));
       }

@@ -169,8 +169,6 @@ class UnetGenerator(nn.Module):
         self.set_precision(prec)
         # engine state (not parameters / buffers: state_dict stays identical to the reference's)
         self._flat = None
-        self._grad_sumsq = None
-        self._grad_sumsq_fresh = False
         self._ws = None
         self._ws_key = None
         self._fwd_token = 0
@@ -311,11 +309,6 @@ class UnetGenerator(nn.Module):
         self._flat = dict(p=flat_p, g=flat_g, params=params, offs=offs, ptrs=[p.data_ptr() for p in params],
                           gviews=[self._view_like(flat_g, o, p) for p, o in zip(params, offs)],
                           stage_slices=stage_slices, tail=(tail_begin, off), m=None, v=None, step=0)
-        # (adp_unet_desc.grad_sumsq covers conv / convT weights of levels >= 1: usable when exactly those form the bulk)
-        lv = self.levels()
-        hidden = [lv[i][k].weight for i in range(1, len(lv)) for k in ("conv", "convT")]
-        outer = [lv[0]["conv"].weight, lv[0]["convT"].weight]
-        self._flat["sumsq_overlap_ok"] = all(self._is_bulk(w) for w in hidden) and not any(self._is_bulk(w) for w in outer)
         for lv in self.levels():
             for bn in (lv["bn_down"], lv["bn_up"]):
                 if bn is not None:
@@ -450,11 +443,6 @@ class UnetGenerator(nn.Module):
             dy = dy.float()
         params, grads = self._level_array(False, self._fwd_mirror), self._level_array(True)
         groups = self.stage_groups or [(0, 2 * self.num_downs)]
-        # the optimiser's sum-of-squares accumulator: the hidden layers' weight gradients add themselves as they are written
-        # (only when this rank's gradients are final after backward, i.e. no reducer hook rewrites them)
-        acc = self._grad_sumsq if (self.grad_ready_hook is None and f["sumsq_overlap_ok"]) else None
-        desc.grad_sumsq = acc.data_ptr() if acc is not None else None
-        self._grad_sumsq_fresh = False
         with torch.cuda.device(x.device):
             for gi, (b, e) in enumerate(groups):
                 _lib.check(lib.adp_unet_backward_stages(ctypes.byref(desc), x.data_ptr(), y.data_ptr(), dy.data_ptr(),
@@ -462,21 +450,9 @@ class UnetGenerator(nn.Module):
                                                         _lib.stream_ptr()))
                 if self.grad_ready_hook is not None:
                     self.grad_ready_hook(gi)
-        self._grad_sumsq_fresh = acc is not None
         for p, g in zip(f["params"], f["gviews"]):
             if p.requires_grad:
                 p.grad = g
-
-    def attach_grad_sumsq(self, acc):
-        """acc: float64[1] CUDA tensor (or None).  Every backward pass then leaves the sum of squares of the bulk (hidden-layer
-        weight) gradients in it; FusedClipAdamW adds the tail and skips its own pass over the flat gradient buffer."""
-        self._grad_sumsq = acc
-        self._grad_sumsq_fresh = False
-
-    def take_grad_sumsq(self):
-        """True once per backward pass that filled the attached accumulator."""
-        fresh, self._grad_sumsq_fresh = self._grad_sumsq_fresh, False
-        return fresh
 
     # ------------------------------------------------------------------ state_dict compatibility
     def load_state_dict(self, state_dict, strict=True, assign=False):

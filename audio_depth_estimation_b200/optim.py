@@ -6,8 +6,6 @@ by two kernels over the flat fp32 parameter / gradient / moment buffers (adp_gra
 adp_clip_adamw_step).  Defaults are torch.optim.AdamW's: betas (0.9, 0.999), eps 1e-8, weight
 decay 0.01 on every parameter.
 """
-import os
-
 import torch
 
 from . import _lib
@@ -64,8 +62,6 @@ class FusedClipAdamW(_LrShim):
                 st["m"].copy_(old["m"])
                 st["v"].copy_(old["v"])
             self._state = st
-            if self.reducer is None and hasattr(self.model, "attach_grad_sumsq") and os.environ.get("ADP_SUMSQ_OVERLAP", "1") != "0":
-                self.model.attach_grad_sumsq(st["sumsq"])      # backward leaves the bulk of the global norm here
         # bf16 models: the update also writes bf16(p) into the model's mirror, which replaces the per-forward casts
         self._mirrored = getattr(self.model, "precision", None) == "bf16" and hasattr(self.model, "bf16_mirror")
         mirror = self.model.bf16_mirror() if self._mirrored else None
@@ -91,18 +87,11 @@ class FusedClipAdamW(_LrShim):
         red = self.reducer
         with torch.cuda.device(p.device):
             s = _lib.stream_ptr()
+            st["sumsq"].zero_()
             if red is None:
                 every, n = refs([(0, p.numel())])
-                if hasattr(self.model, "take_grad_sumsq") and self.model.take_grad_sumsq():
-                    # the hidden layers' weight gradients were summed as they were written (adp_unet_desc.grad_sumsq):
-                    # only the tail (BatchNorm parameters, bias, thin layers) is left
-                    tail, n_tail = refs([self.model.tail_slice()])
-                    _lib.check(lib.adp_grad_sumsq(tail, n_tail, st["sumsq"].data_ptr(), s))
-                else:
-                    st["sumsq"].zero_()
-                    _lib.check(lib.adp_grad_sumsq(every, n, st["sumsq"].data_ptr(), s))
+                _lib.check(lib.adp_grad_sumsq(every, n, st["sumsq"].data_ptr(), s))
             else:
-                st["sumsq"].zero_()
                 # global norm: this rank's pieces summed over the ranks, plus the (replicated) tail once
                 own, n_own = refs(red.owned_pieces())
                 _lib.check(lib.adp_grad_sumsq(own, n_own, st["sumsq"].data_ptr(), s))

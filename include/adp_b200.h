@@ -188,10 +188,6 @@ typedef struct adp_unet_desc {
   int inference_only;     /* 1 (with training = 0): no backward pass will follow -- eval-mode BatchNorm scale/shift and the
                            * activations are applied in the convolution epilogues (test.py:231-241) and the workspace
                            * does not keep the raw convolution outputs the backward pass would need */
-  double* grad_sumsq;     /* optional (NULL = off), backward only: one double.  Zeroed when backward stage 0 starts; every
-                           * weight gradient of the hidden layers (conv_w / convT_w of levels >= 1) adds its sum of squares
-                           * right after it is written, on the stream that wrote it -- the bulk of clip_grad_norm_'s global
-                           * norm (train.py:689) then costs no extra pass over 218 MB of gradients on the critical path */
 } adp_unet_desc;
 
 typedef struct adp_unet_level {      /* level 0 = outermost block */

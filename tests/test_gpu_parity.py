@@ -806,33 +806,6 @@ def test_optimizer_vs_oracle_multi_step():
         assert np.abs(flat_p.cpu().numpy() - ref_p[0].numpy()).max() <= 1e-6
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32"])
-def test_gradient_norm_accumulated_during_backward_equals_the_full_pass(precision):
-    """adp_unet_desc.grad_sumsq: every hidden layer's weight gradient adds its sum of squares as it is written (on the
-    weight-gradient side stream); FusedClipAdamW adds the tail.  The clip norm it then reports must equal the norm of the
-    flat gradient buffer (torch), and a step() without a fresh backward must fall back to the full pass."""
-    from audio_depth_estimation_b200.optim import FusedClipAdamW
-    case = ("unet_128", 64, 3, 128, False, 30.0, 940, True, False) if precision == "bf16" else ("unet_128", 16, 2, 128, False, 30.0, 941, True, False)
-    _, net, x, gt = build_case(case, precision)
-    net.train()
-    opt = FusedClipAdamW(net, lr=0.0, weight_decay=0.0, max_norm=1.0)        # lr 0: the weights do not move
-    net(x)
-    opt._buffers()                                                             # attaches the accumulator
-    lib = _lib.load()
-    for rep in range(2):
-        y = net(x)
-        y.backward(torch.ones_like(y) * 1e-2)
-        flat_g = net.flat_buffers()[1]
-        want = float(flat_g.double().norm())
-        l0 = lib.adp_launch_count()
-        got = float(opt.step().item())
-        n_fast = lib.adp_launch_count() - l0
-        assert abs(got - want) <= 1e-5 * want, (got, want)
-        l0 = lib.adp_launch_count()
-        again = float(opt.step().item())                                      # no backward in between: full pass
-        assert lib.adp_launch_count() - l0 >= n_fast and abs(again - want) <= 1e-5 * want
-
-
 def test_train_step_end_to_end_loss_decreases():
     """waveform -> feature -> U-Net -> loss -> backward -> clip+AdamW, a few steps on one batch."""
     from audio_depth_estimation_b200.models.unetbaseline_model import define_G
