@@ -94,6 +94,11 @@ struct IgemmParams {
   int epi, stat_by_col;
   float escale;
   int* stat_m; float* stat_l; const float* delta; const bf16* pmat;
+  // 1 x 1 bottleneck (E8 / D8 at the innermost level): a 4x4 stride-2 window over a 2 x 2 input only ever sees taps
+  // (1..2, 1..2), a transposed conv from one input pixel uses one tap per output parity -- the other 12 taps multiply the
+  // zero padding, so their k-blocks (75 % of the weight bytes) are skipped
+  unsigned tap_lut;                   // mode 0: nibble i = i-th tap to visit (0 = all 16 in order)
+  int one_tap;                        // mode 1: the single valid tap (th, tw) = (1 - pa, 1 - pb) per parity class
   int halo;                           // 0, or the HALO instantiation: 4 = parity mode, 3 = 3x3 rows
   int wmode;                          // modes 2/4: 1 = weights through the MN-major 3-D map (N | taps | Ct), taps reversed
   int f32_rows;                       // modes 2/4: write fp32 [pixels][N] to out_f32 instead of bf16 (any BLOCK_N)
@@ -261,13 +266,14 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
           } else if (p.mode == 0) {
             // 4x4 stride-2 window over the (2C | W/2 | row parity | H/2 | B) view: tap row kh -> (row offset, row parity)
             // = kh:0 (-1,1) 1 (0,0) 2 (0,1) 3 (+1,0); with an explicit border (pad_in) row 2oy+kh -> (kh >> 1, kh & 1)
-            const int kh = tap >> 2, kw = tap & 3;
+            const int atap = p.tap_lut ? (int)((p.tap_lut >> (4 * tap)) & 15u) : tap;
+            const int kh = atap >> 2, kw = atap & 3;
             const int di = p.pad_in ? (kh >> 1) : (kh + 1) / 2 - 1, ra = p.pad_in ? (kh & 1) : (kh + 1) & 1;
             const int dj = p.pad_in ? (kw >> 1) : (kw + 1) / 2 - 1, rb = p.pad_in ? (kw & 1) : (kw + 1) & 1;
             tma_load_5d(a_dst, &p.tmA0, &full_bar[s], rb * p.Ct + ch, c.x0 + dj, ra, c.y0c + di, c.b0);
-            tma_load_2d(b_dst, &p.tmW, &full_bar[s], tap * p.Ct + ch, c.n0);
+            tma_load_2d(b_dst, &p.tmW, &full_bar[s], atap * p.Ct + ch, c.n0);
           } else if (p.mode == 1) {
-            const int th = tap >> 1, tw = tap & 1;
+            const int th = p.one_tap ? 1 - c.pa : tap >> 1, tw = p.one_tap ? 1 - c.pb : tap & 1;
             const int cx = c.x0 + c.pb - 1 + tw, cy = c.y0c + c.pa - 1 + th;
             if (ch < p.C0) tma_load_4d(a_dst, &p.tmA0, &full_bar[s], ch, cx, cy, c.b0);
             else tma_load_4d(a_dst, &p.tmA1, &full_bar[s], ch - p.C0, cx, cy, c.b0);
@@ -647,6 +653,16 @@ int pick_block_n(int N, int N0, int N1) {
   return 0;
 }
 
+// The deepest, weight-streaming layers (a handful of 128-pixel tiles, K split over the SMs): 128-wide N tiles halve what
+// every CTA streams and reduces, and double the CTAs that share a K range (measured per launch at B = 64: E6 17.9 -> 14.7 us,
+// E7 13.6 -> 10.4, D7 14.4 -> 11.5; from 64 tiles up -- E5, D6 -- the 256-wide tile wins again, as it does on every large layer)
+int narrow_block_n_for_few_tiles(int bn, int m_tiles_x_par, int N, int N0, int N1) {
+  if (bn != 256 || g_max_block_n < 256) return bn;
+  if ((long long)m_tiles_x_par * (N / 256) > sm_count() / 4) return bn;
+  if (N % 128 != 0 || (N1 != 0 && N0 % 128 != 0)) return bn;
+  return 128;
+}
+
 bool tile_geometry(int B, int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
   if (!pow2(Hs) || !pow2(Ws)) return false;
   *Wt = Ws < TILE_M ? Ws : TILE_M;
@@ -660,6 +676,7 @@ bool tile_geometry(int B, int Hs, int Ws, int* Wt, int* Ht, int* Bt) {
 int g_halo = 1;            // "tc_halo" / ADP_TC_HALO: 0 = one TMA box per tap, 1 = halo windows (narrow-N parity and 3x3 layers)
 int g_stats = 1;           // "tc_stats" / ADP_TC_STATS: BatchNorm statistics accumulated by the convolution epilogue
 int g_alt = 1;             // "tc_alt" / ADP_TC_ALT: two alternating epilogue groups for the thin pointwise layers
+int g_skip_pad_taps = 1;   // "tc_skip_pad_taps" / ADP_TC_SKIP_PAD_TAPS: 1 x 1 bottleneck layers visit only the taps that see data
 
 template <int BLOCK_N, int EG, bool ATT, int HALO, bool ALT = false>
 int launch_persist(const IgemmParams& p, int ctas, cudaStream_t s) {
@@ -766,6 +783,8 @@ struct TcEnvInit {
     if (se) g_stats = atoi(se);
     const char* ae = getenv("ADP_TC_ALT");
     if (ae) g_alt = atoi(ae);
+    const char* pe = getenv("ADP_TC_SKIP_PAD_TAPS");
+    if (pe) g_skip_pad_taps = atoi(pe);
   }
 } g_tc_env_init;
 
@@ -803,6 +822,7 @@ int tc_set_option(const char* name, int value) {
   if (!strcmp(name, "tc_halo")) slot = &g_halo;
   else if (!strcmp(name, "tc_stats")) slot = &g_stats;
   else if (!strcmp(name, "tc_alt")) slot = &g_alt;
+  else if (!strcmp(name, "tc_skip_pad_taps")) slot = &g_skip_pad_taps;
   else if (!strcmp(name, "tc_max_bn")) slot = &g_max_block_n;
   if (!slot) return -1;
   const int prev = *slot;
@@ -837,13 +857,18 @@ int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, 
   memset(&p, 0, sizeof(p));
   const int Ho = Hi / 2, Wo = Wi / 2, N = N0 + N1;
   ADP_CHECK_ARG(tile_geometry(B, Ho, Wo, &p.Wt, &p.Ht, &p.Bt), "tc_gather_conv: unsupported spatial size %dx%d", Hi, Wi);
-  const int bn = pick_block_n(N, N0, N1);
+  int bn = pick_block_n(N, N0, N1);
   ADP_CHECK_ARG(bn != 0 && C % TILE_K == 0, "tc_gather_conv: unsupported channels C=%d N0=%d N1=%d", C, N0, N1);
   p.tiles_w = Wo / p.Wt; p.tiles_h = Ho / p.Ht;
+  if (g_scratch) bn = narrow_block_n_for_few_tiles(bn, p.tiles_w * p.tiles_h * adp_cdiv(B, p.Bt), N, N0, N1);
   p.B = B; p.Hs = Ho; p.Ws = Wo; p.mode = 0; p.C0 = C; p.C1 = 0; p.Ct = C; p.N = N; p.N0 = N0; p.N1 = N1;
   p.kblocks = 16 * (C / TILE_K);
   p.y0 = (bf16*)y0; p.y1 = (bf16*)y1;
   p.pad_in = ex && ex->pad_in ? 1 : 0;
+  if (Ho == 1 && Wo == 1 && !p.pad_in && g_skip_pad_taps) {      // taps 5, 6, 9, 10 = (kh, kw) in {1, 2} x {1, 2}
+    p.tap_lut = 0xA965u;
+    p.kblocks = 4 * (C / TILE_K);
+  }
   {  // x viewed as (2C | Wi/2 | 2 | Hi/2 | B); with an explicit border the tensor is [B, Hi+2, Wi+2, C]
     const int Hp = Hi + 2 * p.pad_in, Wp = Wi + 2 * p.pad_in;
     uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)Wp / 2, 2, (uint64_t)Hp / 2, (uint64_t)B};
@@ -870,8 +895,9 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   ADP_CHECK_ARG(tile_geometry(B, Hi, Wi, &p.Wt, &p.Ht, &p.Bt), "tc_parity_convT: unsupported spatial size %dx%d", Hi, Wi);
-  const int bn = pick_block_n(N, N, 0);
+  int bn = pick_block_n(N, N, 0);
   ADP_CHECK_ARG(bn >= 64 && C0 % TILE_K == 0 && C1 % TILE_K == 0, "tc_parity_convT: unsupported channels");
+  if (g_scratch) bn = narrow_block_n_for_few_tiles(bn, (Wi / p.Wt) * (Hi / p.Ht) * adp_cdiv(B, p.Bt) * 4, N, N, 0);
   const int Ct = C0 + C1;
   // narrow-N layers are bound by L2 -> SM operand traffic: load the tile's input window once per channel chunk (HALO)
   const bool halo = g_halo && (bn == 64 || bn == 128) && Hi >= 16 && Wi >= 8 && Hi % 16 == 0 && Wi % 8 == 0 &&
@@ -880,6 +906,10 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
   p.tiles_w = Wi / p.Wt; p.tiles_h = Hi / p.Ht;
   p.B = B; p.Hs = Hi; p.Ws = Wi; p.mode = 1; p.C0 = C0; p.C1 = C1; p.Ct = Ct; p.N = N; p.N0 = N; p.N1 = 0;
   p.kblocks = (halo ? 1 : 4) * (Ct / TILE_K);
+  if (Hi == 1 && Wi == 1 && !halo && g_skip_pad_taps) {
+    p.one_tap = 1;
+    p.kblocks = Ct / TILE_K;
+  }
   p.y0 = (bf16*)y; p.y1 = nullptr;
   for (int h = 0; h < 2; ++h) {
     const int C = h == 0 ? C0 : C1;

@@ -37,6 +37,7 @@ struct WgradParams {
   int taps_total;     // 16 or 9
   int ldn, n_off;     // dw row pitch per tap (total input channels) and column offset of this G tensor
   int g_pad;          // 4x4 mode: G carries an explicit one-pixel border (row 2i+kh of the padded tensor, never out of bounds)
+  int skip_edge_rows; // 4x4 mode, Hs == 1 without a border: kernel rows 0 and 3 are all padding
 };
 
 template <int NT>
@@ -69,6 +70,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   const int m0 = blockIdx.x * WG_M;
   const int n0 = blockIdx.y * NT;
   const int kh = blockIdx.z % NTAPS;             // tap group = kernel row
+  // 4x4 stride-2 window over a two-row G (the 1 x 1 bottleneck): kernel rows 0 and 3 only meet the zero padding, their
+  // gradient is exactly zero and dw is zeroed by the caller
+  if (!K3 && p.skip_edge_rows && (kh == 0 || kh == 3)) return;
   const int split = blockIdx.z / NTAPS;
   const int kb_begin = split * p.kb_per_split;
   const int kb_end = min(kb_begin + p.kb_per_split, p.kblocks);
@@ -414,6 +418,7 @@ int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int 
     ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmS0 : &p.tmS1, h == 0 ? s0 : s1, 4, dims, str, box));
   }
   p.g_pad = g_pad ? 1 : 0;
+  p.skip_edge_rows = (Hs == 1 && !p.g_pad) ? 1 : 0;
   {  // G [B, 2Hs, 2Ws, N] viewed as (2N | Ws | 2 | Hs | B); with a border: [B, 2Hs+2, 2Ws+2, N] as (2N | Ws+1 | 2 | Hs+1 | B)
     const int Hg = 2 * Hs + 2 * p.g_pad, Wg = 2 * Ws + 2 * p.g_pad;
     uint64_t dims[5] = {(uint64_t)2 * N, (uint64_t)Wg / 2, 2, (uint64_t)Hg / 2, (uint64_t)B};
