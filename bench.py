@@ -325,7 +325,7 @@ def run_ours(args):
         # idle time lands between a family's start event and its kernel.  The profiled steps therefore run BEHIND a spin
         # kernel that keeps the GPU busy while the host enqueues the whole step; the kernels then execute back to back, as
         # they do in the replayed graph, and the event brackets hold device time only.
-        spin_cycles = int(1.5 * (ms_eager / args.steps) * 1e-3 * 2.0e9)
+        spin_cycles = int(min(1.5 * (ms_eager / args.steps), 20.0) * 1e-3 * 2.0e9)      # (capped: under a profiler steps take seconds)
         lib.adp_profile_enable(1)
         for _ in range(args.steps):
             torch.cuda._sleep(spin_cycles)

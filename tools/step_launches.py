@@ -12,6 +12,8 @@ def load(path):
         name = re.sub(r"^void ", "", name)
         name = re.sub(r"adp::<unnamed>::|adp::\(anonymous namespace\)::", "", name)
         name = re.sub(r"\(.*$", "", name)
+        if "spin_kernel" in name:
+            continue
         rows.append((name[:52], row["Grid Size"].replace(" ", ""), float(row["Metric Value"]) / 1000.0))
     starts = [i for i, r in enumerate(rows) if r[0].startswith("stft_frames_kernel")]
     if len(starts) >= 2:
