@@ -143,8 +143,11 @@ def test_new_host_entry_points_refuse_cpu_and_unsupported_configs(tmp_path):
         FusedClipAdamWParams([torch.nn.Parameter(torch.zeros(4))])
     with pytest.raises(NotImplementedError):
         BinauralAttentionDepthNet(base_channels=32)
-    with pytest.raises(NotImplementedError):
-        Up(128, 64, bilinear=False)
+    up = Up(128, 64, bilinear=False)          # round 2: the transposed-conv decoder is built (reference :65-67)
+    assert isinstance(up.up, torch.nn.ConvTranspose2d) and up.up.weight.shape == (128, 64, 2, 2)
+    assert up.conv.double_conv[0].weight.shape == (64, 128, 3, 3)
+    sd_ct = BinauralAttentionDepthNet(64, False, 96, 30.0, [5]).state_dict()
+    assert sd_ct["up1.up.weight"].shape == (1024, 512, 2, 2) and sd_ct["left_encoder.down4.maxpool_conv.1.double_conv.3.weight"].shape[0] == 1024
     assert checkpoint_path("exp", 3, root=str(tmp_path)).endswith(os.path.join("exp", "checkpoint_3.pth"))
     # every conv weight of the mirror lives in channels_last memory (the layout the kernels read), also after .to()/.float()
     net = BinauralAttentionDepthNet(64, True, 128, 30.0, [5]).float()
