@@ -432,8 +432,7 @@ int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int 
   static int waves = getenv("ADP_WG_WAVES") ? atoi(getenv("ADP_WG_WAVES")) : 1;
   const int eff_waves = NT == 64 ? 2 * waves : waves;      // the narrow-N tiles are short: two waves balance better
   // (rounded down: 152 or 160 CTAs on 148 SMs cost a second, nearly empty wave -- E3 / E4 at B = 64)
-  static int round_near = getenv("ADP_WG_ROUND") ? atoi(getenv("ADP_WG_ROUND")) : 0;
-  int splits = (int)(((long long)eff_waves * sm_count() + (round_near ? ctas / 2 : 0)) / ctas);
+  int splits = (int)(((long long)eff_waves * sm_count()) / ctas);
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits < 1) splits = 1;
   p.kb_per_split = adp_cdiv(p.kblocks, splits);
