@@ -96,6 +96,7 @@ SIGNATURES = {
     "adp_depth_head_backward": (_i, [_vp, _vp, _vp, _f, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
     "adp_first_conv_k4s2_fprop": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _f, _i, _i, _i, _vp]),
     "adp_first_conv_k4s2_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "adp_first_conv_k4s2_wgrad_act": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp]),
     "adp_last_convT_k4s2_dgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "adp_last_convT_k4s2_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "adp_set_option": (_i, [C.c_char_p, _i]),

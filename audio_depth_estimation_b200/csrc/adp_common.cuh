@@ -304,6 +304,8 @@ bool thin_tc_supported(int B, int Cin, int H, int W);
 int thin_tc_first_conv(const float* x, const void* w_pad, void* a, float slope0, void* r, float slope1, const float* center,
                        int pad_out, int B, int H, int W, cudaStream_t s);
 int thin_tc_first_wgrad(const float* x, const void* g_e, float* dw, int B, int H, int W, cudaStream_t s);
+int thin_tc_first_wgrad_act(const float* x, const void* gA, const void* gB, const void* r, float slope, float* dw, int B, int H,
+                            int W, cudaStream_t s);
 int thin_tc_last_dgrad(const float* du, const void* w_pad, void* g0, void* g1, int B, int Hi, int Wi, cudaStream_t s);
 int thin_tc_last_wgrad(const void* x0, const void* x1, const float* du, float* dw, int B, int Hi, int Wi, cudaStream_t s);
 int thin_pad_rows(const float* src, void* dst, int R, int K, int dup, cudaStream_t s);

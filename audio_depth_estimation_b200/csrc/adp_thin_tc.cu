@@ -348,21 +348,24 @@ constexpr int TW_THREADS = 192;             // warp 0 TMA, warp 1 MMA, warps 2-5
 constexpr int TW_STAGES = 3;
 
 struct ThinWgradParams {
-  CUtensorMap tmImg, tmS0, tmS1;
+  CUtensorMap tmImg, tmS0, tmS1, tmS2;
+  float slope;                              // ACT: S = gA * (r > 0 ? 1 : slope) + (r > 0 ? gB : 0), formed in shared memory
   int B, Ho, Wo, CW, RH, BW, BH;
   int tiles_x, tiles_y, ntiles;
   float* dw;
   uint32_t box_bytes;
 };
 
-template <bool FOLD>
+template <bool FOLD, bool ACT = false>
 struct ThinWgradSmem {
   static constexpr int KROWS = FOLD ? 64 : 128;
   static constexpr int HALF = KROWS * 128;                 // one [KROWS][64] bf16 region
   static constexpr int A_BYTES = 2 * HALF;
   static constexpr int B_BYTES = (FOLD ? 2 : 1) * HALF;
-  static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int OFF_X = TW_STAGES * STAGE;
+  static constexpr int EXTRA = ACT ? 2 * A_BYTES : 0;      // ACT: the tiles of gB and r next to gA's (which becomes S in place)
+  static constexpr int STAGE = A_BYTES + B_BYTES + EXTRA;
+  static constexpr int STAGES = ACT ? 2 : TW_STAGES;
+  static constexpr int OFF_X = STAGES * STAGE;
   static constexpr int OFF_BAR = OFF_X + TP_XS * TP_XSTAGE;
   static constexpr int BYTES = OFF_BAR + 256 + 1024;
   static constexpr int NT = FOLD ? 128 : 64;
@@ -372,9 +375,11 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, flo
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool FOLD>
+template <bool FOLD, bool ACT = false>
 __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const __grid_constant__ ThinWgradParams p) {
-  using S = ThinWgradSmem<FOLD>;
+  static_assert(!ACT || FOLD, "the fused activation backward belongs to the first conv's weight gradient");
+  using S = ThinWgradSmem<FOLD, ACT>;
+  constexpr int STAGES = S::STAGES;
   constexpr int KSTEPS = S::KROWS / 16;
   constexpr int NT = S::NT;
   extern __shared__ unsigned char smem_raw[];
@@ -382,9 +387,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* x_full = bars;                  // [XS]
   uint64_t* x_empty = x_full + TP_XS;       // [XS]
-  uint64_t* full = x_empty + TP_XS;         // [STAGES]  TMA bytes of S + the 4 builder warps
+  uint64_t* full = x_empty + TP_XS;         // [STAGES]  TMA bytes of S + the 4 builder warps (ACT: the builder warps only)
   uint64_t* empty = full + TW_STAGES;       // [STAGES]
-  uint64_t* accum_bar = empty + TW_STAGES;
+  uint64_t* loaded = empty + TW_STAGES;     // [STAGES]  ACT: the three source tiles have landed
+  uint64_t* accum_bar = loaded + TW_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int worker = (int)blockIdx.x, nworkers = (int)gridDim.x;
@@ -392,9 +398,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
   if (threadIdx.x == 0) {
     prefetch_tmap(&p.tmImg);
     prefetch_tmap(&p.tmS0);
-    if (!FOLD) prefetch_tmap(&p.tmS1);
+    if (!FOLD || ACT) prefetch_tmap(&p.tmS1);
+    if (ACT) prefetch_tmap(&p.tmS2);
     for (int s = 0; s < TP_XS; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 4); }
-    for (int s = 0; s < TW_STAGES; ++s) { mbar_init(&full[s], 5); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], ACT ? 4 : 5); mbar_init(&empty[s], 1); mbar_init(&loaded[s], 1); }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
@@ -416,6 +423,19 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
         if (++sx == TP_XS) { sx = 0; phx ^= 1u; }
         mbar_wait(&empty[s], ph ^ 1);
         unsigned char* a_dst = smem + s * S::STAGE;
+        if (ACT) {
+          mbar_expect_tx(&loaded[s], 3 * S::A_BYTES);
+          unsigned char* e_dst = a_dst + S::A_BYTES + S::B_BYTES;
+          const int cx = tx * (p.CW / 2), cy = b * p.Ho + ty * p.RH;
+          tma_load_3d(a_dst, &p.tmS0, &loaded[s], 0, cx, cy);
+          tma_load_3d(a_dst + S::HALF, &p.tmS0, &loaded[s], 64, cx, cy);
+          tma_load_3d(e_dst, &p.tmS1, &loaded[s], 0, cx, cy);
+          tma_load_3d(e_dst + S::HALF, &p.tmS1, &loaded[s], 64, cx, cy);
+          tma_load_3d(e_dst + S::A_BYTES, &p.tmS2, &loaded[s], 0, cx, cy);
+          tma_load_3d(e_dst + S::A_BYTES + S::HALF, &p.tmS2, &loaded[s], 64, cx, cy);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+          continue;
+        }
         mbar_expect_tx(&full[s], S::A_BYTES);
         if (FOLD) {
           tma_load_3d(a_dst, &p.tmS0, &full[s], 0, tx * (p.CW / 2), b * p.Ho + ty * p.RH);
@@ -424,7 +444,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
           tma_load_3d(a_dst, &p.tmS0, &full[s], 0, tx * p.CW, b * p.Ho + ty * p.RH);
           tma_load_3d(a_dst + S::HALF, &p.tmS1, &full[s], 0, tx * p.CW, b * p.Ho + ty * p.RH);
         }
-        if (++s == TW_STAGES) { s = 0; ph ^= 1u; }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -445,7 +465,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
         }
         first = 0;
         umma_commit(&empty[s]);
-        if (++s == TW_STAGES) { s = 0; ph ^= 1u; }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
       umma_commit(accum_bar);
     }
@@ -459,13 +479,33 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
       mbar_wait(&empty[s], ph ^ 1);
       unsigned char* b_dst = smem + s * S::STAGE + S::A_BYTES;
       const float* xs = reinterpret_cast<const float*>(smem + S::OFF_X + sx * TP_XSTAGE);
+      if (ACT) {
+        // S = dL/de of the first conv, formed in place from the three tiles (same swizzled layout: pure element-wise):
+        //   gz = gA * lrelu'(e, slope) + gB * relu'(e),  e > 0 <=> r = ReLU(e) > 0   (models/unetbaseline_model.py:187-192)
+        mbar_wait(&loaded[s], ph);
+        uint4* ga = reinterpret_cast<uint4*>(smem + s * S::STAGE);
+        const uint4* gb = reinterpret_cast<const uint4*>(smem + s * S::STAGE + S::A_BYTES + S::B_BYTES);
+        const uint4* rr = gb + S::A_BYTES / 16;
+#pragma unroll
+        for (int i = 0; i < S::A_BYTES / 16 / 128; ++i) {
+          const int c = i * 128 + pidx;
+          const float8 a = cvt8(ga[c]), bq = cvt8(gb[c]), r8 = cvt8(rr[c]);
+          float8 o;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o.v[k] = r8.v[k] > 0.f ? a.v[k] + bq.v[k] : a.v[k] * p.slope;
+          uint4 u;
+          u.x = pack_bf16x2(o.v[0], o.v[1]); u.y = pack_bf16x2(o.v[2], o.v[3]);
+          u.z = pack_bf16x2(o.v[4], o.v[5]); u.w = pack_bf16x2(o.v[6], o.v[7]);
+          ga[c] = u;
+        }
+      }
       if (FOLD) build_patch_row<2, true>(xs, p.BW, p.BH, li, lj, b_dst + (lj & 1) * S::HALF, li * (p.CW / 2) + (lj >> 1));
       else build_patch_row<1, false, true>(xs, p.BW, p.BH, li, lj, b_dst, pidx);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&full[s]); mbar_arrive(&x_empty[sx]); }
       if (++sx == TP_XS) { sx = 0; phx ^= 1u; }
-      if (++s == TW_STAGES) { s = 0; ph ^= 1u; }
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
     // ---- final epilogue: accumulator row m = q * 32 + lane
     const int q = warp & 3;
@@ -500,12 +540,12 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
   }
 }
 
-template <bool FOLD>
+template <bool FOLD, bool ACT = false>
 int launch_thin_wgrad(ThinWgradParams& p, cudaStream_t s) {
-  using S = ThinWgradSmem<FOLD>;
-  ADP_SMEM_ATTR((thin_patch_wgrad_kernel<FOLD>), S::BYTES);
+  using S = ThinWgradSmem<FOLD, ACT>;
+  ADP_SMEM_ATTR((thin_patch_wgrad_kernel<FOLD, ACT>), S::BYTES);
   const int ctas = p.ntiles < sm_count() ? p.ntiles : sm_count();
-  thin_patch_wgrad_kernel<FOLD><<<ctas, TW_THREADS, S::BYTES, s>>>(p);
+  thin_patch_wgrad_kernel<FOLD, ACT><<<ctas, TW_THREADS, S::BYTES, s>>>(p);
   adp_count_tc_launch();
   ADP_LAUNCH_CHECK();
   return ADP_OK;
@@ -557,6 +597,24 @@ int thin_tc_first_wgrad(const float* x, const void* g_e, float* dw, int B, int H
   uint32_t box[3] = {64, (uint32_t)p.CW / 2, (uint32_t)p.RH};
   ADP_TRY(make_tmap_bf16(&p.tmS0, g_e, 3, dims, str, box));
   return launch_thin_wgrad<true>(p, s);
+}
+
+// E1 weight gradient with the activation backward of level 0 folded in: dL/de = gA * lrelu'(e, slope) + gB * relu'(e) is
+// formed tile by tile in shared memory from gA, gB and r = ReLU(e) (all bf16 [B,H/2,W/2,64]) and never written to HBM
+int thin_tc_first_wgrad_act(const float* x, const void* gA, const void* gB, const void* r, float slope, float* dw, int B, int H,
+                            int W, cudaStream_t s) {
+  ThinWgradParams p;
+  ADP_TRY(fill_wgrad_params(&p, x, B, 2, H, W, dw));
+  p.slope = slope;
+  const void* src[3] = {gA, gB, r};
+  CUtensorMap* maps[3] = {&p.tmS0, &p.tmS1, &p.tmS2};
+  for (int i = 0; i < 3; ++i) {
+    uint64_t dims[3] = {128, (uint64_t)p.Wo / 2, (uint64_t)B * p.Ho};
+    uint64_t str[2] = {128 * 2, (uint64_t)(p.Wo / 2) * 128 * 2};
+    uint32_t box[3] = {64, (uint32_t)p.CW / 2, (uint32_t)p.RH};
+    ADP_TRY(make_tmap_bf16(maps[i], src[i], 3, dims, str, box));
+  }
+  return launch_thin_wgrad<true, true>(p, s);
 }
 
 // D1 weight gradient: dw fp32 [128][16] += sum_pix (x0|x1)[pix][c] * du-patch; x0, x1 bf16 [B,Hi,Wi,64]; dw zeroed by the caller

@@ -536,7 +536,11 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       const int l = 2 * D - 1 - st;
       const LevelPlan& L = p.lv[l];
       const long long rows = (long long)B * L.hout * L.hout;
-      {
+      // level 0 on the shared-memory patch route: dL/de[0] = gA * lrelu' + gB * relu' is formed inside the weight-gradient
+      // kernel (its only consumer) and never written
+      const bool fuse_act0 = l == 0 && thin_tc_bwd && thin_fused_enabled() && L.cin == 2 && L.cout == 64 &&
+                             thin_tc_supported(B, 2, L.hin, L.hin);
+      if (!fuse_act0) {
       ProfScope eprof(PROF_ELEM, s, (double)rows * L.cout * p.esz * (l == D - 1 ? 3.0 : 4.0));   // x, gA[, gB] -> dx
       if (l == D - 1) {
         ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.e), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_r), 0.f,
@@ -563,8 +567,10 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, sw));
       if (l == 0 && thin_tc_bwd) {
         ProfScope prof(PROF_THIN, s, 2.0 * B * L.hout * L.hout * 16.0 * L.cin * L.cout);
-        if (thin_fused_enabled() && L.cin == 2 && thin_tc_supported(B, 2, L.hin, L.hin)) {
-          ADP_TRY(thin_tc_first_wgrad(x, at(ws, L.g_e), grads[0].conv_w, B, L.hin, L.hin, s));     // (dw zeroed above)
+        if (fuse_act0) {       // (dw zeroed above; e > 0 <=> r = ReLU(e) > 0: a[0] may be stored centred, r[0] never is)
+          ADP_TRY(thin_tc_first_wgrad_act(x, at(ws, L.g_a), at(ws, L.g_r), at(ws, L.r), 0.2f, grads[0].conv_w, B, L.hin, L.hin, s));
+        } else if (thin_fused_enabled() && L.cin == 2 && thin_tc_supported(B, 2, L.hin, L.hin)) {
+          ADP_TRY(thin_tc_first_wgrad(x, at(ws, L.g_e), grads[0].conv_w, B, L.hin, L.hin, s));
         } else {
           float* Dt = reinterpret_cast<float*>(at(ws, p.dthin));
           // pixel pairs folded into 128 "channels": D[(h,n)][(h',t)], the two diagonal blocks are the gradient
@@ -655,6 +661,12 @@ extern "C" int adp_first_conv_k4s2_wgrad(const float* x, const void* g_e, float*
   ADP_CHECK_ARG(x && g_e && dw, "first_conv_wgrad: null pointer");
   ADP_CHECK_ARG(thin_tc_supported(B, 2, H, W), "first_conv_wgrad: unsupported shape %dx%dx%d", B, H, W);
   return thin_tc_first_wgrad(x, g_e, dw, B, H, W, (cudaStream_t)stream);
+}
+extern "C" int adp_first_conv_k4s2_wgrad_act(const float* x, const void* gA, const void* gB, const void* r, float slope, float* dw,
+                                             int B, int H, int W, void* stream) {
+  ADP_CHECK_ARG(x && gA && gB && r && dw, "first_conv_wgrad_act: null pointer");
+  ADP_CHECK_ARG(thin_tc_supported(B, 2, H, W), "first_conv_wgrad_act: unsupported shape %dx%dx%d", B, H, W);
+  return thin_tc_first_wgrad_act(x, gA, gB, r, slope, dw, B, H, W, (cudaStream_t)stream);
 }
 extern "C" int adp_last_convT_k4s2_dgrad(const float* du, const float* wT, void* w_scratch, void* g0, void* g1, int B, int Hi,
                                          int Wi, void* stream) {

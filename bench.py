@@ -51,10 +51,10 @@ FLOP_STEP = 35.72e9                 # whole U-Net fwd+bwd
 BYTES_FEATURE = 586544              # waveform in, [2,256,256] fp32 feature out
 BYTES_LOSS = 786432                 # pred + gt in, dpred out
 # thin layers, bf16 activations: E1 fwd (x fp32 in; a, r out), D1 fwd (r, q in; y fp32 out), D1 bwd (du in; r, q in for the
-# weight gradient; g_r, g_q out), E1 wgrad (g_e and x in)
+# weight gradient; g_r, g_q out), E1 wgrad with the level-0 activation backward folded in (g_a, g_r, r and x in)
 _ACT0 = 64 * 128 * 128 * 2          # one [64,128,128] bf16 activation
 _IMG = 256 * 256 * 4
-BYTES_THIN = (2 * _IMG + 2 * _ACT0) + (2 * _ACT0 + _IMG) + (_IMG + 2 * _ACT0 + 2 * _ACT0) + (_ACT0 + 2 * _IMG)
+BYTES_THIN = (2 * _IMG + 2 * _ACT0) + (2 * _ACT0 + _IMG) + (_IMG + 2 * _ACT0 + 2 * _ACT0) + (3 * _ACT0 + 2 * _IMG)
 N_PARAMS_FLAT = 54408833
 
 

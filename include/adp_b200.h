@@ -162,6 +162,11 @@ int adp_convT2d_k4s2_wgrad(int dtype, const void* x0, int c0, const void* x1, in
 int adp_first_conv_k4s2_fprop(const float* x, const float* w1, void* w_scratch, void* a, float slope0, void* r,
                               float slope1, int B, int H, int W, void* stream);
 int adp_first_conv_k4s2_wgrad(const float* x, const void* g_e, float* dw, int B, int H, int W, void* stream);
+/* the same with the activation backward of that level folded in: dL/de = gA * (r > 0 ? 1 : slope) + (r > 0 ? gB : 0)
+ * (gA: gradient of the LeakyReLU(slope) branch, gB: of the ReLU skip branch, r = ReLU(e); all bf16 [B,H/2,W/2,64]) is formed
+ * in shared memory and never written (models/unetbaseline_model.py:187-192, :231-235). */
+int adp_first_conv_k4s2_wgrad_act(const float* x, const void* gA, const void* gB, const void* r, float slope, float* dw,
+                                  int B, int H, int W, void* stream);
 int adp_last_convT_k4s2_dgrad(const float* du, const float* wT, void* w_scratch, void* g0, void* g1, int B, int Hi,
                               int Wi, void* stream);
 int adp_last_convT_k4s2_wgrad(const void* x0, const void* x1, const float* du, float* dw, int B, int Hi, int Wi,

@@ -675,6 +675,18 @@ def test_thin_layer_kernels_vs_torch(B, H):
     wg = w.clone().requires_grad_(True)
     F.conv2d(xs, wg, stride=2, padding=1).backward(ge.float().permute(0, 3, 1, 2))
     assert rel_to_max(dw.permute(0, 3, 1, 2).cpu(), wg.grad.cpu()) <= 2e-4
+    # ---- the same with the level-0 activation backward folded in: dL/de formed in shared memory from gA, gB, r
+    gA = (torch.randn(B, Ho, Ho, 64, generator=g) * 0.1).to(DEV).to(torch.bfloat16)
+    gB = (torch.randn(B, Ho, Ho, 64, generator=g) * 0.1).to(DEV).to(torch.bfloat16)
+    rr = torch.relu(torch.randn(B, Ho, Ho, 64, generator=g)).to(DEV).to(torch.bfloat16)
+    dw2 = torch.zeros(64, 4, 4, 2, device=DEV)
+    _lib.check(lib.adp_first_conv_k4s2_wgrad_act(x.data_ptr(), gA.data_ptr(), gB.data_ptr(), rr.data_ptr(), 0.2, dw2.data_ptr(),
+                                                 B, H, H, None))
+    pos = rr.float() > 0
+    gz = _bf16r(torch.where(pos, gA.float() + gB.float(), gA.float() * 0.2))
+    wg = w.clone().requires_grad_(True)
+    F.conv2d(xs, wg, stride=2, padding=1).backward(gz.permute(0, 3, 1, 2))
+    assert rel_to_max(dw2.permute(0, 3, 1, 2).cpu(), wg.grad.cpu()) <= 2e-4
     # ---- D1: ConvTranspose2d(128 -> 1) backward
     du = (torch.randn(B, 1, H, H, generator=g) * 0.1).to(DEV)
     wT = (torch.randn(128, 1, 4, 4, generator=g) * 0.02).to(DEV)
