@@ -169,12 +169,16 @@ class DevicePrefetcher:
 
 class TrainStep:
     def __init__(self, cfg, model, lr=None, max_norm=1.0, process_group=None, stages_per_group=2,
-                 waveform_input=True, cuda_graph=False, shard_optimizer=False):
+                 waveform_input=True, cuda_graph=False, shard_optimizer=None):
         """cuda_graph=True records the whole step (feature -> forward -> loss -> backward -> clip+AdamW) once, after
         two eager warm-up steps, and replays it for every later batch of the same shape.  With several ranks the NCCL
         all-reduces are recorded into the graph as well (every rank must record and replay in lock-step)."""
         self.cfg = cfg
         self.cuda_graph = bool(cuda_graph)
+        if shard_optimizer is None:
+            # reduce-scatter + sharded clip/AdamW + bf16 all-gather pays from 4 ranks up (measured on 8 B200s: 4.19 against
+            # 4.34 ms per step; a tie at 2 ranks); same weights either way (tools/nccl_parity.py)
+            shard_optimizer = dist.is_initialized() and dist.get_world_size(process_group) >= 4
         self.shard_optimizer = bool(shard_optimizer)
         self._graph = None
         self._static = None
@@ -183,7 +187,7 @@ class TrainStep:
         self._graph_lr = None
         self.model = model
         self.transform = SpectrogramTransform.for_cfg(cfg) if waveform_input else None
-        self.reducer = GradientReducer(model, process_group, stages_per_group, shard=shard_optimizer)
+        self.reducer = GradientReducer(model, process_group, stages_per_group, shard=self.shard_optimizer)
         self.shard_optimizer = self.reducer.shard
         self.criterion = DepthCriterion.from_cfg(cfg, reduce_fn=self.reducer.reduce_loss_sums
                                                  if self.reducer.world > 1 else None)

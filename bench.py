@@ -391,7 +391,7 @@ def run_ours(args):
                    "tensor_core_path": bool(args.precision == "bf16"),
                    "launch": "whole step replayed from one CUDA graph" if use_graph else "eager launches",
                    "eager_ms_per_step": ms_eager / args.steps,
-                   "optimizer": ("reduce-scatter + sharded clip/AdamW + bf16 all-gather" if (world > 1 and args.shard_optimizer)
+                   "optimizer": ("reduce-scatter + sharded clip/AdamW + bf16 all-gather" if (world > 1 and step.shard_optimizer)
                                  else ("all-reduce + replicated clip/AdamW" if world > 1 else "fused clip/AdamW")),
                    "parity": PARITY_NOTE},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(wave_h.numel() * 4 + gt_h.numel() * 4),
@@ -444,7 +444,7 @@ def main():
                     "reference arm takes 64 when K + W <= 30)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--stages-per-group", type=int, default=2)
-    ap.add_argument("--shard-optimizer", action="store_true", help="multi-GPU: reduce-scatter + sharded clip/AdamW + bf16 "
+    ap.add_argument("--shard-optimizer", action=argparse.BooleanOptionalAction, default=None, help="multi-GPU: reduce-scatter + sharded clip/AdamW + bf16 "
                     "all-gather instead of all-reduce + replicated AdamW")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
