@@ -98,7 +98,8 @@ SIGNATURES = {
     "adp_first_conv_k4s2_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "adp_first_conv_k4s2_wgrad_act": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp]),
     "adp_last_convT_k4s2_dgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "adp_last_convT_k4s2_wgrad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "adp_last_convT_k4s2_wgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "adp_last_convT_k4s2_fprop": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
     "adp_set_option": (_i, [C.c_char_p, _i]),
     "adp_profile_read_n": (_i, [_i, _vp, _vp, _vp]),
     "adp_selftest_umma_offset": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -307,7 +307,13 @@ int thin_tc_first_wgrad(const float* x, const void* g_e, float* dw, int B, int H
 int thin_tc_first_wgrad_act(const float* x, const void* gA, const void* gB, const void* r, float slope, float* dw, int B, int H,
                             int W, cudaStream_t s);
 int thin_tc_last_dgrad(const float* du, const void* w_pad, void* g0, void* g1, int B, int Hi, int Wi, cudaStream_t s);
-int thin_tc_last_wgrad(const void* x0, const void* x1, const float* du, float* dw, int B, int Hi, int Wi, cudaStream_t s);
+// x1_scale / x1_shift given: x1 is t, the raw output of the previous transposed conv, and q = ReLU(t * scale + shift) is
+// formed in shared memory (the forward pass then never wrote q: thin_tc_last_fwd)
+int thin_tc_last_wgrad(const void* x0, const void* x1, const float* du, float* dw, int B, int Hi, int Wi, cudaStream_t s,
+                       const float* x1_scale = nullptr, const float* x1_shift = nullptr);
+bool thin_tc_last_fwd_supported(int B, int Hi, int Wi);
+int thin_tc_last_fwd(const void* x0, const void* x1, const float* scale, const float* shift, const void* w16, const float* bias,
+                     int final_sigmoid, float* y, int B, int Hi, int Wi, cudaStream_t s);
 int thin_pad_rows(const float* src, void* dst, int R, int K, int dup, cudaStream_t s);
 int thin_fold_wgrad(const float* D, float* dw, int mode, int K, cudaStream_t s);
 // y[pix][n] = sum_c (x0|x1)[pix][c] * w_nk[n][c] over NHWC pixels (adp_conv_tc.cu)

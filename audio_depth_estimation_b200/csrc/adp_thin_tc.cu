@@ -281,6 +281,214 @@ __global__ void __launch_bounds__(TP_THREADS, 1) thin_patch_gemm_kernel(const __
   }
 }
 
+// ------------------------------------------------------------------ D1 forward: ConvTranspose2d(128 -> 1) + bias + ReLU | Sigmoid
+// y[b, 2i+a, 2j+c] = act(bias + sum over the 2 x 2 taps that land there of P[b, i', j'][kh*4+kw]),  P[pix][t] = sum_ch (r|q)[pix][ch] w[ch][t].
+// One input row (Wi = 128 pixels) is one M = 128 tile: P_i = [128 x 128 ch] . [128 ch x 16 taps] on the tensor core (N = 16,
+// 8 K steps).  A CTA walks a band of consecutive rows; the epilogue keeps the last three P rows in shared memory, so output
+// rows 2i-1 and 2i are finished as soon as P_i exists (plus 2i+1 at the bottom of an image) -- P never goes to HBM and
+// there is no col2im pass.  The second input half may arrive as t, the raw output of the previous transposed conv: the
+// BatchNorm + ReLU that makes q = ReLU(t * scale + shift) is applied to the tile in shared memory (then q is never written
+// by the forward pass either).
+constexpr int TL_THREADS = 320;             // warp 0 TMA, warp 1 MMA, warps 2-5 tile transform, warps 6-9 epilogue
+constexpr int TL_STAGES = 4;
+constexpr int TL_HALF = 128 * 128;          // [128 pixels][64 ch] bf16
+constexpr int TL_PSTRIDE = 20;              // floats per pixel in the P ring (16 taps + padding: conflict-free float4 rows)
+
+struct ThinLastFwdParams {
+  CUtensorMap tmR, tmT, tmW;
+  int B, Hi, Wi, rows;
+  const float* bn_scale; const float* bn_shift;     // NULL: the second tensor already holds q
+  const float* bias; int final_sigmoid;
+  float* y;
+};
+
+struct ThinLastSmem {
+  static constexpr int OFF_W = TL_STAGES * 2 * TL_HALF;          // two [16 taps][64 ch] tiles
+  static constexpr int OFF_P = OFF_W + 2 * 2048;                 // 3 x [128 pixels][TL_PSTRIDE] floats
+  static constexpr int OFF_TAB = OFF_P + 3 * 128 * TL_PSTRIDE * 4;
+  static constexpr int OFF_BAR = OFF_TAB + 2 * 64 * 4;
+  static constexpr int BYTES = OFF_BAR + 256 + 1024;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(TL_THREADS, 1) thin_last_fwd_kernel(const __grid_constant__ ThinLastFwdParams p) {
+  using S = ThinLastSmem;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* full = bars;                     // [STAGES] TMA bytes
+  uint64_t* ready = full + TL_STAGES;        // [STAGES] tile transformed (4 warps)
+  uint64_t* empty = ready + TL_STAGES;       // [STAGES]
+  uint64_t* tfull = empty + TL_STAGES;       // [2]
+  uint64_t* tempty = tfull + 2;              // [2]
+  uint64_t* w_bar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* tab = reinterpret_cast<float*>(smem + S::OFF_TAB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // this CTA's band of rows g = b * Hi + i, preceded by one halo row (P only) when the band starts inside an image
+  const int g_begin = (int)((long long)blockIdx.x * p.rows / gridDim.x), g_end = (int)((long long)(blockIdx.x + 1) * p.rows / gridDim.x);
+  const int halo = (g_begin % p.Hi) != 0 ? 1 : 0;
+  const int g_first = g_begin - halo, ntiles = g_end - g_first;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.tmR);
+    prefetch_tmap(&p.tmT);
+    prefetch_tmap(&p.tmW);
+    for (int s = 0; s < TL_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 32);
+  if (p.bn_scale && threadIdx.x >= 64 && threadIdx.x < 128) {
+    tab[threadIdx.x - 64] = p.bn_scale[threadIdx.x - 64];
+    tab[threadIdx.x] = p.bn_shift[threadIdx.x - 64];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(w_bar, 2 * 2048);
+      tma_load_2d(smem + S::OFF_W, &p.tmW, w_bar, 0, 0);
+      tma_load_2d(smem + S::OFF_W + 2048, &p.tmW, w_bar, 64, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int k = 0; k < ntiles; ++k) {
+        mbar_wait(&empty[s], ph ^ 1);
+        unsigned char* dst = smem + s * 2 * TL_HALF;
+        mbar_expect_tx(&full[s], 2 * TL_HALF);
+        tma_load_3d(dst, &p.tmR, &full[s], 0, 0, g_first + k);
+        tma_load_3d(dst + TL_HALF, &p.tmT, &full[s], 0, 0, g_first + k);
+        if (++s == TL_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128, 16, 0, 0);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t b_desc0 = umma_smem_desc(smem_base + S::OFF_W, 16, 1024);
+      mbar_wait(w_bar, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int k = 0; k < ntiles; ++k) {
+        const uint32_t buf = (uint32_t)k & 1u, use = (uint32_t)k >> 1;
+        mbar_wait(&tempty[buf], (use & 1u) ^ 1u);
+        mbar_wait(&ready[s], ph);
+        tc_fence_after();
+        const uint64_t a_desc0 = umma_smem_desc(smem_base + s * 2 * TL_HALF, 16, 1024);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_base + buf * 16, a_desc0 + (uint64_t)((h * TL_HALF) >> 4) + (uint64_t)(kk * 2),
+                      b_desc0 + (uint64_t)((h * 2048) >> 4) + (uint64_t)(kk * 2), idesc, (h | kk) != 0 ? 1u : 0u);
+        umma_commit(&empty[s]);
+        umma_commit(&tfull[buf]);
+        if (++s == TL_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== q = ReLU(t * scale + shift) on the staged tile, in place =====================
+    const int tid = (warp - 2) * 32 + lane;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int k = 0; k < ntiles; ++k) {
+      mbar_wait(&full[s], ph);
+      if (p.bn_scale) {
+        uint4* tq = reinterpret_cast<uint4*>(smem + s * 2 * TL_HALF + TL_HALF);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int c = it * 128 + tid;                       // 16-byte chunk: row c >> 3, physical position c & 7
+          const int ch0 = (((c & 7) ^ ((c >> 3) & 7)) << 3);  // its 8 channels (SWIZZLE_128B: logical = physical ^ (row & 7))
+          const float4 sc0 = *reinterpret_cast<const float4*>(tab + ch0), sc1 = *reinterpret_cast<const float4*>(tab + ch0 + 4);
+          const float4 sh0 = *reinterpret_cast<const float4*>(tab + 64 + ch0), sh1 = *reinterpret_cast<const float4*>(tab + 64 + ch0 + 4);
+          const float8 t = cvt8(tq[c]);
+          uint4 u;
+          u.x = pack_bf16x2(fmaxf(fmaf(t.v[0], sc0.x, sh0.x), 0.f), fmaxf(fmaf(t.v[1], sc0.y, sh0.y), 0.f));
+          u.y = pack_bf16x2(fmaxf(fmaf(t.v[2], sc0.z, sh0.z), 0.f), fmaxf(fmaf(t.v[3], sc0.w, sh0.w), 0.f));
+          u.z = pack_bf16x2(fmaxf(fmaf(t.v[4], sc1.x, sh1.x), 0.f), fmaxf(fmaf(t.v[5], sc1.y, sh1.y), 0.f));
+          u.w = pack_bf16x2(fmaxf(fmaf(t.v[6], sc1.z, sh1.z), 0.f), fmaxf(fmaf(t.v[7], sc1.w, sh1.w), 0.f));
+          tq[c] = u;
+        }
+        fence_proxy_async();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready[s]);
+      if (++s == TL_STAGES) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    // ===================== epilogue: lane = pixel j of the row =====================
+    const int q = warp & 3;
+    const int j = q * 32 + lane;
+    float* pring = reinterpret_cast<float*>(smem + S::OFF_P);
+    const float bias = p.bias ? p.bias[0] : 0.f;
+    const int Wo = 2 * p.Wi, Ho = 2 * p.Hi;
+    for (int k = 0; k < ntiles; ++k) {
+      const uint32_t buf = (uint32_t)k & 1u, use = (uint32_t)k >> 1;
+      const int g = g_first + k, b = g / p.Hi, i = g - b * p.Hi;
+      mbar_wait(&tfull[buf], use & 1u);
+      tc_fence_after();
+      float v[16];
+      tmem_ld16(tmem_base + buf * 16 + ((uint32_t)(q * 32) << 16), v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      float* cur = pring + (k % 3) * 128 * TL_PSTRIDE;
+      const float* prev = pring + ((k + 2) % 3) * 128 * TL_PSTRIDE;
+#pragma unroll
+      for (int t4 = 0; t4 < 16; t4 += 4)
+        *reinterpret_cast<float4*>(cur + j * TL_PSTRIDE + t4) = make_float4(v[t4], v[t4 + 1], v[t4 + 2], v[t4 + 3]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps: P_i complete (3 slots: one barrier per row)
+      if (halo && k == 0) continue;                          // (P only: the rows this one finishes belong to the previous band)
+      // output (oy, 2j + c): rows (i', kh) and columns (j', kw) of the taps that land there
+      auto emit_row = [&](int oy, const float* pa, int kha, const float* pb, int khb) {
+        float u0 = bias, u1 = bias;                          // c = 0: (j-1, kw 3), (j, kw 1);  c = 1: (j, kw 2), (j+1, kw 0)
+        if (pa) {
+          if (j > 0) u0 += pa[(j - 1) * TL_PSTRIDE + kha * 4 + 3];
+          u0 += pa[j * TL_PSTRIDE + kha * 4 + 1];
+          u1 += pa[j * TL_PSTRIDE + kha * 4 + 2];
+          if (j + 1 < p.Wi) u1 += pa[(j + 1) * TL_PSTRIDE + kha * 4 + 0];
+        }
+        if (pb) {
+          if (j > 0) u0 += pb[(j - 1) * TL_PSTRIDE + khb * 4 + 3];
+          u0 += pb[j * TL_PSTRIDE + khb * 4 + 1];
+          u1 += pb[j * TL_PSTRIDE + khb * 4 + 2];
+          if (j + 1 < p.Wi) u1 += pb[(j + 1) * TL_PSTRIDE + khb * 4 + 0];
+        }
+        if (p.final_sigmoid) { u0 = 1.f / (1.f + expf(-u0)); u1 = 1.f / (1.f + expf(-u1)); }
+        else { u0 = fmaxf(u0, 0.f); u1 = fmaxf(u1, 0.f); }
+        *reinterpret_cast<float2*>(p.y + ((size_t)b * Ho + oy) * Wo + 2 * j) = make_float2(u0, u1);
+      };
+      // oy = 2i - 1 (a = 1 of row i-1): rows i-1 (kh 2) and i (kh 0);  oy = 2i (a = 0): rows i-1 (kh 3) and i (kh 1)
+      if (i > 0) emit_row(2 * i - 1, prev, 2, cur, 0);
+      emit_row(2 * i, i > 0 ? prev : nullptr, 3, cur, 1);
+      if (i == p.Hi - 1) emit_row(2 * i + 1, cur, 2, nullptr, 0);      // bottom edge: row i (kh 2) only
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
 // fp32 image planes [B][CIN][H][W] as a 4-D tensor map (W | H | CIN | B), no swizzle, zero fill outside
 int make_tmap_image(CUtensorMap* out, const float* img, int B, int CIN, int H, int W, int BW, int BH) {
   EncodeTiledFn fn = encode_tiled_fn();
@@ -349,15 +557,17 @@ constexpr int TW_STAGES = 3;
 
 struct ThinWgradParams {
   CUtensorMap tmImg, tmS0, tmS1, tmS2;
-  float slope;                              // ACT: S = gA * (r > 0 ? 1 : slope) + (r > 0 ? gB : 0), formed in shared memory
+  float slope;                              // XF 1: S = gA * (r > 0 ? 1 : slope) + (r > 0 ? gB : 0), formed in shared memory
+  const float* bn_scale; const float* bn_shift;   // XF 2: the second S half arrives as t, q = ReLU(t * scale + shift) is formed in shared memory
   int B, Ho, Wo, CW, RH, BW, BH;
   int tiles_x, tiles_y, ntiles;
   float* dw;
   uint32_t box_bytes;
 };
 
-template <bool FOLD, bool ACT = false>
+template <bool FOLD, int XF = 0>
 struct ThinWgradSmem {
+  static constexpr bool ACT = XF == 1;
   static constexpr int KROWS = FOLD ? 64 : 128;
   static constexpr int HALF = KROWS * 128;                 // one [KROWS][64] bf16 region
   static constexpr int A_BYTES = 2 * HALF;
@@ -367,7 +577,8 @@ struct ThinWgradSmem {
   static constexpr int STAGES = ACT ? 2 : TW_STAGES;
   static constexpr int OFF_X = STAGES * STAGE;
   static constexpr int OFF_BAR = OFF_X + TP_XS * TP_XSTAGE;
-  static constexpr int BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int OFF_TAB = OFF_BAR + 256;            // XF 2: scale | shift, 2 x 64 floats
+  static constexpr int BYTES = OFF_TAB + 512 + 1024;
   static constexpr int NT = FOLD ? 128 : 64;
 };
 
@@ -375,10 +586,12 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, flo
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool FOLD, bool ACT = false>
+template <bool FOLD, int XF = 0>
 __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const __grid_constant__ ThinWgradParams p) {
+  constexpr bool ACT = XF == 1, QBN = XF == 2;
   static_assert(!ACT || FOLD, "the fused activation backward belongs to the first conv's weight gradient");
-  using S = ThinWgradSmem<FOLD, ACT>;
+  static_assert(!QBN || !FOLD, "the BatchNorm + ReLU on load belongs to the last transposed conv's weight gradient");
+  using S = ThinWgradSmem<FOLD, XF>;
   constexpr int STAGES = S::STAGES;
   constexpr int KSTEPS = S::KROWS / 16;
   constexpr int NT = S::NT;
@@ -401,11 +614,16 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
     if (!FOLD || ACT) prefetch_tmap(&p.tmS1);
     if (ACT) prefetch_tmap(&p.tmS2);
     for (int s = 0; s < TP_XS; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 4); }
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], ACT ? 4 : 5); mbar_init(&empty[s], 1); mbar_init(&loaded[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], (ACT || QBN) ? 4 : 5); mbar_init(&empty[s], 1); mbar_init(&loaded[s], 1); }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, NT);
+  float* tab = reinterpret_cast<float*>(smem + S::OFF_TAB);
+  if (QBN && threadIdx.x >= 64 && threadIdx.x < 128) {
+    tab[threadIdx.x - 64] = p.bn_scale[threadIdx.x - 64];
+    tab[threadIdx.x] = p.bn_shift[threadIdx.x - 64];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -436,13 +654,14 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
           if (++s == STAGES) { s = 0; ph ^= 1u; }
           continue;
         }
-        mbar_expect_tx(&full[s], S::A_BYTES);
+        uint64_t* a_bar = QBN ? &loaded[s] : &full[s];
+        mbar_expect_tx(a_bar, S::A_BYTES);
         if (FOLD) {
           tma_load_3d(a_dst, &p.tmS0, &full[s], 0, tx * (p.CW / 2), b * p.Ho + ty * p.RH);
           tma_load_3d(a_dst + S::HALF, &p.tmS0, &full[s], 64, tx * (p.CW / 2), b * p.Ho + ty * p.RH);
         } else {
-          tma_load_3d(a_dst, &p.tmS0, &full[s], 0, tx * p.CW, b * p.Ho + ty * p.RH);
-          tma_load_3d(a_dst + S::HALF, &p.tmS1, &full[s], 0, tx * p.CW, b * p.Ho + ty * p.RH);
+          tma_load_3d(a_dst, &p.tmS0, a_bar, 0, tx * p.CW, b * p.Ho + ty * p.RH);
+          tma_load_3d(a_dst + S::HALF, &p.tmS1, a_bar, 0, tx * p.CW, b * p.Ho + ty * p.RH);
         }
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
@@ -499,6 +718,26 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
           ga[c] = u;
         }
       }
+      if (QBN) {
+        // q = ReLU(t * scale + shift) on the second S half, in place (chunk at physical position c & 7 of row c >> 3 holds
+        // the channels 8 * ((c & 7) ^ (row & 7)) ..)
+        mbar_wait(&loaded[s], ph);
+        uint4* tq = reinterpret_cast<uint4*>(smem + s * S::STAGE + S::HALF);
+#pragma unroll
+        for (int it = 0; it < S::HALF / 16 / 128; ++it) {
+          const int c = it * 128 + pidx;
+          const int ch0 = (((c & 7) ^ ((c >> 3) & 7)) << 3);
+          const float4 sc0 = *reinterpret_cast<const float4*>(tab + ch0), sc1 = *reinterpret_cast<const float4*>(tab + ch0 + 4);
+          const float4 sh0 = *reinterpret_cast<const float4*>(tab + 64 + ch0), sh1 = *reinterpret_cast<const float4*>(tab + 64 + ch0 + 4);
+          const float8 t = cvt8(tq[c]);
+          uint4 u;
+          u.x = pack_bf16x2(fmaxf(fmaf(t.v[0], sc0.x, sh0.x), 0.f), fmaxf(fmaf(t.v[1], sc0.y, sh0.y), 0.f));
+          u.y = pack_bf16x2(fmaxf(fmaf(t.v[2], sc0.z, sh0.z), 0.f), fmaxf(fmaf(t.v[3], sc0.w, sh0.w), 0.f));
+          u.z = pack_bf16x2(fmaxf(fmaf(t.v[4], sc1.x, sh1.x), 0.f), fmaxf(fmaf(t.v[5], sc1.y, sh1.y), 0.f));
+          u.w = pack_bf16x2(fmaxf(fmaf(t.v[6], sc1.z, sh1.z), 0.f), fmaxf(fmaf(t.v[7], sc1.w, sh1.w), 0.f));
+          tq[c] = u;
+        }
+      }
       if (FOLD) build_patch_row<2, true>(xs, p.BW, p.BH, li, lj, b_dst + (lj & 1) * S::HALF, li * (p.CW / 2) + (lj >> 1));
       else build_patch_row<1, false, true>(xs, p.BW, p.BH, li, lj, b_dst, pidx);
       fence_proxy_async();
@@ -540,12 +779,12 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
   }
 }
 
-template <bool FOLD, bool ACT = false>
+template <bool FOLD, int XF = 0>
 int launch_thin_wgrad(ThinWgradParams& p, cudaStream_t s) {
-  using S = ThinWgradSmem<FOLD, ACT>;
-  ADP_SMEM_ATTR((thin_patch_wgrad_kernel<FOLD, ACT>), S::BYTES);
+  using S = ThinWgradSmem<FOLD, XF>;
+  ADP_SMEM_ATTR((thin_patch_wgrad_kernel<FOLD, XF>), S::BYTES);
   const int ctas = p.ntiles < sm_count() ? p.ntiles : sm_count();
-  thin_patch_wgrad_kernel<FOLD, ACT><<<ctas, TW_THREADS, S::BYTES, s>>>(p);
+  thin_patch_wgrad_kernel<FOLD, XF><<<ctas, TW_THREADS, S::BYTES, s>>>(p);
   adp_count_tc_launch();
   ADP_LAUNCH_CHECK();
   return ADP_OK;
@@ -588,6 +827,40 @@ int thin_tc_last_dgrad(const float* du, const void* w_pad, void* g0, void* g1, i
   return launch_thin_fwd<1, false, 128>(p, s);
 }
 
+bool thin_tc_last_fwd_supported(int B, int Hi, int Wi) {
+  return adp_device_is_sm100() && encode_tiled_fn() && B >= 1 && Hi >= 1 && Wi == 128 && (long long)B * Hi < (1LL << 30);
+}
+
+// D1 forward: x0 = r, x1 = t (scale / shift given: q = ReLU(t * scale + shift) is formed in shared memory) or q (scale NULL);
+// both bf16 [B,Hi,128,64]; w16: bf16 [16 taps][128 ch] (cast_transpose_taps); y fp32 [B,1,2Hi,256] = act(bias + convT)
+int thin_tc_last_fwd(const void* x0, const void* x1, const float* scale, const float* shift, const void* w16, const float* bias,
+                     int final_sigmoid, float* y, int B, int Hi, int Wi, cudaStream_t s) {
+  ADP_CHECK_ARG(thin_tc_last_fwd_supported(B, Hi, Wi), "thin_tc_last_fwd: unsupported shape %dx%dx%d (needs Wi = 128)", B, Hi, Wi);
+  ThinLastFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Hi = Hi; p.Wi = Wi; p.rows = B * Hi;
+  p.bn_scale = scale; p.bn_shift = scale ? shift : nullptr;
+  p.bias = bias; p.final_sigmoid = final_sigmoid; p.y = y;
+  for (int h = 0; h < 2; ++h) {
+    uint64_t dims[3] = {64, (uint64_t)Wi, (uint64_t)B * Hi};
+    uint64_t str[2] = {64 * 2, (uint64_t)Wi * 64 * 2};
+    uint32_t box[3] = {64, 128, 1};
+    ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmR : &p.tmT, h == 0 ? x0 : x1, 3, dims, str, box));
+  }
+  {
+    uint64_t dims[2] = {128, 16};
+    uint64_t str[1] = {128 * 2};
+    uint32_t box[2] = {64, 16};
+    ADP_TRY(make_tmap_bf16(&p.tmW, w16, 2, dims, str, box));
+  }
+  ADP_SMEM_ATTR(thin_last_fwd_kernel, ThinLastSmem::BYTES);
+  const int ctas = p.rows < sm_count() ? p.rows : sm_count();
+  thin_last_fwd_kernel<<<ctas, TL_THREADS, ThinLastSmem::BYTES, s>>>(p);
+  adp_count_tc_launch();
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
 // E1 weight gradient: dw fp32 [64][16][2] += sum_pix g_e[pix][n] * x-patch; g_e bf16 [B,H/2,W/2,64]; dw zeroed by the caller
 int thin_tc_first_wgrad(const float* x, const void* g_e, float* dw, int B, int H, int W, cudaStream_t s) {
   ThinWgradParams p;
@@ -614,19 +887,22 @@ int thin_tc_first_wgrad_act(const float* x, const void* gA, const void* gB, cons
     uint32_t box[3] = {64, (uint32_t)p.CW / 2, (uint32_t)p.RH};
     ADP_TRY(make_tmap_bf16(maps[i], src[i], 3, dims, str, box));
   }
-  return launch_thin_wgrad<true, true>(p, s);
+  return launch_thin_wgrad<true, 1>(p, s);
 }
 
 // D1 weight gradient: dw fp32 [128][16] += sum_pix (x0|x1)[pix][c] * du-patch; x0, x1 bf16 [B,Hi,Wi,64]; dw zeroed by the caller
-int thin_tc_last_wgrad(const void* x0, const void* x1, const float* du, float* dw, int B, int Hi, int Wi, cudaStream_t s) {
+int thin_tc_last_wgrad(const void* x0, const void* x1, const float* du, float* dw, int B, int Hi, int Wi, cudaStream_t s,
+                       const float* x1_scale, const float* x1_shift) {
   ThinWgradParams p;
   ADP_TRY(fill_wgrad_params(&p, du, B, 1, 2 * Hi, 2 * Wi, dw));
+  p.bn_scale = x1_scale; p.bn_shift = x1_shift;
   for (int h = 0; h < 2; ++h) {
     uint64_t dims[3] = {64, (uint64_t)p.Wo, (uint64_t)B * p.Ho};
     uint64_t str[2] = {64 * 2, (uint64_t)p.Wo * 64 * 2};
     uint32_t box[3] = {64, (uint32_t)p.CW, (uint32_t)p.RH};
     ADP_TRY(make_tmap_bf16(h == 0 ? &p.tmS0 : &p.tmS1, h == 0 ? x0 : x1, 3, dims, str, box));
   }
+  if (x1_scale) return launch_thin_wgrad<false, 2>(p, s);      // x1 = t: q = ReLU(t * scale + shift) formed on load
   return launch_thin_wgrad<false>(p, s);
 }
 

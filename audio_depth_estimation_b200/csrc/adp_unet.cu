@@ -140,6 +140,12 @@ bool thin_fused_enabled() {
   return g_thin_fused != 0;
 }
 
+int g_d1_fused = -1;      // "d1_fused" / ADP_D1_FUSED=0: D1 forward as pointwise GEMM + col2im over a stored q[0]
+bool d1_fused_enabled() {
+  if (g_d1_fused < 0) g_d1_fused = getenv("ADP_D1_FUSED") ? atoi(getenv("ADP_D1_FUSED")) : 1;
+  return g_d1_fused != 0;
+}
+
 int g_center = -1;    // "center" / ADP_CENTER=0 switches the first-level centring off
 bool center_enabled() {
   if (g_center < 0) g_center = getenv("ADP_CENTER") ? atoi(getenv("ADP_CENTER")) : 1;
@@ -164,6 +170,16 @@ bool use_center(const adp_unet_desc* d, const Plan& p, bool tc) {
   return L1.bn_down && L0.cout == 64 && tc_supported_pointwise16(p.B, L0.hout, L0.hout, L0.cout, L0.t_c1) &&
          tc_supported_gather(p.B, L1.hin, L1.hin, L1.cin, L1.cout, 0) &&
          tc_supported_wgrad(p.B, L1.hout, L1.hout, L1.cout, 0, L1.cin) && d->out_ch == 1;
+}
+
+// D1 on the band kernel (adp_thin_tc.cu: thin_tc_last_fwd): its second input half is read as t[0] with the up-norm + ReLU
+// applied in shared memory, so q[0] is never written by a forward pass that will be back-propagated; the weight gradient
+// of D1 re-forms it the same way.  Forward and backward take the same decision from the descriptor alone.
+bool use_d1_fused(const Plan& p, bool tc) {
+  if (!tc || !p.thin_tc || p.D < 2 || !thin_fused_enabled() || !d1_fused_enabled()) return false;
+  const LevelPlan& L0 = p.lv[0];
+  return L0.cout == 64 && L0.t_c1 == 64 && tc_supported_pointwise16(p.B, L0.hout, L0.hout, L0.cout, L0.t_c1) &&
+         thin_tc_last_fwd_supported(p.B, L0.hout, L0.hout);
 }
 
 // ---- family dispatch: tensor cores when the operands are bf16 and the shape is supported
@@ -329,6 +345,8 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     }
   }
   // ---- decoder
+  const bool d1_fused = tc_head && use_d1_fused(p, tc);
+  bool q0_folded = false;
   for (int l = D - 1; l >= 1; --l) {
     const LevelPlan& L = p.lv[l];
     const LevelPlan& O = p.lv[l - 1];  // output lives at level l-1's resolution
@@ -352,7 +370,17 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     ADP_TRY(conv_parity(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, params[l].convT_w,
                         tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, O.t), B, L.hout, L.hout, L.t_cout, s, &ex,
                         deep_level(O.hout)));
+    if (l == 1) q0_folded = folded != 0;
     if (folded) continue;
+    if (l == 1 && d1_fused) {      // only the coefficients: q[0] = ReLU(t[0] * scale + shift) is formed inside D1's kernels
+      BnBuf bn = bnbuf(ws, L.bn_up_f, L.t_cout);
+      const BnFin fin{sums, 1.0 / (double)rows, rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f, params[l].bn_up_w, params[l].bn_up_b, params[l].bn_up_rm, params[l].bn_up_rv,
+                      d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd, nullptr};
+      ProfScope eprof(PROF_ELEM, s, d->training && !fused ? (double)rows * L.t_cout * p.esz : 0.0);
+      if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));
+      ADP_TRY(bn_finalize(fin, L.t_cout, s));
+      continue;
+    }
     ProfScope eprof(PROF_ELEM, s, (double)rows * L.t_cout * p.esz * 2.0);
     BnBuf bn = bnbuf(ws, L.bn_up_f, L.t_cout);
     const BnFin fin{sums, 1.0 / (double)rows, rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f, params[l].bn_up_w, params[l].bn_up_b, params[l].bn_up_rm, params[l].bn_up_rv,
@@ -367,7 +395,11 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   {
     const LevelPlan& L = p.lv[0];
     ProfScope prof(PROF_THIN, s, 2.0 * B * L.hout * L.hout * 16.0 * (L.cout + L.t_c1));
-    if (tc_head) {
+    if (d1_fused) {
+      BnBuf bn = bnbuf(ws, p.lv[1].bn_up_f, 64);
+      ADP_TRY(thin_tc_last_fwd(at(ws, L.r), q0_folded ? at(ws, L.q) : at(ws, L.t), q0_folded ? nullptr : bn.scale, bn.shift,
+                               at(ws, p.w16_last), params[0].convT_bias, d->final_sigmoid, y, B, L.hout, L.hout, s));
+    } else if (tc_head) {
       float* P = reinterpret_cast<float*>(at(ws, p.p_last));
       ADP_TRY(tc_pointwise16(at(ws, L.r), L.cout, at(ws, L.q), L.t_c1, at(ws, p.w16_last), P, B, L.hout, L.hout, s));
       ADP_TRY(last_convT_col2im(P, params[0].convT_bias, d->final_sigmoid, y, B, L.hout, L.hout, s));
@@ -414,6 +446,11 @@ int unet_set_option(const char* name, int value) {
   if (!strcmp(name, "center")) {
     const int prev = center_enabled() ? 1 : 0;
     g_center = value ? 1 : 0;
+    return prev;
+  }
+  if (!strcmp(name, "d1_fused")) {
+    const int prev = d1_fused_enabled() ? 1 : 0;
+    g_d1_fused = value ? 1 : 0;
     return prev;
   }
   if (!strcmp(name, "thin_fused")) {
@@ -500,7 +537,12 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         ProfScope prof(PROF_THIN, s, 4.0 * B * L.hout * L.hout * 16.0 * Ct);
         if (thin_fused_enabled() && L.cout == 64 && L.t_c1 == 64 && thin_tc_supported(B, 1, d->size, d->size)) {
           ADP_CUDA(cudaMemsetAsync(grads[0].convT_w, 0, sizeof(float) * 16 * Ct, s));
-          ADP_TRY(thin_tc_last_wgrad(at(ws, L.r), at(ws, L.q), du, grads[0].convT_w, B, L.hout, L.hout, s));
+          if (use_d1_fused(p, tc)) {     // q[0] was never written: re-formed from t[0] on load
+            BnBuf bn0 = bnbuf(ws, p.lv[1].bn_up_f, 64);
+            ADP_TRY(thin_tc_last_wgrad(at(ws, L.r), at(ws, L.t), du, grads[0].convT_w, B, L.hout, L.hout, s, bn0.scale, bn0.shift));
+          } else {
+            ADP_TRY(thin_tc_last_wgrad(at(ws, L.r), at(ws, L.q), du, grads[0].convT_w, B, L.hout, L.hout, s));
+          }
           ADP_TRY(thin_tc_last_dgrad(du, at(ws, p.wLpad), at(ws, L.g_r), at(ws, L.g_q), B, L.hout, L.hout, s));
         } else {
           float* Dt = reinterpret_cast<float*>(at(ws, p.dthin));
@@ -676,9 +718,18 @@ extern "C" int adp_last_convT_k4s2_dgrad(const float* du, const float* wT, void*
   ADP_TRY(thin_pad_rows(wT, w_scratch, 128, 16, 0, s));
   return thin_tc_last_dgrad(du, w_scratch, g0, g1, B, Hi, Wi, s);
 }
-extern "C" int adp_last_convT_k4s2_wgrad(const void* x0, const void* x1, const float* du, float* dw, int B, int Hi, int Wi,
-                                         void* stream) {
-  ADP_CHECK_ARG(x0 && x1 && du && dw, "last_convT_wgrad: null pointer");
+extern "C" int adp_last_convT_k4s2_wgrad(const void* x0, const void* x1, const float* x1_scale, const float* x1_shift,
+                                         const float* du, float* dw, int B, int Hi, int Wi, void* stream) {
+  ADP_CHECK_ARG(x0 && x1 && du && dw && ((x1_scale != nullptr) == (x1_shift != nullptr)), "last_convT_wgrad: bad pointers");
   ADP_CHECK_ARG(thin_tc_supported(B, 1, 2 * Hi, 2 * Wi), "last_convT_wgrad: unsupported shape %dx%dx%d", B, Hi, Wi);
-  return thin_tc_last_wgrad(x0, x1, du, dw, B, Hi, Wi, (cudaStream_t)stream);
+  return thin_tc_last_wgrad(x0, x1, du, dw, B, Hi, Wi, (cudaStream_t)stream, x1_scale, x1_shift);
+}
+extern "C" int adp_last_convT_k4s2_fprop(const void* x0, const void* x1, const float* x1_scale, const float* x1_shift,
+                                         const float* wT, void* w_scratch, const float* bias, int final_sigmoid, float* y,
+                                         int B, int Hi, int Wi, void* stream) {
+  ADP_CHECK_ARG(x0 && x1 && wT && w_scratch && y && ((x1_scale != nullptr) == (x1_shift != nullptr)), "last_convT_fprop: bad pointers");
+  ADP_CHECK_ARG(thin_tc_last_fwd_supported(B, Hi, Wi), "last_convT_fprop: unsupported shape %dx%dx%d (input width must be 128)", B, Hi, Wi);
+  cudaStream_t s = (cudaStream_t)stream;
+  ADP_TRY(cast_transpose_taps(wT, w_scratch, 128, 1, s));         // [128][16] -> bf16 [16][128]
+  return thin_tc_last_fwd(x0, x1, x1_scale, x1_shift, w_scratch, bias, final_sigmoid, y, B, Hi, Wi, s);
 }

@@ -169,8 +169,17 @@ int adp_first_conv_k4s2_wgrad_act(const float* x, const void* gA, const void* gB
                                   int B, int H, int W, void* stream);
 int adp_last_convT_k4s2_dgrad(const float* du, const float* wT, void* w_scratch, void* g0, void* g1, int B, int Hi,
                               int Wi, void* stream);
-int adp_last_convT_k4s2_wgrad(const void* x0, const void* x1, const float* du, float* dw, int B, int Hi, int Wi,
-                              void* stream);
+/* x1_scale / x1_shift [64] (both or neither): x1 holds t, the tensor the BatchNorm + ReLU in front of the second input
+ * half was applied to, and q = ReLU(t * scale + shift) is formed in shared memory (:218-223) -- the forward pass below then
+ * never materialises q. */
+int adp_last_convT_k4s2_wgrad(const void* x0, const void* x1, const float* x1_scale, const float* x1_shift,
+                              const float* du, float* dw, int B, int Hi, int Wi, void* stream);
+/* forward of the outermost ConvTranspose2d(128 -> 1) + bias + ReLU | Sigmoid (:196-206), input width 128: one tensor-core
+ * product per input row, the 2 x 2 taps of every output pixel combined from the last three rows kept in shared memory (no
+ * col2im pass).  y fp32 [B,1,2Hi,256]; w_scratch: 4 KB. */
+int adp_last_convT_k4s2_fprop(const void* x0, const void* x1, const float* x1_scale, const float* x1_shift,
+                              const float* wT, void* w_scratch, const float* bias, int final_sigmoid, float* y,
+                              int B, int Hi, int Wi, void* stream);
 /* 1 = use tcgen05 kernels for bf16 tensors where supported (default), 0 = SIMT only.
  * Returns the previous setting.  (Also: environment ADP_TC=0.) */
 int adp_set_tensor_core(int on);

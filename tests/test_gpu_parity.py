@@ -701,11 +701,35 @@ def test_thin_layer_kernels_vs_torch(B, H):
     x0 = (torch.rand(B, Ho, Ho, 64, generator=g)).to(DEV).to(torch.bfloat16)
     x1 = (torch.rand(B, Ho, Ho, 64, generator=g) - 0.3).to(DEV).to(torch.bfloat16)
     dwT = torch.zeros(128, 16, device=DEV)
-    _lib.check(lib.adp_last_convT_k4s2_wgrad(x0.data_ptr(), x1.data_ptr(), du.data_ptr(), dwT.data_ptr(), B, Ho, Ho, None))
+    _lib.check(lib.adp_last_convT_k4s2_wgrad(x0.data_ptr(), x1.data_ptr(), None, None, du.data_ptr(), dwT.data_ptr(), B, Ho, Ho, None))
     wg = wT.clone().requires_grad_(True)
     xin = torch.cat([x0, x1], dim=3).float().permute(0, 3, 1, 2)
     F.conv_transpose2d(xin, wg, stride=2, padding=1).backward(_bf16r(du))
     assert rel_to_max(dwT.cpu(), wg.grad.reshape(128, 16).cpu()) <= 2e-4
+    # ---- the same with q = ReLU(t * scale + shift) formed on load from t (the forward pass never wrote q)
+    tq = (torch.randn(B, Ho, Ho, 64, generator=g) * 0.7 + 0.2).to(DEV).to(torch.bfloat16)
+    sc = (0.5 + torch.rand(64, generator=g)).to(DEV)
+    sh = (0.2 * torch.randn(64, generator=g)).to(DEV)
+    qq = torch.relu(tq.float() * sc + sh).to(torch.bfloat16)
+    dwT2 = torch.zeros(128, 16, device=DEV)
+    _lib.check(lib.adp_last_convT_k4s2_wgrad(x0.data_ptr(), tq.data_ptr(), sc.data_ptr(), sh.data_ptr(), du.data_ptr(),
+                                             dwT2.data_ptr(), B, Ho, Ho, None))
+    wg = wT.clone().requires_grad_(True)
+    xin = torch.cat([x0, qq], dim=3).float().permute(0, 3, 1, 2)
+    F.conv_transpose2d(xin, wg, stride=2, padding=1).backward(_bf16r(du))
+    assert rel_to_max(dwT2.cpu(), wg.grad.reshape(128, 16).cpu()) <= 2e-4
+    # ---- D1 forward on the band kernel (input width 128): both input forms, both heads
+    if Ho == 128:
+        bias = torch.tensor([0.05], device=DEV)
+        for sig in (0, 1):
+            for form in ("q", "t"):
+                y = torch.empty(B, 1, H, H, device=DEV)
+                second, s0, s1 = (qq, None, None) if form == "q" else (tq, sc.data_ptr(), sh.data_ptr())
+                _lib.check(lib.adp_last_convT_k4s2_fprop(x0.data_ptr(), second.data_ptr(), s0, s1, wTm.data_ptr(), scratch.data_ptr(),
+                                                         bias.data_ptr(), sig, y.data_ptr(), B, Ho, Ho, None))
+                u = F.conv_transpose2d(torch.cat([x0, qq], dim=3).float().permute(0, 3, 1, 2), _bf16r(wT), bias, stride=2, padding=1)
+                ref = torch.sigmoid(u) if sig else torch.relu(u)
+                assert float((y - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max())), (sig, form, float((y - ref).abs().max()))
 
 
 @pytest.mark.parametrize("netG,size,batch", [("unet_256", 256, 2), ("unet_128", 128, 3), ("unet_256", 512, 1)])
@@ -744,6 +768,49 @@ def test_thin_layers_patch_tiles_built_in_shared_memory(netG, size, batch):
         else:                            # (the bottleneck layers amplify single bf16 flips at these tiny batches)
             cos = float((a * b).sum() / max(float(a.norm() * b.norm()), 1e-30))
             assert cos >= 0.98 and abs(float(a.norm() / b.norm()) - 1.0) <= 0.1, (n, cos, float(a.norm() / b.norm()))
+
+
+@pytest.mark.parametrize("mode", ["train", "eval", "infer"])
+def test_d1_forward_band_kernel_inside_the_network(mode):
+    """"d1_fused": D1's forward as one band kernel that reads t[0] and applies the up-norm + ReLU in shared memory (q[0] is
+    never written; the weight gradient re-forms it), against pointwise GEMM + col2im over a stored q[0].  The depth map
+    must agree to fp32 summation order; in "infer" (no_grad, folded BatchNorm) q[0] comes from the conv epilogue."""
+    lib = _lib.load()
+    case = ("unet_256", 64, 3, 256, False, 30.0, 960, True, True)
+    ys, gs = [], []
+    for fused in (1, 0):
+        prev = lib.adp_set_option(b"d1_fused", fused)
+        assert prev in (0, 1)
+        try:
+            _, net, x, gt = build_case(case, "bf16")
+            net.train(mode == "train")
+            if mode == "infer":
+                with torch.no_grad():
+                    ys.append(net(x).cpu().numpy())
+                continue
+            y = net(x)
+            y.backward(torch.ones_like(y) * 1e-3)
+            ys.append(y.detach().cpu().numpy())
+            gs.append({n: prm.grad.detach().double().cpu() for n, prm in net.named_parameters()})
+        finally:
+            lib.adp_set_option(b"d1_fused", prev)
+    assert np.isfinite(ys[0]).all() and np.abs(ys[0]).max() > 0
+    # (train mode: the batch statistics upstream come from fp64 atomics in arrival order, single bf16 flips from run to run)
+    assert rel_to_max(ys[0], ys[1]) <= (1.5e-2 if mode == "train" else 8e-3), rel_to_max(ys[0], ys[1])
+    if gs:
+        names = list(gs[0])
+        last_w = [n for n in names if gs[0][n].dim() == 4][-1]
+        for n in names:
+            a, b = gs[0][n], gs[1][n]
+            if float(b.norm()) == 0:
+                continue
+            cos = float((a * b).sum() / max(float(a.norm() * b.norm()), 1e-30))
+            outer = n.count("model.") <= 4
+            floor = (0.995 if mode == "eval" else 0.98) if outer else 0.95      # (train: batch statistics of 3 samples)
+            assert cos >= floor and abs(float(a.norm() / b.norm()) - 1.0) <= (0.03 if outer else 0.1), \
+                (n, cos, float(a.norm() / b.norm()))
+        a, b = gs[0][last_w], gs[1][last_w]
+        assert float((a - b).norm() / b.norm()) <= 2e-2
 
 
 def test_config5_eval_inference_b64_vs_oracle_and_b1024_batch_invariance():
