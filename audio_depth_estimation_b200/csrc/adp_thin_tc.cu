@@ -406,6 +406,14 @@ __global__ void __launch_bounds__(TL_THREADS, 1) thin_last_fwd_kernel(const __gr
   } else if (warp < 6) {
     // ===================== q = ReLU(t * scale + shift) on the staged tile, in place =====================
     const int tid = (warp - 2) * 32 + lane;
+    // thread tid handles the 16-byte chunks c = it * 128 + tid: row c >> 3 = it * 16 + (tid >> 3), physical position tid & 7, so
+    // its 8 channels (SWIZZLE_128B: logical chunk = physical ^ (row & 7)) are the same for every chunk: coefficients in registers
+    const int ch0 = (((tid & 7) ^ ((tid >> 3) & 7)) << 3);
+    float4 sc0 = make_float4(0.f, 0.f, 0.f, 0.f), sc1 = sc0, sh0 = sc0, sh1 = sc0;
+    if (p.bn_scale) {
+      sc0 = *reinterpret_cast<const float4*>(tab + ch0); sc1 = *reinterpret_cast<const float4*>(tab + ch0 + 4);
+      sh0 = *reinterpret_cast<const float4*>(tab + 64 + ch0); sh1 = *reinterpret_cast<const float4*>(tab + 64 + ch0 + 4);
+    }
     int s = 0;
     uint32_t ph = 0;
     for (int k = 0; k < ntiles; ++k) {
@@ -414,10 +422,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) thin_last_fwd_kernel(const __gr
         uint4* tq = reinterpret_cast<uint4*>(smem + s * 2 * TL_HALF + TL_HALF);
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int c = it * 128 + tid;                       // 16-byte chunk: row c >> 3, physical position c & 7
-          const int ch0 = (((c & 7) ^ ((c >> 3) & 7)) << 3);  // its 8 channels (SWIZZLE_128B: logical = physical ^ (row & 7))
-          const float4 sc0 = *reinterpret_cast<const float4*>(tab + ch0), sc1 = *reinterpret_cast<const float4*>(tab + ch0 + 4);
-          const float4 sh0 = *reinterpret_cast<const float4*>(tab + 64 + ch0), sh1 = *reinterpret_cast<const float4*>(tab + 64 + ch0 + 4);
+          const int c = it * 128 + tid;
           const float8 t = cvt8(tq[c]);
           uint4 u;
           u.x = pack_bf16x2(fmaxf(fmaf(t.v[0], sc0.x, sh0.x), 0.f), fmaxf(fmaf(t.v[1], sc0.y, sh0.y), 0.f));
@@ -723,12 +728,13 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
         // the channels 8 * ((c & 7) ^ (row & 7)) ..)
         mbar_wait(&loaded[s], ph);
         uint4* tq = reinterpret_cast<uint4*>(smem + s * S::STAGE + S::HALF);
+        // (row & 7 of chunk it * 128 + pidx is (pidx >> 3) & 7 for every it: one set of 8 channels per thread)
+        const int ch0 = (((pidx & 7) ^ ((pidx >> 3) & 7)) << 3);
+        const float4 sc0 = *reinterpret_cast<const float4*>(tab + ch0), sc1 = *reinterpret_cast<const float4*>(tab + ch0 + 4);
+        const float4 sh0 = *reinterpret_cast<const float4*>(tab + 64 + ch0), sh1 = *reinterpret_cast<const float4*>(tab + 64 + ch0 + 4);
 #pragma unroll
         for (int it = 0; it < S::HALF / 16 / 128; ++it) {
           const int c = it * 128 + pidx;
-          const int ch0 = (((c & 7) ^ ((c >> 3) & 7)) << 3);
-          const float4 sc0 = *reinterpret_cast<const float4*>(tab + ch0), sc1 = *reinterpret_cast<const float4*>(tab + ch0 + 4);
-          const float4 sh0 = *reinterpret_cast<const float4*>(tab + 64 + ch0), sh1 = *reinterpret_cast<const float4*>(tab + 64 + ch0 + 4);
           const float8 t = cvt8(tq[c]);
           uint4 u;
           u.x = pack_bf16x2(fmaxf(fmaf(t.v[0], sc0.x, sh0.x), 0.f), fmaxf(fmaf(t.v[1], sc0.y, sh0.y), 0.f));
