@@ -172,6 +172,7 @@ CONV_SHAPES = [  # B, H, Cin, Cout
     (2, 16, 16, 32), (3, 8, 32, 16), (1, 32, 64, 128), (2, 4, 128, 128), (4, 2, 64, 64), (2, 64, 64, 64),
     (3, 2, 256, 256), (5, 16, 128, 256), (2, 128, 64, 128), (70, 2, 128, 128),
     (6, 64, 128, 256),                       # dgrad on the halo-window kernel with a 128-wide N tile
+    (20, 64, 64, 128), (40, 32, 128, 64),    # more tiles than SMs with N tiles of 128 / 64 (1 and 2 channel chunks)
 ]
 
 
@@ -228,6 +229,7 @@ CONVT_SHAPES = [  # B, Hin, C0, C1, Cout
     (2, 8, 32, 32, 16), (3, 4, 64, 0, 64), (1, 16, 64, 64, 32), (2, 2, 128, 128, 128), (2, 1, 64, 0, 64),
     (2, 32, 64, 64, 64), (3, 1, 256, 0, 256), (5, 8, 128, 128, 128), (2, 64, 128, 128, 64), (70, 1, 128, 0, 128),
     (20, 16, 64, 64, 128), (3, 64, 64, 0, 128), (5, 32, 192, 64, 64),     # halo-window kernel: one tile row, N = 128, 3+1 chunks
+    (24, 32, 64, 64, 64),                                                 # dgrad with a split output on a grid larger than the machine
 ]
 
 
