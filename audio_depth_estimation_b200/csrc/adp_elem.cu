@@ -313,18 +313,29 @@ bn_affine_act8_kernel(const T* __restrict__ x, long long n8, int C, const adp::B
 #pragma unroll
     for (int k = 0; k < 8; ++k) { const float2 t = coef_s[c + k]; sc.v[k] = t.x; sh.v[k] = t.y; }
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
-    float8 v = ld8(x + 8 * i);
+  // (4 independent loads in flight per thread: the mid-size layers, 16-67 MB, are latency- not bandwidth-bound)
+  constexpr int U = 4;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n8; i0 += U * stride) {
+    typename Raw8<T>::type raw[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v.v[k] = fmaf(v.v[k], sc.v[k], sh.v[k]);
-    float8 o;
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * stride < n8) raw[u] = ldraw8(x + 8 * (i0 + u * stride));
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o.v[k] = lrelu(v.v[k], slope0);
-    st8(out0 + 8 * i, o);
-    if (out1) {
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n8) break;
+      float8 v = cvt8(raw[u]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = lrelu(v.v[k], slope1);
-      st8(out1 + 8 * i, o);
+      for (int k = 0; k < 8; ++k) v.v[k] = fmaf(v.v[k], sc.v[k], sh.v[k]);
+      float8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = lrelu(v.v[k], slope0);
+      st8(out0 + 8 * i, o);
+      if (out1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = lrelu(v.v[k], slope1);
+        st8(out1 + 8 * i, o);
+      }
     }
   }
 }
