@@ -38,6 +38,34 @@ void adp_count_tc_launch();
     }                                                                               \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// A kernel launched through adp::launch_k with "pdl" on may become resident while its predecessor on the stream is still
+// running: its blocks do their set-up (barrier init, TMEM allocation, descriptor prefetch, coefficient loads from
+// parameters) and then block in pdl_wait() until the predecessor has completed and its writes are visible.  Every kernel
+// launched that way MUST call pdl_wait() before its first access to global memory that another kernel wrote or reads
+// (it is a no-op for a normal launch).  pdl_trigger() lets the NEXT kernel's blocks be scheduled as soon as all of
+// ours have started; correctness never depends on it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+namespace adp {
+int pdl_enabled();      // "pdl" option / ADP_PDL (adp_api.cu)
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr = {};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<A&&>(args)...);
+}
+}  // namespace adp
+
 #define ADP_TRY(call)            \
   do {                           \
     int r_ = (call);             \
@@ -236,12 +264,22 @@ int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const floa
 // staged in shared memory).  tensors = 1 (forward) / 3 (backward) slabs must fit: bn_small_ok.
 bool bn_small_ok(int dtype, long long rows, int C, int tensors);
 // batch statistics (f.training must be 1) -> scale/shift/mean/invstd + running statistics -> out0 [, out1]
+// partial != NULL: x has not been written yet -- partial holds the fp32 split-K sums [rows][C] a tensor-core convolution
+// left un-finished (ConvExtras::deferred); they are rounded into x here and cleared
 int bn_small_fwd(int dtype, const void* x, long long rows, int C, const BnFin& f, float slope0, void* out0, float slope1,
-                 void* out1, cudaStream_t s);
+                 void* out1, cudaStream_t s, float* partial = nullptr);
+// gA of bn_small_bwd taken from un-finished split-K sums: [rows][ld] fp32, this layer's C channels at column off; columns
+// [0, side_c) (side_c <= off) are finished into side [rows][side_c] on the way (side may be NULL); all of it is cleared
+struct BnSmallPartial {
+  float* partial;
+  int ld, off;
+  void* side;
+  int side_c;
+};
 // act_bn_bwd_reduce + act_bn_bwd_apply (mode 1 or 2); sums (optional, double [2C]) receives sum gz / sum gz*xhat
 int bn_small_bwd(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift, const float* mean,
                  const float* invstd, const void* gA, float slope0, const void* gB, float slope1, int mode, void* dx,
-                 float* dgamma, float* dbeta, double* sums, cudaStream_t s);
+                 float* dgamma, float* dbeta, double* sums, cudaStream_t s, const BnSmallPartial* pp = nullptr);
 // dgamma[c] = sums[C+c], dbeta[c] = sums[c]
 int bn_param_grads(const double* sums, int C, float* dgamma, float* dbeta, cudaStream_t s);
 // final head: y = act(u + bias); du = dy*act'(y) ; dbias[0] += sum du   (out_ch == 1)
@@ -331,6 +369,10 @@ struct ConvExtras {
   float slope0, slope1;
   void* y_act0; void* y_act1;
   int* fold_done;
+  // gather / parity, split-K launch on a scratch the engine keeps clean: leave the fp32 partial sums [pixels][N0+N1]
+  // un-finished for the consumer (bn_small_fwd / bn_small_bwd round and clear them: one launch less per layer);
+  // *deferred = the sums then, else untouched
+  float** deferred;
 };
 int tc_pointwise(const void* x0, int C0, const void* x1, int C1, const void* w_nk, void* y0, int N0, void* y1, int N1,
                  int act_dual, float slope0, float slope1, int B, int Hi, int Wi, cudaStream_t s,
@@ -362,8 +404,11 @@ int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, 
 int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* w_kn, void* y,
                     int B, int Hi, int Wi, int N, cudaStream_t s, const ConvExtras* ex = nullptr);
 // g_pad = 1: G is [B, 2Hs+2, 2Ws+2, N] with an explicit one-pixel border (its values enter the sums)
+// overwrite = 1 (only where tc_wgrad_can_overwrite says so): dw is stored instead of added to and need not be zeroed
 int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int N,
-             float* dw, int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0);
+             float* dw, int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0, int overwrite = 0);
+bool tc_wgrad_can_overwrite(int B, int Hs, int Ws, int M0, int M1, int N);
+int tc_wgrad_set_store(int on);      // "wg_store" option; returns the previous value
 // 3x3 / stride 1 / pad 1 on the same kernel (binaural_attention_model.py DoubleConv).  wmode 0: w = bf16 [N][9][Ct]
 // (forward); wmode 1: w = bf16 [Ct][9][N] read MN-major with reversed taps (data gradient through the forward weight).
 // scratch: fp32 [pixels][N] for split-K on small grids, or NULL.
@@ -385,7 +430,8 @@ struct GemmEpilogue {
 int tc_gemm_rows(const void* a0, int K0, const void* a1, int K1, const void* bm, int b_kn, void* c16_0, int N0, void* c16_1,
                  int N1, float* c32, long long M, cudaStream_t s, const GemmEpilogue* epi = nullptr);
 // fp32 scratch used to split the K range of deep, small-M layers across CTAs (NULL: never split)
-void tc_set_scratch(void* ptr, size_t bytes);
+// clean: the caller has zeroed it on the launching stream; split launches then skip their memset and re-zero what they used
+void tc_set_scratch(void* ptr, size_t bytes, bool clean = false);
 // switches ("tc_halo", "tc_max_bn", "tc_stats"): returns the previous value, -1 for an unknown name
 int tc_set_option(const char* name, int value);
 int unet_set_option(const char* name, int value);      // "side_stream"

@@ -216,10 +216,12 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
       for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) stats_of(e)[i] = 0.f;
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // everything above is set-up; operands, outputs and statistics belong to the stream order from here
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -627,16 +629,20 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
   }
 }
 
-// fp32 partial sums [pixels][N] -> bf16 outputs (split at N0)
+// fp32 partial sums [pixels][N] -> bf16 outputs (split at N0); rezero: the sums are cleared as they are read, so a scratch
+// that was zero before the convolution is zero again afterwards (the engine clears it once per pass instead of per layer)
 __global__ void __launch_bounds__(256)
-finish_partial_kernel(const float* __restrict__ partial, long long pixels, int N, int N0, int N1, bf16* __restrict__ y0,
-                      bf16* __restrict__ y1) {
+finish_partial_kernel(float* __restrict__ partial, long long pixels, int N, int N0, int N1, bf16* __restrict__ y0,
+                      bf16* __restrict__ y1, int rezero) {
+  pdl_trigger();
+  pdl_wait();
   const long long n4 = pixels * N / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const long long e = 4 * i;
     const long long pix = e / N;
     const int n = (int)(e - pix * N);
     float4 v = ld4(partial + e);
+    if (rezero) st4(partial + e, make_float4(0.f, 0.f, 0.f, 0.f));
     if (n < N0) st4(y0 + pix * N0 + n, v);
     else st4(y1 + pix * N1 + (n - N0), v);
   }
@@ -686,7 +692,7 @@ int launch_persist(const IgemmParams& p, int ctas, cudaStream_t s) {
     return ADP_ERR_ARG;
   }
   ADP_SMEM_ATTR((tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO, ALT>), PS::BYTES);
-  tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO, ALT><<<ctas, 64 + 128 * EG, PS::BYTES, s>>>(p);
+  (void)launch_k(tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO, ALT>, dim3(ctas), dim3(64 + 128 * EG), PS::BYTES, s, p);
   return ADP_OK;
 }
 
@@ -740,7 +746,8 @@ int pick_splits(const IgemmParams& p, int block_n, bool have_scratch, size_t scr
   return splits;
 }
 
-int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes, cudaStream_t s) {
+int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes, cudaStream_t s, bool scratch_clean = false,
+              float** deferred = nullptr) {
   const int m_tiles = p.tiles_w * p.tiles_h * adp_cdiv(p.B, p.Bt);
   const int n_tiles = p.N / block_n;
   const int par = p.mode == 1 ? 4 : 1;
@@ -752,9 +759,10 @@ int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes,
   splits = adp_cdiv(p.kblocks, p.kb_per_split);
   p.splits = splits;
   if (splits > 1 && p.stats) { adp_set_error("tc igemm: fused statistics with a split K range"); return ADP_ERR_ARG; }
-  if (p.f32_rows && splits > 1) scratch = p.out_f32;      // fp32 result: the split-K partial sums ARE the output
+  if (p.f32_rows && splits > 1) { scratch = p.out_f32; scratch_clean = false; }   // fp32 result: the split-K partial sums ARE the output
   p.partial = splits > 1 ? scratch : nullptr;
-  if (splits > 1) ADP_CUDA(cudaMemsetAsync(scratch, 0, (size_t)out_pixels * p.N * sizeof(float), s));
+  // (a clean scratch is all zero on entry and left all zero by finish_partial_kernel: no per-layer memset node)
+  if (splits > 1 && !scratch_clean) ADP_CUDA(cudaMemsetAsync(scratch, 0, (size_t)out_pixels * p.N * sizeof(float), s));
   dim3 grid(m_tiles * par, n_tiles, splits);
   switch (block_n) {
     case 256: ADP_TRY(launch_igemm<256>(p, grid, s)); break;
@@ -764,10 +772,13 @@ int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes,
     case 16: ADP_TRY(launch_igemm<16>(p, grid, s)); break;
     default: adp_set_error("tc igemm: bad BLOCK_N %d", block_n); return ADP_ERR_ARG;
   }
-  if (splits > 1 && !p.f32_rows) {
+  if (splits > 1 && !p.f32_rows && scratch_clean && deferred) {
+    *deferred = scratch;         // the consumer finishes (and clears) the sums
+  } else if (splits > 1 && !p.f32_rows) {
     long long n4 = out_pixels * p.N / 4;
     int blocks = (int)((n4 + 255) / 256 < (long long)sm_count() * 8 ? (n4 + 255) / 256 : (long long)sm_count() * 8);
-    finish_partial_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, s>>>(scratch, out_pixels, p.N, p.N0, p.N1, p.y0, p.y1);
+    (void)launch_k(finish_partial_kernel, dim3(blocks < 1 ? 1 : blocks), dim3(256), 0, s, scratch, out_pixels, p.N, p.N0, p.N1,
+                   p.y0, p.y1, scratch_clean ? 1 : 0);
     ADP_LAUNCH_CHECK();
   }
   return ADP_OK;
@@ -792,6 +803,7 @@ struct TcEnvInit {
 // e.g. one per device, do not see each other's workspace)
 thread_local float* g_scratch = nullptr;
 thread_local size_t g_scratch_bytes = 0;
+thread_local bool g_scratch_clean = false;      // the caller cleared it once and every split launch leaves it cleared
 
 // eval-mode BatchNorm + activation(s) in the epilogue: needs the staged bf16 path of one un-split launch
 bool fold_bn_act(IgemmParams& p, int block_n, const ConvExtras* ex) {
@@ -830,9 +842,10 @@ int tc_set_option(const char* name, int value) {
   return prev;
 }
 
-void tc_set_scratch(void* ptr, size_t bytes) {
+void tc_set_scratch(void* ptr, size_t bytes, bool clean) {
   g_scratch = reinterpret_cast<float*>(ptr);
   g_scratch_bytes = bytes;
+  g_scratch_clean = clean && ptr != nullptr;
 }
 
 bool tc_supported_gather(int B, int Hi, int Wi, int C, int N0, int N1) {
@@ -887,7 +900,7 @@ int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, 
     if (ex->stats_done) *ex->stats_done = 1;
   }
   fold_bn_act(p, bn, ex);
-  return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
+  return run_igemm(p, bn, g_scratch, g_scratch_bytes, s, g_scratch_clean, ex ? ex->deferred : nullptr);
 }
 
 int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* w_kn, void* y, int B, int Hi, int Wi, int N,
@@ -931,7 +944,7 @@ int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* 
     if (ex->stats_done) *ex->stats_done = 1;
   }
   fold_bn_act(p, bn, ex);
-  return run_igemm(p, bn, g_scratch, g_scratch_bytes, s);
+  return run_igemm(p, bn, g_scratch, g_scratch_bytes, s, g_scratch_clean, ex ? ex->deferred : nullptr);
 }
 
 bool tc_supported_pointwise16(int B, int Hi, int Wi, int C0, int C1) {

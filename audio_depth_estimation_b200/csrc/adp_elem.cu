@@ -242,6 +242,8 @@ __device__ __forceinline__ void col_reduce16(float (&v)[16], int C, int c0_block
 template <class T>
 __global__ void __launch_bounds__(256)
 bn_stats8_kernel(const T* __restrict__ x, long long rows, int C, double* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   float v[16];
 #pragma unroll
@@ -269,6 +271,8 @@ template <class T, bool FIXED>
 __global__ void __launch_bounds__(EW_THREADS)
 affine_act8_kernel(const T* __restrict__ x, long long n8, int C, const float* __restrict__ scale,
                    const float* __restrict__ shift, float slope0, T* __restrict__ out0, float slope1, T* __restrict__ out1) {
+  pdl_trigger();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   float8 sc, sh;
   if (FIXED && scale) { const int c = (threadIdx.x * 8) % C; sc = ld8(scale + c); sh = ld8(shift + c); }
@@ -298,6 +302,8 @@ template <class T>
 __global__ void __launch_bounds__(EW_THREADS)
 bn_affine_act8_kernel(const T* __restrict__ x, long long n8, int C, const adp::BnFin f, float slope0, T* __restrict__ out0,
                       float slope1, T* __restrict__ out1) {
+  pdl_trigger();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   // the block derives the C coefficient pairs once (C <= 2048), every thread then picks up its 8 channels
   __shared__ float2 coef_s[2048];
@@ -386,6 +392,8 @@ act_bn_bwd_reduce8_kernel(const T* __restrict__ x, long long rows, int C, const 
                           const float* __restrict__ shift, const float* __restrict__ mean,
                           const float* __restrict__ invstd, const T* __restrict__ gA, float slope0,
                           const T* __restrict__ gB, float slope1, double* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int CH16 = (int)(sizeof(T) * 8 / 16);                 // 16-byte chunks per 8 elements
   extern __shared__ __align__(16) unsigned char red_smem[];      // [STAGES][ROWS][3][CH16][256] x 16 B
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -467,6 +475,8 @@ act_bn_bwd_apply8_kernel(const T* __restrict__ x, long long n8, long long rows, 
                          const float* __restrict__ invstd, const T* __restrict__ gA, float slope0,
                          const T* __restrict__ gB, float slope1, const double* __restrict__ sums, int mode,
                          T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_trigger();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const float inv_m = 1.f / (float)rows;
   if (dgamma && blockIdx.x == 0) {     // dbeta = sum gz, dgamma = sum gz * xhat
@@ -593,11 +603,42 @@ __device__ __forceinline__ void slab_block_reduce16(float (&v)[16], double (&tot
   }
 }
 
+// Split-K partial sums handed over un-finished by a tensor-core convolution (ConvExtras::deferred): 8 fp32 sums are read,
+// cleared (the scratch stays all zero for the next split launch) and rounded to T exactly as finish_partial_kernel would
+// have stored them -- the bf16 tensor in between is never written unless somebody else reads it.
+__device__ __forceinline__ uint4 round_raw8(const float8& a, const bf16*) {
+  uint4 u;
+  u.x = pack_bf16x2_(a.v[0], a.v[1]); u.y = pack_bf16x2_(a.v[2], a.v[3]);
+  u.z = pack_bf16x2_(a.v[4], a.v[5]); u.w = pack_bf16x2_(a.v[6], a.v[7]);
+  return u;
+}
+__device__ __forceinline__ raw8f round_raw8(const float8& a, const float*) {
+  raw8f r;
+  r.a = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  r.b = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
+  return r;
+}
+__device__ __forceinline__ void straw8(bf16* p, const uint4& q) { *reinterpret_cast<uint4*>(p) = q; }
+__device__ __forceinline__ void straw8(float* p, const raw8f& q) {
+  *reinterpret_cast<float4*>(p) = q.a;
+  *reinterpret_cast<float4*>(p + 4) = q.b;
+}
+template <class T>
+__device__ __forceinline__ typename Raw8<T>::type take_partial8(float* part) {
+  const float8 a = ld8(part);
+  float8 z;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) z.v[i] = 0.f;
+  st8(part, z);
+  return round_raw8(a, (const T*)nullptr);
+}
+
 // forward: batch statistics (training) + normalise + one or two activations; slab[rows] of 8 channels in shared memory
+// (partial != NULL: x is still the fp32 split-K sums [rows][C] of the convolution; it is finished here and written to xw)
 template <class T>
 __global__ void __launch_bounds__(SMALL_THREADS)
 bn_small_fwd_kernel(const T* __restrict__ x, int rows, int C, const adp::BnFin f, float slope0, T* __restrict__ out0,
-                    float slope1, T* __restrict__ out1) {
+                    float slope1, T* __restrict__ out1, float* __restrict__ partial, T* __restrict__ xw) {
   extern __shared__ __align__(16) unsigned char slab_raw[];
   typedef typename Raw8<T>::type R8;
   R8* slab = reinterpret_cast<R8*>(slab_raw);
@@ -605,8 +646,16 @@ bn_small_fwd_kernel(const T* __restrict__ x, int rows, int C, const adp::BnFin f
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  pdl_trigger();
+  pdl_wait();
   for (int r = threadIdx.x; r < rows; r += SMALL_THREADS) {
-    const R8 q = ldraw8(x + (size_t)r * C + c0);
+    R8 q;
+    if (partial) {
+      q = take_partial8<T>(partial + (size_t)r * C + c0);
+      straw8(xw + (size_t)r * C + c0, q);            // the raw convolution output: the backward pass normalises it again
+    } else {
+      q = ldraw8(x + (size_t)r * C + c0);
+    }
     slab[r] = q;
     const float8 a = cvt8(q);
 #pragma unroll
@@ -651,31 +700,44 @@ bn_small_fwd_kernel(const T* __restrict__ x, int rows, int C, const adp::BnFin f
 }
 
 // backward of activation(s) + BatchNorm (mode 2: batch statistics, 1: eval): x, gA, gB staged once; dgamma / dbeta written
+// pp.partial != NULL: gA is still the fp32 split-K sums of the data-gradient convolution, [rows][pp.ld] at column pp.off
+// (finished here, in registers: the bf16 gA tensor has no other reader); columns [0, pp.side_c) of the same sums belong to
+// another tensor (the skip-connection gradient of a decoder layer) and are finished into pp.side [rows][pp.side_c].
 template <class T>
 __global__ void __launch_bounds__(SMALL_THREADS)
 bn_small_bwd_kernel(const T* __restrict__ x, int rows, int C, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const T* __restrict__ gA, float slope0,
                     const T* __restrict__ gB, float slope1, int mode, T* __restrict__ dx, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, double* __restrict__ sums) {
+                    float* __restrict__ dbeta, double* __restrict__ sums, const adp::BnSmallPartial pp) {
   extern __shared__ __align__(16) unsigned char slab_raw[];
   typedef typename Raw8<T>::type R8;
   R8* sx = reinterpret_cast<R8*>(slab_raw);
   R8* sg = sx + rows;                                  // gz (computed once), stored as fp32 pairs would double the slab:
   const int c0 = blockIdx.x * 8;                       // keep gA and gB raw instead and recompute gz in the second pass
   R8* sb = sg + rows;
+  pdl_trigger();
+  pdl_wait();
   const float8 sc = ld8(scale + c0), sh = ld8(shift + c0), mu = ld8(mean + c0), is = ld8(invstd + c0);
+  const bool hasA = gA != nullptr || pp.partial != nullptr;
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  if (pp.partial && pp.side) {
+    T* side = reinterpret_cast<T*>(pp.side);
+    for (int j = blockIdx.x; j < pp.side_c / 8; j += gridDim.x)
+      for (int r = threadIdx.x; r < rows; r += SMALL_THREADS)
+        straw8(side + (size_t)r * pp.side_c + 8 * j, take_partial8<T>(pp.partial + (size_t)r * pp.ld + 8 * j));
+  }
   for (int r = threadIdx.x; r < rows; r += SMALL_THREADS) {
     const size_t off = (size_t)r * C + c0;
     GzIn in;
     const R8 qx = ldraw8(x + off);
     sx[r] = qx;
     in.x = cvt8(qx);
-    if (gA) { const R8 q = ldraw8(gA + off); sg[r] = q; in.a = cvt8(q); }
+    if (pp.partial) { const R8 q = take_partial8<T>(pp.partial + (size_t)r * pp.ld + pp.off + c0); sg[r] = q; in.a = cvt8(q); }
+    else if (gA) { const R8 q = ldraw8(gA + off); sg[r] = q; in.a = cvt8(q); }
     if (gB) { const R8 q = ldraw8(gB + off); sb[r] = q; in.b = cvt8(q); }
-    const float8 g = gz_compute(in, &sc, &sh, gA != nullptr, slope0, gB != nullptr, slope1);
+    const float8 g = gz_compute(in, &sc, &sh, hasA, slope0, gB != nullptr, slope1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i] += g.v[i]; v[8 + i] = fmaf(g.v[i], (in.x.v[i] - mu.v[i]) * is.v[i], v[8 + i]); }
   }
@@ -700,9 +762,9 @@ bn_small_bwd_kernel(const T* __restrict__ x, int rows, int C, const float* __res
   for (int r = threadIdx.x; r < rows; r += SMALL_THREADS) {
     GzIn in;
     in.x = cvt8(sx[r]);
-    if (gA) in.a = cvt8(sg[r]);
+    if (hasA) in.a = cvt8(sg[r]);
     if (gB) in.b = cvt8(sb[r]);
-    float8 g = gz_compute(in, &sc, &sh, gA != nullptr, slope0, gB != nullptr, slope1);
+    float8 g = gz_compute(in, &sc, &sh, hasA, slope0, gB != nullptr, slope1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) g.v[i] = fmaf(cA[i], g.v[i], fmaf(cB[i], in.x.v[i], cC[i]));
     st8(dx + (size_t)r * C + c0, g);
@@ -713,6 +775,8 @@ bn_small_bwd_kernel(const T* __restrict__ x, int rows, int C, const float* __res
 __global__ void __launch_bounds__(EW_THREADS)
 head_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, long long n, int final_sigmoid,
                 float* __restrict__ du, float* __restrict__ dbias) {
+  pdl_trigger();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -812,25 +876,30 @@ bool bn_small_ok(int dtype, long long rows, int C, int tensors) {
 }
 
 int bn_small_fwd(int dtype, const void* x, long long rows, int C, const BnFin& f, float slope0, void* out0, float slope1,
-                 void* out1, cudaStream_t s) {
+                 void* out1, cudaStream_t s, float* partial) {
   const int smem = (int)(rows * (dtype == ADP_F32 ? 32 : 16));
   ADP_SMEM_ATTR(bn_small_fwd_kernel<float>, 200 * 1024);
   ADP_SMEM_ATTR(bn_small_fwd_kernel<bf16>, 200 * 1024);
-  ADP_DISPATCH_T(dtype, (bn_small_fwd_kernel<T><<<C / 8, SMALL_THREADS, smem, s>>>((const T*)x, (int)rows, C, f, slope0, (T*)out0,
-                                                                                  slope1, (T*)out1));)
+  ADP_DISPATCH_T(dtype, (void)launch_k(bn_small_fwd_kernel<T>, dim3(C / 8), dim3(SMALL_THREADS), smem, s, (const T*)x, (int)rows, C, f,
+                                       slope0, (T*)out0, slope1, (T*)out1, partial, (T*)const_cast<void*>(x));)
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }
 
 int bn_small_bwd(int dtype, const void* x, long long rows, int C, const float* scale, const float* shift, const float* mean,
                  const float* invstd, const void* gA, float slope0, const void* gB, float slope1, int mode, void* dx,
-                 float* dgamma, float* dbeta, double* sums, cudaStream_t s) {
+                 float* dgamma, float* dbeta, double* sums, cudaStream_t s, const BnSmallPartial* pp) {
   const int smem = (int)(rows * (dtype == ADP_F32 ? 32 : 16) * 3);
+  BnSmallPartial part;
+  memset(&part, 0, sizeof(part));
+  if (pp) part = *pp;
+  ADP_CHECK_ARG(!part.partial || (part.ld % 8 == 0 && part.off % 8 == 0 && part.side_c % 8 == 0 && part.off + C <= part.ld &&
+                                  part.side_c <= part.off), "bn_small_bwd: bad partial-sum layout");
   ADP_SMEM_ATTR(bn_small_bwd_kernel<float>, 200 * 1024);
   ADP_SMEM_ATTR(bn_small_bwd_kernel<bf16>, 200 * 1024);
-  ADP_DISPATCH_T(dtype, (bn_small_bwd_kernel<T><<<C / 8, SMALL_THREADS, smem, s>>>(
-                            (const T*)x, (int)rows, C, scale, shift, mean, invstd, (const T*)gA, slope0, (const T*)gB, slope1,
-                            mode, (T*)dx, dgamma, dbeta, sums));)
+  ADP_DISPATCH_T(dtype, (void)launch_k(bn_small_bwd_kernel<T>, dim3(C / 8), dim3(SMALL_THREADS), smem, s, (const T*)x, (int)rows, C,
+                                       scale, shift, mean, invstd, (const T*)gA, slope0, (const T*)gB, slope1, mode, (T*)dx,
+                                       dgamma, dbeta, sums, part);)
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }
@@ -839,7 +908,7 @@ int bn_stats(int dtype, const void* x, long long rows, int C, double* sums, cuda
   ADP_CHECK_ARG(C % 4 == 0, "bn_stats: C %% 4 != 0");
   if (C % 8 == 0) {
     ColLaunch L = col_launch8(rows, C);
-    ADP_DISPATCH_T(dtype, bn_stats8_kernel<T><<<L.grid, L.block, 0, s>>>((const T*)x, rows, C, sums);)
+    ADP_DISPATCH_T(dtype, (void)launch_k(bn_stats8_kernel<T>, dim3(L.grid), dim3(L.block), 0, s, (const T*)x, rows, C, sums);)
     ADP_LAUNCH_CHECK();
     return ADP_OK;
   }
@@ -858,7 +927,7 @@ int bn_affine_act(int dtype, const void* x, long long rows, int C, const BnFin& 
                   void* out1, cudaStream_t s) {
   if (C % 8 == 0 && 2048 % C == 0) {
     const long long n8 = rows * C / 8;
-    ADP_DISPATCH_T(dtype, (bn_affine_act8_kernel<T><<<ew_grid(n8), EW_THREADS, 0, s>>>((const T*)x, n8, C, f, slope0, (T*)out0,
+    ADP_DISPATCH_T(dtype, ((void)launch_k(bn_affine_act8_kernel<T>, dim3(ew_grid(n8)), dim3(EW_THREADS), 0, s, (const T*)x, n8, C, f, slope0, (T*)out0,
                                                                                      slope1, (T*)out1));)
     ADP_LAUNCH_CHECK();
     return ADP_OK;
@@ -873,11 +942,9 @@ int affine_act(int dtype, const void* x, long long rows, int C, const float* sca
   if (C % 8 == 0) {
     long long n8 = rows * C / 8;
     if (2048 % C == 0) {
-      ADP_DISPATCH_T(dtype, (affine_act8_kernel<T, true><<<ew_grid(n8), EW_THREADS, 0, s>>>(
-                                (const T*)x, n8, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1));)
+      ADP_DISPATCH_T(dtype, ((void)launch_k(affine_act8_kernel<T, true>, dim3(ew_grid(n8)), dim3(EW_THREADS), 0, s, (const T*)x, n8, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1));)
     } else {
-      ADP_DISPATCH_T(dtype, (affine_act8_kernel<T, false><<<ew_grid(n8), EW_THREADS, 0, s>>>(
-                                (const T*)x, n8, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1));)
+      ADP_DISPATCH_T(dtype, ((void)launch_k(affine_act8_kernel<T, false>, dim3(ew_grid(n8)), dim3(EW_THREADS), 0, s, (const T*)x, n8, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1));)
     }
     ADP_LAUNCH_CHECK();
     return ADP_OK;
@@ -898,8 +965,7 @@ int act_bn_bwd_reduce(int dtype, const void* x, long long rows, int C, const flo
     const size_t smem = (size_t)RED_STAGES * RED_ROWS * 3 * 256 * (dtype == ADP_F32 ? 32 : 16);
     ADP_SMEM_ATTR(act_bn_bwd_reduce8_kernel<float>, RED_STAGES * RED_ROWS * 3 * 256 * 32);
     ADP_SMEM_ATTR(act_bn_bwd_reduce8_kernel<bf16>, RED_STAGES * RED_ROWS * 3 * 256 * 16);
-    ADP_DISPATCH_T(dtype, act_bn_bwd_reduce8_kernel<T><<<L.grid, L.block, smem, s>>>(
-                              (const T*)x, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0, (const T*)gB,
+    ADP_DISPATCH_T(dtype, (void)launch_k(act_bn_bwd_reduce8_kernel<T>, dim3(L.grid), dim3(L.block), smem, s, (const T*)x, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0, (const T*)gB,
                               slope1, sums);)
     ADP_LAUNCH_CHECK();
     return ADP_OK;
@@ -922,12 +988,10 @@ int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const floa
       const size_t smem = (size_t)RED_STAGES * RED_ROWS * 3 * 256 * (dtype == ADP_F32 ? 32 : 16);
       ADP_SMEM_ATTR((act_bn_bwd_apply8_kernel<float, true>), RED_STAGES * RED_ROWS * 3 * 256 * 32);
       ADP_SMEM_ATTR((act_bn_bwd_apply8_kernel<bf16, true>), RED_STAGES * RED_ROWS * 3 * 256 * 16);
-      ADP_DISPATCH_T(dtype, (act_bn_bwd_apply8_kernel<T, true><<<ew_grid(n8), EW_THREADS, smem, s>>>(
-                                (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
+      ADP_DISPATCH_T(dtype, ((void)launch_k(act_bn_bwd_apply8_kernel<T, true>, dim3(ew_grid(n8)), dim3(EW_THREADS), smem, s, (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
                                 (const T*)gB, slope1, sums, mode, (T*)dx, dgamma, dbeta));)
     } else {
-      ADP_DISPATCH_T(dtype, (act_bn_bwd_apply8_kernel<T, false><<<ew_grid(n8), EW_THREADS, 0, s>>>(
-                                (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
+      ADP_DISPATCH_T(dtype, ((void)launch_k(act_bn_bwd_apply8_kernel<T, false>, dim3(ew_grid(n8)), dim3(EW_THREADS), 0, s, (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
                                 (const T*)gB, slope1, sums, mode, (T*)dx, dgamma, dbeta));)
     }
     ADP_LAUNCH_CHECK();
@@ -954,7 +1018,7 @@ int head_bwd(const float* y, const float* dy, long long n, int final_sigmoid, fl
   long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  head_bwd_kernel<<<(int)blocks, EW_THREADS, 0, s>>>(y, dy, n, final_sigmoid, du, dbias);
+  (void)launch_k(head_bwd_kernel, dim3((int)blocks), dim3(EW_THREADS), 0, s, y, dy, n, final_sigmoid, du, dbias);
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }

@@ -38,6 +38,7 @@ struct Plan {
   // first-level centring (see use_center): per-input-channel sums of x, the constants m[cout0] / T[cout1]
   size_t xsum, center_m, center_T;
   size_t tc_scratch, tc_scratch_bytes;  // fp32 split-K partial sums of the tensor-core convolutions
+  size_t tc_scratch_clear;              // leading bytes a split launch can touch
   size_t sums_begin, sums_end;   // forward BN sums region (zeroed every forward)
   size_t bsums_begin, bsums_end; // backward sums region
   size_t total;
@@ -101,6 +102,18 @@ int make_plan(const adp_unet_desc* d, Plan* p) {
   // a layer only splits K when it has fewer tiles than SMs, i.e. fewer than ~148*128*128 outputs
   p->tc_scratch_bytes = d->dtype == ADP_BF16 ? (size_t)16 << 20 : 0;
   p->tc_scratch = take(p->tc_scratch_bytes);
+  // the largest fp32 output a split launch can leave there: what the per-step memset has to cover
+  p->tc_scratch_clear = 0;
+  for (int l = 1; l < D && p->tc_scratch_bytes; ++l) {
+    const LevelPlan& L = p->lv[l];
+    const size_t px = (size_t)d->batch * L.hout * L.hout;
+    const size_t cand[4] = {px * L.cout * 4,                      // encoder conv output / its input gradient one level down
+                            4 * px * L.t_cout * 4,                // decoder convT output
+                            px * (L.cout + L.t_c1) * 4,           // decoder convT input gradient
+                            4 * px * L.cin * 4};                  // encoder conv input gradient
+    for (size_t c : cand)
+      if (c <= p->tc_scratch_bytes && c > p->tc_scratch_clear) p->tc_scratch_clear = c;
+  }
   p->p_last = take(d->dtype == ADP_BF16 ? (size_t)d->batch * p->lv[0].hout * p->lv[0].hout * 16 * sizeof(float) : 0);
   p->w16_last = take((size_t)16 * (p->lv[0].cout + p->lv[0].t_c1) * 2);
   {
@@ -200,13 +213,26 @@ int conv_parity(int dtype, const void* x0, int C0, const void* x1, int C1, const
     return tc_parity_convT(x0, C0, x1, C1, wb, y, B, Hi, Wi, N, s, ex);
   return simt_parity_convT(dtype, x0, C0, x1, C1, w, y, B, Hi, Wi, N, s);
 }
+// the weight gradient is ADDED into dw (the caller zeroes it) unless conv_wgrad_overwrites() is true and overwrite = true
+bool conv_wgrad_overwrites(int dtype, int M0, int M1, int N, int B, int Hs, int Ws) {
+  return use_tc(dtype) && tc_supported_wgrad(B, Hs, Ws, M0, M1, N) && tc_wgrad_can_overwrite(B, Hs, Ws, M0, M1, N);
+}
 int conv_wgrad(int dtype, const void* s0, int M0, const void* s1, int M1, const void* g, int N, float* dw,
-               int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0, bool deep = false) {
+               int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0, bool deep = false, bool overwrite = false) {
   ProfScope prof(deep ? PROF_WGRAD_DEEP : PROF_WGRAD, s, 2.0 * B * Hs * Ws * 16.0 * (double)N * (M0 + M1));
   if (use_tc(dtype) && tc_supported_wgrad(B, Hs, Ws, M0, M1, N))
-    return tc_wgrad(s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s, g_pad);
+    return tc_wgrad(s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s, g_pad, overwrite ? 1 : 0);
+  ADP_CHECK_ARG(!overwrite, "conv_wgrad: overwrite needs the tensor-core path");
   ADP_CHECK_ARG(!g_pad, "conv_wgrad: padded operand needs the tensor-core path");
   return simt_wgrad(dtype, s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s);
+}
+
+// "defer_finish" / ADP_DEFER_FINISH=0: every split-K launch finishes its own sums (the A/B partner of the hand-over to
+// the single-launch BatchNorm kernels)
+int g_defer_finish = -1;
+bool defer_finish_enabled() {
+  if (g_defer_finish < 0) g_defer_finish = getenv("ADP_DEFER_FINISH") ? atoi(getenv("ADP_DEFER_FINISH")) : 1;
+  return g_defer_finish != 0;
 }
 
 int check_params(const adp_unet_desc* d, const Plan& p, const adp_unet_level* params) {
@@ -244,7 +270,10 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
   const int D = p.D, B = p.B, dt = d->dtype;
   auto w16 = [&](const void* mirror, size_t off) -> void* { return mirror ? const_cast<void*>(mirror) : (void*)at(ws, off); };
   const bool tc = use_tc(dt);
-  tc_set_scratch(p.tc_scratch_bytes ? at(ws, p.tc_scratch) : nullptr, p.tc_scratch_bytes);
+  // split-K partial sums: cleared once per step here, every split launch (forward and backward) re-zeroes what it used --
+  // one memset node instead of one per split layer and pass
+  if (tc && p.tc_scratch_clear) ADP_CUDA(cudaMemsetAsync(at(ws, p.tc_scratch), 0, p.tc_scratch_clear, s));
+  tc_set_scratch(p.tc_scratch_bytes ? at(ws, p.tc_scratch) : nullptr, p.tc_scratch_bytes, tc && p.tc_scratch_bytes);
 
   const bool tc_head = tc && d->out_ch == 1 &&
                        tc_supported_pointwise16(B, p.lv[0].hout, p.lv[0].hout, p.lv[0].cout, p.lv[0].t_c1);
@@ -310,6 +339,9 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     ConvExtras ex;
     memset(&ex, 0, sizeof(ex));
     if (L.bn_down && d->training) { ex.stats = sums; ex.stats_done = &fused; }
+    // a split-K launch of a small level hands its fp32 sums to the single-launch BatchNorm below (no finishing launch)
+    float* part = nullptr;
+    if (L.bn_down && d->training && defer_finish_enabled() && bn_small_ok(dt, rows, L.cout, 1)) ex.deferred = &part;
     ex.pad_in = (l == 1 && center) ? 1 : 0;
     int folded = 0;
     if (fold && L.bn_down) {
@@ -335,8 +367,9 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
                       d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd,
                       (l == 1 && center) ? cen_T : nullptr};
       if (d->training && !fused && bn_small_ok(dt, rows, L.cout, 1)) {
-        ADP_TRY(bn_small_fwd(dt, at(ws, L.e), rows, L.cout, fin, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), s));
+        ADP_TRY(bn_small_fwd(dt, at(ws, L.e), rows, L.cout, fin, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), s, part));
       } else {
+        ADP_CHECK_ARG(!part, "unet_forward: un-finished partial sums without a consumer (level %d)", l);
         if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, L.e), rows, L.cout, sums, s));
         ADP_TRY(bn_affine_act(dt, at(ws, L.e), rows, L.cout, fin, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), s));
       }
@@ -356,6 +389,8 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     ConvExtras ex;
     memset(&ex, 0, sizeof(ex));
     if (d->training) { ex.stats = sums; ex.stats_done = &fused; }
+    float* part = nullptr;
+    if (d->training && defer_finish_enabled() && !(l == 1 && d1_fused) && bn_small_ok(dt, rows, L.t_cout, 1)) ex.deferred = &part;
     int folded = 0;
     if (fold) {
       BnBuf bnf = bnbuf(ws, L.bn_up_f, L.t_cout);
@@ -386,8 +421,9 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     const BnFin fin{sums, 1.0 / (double)rows, rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f, params[l].bn_up_w, params[l].bn_up_b, params[l].bn_up_rm, params[l].bn_up_rv,
                     d->training, d->bn_eps, d->bn_momentum, bn.scale, bn.shift, bn.mean, bn.invstd, nullptr};
     if (d->training && !fused && bn_small_ok(dt, rows, L.t_cout, 1)) {
-      ADP_TRY(bn_small_fwd(dt, at(ws, O.t), rows, L.t_cout, fin, 0.f, at(ws, O.q), 0.f, nullptr, s));
+      ADP_TRY(bn_small_fwd(dt, at(ws, O.t), rows, L.t_cout, fin, 0.f, at(ws, O.q), 0.f, nullptr, s, part));
     } else {
+      ADP_CHECK_ARG(!part, "unet_forward: un-finished partial sums without a consumer (up level %d)", l);
       if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, O.t), rows, L.t_cout, sums, s));
       ADP_TRY(bn_affine_act(dt, at(ws, O.t), rows, L.t_cout, fin, 0.f, at(ws, O.q), 0.f, nullptr, s));
     }
@@ -453,6 +489,12 @@ int unet_set_option(const char* name, int value) {
     g_d1_fused = value ? 1 : 0;
     return prev;
   }
+  if (!strcmp(name, "defer_finish")) {
+    const int prev = defer_finish_enabled() ? 1 : 0;
+    g_defer_finish = value ? 1 : 0;
+    return prev;
+  }
+  if (!strcmp(name, "wg_store")) return tc_wgrad_set_store(value);
   if (!strcmp(name, "thin_fused")) {
     const int prev = thin_fused_enabled() ? 1 : 0;
     g_thin_fused = value ? 1 : 0;
@@ -480,11 +522,14 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
   const bool tc = use_tc(dt);
   const bool thin_tc_bwd = tc && p.thin_tc && tc_supported_pointwise16(B, p.lv[0].hout, p.lv[0].hout, p.lv[0].cout, p.lv[0].t_c1);
   const int bn_mode = d->training ? 2 : 1;
-  tc_set_scratch(p.tc_scratch_bytes ? at(ws, p.tc_scratch) : nullptr, p.tc_scratch_bytes);
+  // (split-K partial sums: cleared by the forward pass that filled this workspace, left cleared by every split launch)
+  tc_set_scratch(p.tc_scratch_bytes ? at(ws, p.tc_scratch) : nullptr, p.tc_scratch_bytes, tc && p.tc_scratch_bytes);
   const bool center = thin_tc_bwd && use_center(d, p, tc);     // (same decision as the forward pass that filled the workspace)
 
   // BatchNorm + ReLU backward of q[l] (up-norm of level l+1): g_q[l] -> g_t[l]
-  auto up_norm_bwd = [&](int l) -> int {
+  // (part: the data-gradient convolution left its split-K sums [rows][cout + t_c1] un-finished -- g_q[l] is taken from
+  // them, the skip half is finished into g_r[l] on the way)
+  auto up_norm_bwd = [&](int l, float* part) -> int {
     const LevelPlan& L = p.lv[l];
     const LevelPlan& U = p.lv[l + 1];
     const long long rows = (long long)B * L.hout * L.hout;
@@ -492,9 +537,12 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
     BnBuf bn = bnbuf(ws, U.bn_up_f, C);
     double* bs = reinterpret_cast<double*>(at(ws, U.bsums_up));
     ProfScope eprof(PROF_ELEM, s, (double)rows * C * p.esz * 3.0);      // x, g -> dx
-    if (bn_small_ok(dt, rows, C, 3))
+    if (bn_small_ok(dt, rows, C, 3)) {
+      const BnSmallPartial pp{part, L.cout + L.t_c1, L.cout, at(ws, L.g_r), L.cout};
       return bn_small_bwd(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f, nullptr, 0.f,
-                          bn_mode, at(ws, L.g_t), grads[l + 1].bn_up_w, grads[l + 1].bn_up_b, bs, s);
+                          bn_mode, at(ws, L.g_t), grads[l + 1].bn_up_w, grads[l + 1].bn_up_b, bs, s, part ? &pp : nullptr);
+    }
+    ADP_CHECK_ARG(!part, "unet_backward: un-finished partial sums without a consumer (up level %d)", l);
     ADP_TRY(act_bn_bwd_reduce(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f,
                               nullptr, 0.f, bs, s));
     ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.t), rows, C, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_q), 0.f,
@@ -524,6 +572,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
     return side->stream;
   };
 
+  float* part_a = nullptr;      // un-finished split-K sums of g_a[l - 1], handed from encoder stage l to stage l - 1
   for (int st = stage_begin; st < stage_end; ++st) {
     if (st == 0) {
       const LevelPlan& L = p.lv[0];
@@ -558,7 +607,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         ADP_TRY(last_convT_dgrad(dt, du, params[0].convT_w, at(ws, L.g_r), L.cout, at(ws, L.g_q), L.t_c1, B, L.hout,
                                  L.hout, s));
       }
-      ADP_TRY(up_norm_bwd(0));
+      ADP_TRY(up_norm_bwd(0, nullptr));
     } else if (st < D) {
       const int l = st;
       const LevelPlan& L = p.lv[l];
@@ -566,14 +615,21 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       const int Ct = L.cout + L.t_c1;
       {
         cudaStream_t sw = wgrad_stream(st);
-        ADP_CUDA(cudaMemsetAsync(grads[l].convT_w, 0, sizeof(float) * 16 * (size_t)Ct * L.t_cout, sw));
+        const bool ow = conv_wgrad_overwrites(dt, L.cout, L.t_c1, L.t_cout, B, L.hout, L.hout);   // stored, not accumulated
+        if (!ow) ADP_CUDA(cudaMemsetAsync(grads[l].convT_w, 0, sizeof(float) * 16 * (size_t)Ct * L.t_cout, sw));
         ADP_TRY(conv_wgrad(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, at(ws, O.g_t), L.t_cout,
-                           grads[l].convT_w, B, L.hout, L.hout, sw, 0, deep_level(O.hout)));
+                           grads[l].convT_w, B, L.hout, L.hout, sw, 0, deep_level(O.hout), ow));
       }
+      float* part = nullptr;
+      ConvExtras gex;
+      memset(&gex, 0, sizeof(gex));
+      if (l < D - 1 && defer_finish_enabled() && L.t_c1 == p.lv[l + 1].t_cout &&
+          bn_small_ok(dt, (long long)B * L.hout * L.hout, L.t_c1, 3))
+        gex.deferred = &part;
       ADP_TRY(conv_gather(dt, at(ws, O.g_t), params[l].convT_w, tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, L.g_r),
-                          L.cout, L.t_c1 ? at(ws, L.g_q) : nullptr, L.t_c1, B, O.hout, O.hout, L.t_cout, s, nullptr,
+                          L.cout, L.t_c1 ? at(ws, L.g_q) : nullptr, L.t_c1, B, O.hout, O.hout, L.t_cout, s, &gex,
                           deep_level(O.hout)));
-      if (l < D - 1) ADP_TRY(up_norm_bwd(l));
+      if (l < D - 1) ADP_TRY(up_norm_bwd(l, part));
     } else {
       const int l = 2 * D - 1 - st;
       const LevelPlan& L = p.lv[l];
@@ -591,8 +647,11 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
         double* bs = reinterpret_cast<double*>(at(ws, L.bsums_down));
         if (bn_small_ok(dt, rows, L.cout, 3)) {
+          const BnSmallPartial pp{part_a, L.cout, 0, nullptr, 0};
           ADP_TRY(bn_small_bwd(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd, at(ws, L.g_a), 0.2f,
-                               at(ws, L.g_r), 0.f, bn_mode, at(ws, L.g_e), grads[l].bn_down_w, grads[l].bn_down_b, bs, s));
+                               at(ws, L.g_r), 0.f, bn_mode, at(ws, L.g_e), grads[l].bn_down_w, grads[l].bn_down_b, bs, s,
+                               part_a ? &pp : nullptr));
+          part_a = nullptr;
         } else {
           ADP_TRY(act_bn_bwd_reduce(dt, at(ws, L.e), rows, L.cout, bn.scale, bn.shift, bn.mean, bn.invstd,
                                     at(ws, L.g_a), 0.2f, at(ws, L.g_r), 0.f, bs, s));
@@ -606,7 +665,9 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       }
       }
       cudaStream_t sw = l > 0 ? wgrad_stream(st) : s;
-      ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, sw));
+      // (eval-mode centring adds a correction into dw afterwards: fine either way, the product is complete by then)
+      const bool ow = l > 0 && conv_wgrad_overwrites(dt, L.cout, 0, L.cin, B, L.hout, L.hout);
+      if (!ow) ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, sw));
       if (l == 0 && thin_tc_bwd) {
         ProfScope prof(PROF_THIN, s, 2.0 * B * L.hout * L.hout * 16.0 * L.cin * L.cout);
         if (fuse_act0) {       // (dw zeroed above; e > 0 <=> r = ReLU(e) > 0: a[0] may be stored centred, r[0] never is)
@@ -626,14 +687,21 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         const LevelPlan& I = p.lv[l - 1];
         const bool cen = l == 1 && center;
         ADP_TRY(conv_wgrad(dt, at(ws, L.g_e), L.cout, nullptr, 0, at(ws, I.a), L.cin, grads[l].conv_w, B, L.hout,
-                           L.hout, sw, cen ? 1 : 0, deep_level(L.hout)));
+                           L.hout, sw, cen ? 1 : 0, deep_level(L.hout), ow));
         if (cen && !d->training) {   // eval-mode BatchNorm: sum_pixels dL/de = scale * sum gz is not zero
           BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
           ADP_TRY(center_wgrad_fix(grads[l].conv_w, reinterpret_cast<const float*>(at(ws, p.center_m)), bn.scale,
                                    reinterpret_cast<const double*>(at(ws, L.bsums_down)), L.cout, L.cin, sw));
         }
+        // the consumer of g_a[l - 1] is the next stage's single-launch BatchNorm backward, when it runs in this call
+        ConvExtras pex;
+        memset(&pex, 0, sizeof(pex));
+        ADP_CHECK_ARG(!part_a, "unet_backward: un-finished partial sums without a consumer (level %d)", l);
+        if (st + 1 < stage_end && l - 1 >= 1 && I.bn_down && defer_finish_enabled() &&
+            bn_small_ok(dt, (long long)B * I.hout * I.hout, I.cout, 3))
+          pex.deferred = &part_a;
         ADP_TRY(conv_parity(dt, at(ws, L.g_e), L.cout, nullptr, 0, params[l].conv_w, tc ? w16(params[l].conv_w_bf16, L.wb_conv) : nullptr,
-                            at(ws, I.g_a), B, L.hout, L.hout, L.cin, s, nullptr, deep_level(L.hout)));
+                            at(ws, I.g_a), B, L.hout, L.hout, L.cin, s, &pex, deep_level(L.hout)));
       }
     }
   }

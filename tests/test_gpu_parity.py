@@ -815,6 +815,63 @@ def test_d1_forward_band_kernel_inside_the_network(mode):
         assert float((a - b).norm() / b.norm()) <= 2e-2
 
 
+def _step_grads(case, mode, opts):
+    """One forward + backward of build_case(case) under the given library options; (y, {name: grad})."""
+    lib = _lib.load()
+    prev = {k: lib.adp_set_option(k, v) for k, v in opts.items()}
+    assert all(v in (0, 1) for v in prev.values()), prev
+    try:
+        _, net, x, _ = build_case(case, "bf16")
+        net.train(mode == "train")
+        y = net(x)
+        y.backward(torch.ones_like(y) * 1e-3)
+        torch.cuda.synchronize()
+        return y.detach().cpu().numpy(), {n: prm.grad.detach().double().cpu() for n, prm in net.named_parameters()}
+    finally:
+        for k, v in prev.items():
+            lib.adp_set_option(k, v)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_deferred_split_sums_stored_weight_gradients_and_pdl_match_their_partners(mode):
+    """Round-2 launch fusions against their un-fused partners inside the network (B = 8: five levels split K, the 4x4 and
+    smaller levels run the single-launch BatchNorm):
+    "defer_finish" -- split-K sums handed un-finished to bn_small_fwd / bn_small_bwd (no finish_partial launch, the bf16
+    gradient tensor in between is never written); "wg_store" -- weight gradients of un-split / short-K launches stored
+    instead of added into a zeroed buffer; "pdl" -- programmatic dependent launch of the main-stream kernels."""
+    case = ("unet_256", 64, 8, 256, False, 30.0, 970, True, True)
+    on = {b"defer_finish": 1, b"wg_store": 1, b"pdl": 1}
+    off = {b"defer_finish": 0, b"wg_store": 0, b"pdl": 0}
+    y1, g1 = _step_grads(case, mode, on)
+    y0, g0 = _step_grads(case, mode, off)
+    assert np.isfinite(y1).all() and np.abs(y1).max() > 0
+    # (train mode: batch statistics come from fp64 atomics in arrival order, split-K sums from fp32 atomics: single bf16
+    # flips from run to run, also between two runs of the SAME configuration)
+    assert rel_to_max(y1, y0) <= (1.5e-2 if mode == "train" else 8e-3), rel_to_max(y1, y0)
+    for n in g0:
+        a, b = g1[n], g0[n]
+        assert torch.isfinite(a).all(), n
+        if float(b.norm()) == 0:
+            assert float(a.norm()) == 0, n      # (e.g. the all-padding kernel rows of the 1x1 bottleneck stay exactly zero)
+            continue
+        cos = float((a * b).sum() / max(float(a.norm() * b.norm()), 1e-30))
+        outer = n.count("model.") <= 4
+        floor = (0.995 if mode == "eval" else 0.98) if outer else 0.95
+        assert cos >= floor and abs(float(a.norm() / b.norm()) - 1.0) <= (0.03 if outer else 0.1), \
+            (n, cos, float(a.norm() / b.norm()))
+    # the stored weight gradient alone (eval mode: everything upstream of it is the same computation up to the order of
+    # the fp32 split-K atomics): every element, including the exact zeros of the bottleneck's padding rows
+    if mode == "eval":
+        _, gs = _step_grads(case, mode, {b"defer_finish": 1, b"wg_store": 0, b"pdl": 1})
+        for n in gs:
+            a, b = g1[n], gs[n]
+            if b.dim() == 4 and float(b.norm()) > 0:
+                assert float((a - b).norm() / b.norm()) <= 2e-2, (n, float((a - b).norm() / b.norm()))
+                assert bool(((b == 0) == (a == 0)).all()) or float(((b == 0) != (a == 0)).double().mean()) < 1e-3, n
+
+
+
 def test_config5_eval_inference_b64_vs_oracle_and_b1024_batch_invariance():
     """BASELINE config 5 (test.py:231-241): eval-mode prediction from waveforms.  Under no_grad the running-statistics
     BatchNorm and the activations run in the conv epilogues (adp_unet_desc.inference_only): B = 64 against the fp32 CPU
