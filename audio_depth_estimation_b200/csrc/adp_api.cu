@@ -36,17 +36,6 @@ extern "C" long long adp_tc_launch_count(void) { return g_tc_launches.load(std::
 
 namespace adp {
 
-// programmatic dependent launch of the main-stream kernels ("pdl" option / ADP_PDL; see adp_common.cuh)
-static std::atomic<int> g_pdl{-1};
-int pdl_enabled() {
-  int v = g_pdl.load(std::memory_order_relaxed);
-  if (v < 0) {
-    v = getenv("ADP_PDL") ? (atoi(getenv("ADP_PDL")) != 0) : 0;
-    g_pdl.store(v, std::memory_order_relaxed);
-  }
-  return v;
-}
-
 // ---- optional event timing of kernel families ------------------------------------------
 namespace {
 constexpr int PROF_MAX = 32768;
@@ -124,11 +113,6 @@ extern "C" int adp_set_tensor_core(int on) {
 // the convolution epilogue).  Returns the previous value.
 extern "C" int adp_set_option(const char* name, int value) {
   if (!name) return -1;
-  if (!strcmp(name, "pdl")) {
-    const int was = adp::pdl_enabled();
-    adp::g_pdl.store(value ? 1 : 0, std::memory_order_relaxed);
-    return was;
-  }
   const int prev = adp::tc_set_option(name, value);
   return prev >= 0 ? prev : adp::unet_set_option(name, value);   // "side_stream": weight gradients on a side stream
 }

@@ -38,34 +38,6 @@ void adp_count_tc_launch();
     }                                                                               \
   } while (0)
 
-// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
-// A kernel launched through adp::launch_k with "pdl" on may become resident while its predecessor on the stream is still
-// running: its blocks do their set-up (barrier init, TMEM allocation, descriptor prefetch, coefficient loads from
-// parameters) and then block in pdl_wait() until the predecessor has completed and its writes are visible.  Every kernel
-// launched that way MUST call pdl_wait() before its first access to global memory that another kernel wrote or reads
-// (it is a no-op for a normal launch).  pdl_trigger() lets the NEXT kernel's blocks be scheduled as soon as all of
-// ours have started; correctness never depends on it.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-namespace adp {
-int pdl_enabled();      // "pdl" option / ADP_PDL (adp_api.cu)
-template <typename... P, typename... A>
-inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr = {};
-  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr.val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<A&&>(args)...);
-}
-}  // namespace adp
-
 #define ADP_TRY(call)            \
   do {                           \
     int r_ = (call);             \
@@ -404,11 +376,8 @@ int tc_gather_conv(const void* x, const void* w_nk, void* y0, int N0, void* y1, 
 int tc_parity_convT(const void* x0, int C0, const void* x1, int C1, const void* w_kn, void* y,
                     int B, int Hi, int Wi, int N, cudaStream_t s, const ConvExtras* ex = nullptr);
 // g_pad = 1: G is [B, 2Hs+2, 2Ws+2, N] with an explicit one-pixel border (its values enter the sums)
-// overwrite = 1 (only where tc_wgrad_can_overwrite says so): dw is stored instead of added to and need not be zeroed
 int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int N,
-             float* dw, int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0, int overwrite = 0);
-bool tc_wgrad_can_overwrite(int B, int Hs, int Ws, int M0, int M1, int N);
-int tc_wgrad_set_store(int on);      // "wg_store" option; returns the previous value
+             float* dw, int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0);
 // 3x3 / stride 1 / pad 1 on the same kernel (binaural_attention_model.py DoubleConv).  wmode 0: w = bf16 [N][9][Ct]
 // (forward); wmode 1: w = bf16 [Ct][9][N] read MN-major with reversed taps (data gradient through the forward weight).
 // scratch: fp32 [pixels][N] for split-K on small grids, or NULL.

@@ -216,12 +216,10 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
       for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) stats_of(e)[i] = 0.f;
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC);
-  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();          // everything above is set-up; operands, outputs and statistics belong to the stream order from here
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -634,8 +632,6 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
 __global__ void __launch_bounds__(256)
 finish_partial_kernel(float* __restrict__ partial, long long pixels, int N, int N0, int N1, bf16* __restrict__ y0,
                       bf16* __restrict__ y1, int rezero) {
-  pdl_trigger();
-  pdl_wait();
   const long long n4 = pixels * N / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const long long e = 4 * i;
@@ -692,7 +688,7 @@ int launch_persist(const IgemmParams& p, int ctas, cudaStream_t s) {
     return ADP_ERR_ARG;
   }
   ADP_SMEM_ATTR((tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO, ALT>), PS::BYTES);
-  (void)launch_k(tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO, ALT>, dim3(ctas), dim3(64 + 128 * EG), PS::BYTES, s, p);
+  tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO, ALT><<<ctas, 64 + 128 * EG, PS::BYTES, s>>>(p);
   return ADP_OK;
 }
 
@@ -777,8 +773,8 @@ int run_igemm(IgemmParams& p, int block_n, float* scratch, size_t scratch_bytes,
   } else if (splits > 1 && !p.f32_rows) {
     long long n4 = out_pixels * p.N / 4;
     int blocks = (int)((n4 + 255) / 256 < (long long)sm_count() * 8 ? (n4 + 255) / 256 : (long long)sm_count() * 8);
-    (void)launch_k(finish_partial_kernel, dim3(blocks < 1 ? 1 : blocks), dim3(256), 0, s, scratch, out_pixels, p.N, p.N0, p.N1,
-                   p.y0, p.y1, scratch_clean ? 1 : 0);
+    finish_partial_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, s>>>(scratch, out_pixels, p.N, p.N0, p.N1, p.y0, p.y1,
+                                                                 scratch_clean ? 1 : 0);
     ADP_LAUNCH_CHECK();
   }
   return ADP_OK;

@@ -242,8 +242,6 @@ __device__ __forceinline__ void col_reduce16(float (&v)[16], int C, int c0_block
 template <class T>
 __global__ void __launch_bounds__(256)
 bn_stats8_kernel(const T* __restrict__ x, long long rows, int C, double* __restrict__ sums) {
-  pdl_trigger();
-  pdl_wait();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   float v[16];
 #pragma unroll
@@ -271,8 +269,6 @@ template <class T, bool FIXED>
 __global__ void __launch_bounds__(EW_THREADS)
 affine_act8_kernel(const T* __restrict__ x, long long n8, int C, const float* __restrict__ scale,
                    const float* __restrict__ shift, float slope0, T* __restrict__ out0, float slope1, T* __restrict__ out1) {
-  pdl_trigger();
-  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   float8 sc, sh;
   if (FIXED && scale) { const int c = (threadIdx.x * 8) % C; sc = ld8(scale + c); sh = ld8(shift + c); }
@@ -302,8 +298,6 @@ template <class T>
 __global__ void __launch_bounds__(EW_THREADS)
 bn_affine_act8_kernel(const T* __restrict__ x, long long n8, int C, const adp::BnFin f, float slope0, T* __restrict__ out0,
                       float slope1, T* __restrict__ out1) {
-  pdl_trigger();
-  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   // the block derives the C coefficient pairs once (C <= 2048), every thread then picks up its 8 channels
   __shared__ float2 coef_s[2048];
@@ -392,8 +386,6 @@ act_bn_bwd_reduce8_kernel(const T* __restrict__ x, long long rows, int C, const 
                           const float* __restrict__ shift, const float* __restrict__ mean,
                           const float* __restrict__ invstd, const T* __restrict__ gA, float slope0,
                           const T* __restrict__ gB, float slope1, double* __restrict__ sums) {
-  pdl_trigger();
-  pdl_wait();
   constexpr int CH16 = (int)(sizeof(T) * 8 / 16);                 // 16-byte chunks per 8 elements
   extern __shared__ __align__(16) unsigned char red_smem[];      // [STAGES][ROWS][3][CH16][256] x 16 B
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -475,8 +467,6 @@ act_bn_bwd_apply8_kernel(const T* __restrict__ x, long long n8, long long rows, 
                          const float* __restrict__ invstd, const T* __restrict__ gA, float slope0,
                          const T* __restrict__ gB, float slope1, const double* __restrict__ sums, int mode,
                          T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  pdl_trigger();
-  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const float inv_m = 1.f / (float)rows;
   if (dgamma && blockIdx.x == 0) {     // dbeta = sum gz, dgamma = sum gz * xhat
@@ -582,6 +572,7 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C, fl
 // stages it in shared memory (16 bytes per row and tensor), reduces over the rows and applies -- each tensor is read
 // from L2 / HBM exactly once and the layer is ONE launch.
 constexpr int SMALL_THREADS = 256;
+constexpr int SMALL_U = 4;            // rows a thread has in flight (rows <= 1024: the whole first pass)
 
 template <class T>
 __device__ __forceinline__ void slab_block_reduce16(float (&v)[16], double (&tot)[16]) {
@@ -623,14 +614,11 @@ __device__ __forceinline__ void straw8(float* p, const raw8f& q) {
   *reinterpret_cast<float4*>(p) = q.a;
   *reinterpret_cast<float4*>(p + 4) = q.b;
 }
-template <class T>
-__device__ __forceinline__ typename Raw8<T>::type take_partial8(float* part) {
-  const float8 a = ld8(part);
+__device__ __forceinline__ float8 float8_zero() {
   float8 z;
 #pragma unroll
   for (int i = 0; i < 8; ++i) z.v[i] = 0.f;
-  st8(part, z);
-  return round_raw8(a, (const T*)nullptr);
+  return z;
 }
 
 // forward: batch statistics (training) + normalise + one or two activations; slab[rows] of 8 channels in shared memory
@@ -646,20 +634,34 @@ bn_small_fwd_kernel(const T* __restrict__ x, int rows, int C, const adp::BnFin f
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.f;
-  pdl_trigger();
-  pdl_wait();
-  for (int r = threadIdx.x; r < rows; r += SMALL_THREADS) {
-    R8 q;
-    if (partial) {
-      q = take_partial8<T>(partial + (size_t)r * C + c0);
-      straw8(xw + (size_t)r * C + c0, q);            // the raw convolution output: the backward pass normalises it again
-    } else {
-      q = ldraw8(x + (size_t)r * C + c0);
-    }
-    slab[r] = q;
-    const float8 a = cvt8(q);
+  // (SMALL_U rows per thread at a time: all their loads are in flight before the first store -- the rows of a thread are
+  // otherwise one dependent L2 round trip each, and the kernel is nothing but latency)
+  for (int rb = threadIdx.x; rb < rows; rb += SMALL_U * SMALL_THREADS) {
+    R8 q[SMALL_U];
+    float8 pa[SMALL_U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i] += a.v[i]; v[8 + i] = fmaf(a.v[i], a.v[i], v[8 + i]); }
+    for (int u = 0; u < SMALL_U; ++u) {
+      const int r = rb + u * SMALL_THREADS;
+      if (r < rows) {
+        if (partial) pa[u] = ld8(partial + (size_t)r * C + c0);
+        else q[u] = ldraw8(x + (size_t)r * C + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SMALL_U; ++u) {
+      const int r = rb + u * SMALL_THREADS;
+      if (r < rows) {
+        if (partial) {
+          q[u] = round_raw8(pa[u], (const T*)nullptr);
+          st8(partial + (size_t)r * C + c0, float8_zero());
+          straw8(xw + (size_t)r * C + c0, q[u]);       // the raw convolution output: the backward pass normalises it again
+        }
+        slab[r] = q[u];
+        const float8 a = cvt8(q[u]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] += a.v[i]; v[8 + i] = fmaf(a.v[i], a.v[i], v[8 + i]); }
+      }
+    }
   }
   double tot[16];
   slab_block_reduce16<T>(v, tot);
@@ -715,8 +717,6 @@ bn_small_bwd_kernel(const T* __restrict__ x, int rows, int C, const float* __res
   R8* sg = sx + rows;                                  // gz (computed once), stored as fp32 pairs would double the slab:
   const int c0 = blockIdx.x * 8;                       // keep gA and gB raw instead and recompute gz in the second pass
   R8* sb = sg + rows;
-  pdl_trigger();
-  pdl_wait();
   const float8 sc = ld8(scale + c0), sh = ld8(shift + c0), mu = ld8(mean + c0), is = ld8(invstd + c0);
   const bool hasA = gA != nullptr || pp.partial != nullptr;
   float v[16];
@@ -725,21 +725,55 @@ bn_small_bwd_kernel(const T* __restrict__ x, int rows, int C, const float* __res
   if (pp.partial && pp.side) {
     T* side = reinterpret_cast<T*>(pp.side);
     for (int j = blockIdx.x; j < pp.side_c / 8; j += gridDim.x)
-      for (int r = threadIdx.x; r < rows; r += SMALL_THREADS)
-        straw8(side + (size_t)r * pp.side_c + 8 * j, take_partial8<T>(pp.partial + (size_t)r * pp.ld + 8 * j));
-  }
-  for (int r = threadIdx.x; r < rows; r += SMALL_THREADS) {
-    const size_t off = (size_t)r * C + c0;
-    GzIn in;
-    const R8 qx = ldraw8(x + off);
-    sx[r] = qx;
-    in.x = cvt8(qx);
-    if (pp.partial) { const R8 q = take_partial8<T>(pp.partial + (size_t)r * pp.ld + pp.off + c0); sg[r] = q; in.a = cvt8(q); }
-    else if (gA) { const R8 q = ldraw8(gA + off); sg[r] = q; in.a = cvt8(q); }
-    if (gB) { const R8 q = ldraw8(gB + off); sb[r] = q; in.b = cvt8(q); }
-    const float8 g = gz_compute(in, &sc, &sh, hasA, slope0, gB != nullptr, slope1);
+      for (int rb = threadIdx.x; rb < rows; rb += SMALL_U * SMALL_THREADS) {
+        float8 pa[SMALL_U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i] += g.v[i]; v[8 + i] = fmaf(g.v[i], (in.x.v[i] - mu.v[i]) * is.v[i], v[8 + i]); }
+        for (int u = 0; u < SMALL_U; ++u) {
+          const int r = rb + u * SMALL_THREADS;
+          if (r < rows) pa[u] = ld8(pp.partial + (size_t)r * pp.ld + 8 * j);
+        }
+#pragma unroll
+        for (int u = 0; u < SMALL_U; ++u) {
+          const int r = rb + u * SMALL_THREADS;
+          if (r < rows) {
+            st8(pp.partial + (size_t)r * pp.ld + 8 * j, float8_zero());
+            straw8(side + (size_t)r * pp.side_c + 8 * j, round_raw8(pa[u], (const T*)nullptr));
+          }
+        }
+      }
+  }
+  for (int rb = threadIdx.x; rb < rows; rb += SMALL_U * SMALL_THREADS) {
+    R8 qx[SMALL_U], qa[SMALL_U], qb[SMALL_U];
+    float8 pa[SMALL_U];
+#pragma unroll
+    for (int u = 0; u < SMALL_U; ++u) {
+      const int r = rb + u * SMALL_THREADS;
+      if (r < rows) {
+        const size_t off = (size_t)r * C + c0;
+        qx[u] = ldraw8(x + off);
+        if (pp.partial) pa[u] = ld8(pp.partial + (size_t)r * pp.ld + pp.off + c0);
+        else if (gA) qa[u] = ldraw8(gA + off);
+        if (gB) qb[u] = ldraw8(gB + off);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SMALL_U; ++u) {
+      const int r = rb + u * SMALL_THREADS;
+      if (r < rows) {
+        GzIn in;
+        sx[r] = qx[u];
+        in.x = cvt8(qx[u]);
+        if (pp.partial) {
+          qa[u] = round_raw8(pa[u], (const T*)nullptr);
+          st8(pp.partial + (size_t)r * pp.ld + pp.off + c0, float8_zero());
+        }
+        if (hasA) { sg[r] = qa[u]; in.a = cvt8(qa[u]); }
+        if (gB) { sb[r] = qb[u]; in.b = cvt8(qb[u]); }
+        const float8 g = gz_compute(in, &sc, &sh, hasA, slope0, gB != nullptr, slope1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] += g.v[i]; v[8 + i] = fmaf(g.v[i], (in.x.v[i] - mu.v[i]) * is.v[i], v[8 + i]); }
+      }
+    }
   }
   double tot[16];
   slab_block_reduce16<T>(v, tot);
@@ -775,8 +809,6 @@ bn_small_bwd_kernel(const T* __restrict__ x, int rows, int C, const float* __res
 __global__ void __launch_bounds__(EW_THREADS)
 head_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, long long n, int final_sigmoid,
                 float* __restrict__ du, float* __restrict__ dbias) {
-  pdl_trigger();
-  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -880,7 +912,7 @@ int bn_small_fwd(int dtype, const void* x, long long rows, int C, const BnFin& f
   const int smem = (int)(rows * (dtype == ADP_F32 ? 32 : 16));
   ADP_SMEM_ATTR(bn_small_fwd_kernel<float>, 200 * 1024);
   ADP_SMEM_ATTR(bn_small_fwd_kernel<bf16>, 200 * 1024);
-  ADP_DISPATCH_T(dtype, (void)launch_k(bn_small_fwd_kernel<T>, dim3(C / 8), dim3(SMALL_THREADS), smem, s, (const T*)x, (int)rows, C, f,
+  ADP_DISPATCH_T(dtype, bn_small_fwd_kernel<T><<<C / 8, SMALL_THREADS, smem, s>>>((const T*)x, (int)rows, C, f,
                                        slope0, (T*)out0, slope1, (T*)out1, partial, (T*)const_cast<void*>(x));)
   ADP_LAUNCH_CHECK();
   return ADP_OK;
@@ -897,7 +929,7 @@ int bn_small_bwd(int dtype, const void* x, long long rows, int C, const float* s
                                   part.side_c <= part.off), "bn_small_bwd: bad partial-sum layout");
   ADP_SMEM_ATTR(bn_small_bwd_kernel<float>, 200 * 1024);
   ADP_SMEM_ATTR(bn_small_bwd_kernel<bf16>, 200 * 1024);
-  ADP_DISPATCH_T(dtype, (void)launch_k(bn_small_bwd_kernel<T>, dim3(C / 8), dim3(SMALL_THREADS), smem, s, (const T*)x, (int)rows, C,
+  ADP_DISPATCH_T(dtype, bn_small_bwd_kernel<T><<<C / 8, SMALL_THREADS, smem, s>>>((const T*)x, (int)rows, C,
                                        scale, shift, mean, invstd, (const T*)gA, slope0, (const T*)gB, slope1, mode, (T*)dx,
                                        dgamma, dbeta, sums, part);)
   ADP_LAUNCH_CHECK();
@@ -908,7 +940,7 @@ int bn_stats(int dtype, const void* x, long long rows, int C, double* sums, cuda
   ADP_CHECK_ARG(C % 4 == 0, "bn_stats: C %% 4 != 0");
   if (C % 8 == 0) {
     ColLaunch L = col_launch8(rows, C);
-    ADP_DISPATCH_T(dtype, (void)launch_k(bn_stats8_kernel<T>, dim3(L.grid), dim3(L.block), 0, s, (const T*)x, rows, C, sums);)
+    ADP_DISPATCH_T(dtype, bn_stats8_kernel<T><<<L.grid, L.block, 0, s>>>((const T*)x, rows, C, sums);)
     ADP_LAUNCH_CHECK();
     return ADP_OK;
   }
@@ -927,7 +959,7 @@ int bn_affine_act(int dtype, const void* x, long long rows, int C, const BnFin& 
                   void* out1, cudaStream_t s) {
   if (C % 8 == 0 && 2048 % C == 0) {
     const long long n8 = rows * C / 8;
-    ADP_DISPATCH_T(dtype, ((void)launch_k(bn_affine_act8_kernel<T>, dim3(ew_grid(n8)), dim3(EW_THREADS), 0, s, (const T*)x, n8, C, f, slope0, (T*)out0,
+    ADP_DISPATCH_T(dtype, (bn_affine_act8_kernel<T><<<ew_grid(n8), EW_THREADS, 0, s>>>((const T*)x, n8, C, f, slope0, (T*)out0,
                                                                                      slope1, (T*)out1));)
     ADP_LAUNCH_CHECK();
     return ADP_OK;
@@ -942,9 +974,11 @@ int affine_act(int dtype, const void* x, long long rows, int C, const float* sca
   if (C % 8 == 0) {
     long long n8 = rows * C / 8;
     if (2048 % C == 0) {
-      ADP_DISPATCH_T(dtype, ((void)launch_k(affine_act8_kernel<T, true>, dim3(ew_grid(n8)), dim3(EW_THREADS), 0, s, (const T*)x, n8, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1));)
+      ADP_DISPATCH_T(dtype, (affine_act8_kernel<T, true><<<ew_grid(n8), EW_THREADS, 0, s>>>(
+                                (const T*)x, n8, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1));)
     } else {
-      ADP_DISPATCH_T(dtype, ((void)launch_k(affine_act8_kernel<T, false>, dim3(ew_grid(n8)), dim3(EW_THREADS), 0, s, (const T*)x, n8, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1));)
+      ADP_DISPATCH_T(dtype, (affine_act8_kernel<T, false><<<ew_grid(n8), EW_THREADS, 0, s>>>(
+                                (const T*)x, n8, C, scale, shift, slope0, (T*)out0, slope1, (T*)out1));)
     }
     ADP_LAUNCH_CHECK();
     return ADP_OK;
@@ -965,7 +999,8 @@ int act_bn_bwd_reduce(int dtype, const void* x, long long rows, int C, const flo
     const size_t smem = (size_t)RED_STAGES * RED_ROWS * 3 * 256 * (dtype == ADP_F32 ? 32 : 16);
     ADP_SMEM_ATTR(act_bn_bwd_reduce8_kernel<float>, RED_STAGES * RED_ROWS * 3 * 256 * 32);
     ADP_SMEM_ATTR(act_bn_bwd_reduce8_kernel<bf16>, RED_STAGES * RED_ROWS * 3 * 256 * 16);
-    ADP_DISPATCH_T(dtype, (void)launch_k(act_bn_bwd_reduce8_kernel<T>, dim3(L.grid), dim3(L.block), smem, s, (const T*)x, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0, (const T*)gB,
+    ADP_DISPATCH_T(dtype, act_bn_bwd_reduce8_kernel<T><<<L.grid, L.block, smem, s>>>(
+                              (const T*)x, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0, (const T*)gB,
                               slope1, sums);)
     ADP_LAUNCH_CHECK();
     return ADP_OK;
@@ -988,10 +1023,12 @@ int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const floa
       const size_t smem = (size_t)RED_STAGES * RED_ROWS * 3 * 256 * (dtype == ADP_F32 ? 32 : 16);
       ADP_SMEM_ATTR((act_bn_bwd_apply8_kernel<float, true>), RED_STAGES * RED_ROWS * 3 * 256 * 32);
       ADP_SMEM_ATTR((act_bn_bwd_apply8_kernel<bf16, true>), RED_STAGES * RED_ROWS * 3 * 256 * 16);
-      ADP_DISPATCH_T(dtype, ((void)launch_k(act_bn_bwd_apply8_kernel<T, true>, dim3(ew_grid(n8)), dim3(EW_THREADS), smem, s, (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
+      ADP_DISPATCH_T(dtype, (act_bn_bwd_apply8_kernel<T, true><<<ew_grid(n8), EW_THREADS, smem, s>>>(
+                                (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
                                 (const T*)gB, slope1, sums, mode, (T*)dx, dgamma, dbeta));)
     } else {
-      ADP_DISPATCH_T(dtype, ((void)launch_k(act_bn_bwd_apply8_kernel<T, false>, dim3(ew_grid(n8)), dim3(EW_THREADS), 0, s, (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
+      ADP_DISPATCH_T(dtype, (act_bn_bwd_apply8_kernel<T, false><<<ew_grid(n8), EW_THREADS, 0, s>>>(
+                                (const T*)x, n8, rows, C, scale, shift, mean, invstd, (const T*)gA, slope0,
                                 (const T*)gB, slope1, sums, mode, (T*)dx, dgamma, dbeta));)
     }
     ADP_LAUNCH_CHECK();
@@ -1018,7 +1055,7 @@ int head_bwd(const float* y, const float* dy, long long n, int final_sigmoid, fl
   long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  (void)launch_k(head_bwd_kernel, dim3((int)blocks), dim3(EW_THREADS), 0, s, y, dy, n, final_sigmoid, du, dbias);
+  head_bwd_kernel<<<(int)blocks, EW_THREADS, 0, s>>>(y, dy, n, final_sigmoid, du, dbias);
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }

@@ -28,8 +28,6 @@ __device__ __forceinline__ void loss_accum(float p, float g, float scale, float 
 __global__ void __launch_bounds__(LOSS_THREADS)
 loss_sums_kernel(const float* __restrict__ pred, const float* __restrict__ gt, long long n, float scale,
                  float eps, int use_mask, double* __restrict__ sums) {
-  pdl_trigger();
-  pdl_wait();
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -84,8 +82,6 @@ __device__ __forceinline__ LossScalars loss_scalars(const double* sums, float la
 
 __global__ void loss_value_kernel(const double* __restrict__ sums, float l1_w, float silog_w, float lam,
                                   float* __restrict__ out) {
-  pdl_trigger();
-  pdl_wait();
   LossScalars r = loss_scalars(sums, lam);
   float loss = l1_w * r.l1;
   if (silog_w != 0.f) loss += silog_w * r.silog;
@@ -113,8 +109,6 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 loss_backward_kernel(const float* __restrict__ pred, const float* __restrict__ gt, long long n, float scale,
                      float eps, int use_mask, const double* __restrict__ sums, float l1_w, float silog_w, float lam,
                      const float* __restrict__ grad_scale, float* __restrict__ dpred) {
-  pdl_trigger();
-  pdl_wait();
   const LossScalars r = loss_scalars(sums, lam);
   const float gs = grad_scale ? *grad_scale : 1.f;
   const long long n4 = n >> 2;
@@ -147,7 +141,7 @@ extern "C" int adp_depth_loss_sums(const float* pred, const float* gt, int64_t n
   ADP_CHECK_ARG(pred && gt && sums && n >= 0, "loss_sums: bad arguments");
   ADP_CHECK_ARG(((uintptr_t)pred % 16 == 0) && ((uintptr_t)gt % 16 == 0), "loss_sums: pointers must be 16-byte aligned");
   adp::ProfScope prof(adp::PROF_LOSS, (cudaStream_t)stream, (double)n * 8.0);            // pred, gt in
-  (void)adp::launch_k(loss_sums_kernel, dim3(loss_grid(n)), dim3(LOSS_THREADS), 0, (cudaStream_t)stream, pred, gt, n, scale, eps, use_mask, sums);
+  loss_sums_kernel<<<loss_grid(n), LOSS_THREADS, 0, (cudaStream_t)stream>>>(pred, gt, n, scale, eps, use_mask, sums);
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }
@@ -155,7 +149,7 @@ extern "C" int adp_depth_loss_sums(const float* pred, const float* gt, int64_t n
 extern "C" int adp_depth_loss_value(const double* sums, float l1_w, float silog_w, float lam, float* loss_out,
                                     void* stream) {
   ADP_CHECK_ARG(sums && loss_out, "loss_value: null pointer");
-  (void)adp::launch_k(loss_value_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, sums, l1_w, silog_w, lam, loss_out);
+  loss_value_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sums, l1_w, silog_w, lam, loss_out);
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }
@@ -167,7 +161,7 @@ extern "C" int adp_depth_loss_backward(const float* pred, const float* gt, int64
   adp::ProfScope prof(adp::PROF_LOSS, (cudaStream_t)stream, (double)n * 4.0);            // dpred out (pred, gt counted by loss_sums)
   ADP_CHECK_ARG(((uintptr_t)pred % 16 == 0) && ((uintptr_t)gt % 16 == 0) && ((uintptr_t)dpred % 16 == 0),
                 "loss_backward: pointers must be 16-byte aligned");
-  (void)adp::launch_k(loss_backward_kernel, dim3(loss_grid(n)), dim3(LOSS_THREADS), 0, (cudaStream_t)stream, 
+  loss_backward_kernel<<<loss_grid(n), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
       pred, gt, n, scale, eps, use_mask, sums, l1_w, silog_w, lam, grad_scale, dpred);
   ADP_LAUNCH_CHECK();
   return ADP_OK;

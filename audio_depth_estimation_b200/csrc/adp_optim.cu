@@ -79,8 +79,6 @@ __global__ void adam_tick_kernel(int* __restrict__ step, float* __restrict__ sca
 __global__ void __launch_bounds__(OPT_THREADS)
 clip_adamw_kernel(const __grid_constant__ TensorTable tab, const double* __restrict__ sumsq, AdamArgs a,
                   float* __restrict__ norm_out, const float* __restrict__ dev_scalars) {
-  pdl_trigger();
-  pdl_wait();
   if (dev_scalars) { a.step_size = dev_scalars[0]; a.inv_bc2_sqrt = dev_scalars[1]; }
   const float total = (float)sqrt(*sumsq);
   float coef = a.max_norm > 0.f ? a.max_norm / (total + 1e-6f) : 1.f;
@@ -174,7 +172,7 @@ extern "C" int adp_clip_adamw_step(const adp_tensor_ref* refs_host, int n_tensor
   a.step_size = (float)((double)lr / bc1);
   a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   return for_each_table(refs_host, n_tensors, [&](const TensorTable& tab, int blocks) -> int {
-    (void)adp::launch_k(clip_adamw_kernel, dim3(blocks), dim3(OPT_THREADS), 0, s, tab, sumsq, a, norm_out, nullptr);
+    clip_adamw_kernel<<<blocks, OPT_THREADS, 0, s>>>(tab, sumsq, a, norm_out, nullptr);
     ADP_LAUNCH_CHECK();
     return ADP_OK;
   });
@@ -198,7 +196,7 @@ extern "C" int adp_clip_adamw_step_graph(const adp_tensor_ref* refs_host, int n_
   adam_tick_kernel<<<1, 1, 0, s>>>(step_dev, scratch, lr, beta1, beta2);
   ADP_LAUNCH_CHECK();
   return for_each_table(refs_host, n_tensors, [&](const TensorTable& tab, int blocks) -> int {
-    (void)adp::launch_k(clip_adamw_kernel, dim3(blocks), dim3(OPT_THREADS), 0, s, tab, sumsq, a, norm_out, scratch);
+    clip_adamw_kernel<<<blocks, OPT_THREADS, 0, s>>>(tab, sumsq, a, norm_out, scratch);
     ADP_LAUNCH_CHECK();
     return ADP_OK;
   });

@@ -166,12 +166,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) thin_patch_gemm_kernel(const __
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * NOUT);
-  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -355,8 +353,6 @@ __global__ void __launch_bounds__(TL_THREADS, 1) thin_last_fwd_kernel(const __gr
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 32);
-  pdl_trigger();
-  pdl_wait();                 // (the BatchNorm coefficients below were written by the kernel before this one)
   if (p.bn_scale && threadIdx.x >= 64 && threadIdx.x < 128) {
     tab[threadIdx.x - 64] = p.bn_scale[threadIdx.x - 64];
     tab[threadIdx.x] = p.bn_shift[threadIdx.x - 64];
@@ -533,7 +529,7 @@ int launch_thin_fwd(ThinFwdParams& p, cudaStream_t s) {
   using S = ThinFwdSmem<NOUT>;
   ADP_SMEM_ATTR((thin_patch_gemm_kernel<CIN, SPLIT, NOUT>), S::BYTES);
   const int ctas = p.ntiles < sm_count() ? p.ntiles : sm_count();
-  (void)launch_k(thin_patch_gemm_kernel<CIN, SPLIT, NOUT>, dim3(ctas), dim3(TP_THREADS), S::BYTES, s, p);
+  thin_patch_gemm_kernel<CIN, SPLIT, NOUT><<<ctas, TP_THREADS, S::BYTES, s>>>(p);
   adp_count_tc_launch();
   ADP_LAUNCH_CHECK();
   return ADP_OK;
@@ -629,8 +625,6 @@ __global__ void __launch_bounds__(TW_THREADS, 1) thin_patch_wgrad_kernel(const _
   }
   if (warp == 1) tmem_alloc(tmem_slot, NT);
   float* tab = reinterpret_cast<float*>(smem + S::OFF_TAB);
-  pdl_trigger();
-  pdl_wait();
   if (QBN && threadIdx.x >= 64 && threadIdx.x < 128) {
     tab[threadIdx.x - 64] = p.bn_scale[threadIdx.x - 64];
     tab[threadIdx.x] = p.bn_shift[threadIdx.x - 64];
@@ -796,7 +790,7 @@ int launch_thin_wgrad(ThinWgradParams& p, cudaStream_t s) {
   using S = ThinWgradSmem<FOLD, XF>;
   ADP_SMEM_ATTR((thin_patch_wgrad_kernel<FOLD, XF>), S::BYTES);
   const int ctas = p.ntiles < sm_count() ? p.ntiles : sm_count();
-  (void)launch_k(thin_patch_wgrad_kernel<FOLD, XF>, dim3(ctas), dim3(TW_THREADS), S::BYTES, s, p);
+  thin_patch_wgrad_kernel<FOLD, XF><<<ctas, TW_THREADS, S::BYTES, s>>>(p);
   adp_count_tc_launch();
   ADP_LAUNCH_CHECK();
   return ADP_OK;
@@ -867,7 +861,7 @@ int thin_tc_last_fwd(const void* x0, const void* x1, const float* scale, const f
   }
   ADP_SMEM_ATTR(thin_last_fwd_kernel, ThinLastSmem::BYTES);
   const int ctas = p.rows < sm_count() ? p.rows : sm_count();
-  (void)launch_k(thin_last_fwd_kernel, dim3(ctas), dim3(TL_THREADS), ThinLastSmem::BYTES, s, p);
+  thin_last_fwd_kernel<<<ctas, TL_THREADS, ThinLastSmem::BYTES, s>>>(p);
   adp_count_tc_launch();
   ADP_LAUNCH_CHECK();
   return ADP_OK;

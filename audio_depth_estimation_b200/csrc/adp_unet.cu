@@ -213,26 +213,21 @@ int conv_parity(int dtype, const void* x0, int C0, const void* x1, int C1, const
     return tc_parity_convT(x0, C0, x1, C1, wb, y, B, Hi, Wi, N, s, ex);
   return simt_parity_convT(dtype, x0, C0, x1, C1, w, y, B, Hi, Wi, N, s);
 }
-// the weight gradient is ADDED into dw (the caller zeroes it) unless conv_wgrad_overwrites() is true and overwrite = true
-bool conv_wgrad_overwrites(int dtype, int M0, int M1, int N, int B, int Hs, int Ws) {
-  return use_tc(dtype) && tc_supported_wgrad(B, Hs, Ws, M0, M1, N) && tc_wgrad_can_overwrite(B, Hs, Ws, M0, M1, N);
-}
 int conv_wgrad(int dtype, const void* s0, int M0, const void* s1, int M1, const void* g, int N, float* dw,
-               int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0, bool deep = false, bool overwrite = false) {
+               int B, int Hs, int Ws, cudaStream_t s, int g_pad = 0, bool deep = false) {
   ProfScope prof(deep ? PROF_WGRAD_DEEP : PROF_WGRAD, s, 2.0 * B * Hs * Ws * 16.0 * (double)N * (M0 + M1));
   if (use_tc(dtype) && tc_supported_wgrad(B, Hs, Ws, M0, M1, N))
-    return tc_wgrad(s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s, g_pad, overwrite ? 1 : 0);
-  ADP_CHECK_ARG(!overwrite, "conv_wgrad: overwrite needs the tensor-core path");
+    return tc_wgrad(s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s, g_pad);
   ADP_CHECK_ARG(!g_pad, "conv_wgrad: padded operand needs the tensor-core path");
   return simt_wgrad(dtype, s0, M0, s1, M1, g, N, dw, B, Hs, Ws, s);
 }
 
-// "defer_finish" / ADP_DEFER_FINISH=0: every split-K launch finishes its own sums (the A/B partner of the hand-over to
-// the single-launch BatchNorm kernels)
+// "defer_finish" / ADP_DEFER_FINISH (bit 0: forward, bit 1: backward; 0: every split-K launch finishes its own sums --
+// the A/B partner of the hand-over to the single-launch BatchNorm kernels)
 int g_defer_finish = -1;
-bool defer_finish_enabled() {
-  if (g_defer_finish < 0) g_defer_finish = getenv("ADP_DEFER_FINISH") ? atoi(getenv("ADP_DEFER_FINISH")) : 1;
-  return g_defer_finish != 0;
+int defer_finish_mask() {
+  if (g_defer_finish < 0) g_defer_finish = getenv("ADP_DEFER_FINISH") ? (atoi(getenv("ADP_DEFER_FINISH")) & 3) : 3;
+  return g_defer_finish;
 }
 
 int check_params(const adp_unet_desc* d, const Plan& p, const adp_unet_level* params) {
@@ -341,7 +336,7 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     if (L.bn_down && d->training) { ex.stats = sums; ex.stats_done = &fused; }
     // a split-K launch of a small level hands its fp32 sums to the single-launch BatchNorm below (no finishing launch)
     float* part = nullptr;
-    if (L.bn_down && d->training && defer_finish_enabled() && bn_small_ok(dt, rows, L.cout, 1)) ex.deferred = &part;
+    if (L.bn_down && d->training && (defer_finish_mask() & 1) && bn_small_ok(dt, rows, L.cout, 1)) ex.deferred = &part;
     ex.pad_in = (l == 1 && center) ? 1 : 0;
     int folded = 0;
     if (fold && L.bn_down) {
@@ -390,7 +385,7 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     memset(&ex, 0, sizeof(ex));
     if (d->training) { ex.stats = sums; ex.stats_done = &fused; }
     float* part = nullptr;
-    if (d->training && defer_finish_enabled() && !(l == 1 && d1_fused) && bn_small_ok(dt, rows, L.t_cout, 1)) ex.deferred = &part;
+    if (d->training && (defer_finish_mask() & 1) && !(l == 1 && d1_fused) && bn_small_ok(dt, rows, L.t_cout, 1)) ex.deferred = &part;
     int folded = 0;
     if (fold) {
       BnBuf bnf = bnbuf(ws, L.bn_up_f, L.t_cout);
@@ -490,11 +485,10 @@ int unet_set_option(const char* name, int value) {
     return prev;
   }
   if (!strcmp(name, "defer_finish")) {
-    const int prev = defer_finish_enabled() ? 1 : 0;
-    g_defer_finish = value ? 1 : 0;
+    const int prev = defer_finish_mask();
+    g_defer_finish = value & 3;
     return prev;
   }
-  if (!strcmp(name, "wg_store")) return tc_wgrad_set_store(value);
   if (!strcmp(name, "thin_fused")) {
     const int prev = thin_fused_enabled() ? 1 : 0;
     g_thin_fused = value ? 1 : 0;
@@ -615,15 +609,14 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       const int Ct = L.cout + L.t_c1;
       {
         cudaStream_t sw = wgrad_stream(st);
-        const bool ow = conv_wgrad_overwrites(dt, L.cout, L.t_c1, L.t_cout, B, L.hout, L.hout);   // stored, not accumulated
-        if (!ow) ADP_CUDA(cudaMemsetAsync(grads[l].convT_w, 0, sizeof(float) * 16 * (size_t)Ct * L.t_cout, sw));
+        ADP_CUDA(cudaMemsetAsync(grads[l].convT_w, 0, sizeof(float) * 16 * (size_t)Ct * L.t_cout, sw));
         ADP_TRY(conv_wgrad(dt, at(ws, L.r), L.cout, L.t_c1 ? at(ws, L.q) : nullptr, L.t_c1, at(ws, O.g_t), L.t_cout,
-                           grads[l].convT_w, B, L.hout, L.hout, sw, 0, deep_level(O.hout), ow));
+                           grads[l].convT_w, B, L.hout, L.hout, sw, 0, deep_level(O.hout)));
       }
       float* part = nullptr;
       ConvExtras gex;
       memset(&gex, 0, sizeof(gex));
-      if (l < D - 1 && defer_finish_enabled() && L.t_c1 == p.lv[l + 1].t_cout &&
+      if (l < D - 1 && (defer_finish_mask() & 2) && L.t_c1 == p.lv[l + 1].t_cout &&
           bn_small_ok(dt, (long long)B * L.hout * L.hout, L.t_c1, 3))
         gex.deferred = &part;
       ADP_TRY(conv_gather(dt, at(ws, O.g_t), params[l].convT_w, tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, L.g_r),
@@ -665,9 +658,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       }
       }
       cudaStream_t sw = l > 0 ? wgrad_stream(st) : s;
-      // (eval-mode centring adds a correction into dw afterwards: fine either way, the product is complete by then)
-      const bool ow = l > 0 && conv_wgrad_overwrites(dt, L.cout, 0, L.cin, B, L.hout, L.hout);
-      if (!ow) ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, sw));
+      ADP_CUDA(cudaMemsetAsync(grads[l].conv_w, 0, sizeof(float) * 16 * (size_t)L.cout * L.cin, sw));
       if (l == 0 && thin_tc_bwd) {
         ProfScope prof(PROF_THIN, s, 2.0 * B * L.hout * L.hout * 16.0 * L.cin * L.cout);
         if (fuse_act0) {       // (dw zeroed above; e > 0 <=> r = ReLU(e) > 0: a[0] may be stored centred, r[0] never is)
@@ -687,7 +678,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         const LevelPlan& I = p.lv[l - 1];
         const bool cen = l == 1 && center;
         ADP_TRY(conv_wgrad(dt, at(ws, L.g_e), L.cout, nullptr, 0, at(ws, I.a), L.cin, grads[l].conv_w, B, L.hout,
-                           L.hout, sw, cen ? 1 : 0, deep_level(L.hout), ow));
+                           L.hout, sw, cen ? 1 : 0, deep_level(L.hout)));
         if (cen && !d->training) {   // eval-mode BatchNorm: sum_pixels dL/de = scale * sum gz is not zero
           BnBuf bn = bnbuf(ws, L.bn_down_f, L.cout);
           ADP_TRY(center_wgrad_fix(grads[l].conv_w, reinterpret_cast<const float*>(at(ws, p.center_m)), bn.scale,
@@ -697,7 +688,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
         ConvExtras pex;
         memset(&pex, 0, sizeof(pex));
         ADP_CHECK_ARG(!part_a, "unet_backward: un-finished partial sums without a consumer (level %d)", l);
-        if (st + 1 < stage_end && l - 1 >= 1 && I.bn_down && defer_finish_enabled() &&
+        if (st + 1 < stage_end && l - 1 >= 1 && I.bn_down && (defer_finish_mask() & 2) &&
             bn_small_ok(dt, (long long)B * I.hout * I.hout, I.cout, 3))
           pex.deferred = &part_a;
         ADP_TRY(conv_parity(dt, at(ws, L.g_e), L.cout, nullptr, 0, params[l].conv_w, tc ? w16(params[l].conv_w_bf16, L.wb_conv) : nullptr,

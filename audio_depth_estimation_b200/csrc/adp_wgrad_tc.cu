@@ -38,8 +38,6 @@ struct WgradParams {
   int ldn, n_off;     // dw row pitch per tap (total input channels) and column offset of this G tensor
   int g_pad;          // 4x4 mode: G carries an explicit one-pixel border (row 2i+kh of the padded tensor, never out of bounds)
   int skip_edge_rows; // 4x4 mode, Hs == 1 without a border: kernel rows 0 and 3 are all padding
-  int overwrite;      // one CTA per weight tile and kernel row (no pixel split): dw is stored, not added to -- the caller
-                      // does not zero it (no memset pass over the fp32 gradient, no read-modify-write in L2)
 };
 
 template <int NT>
@@ -74,18 +72,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
   const int kh = blockIdx.z % NTAPS;             // tap group = kernel row
   // 4x4 stride-2 window over a two-row G (the 1 x 1 bottleneck): kernel rows 0 and 3 only meet the zero padding, their
   // gradient is exactly zero and dw is zeroed by the caller
-  if (!K3 && p.skip_edge_rows && (kh == 0 || kh == 3)) {
-    if (p.overwrite) {   // nobody zeroed dw: these taps' gradient is exactly zero, write it
-      constexpr int V = NT / 4;
-      for (int i = threadIdx.x; i < WG_M * NTAPS * V; i += WG_THREADS) {
-        const int c4 = i % V, t = (i / V) % NTAPS, m = m0 + i / (V * NTAPS);
-        if (m < p.M0 + p.M1)
-          *reinterpret_cast<float4*>(p.dw + ((size_t)m * (NTAPS * NTAPS) + kh * NTAPS + t) * p.ldn + p.n_off + n0 + 4 * c4) =
-              make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    return;
-  }
+  if (!K3 && p.skip_edge_rows && (kh == 0 || kh == 3)) return;
   const int split = blockIdx.z / NTAPS;
   const int kb_begin = split * p.kb_per_split;
   const int kb_end = min(kb_begin + p.kb_per_split, p.kblocks);
@@ -177,14 +164,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kw * NT + cc), v);
         if (nkb > 0 && m < p.M0 + p.M1) {
-          if (p.overwrite) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(row + cc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) red_add_v4(row + cc + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-          }
+          for (int i = 0; i < 32; i += 4) red_add_v4(row + cc + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
       }
     }
@@ -417,46 +398,8 @@ bool tc_supported_wgrad(int B, int Hs, int Ws, int M0, int M1, int N) {
   return wg_geometry(Hs, Ws, &Wt, &Ht, &Bt);
 }
 
-namespace {
-// pixel splits of the 4x4 weight gradient: [m_tiles x n_tiles x 4 kernel rows] CTAs, split until the grid fills the machine
-int wgrad_splits(int m_tiles, int n_tiles, int NT, int kblocks) {
-  const long long ctas = (long long)m_tiles * n_tiles * 4;
-  // one resident CTA per SM (160 KB of smem, all 512 TMEM columns): aim at ADP_WG_WAVES (default 1) full waves
-  static int waves = getenv("ADP_WG_WAVES") ? atoi(getenv("ADP_WG_WAVES")) : 1;
-  const int eff_waves = NT == 64 ? 2 * waves : waves;      // the narrow-N tiles are short: two waves balance better
-  // (rounded down: 152 or 160 CTAs on 148 SMs cost a second, nearly empty wave -- E3 / E4 at B = 64)
-  int splits = (int)(((long long)eff_waves * sm_count()) / ctas);
-  if (splits > kblocks) splits = kblocks;
-  if (splits < 1) splits = 1;
-  return splits;
-}
-
-}  // namespace
-
-// true when tc_wgrad(..., overwrite = 1) may be used: the launch would not split the pixel range anyway, or the range is
-// so short (<= ADP_WG_STORE_KB k-blocks of 32 pixels, default 8: the 1x1 / 2x2 levels) that one CTA per tile storing its
-// result beats two CTAs adding theirs into a zeroed buffer (the launch is bound by the fp32 output, not by the math)
-static int g_wg_store = -1;      // "wg_store" / ADP_WG_STORE=0: always accumulate into a zeroed dw
-static bool wg_store_enabled() {
-  if (g_wg_store < 0) g_wg_store = getenv("ADP_WG_STORE") ? atoi(getenv("ADP_WG_STORE")) : 1;
-  return g_wg_store != 0;
-}
-int tc_wgrad_set_store(int on) {
-  const int prev = wg_store_enabled() ? 1 : 0;
-  g_wg_store = on ? 1 : 0;
-  return prev;
-}
-bool tc_wgrad_can_overwrite(int B, int Hs, int Ws, int M0, int M1, int N) {
-  static const int short_kb = getenv("ADP_WG_STORE_KB") ? atoi(getenv("ADP_WG_STORE_KB")) : 8;
-  int Wt, Ht, Bt;
-  if (!wg_store_enabled() || !wg_geometry(Hs, Ws, &Wt, &Ht, &Bt)) return false;
-  const int NT = N % 128 == 0 ? 128 : 64;
-  const int kblocks = (Ws / Wt) * (Hs / Ht) * adp_cdiv(B, Bt);
-  return kblocks <= short_kb || wgrad_splits((M0 + M1) / WG_M, N / NT, NT, kblocks) == 1;
-}
-
 int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int N, float* dw, int B, int Hs, int Ws,
-             cudaStream_t s, int g_pad, int overwrite) {
+             cudaStream_t s, int g_pad) {
   WgradParams p;
   memset(&p, 0, sizeof(p));
   ADP_CHECK_ARG(wg_geometry(Hs, Ws, &p.Wt, &p.Ht, &p.Bt), "tc_wgrad: unsupported spatial size %dx%d", Hs, Ws);
@@ -484,11 +427,14 @@ int tc_wgrad(const void* s0, int M0, const void* s1, int M1, const void* g, int 
     ADP_TRY(make_tmap_bf16(&p.tmG, g, 5, dims, str, box));
   }
   const int m_tiles = (M0 + M1) / WG_M, n_tiles = N / NT;
-  int splits = wgrad_splits(m_tiles, n_tiles, NT, p.kblocks);
-  if (overwrite) {
-    splits = 1;
-    p.overwrite = 1;
-  }
+  const long long ctas = (long long)m_tiles * n_tiles * 4;
+  // one resident CTA per SM (160 KB of smem, all 512 TMEM columns): aim at ADP_WG_WAVES (default 1) full waves
+  static int waves = getenv("ADP_WG_WAVES") ? atoi(getenv("ADP_WG_WAVES")) : 1;
+  const int eff_waves = NT == 64 ? 2 * waves : waves;      // the narrow-N tiles are short: two waves balance better
+  // (rounded down: 152 or 160 CTAs on 148 SMs cost a second, nearly empty wave -- E3 / E4 at B = 64)
+  int splits = (int)(((long long)eff_waves * sm_count()) / ctas);
+  if (splits > p.kblocks) splits = p.kblocks;
+  if (splits < 1) splits = 1;
   p.kb_per_split = adp_cdiv(p.kblocks, splits);
   splits = adp_cdiv(p.kblocks, p.kb_per_split);
   dim3 grid(m_tiles, n_tiles, 4 * splits);
