@@ -232,6 +232,9 @@ int act_bn_bwd_apply(int dtype, const void* x, long long rows, int C, const floa
                      const float* mean, const float* invstd, const void* gA, float slope0,
                      const void* gB, float slope1, const double* sums, int mode, void* dx, float* dgamma, float* dbeta,
                      cudaStream_t s);
+// un-finished split-K sums (ConvExtras::deferred) of a layer without BatchNorm, n = rows * C elements, cleared on the way:
+// mask == NULL: raw = round(sums), act = lrelu(raw, slope);  mask != NULL: act = round(sums) * lrelu'(mask, slope)
+int finish_act(int dtype, float* partial, long long n, const void* mask, float slope, void* raw, void* act, cudaStream_t s);
 // Small tensors (deep levels): the whole BatchNorm layer in ONE launch, each tensor read once (an 8-channel slab per block
 // staged in shared memory).  tensors = 1 (forward) / 3 (backward) slabs must fit: bn_small_ok.
 bool bn_small_ok(int dtype, long long rows, int C, int tensors);

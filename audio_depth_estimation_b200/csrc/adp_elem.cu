@@ -621,6 +621,33 @@ __device__ __forceinline__ float8 float8_zero() {
   return z;
 }
 
+// The innermost level (no BatchNorm) consuming un-finished split-K sums, elementwise over n8 groups of 8 channels:
+//   mask == NULL: raw = round(sums), act = lrelu(raw, slope)                       (forward: e[D-1] and r[D-1])
+//   mask != NULL: act = round(sums) * lrelu'(mask, slope); raw is not written     (backward: dL/de from dL/dr and e)
+template <class T>
+__global__ void __launch_bounds__(EW_THREADS)
+finish_act8_kernel(float* __restrict__ partial, long long n8, const T* __restrict__ mask, float slope, T* __restrict__ raw,
+                   T* __restrict__ act) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float8 a = ld8(partial + 8 * i);
+    st8(partial + 8 * i, float8_zero());
+    const typename Raw8<T>::type q = round_raw8(a, (const T*)nullptr);
+    const float8 v = cvt8(q);
+    float8 o;
+    if (mask) {
+      const float8 m = ld8(mask + 8 * i);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = v.v[k] * lrelu_grad(m.v[k], slope);
+    } else {
+      straw8(raw + 8 * i, q);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = lrelu(v.v[k], slope);
+    }
+    st8(act + 8 * i, o);
+  }
+}
+
 // forward: batch statistics (training) + normalise + one or two activations; slab[rows] of 8 channels in shared memory
 // (partial != NULL: x is still the fp32 split-K sums [rows][C] of the convolution; it is finished here and written to xw)
 template <class T>
@@ -903,8 +930,11 @@ namespace adp {
 
 bool bn_small_ok(int dtype, long long rows, int C, int tensors) {
   static const int on = getenv("ADP_BN_SMALL") ? atoi(getenv("ADP_BN_SMALL")) : 1;
+  // (ADP_BN_SMALL_ROWS: 1024 rows was the break-even of C/8 blocks with one row per thread in flight; with four in flight
+  // and the split-K finish folded in, 4096 rows -- the 8x8 levels at B = 64 -- is 30 us per step ahead of three launches)
+  static const int max_rows = getenv("ADP_BN_SMALL_ROWS") ? atoi(getenv("ADP_BN_SMALL_ROWS")) : 4096;
   const size_t per_row = dtype == ADP_F32 ? 32 : 16;
-  return on && C % 8 == 0 && rows >= 1 && rows <= 1024 && (size_t)rows * per_row * tensors <= 200 * 1024;   // (measured: C/8 blocks stop paying above ~1k rows)
+  return on && C % 8 == 0 && rows >= 1 && rows <= max_rows && (size_t)rows * per_row * tensors <= 200 * 1024;
 }
 
 int bn_small_fwd(int dtype, const void* x, long long rows, int C, const BnFin& f, float slope0, void* out0, float slope1,
@@ -932,6 +962,14 @@ int bn_small_bwd(int dtype, const void* x, long long rows, int C, const float* s
   ADP_DISPATCH_T(dtype, bn_small_bwd_kernel<T><<<C / 8, SMALL_THREADS, smem, s>>>((const T*)x, (int)rows, C,
                                        scale, shift, mean, invstd, (const T*)gA, slope0, (const T*)gB, slope1, mode, (T*)dx,
                                        dgamma, dbeta, sums, part);)
+  ADP_LAUNCH_CHECK();
+  return ADP_OK;
+}
+
+int finish_act(int dtype, float* partial, long long n, const void* mask, float slope, void* raw, void* act, cudaStream_t s) {
+  ADP_CHECK_ARG(partial && act && (mask || raw) && n > 0 && n % 8 == 0, "finish_act: bad arguments");
+  const long long n8 = n / 8;
+  ADP_DISPATCH_T(dtype, finish_act8_kernel<T><<<ew_grid(n8), EW_THREADS, 0, s>>>(partial, n8, (const T*)mask, slope, (T*)raw, (T*)act);)
   ADP_LAUNCH_CHECK();
   return ADP_OK;
 }

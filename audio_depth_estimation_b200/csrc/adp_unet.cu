@@ -336,7 +336,8 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
     if (L.bn_down && d->training) { ex.stats = sums; ex.stats_done = &fused; }
     // a split-K launch of a small level hands its fp32 sums to the single-launch BatchNorm below (no finishing launch)
     float* part = nullptr;
-    if (L.bn_down && d->training && (defer_finish_mask() & 1) && bn_small_ok(dt, rows, L.cout, 1)) ex.deferred = &part;
+    if (d->training && (defer_finish_mask() & 1) && (L.bn_down ? bn_small_ok(dt, rows, L.cout, 1) : L.cout % 8 == 0))
+      ex.deferred = &part;
     ex.pad_in = (l == 1 && center) ? 1 : 0;
     int folded = 0;
     if (fold && L.bn_down) {
@@ -368,6 +369,8 @@ extern "C" int adp_unet_forward(const adp_unet_desc* d, const float* x, const ad
         if (d->training && !fused) ADP_TRY(bn_stats(dt, at(ws, L.e), rows, L.cout, sums, s));
         ADP_TRY(bn_affine_act(dt, at(ws, L.e), rows, L.cout, fin, 0.2f, at(ws, L.a), 0.f, at(ws, L.r), s));
       }
+    } else if (part) {   // innermost level: finish the split-K sums and apply the ReLU in one launch
+      ADP_TRY(finish_act(dt, part, rows * L.cout, nullptr, 0.f, at(ws, L.e), at(ws, L.r), s));
     } else {
       ADP_TRY(affine_act(dt, at(ws, L.e), rows, L.cout, nullptr, nullptr, 0.f, at(ws, L.r), 0.f, nullptr, s));
     }
@@ -567,6 +570,7 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
   };
 
   float* part_a = nullptr;      // un-finished split-K sums of g_a[l - 1], handed from encoder stage l to stage l - 1
+  float* part_r = nullptr;      // un-finished split-K sums of g_r[D - 1], handed from the innermost decoder stage to the encoder's
   for (int st = stage_begin; st < stage_end; ++st) {
     if (st == 0) {
       const LevelPlan& L = p.lv[0];
@@ -619,6 +623,8 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
       if (l < D - 1 && (defer_finish_mask() & 2) && L.t_c1 == p.lv[l + 1].t_cout &&
           bn_small_ok(dt, (long long)B * L.hout * L.hout, L.t_c1, 3))
         gex.deferred = &part;
+      // innermost level: g_r[D-1] has one reader, the activation backward that opens the next stage
+      if (l == D - 1 && (defer_finish_mask() & 2) && st + 1 < stage_end && L.t_c1 == 0 && L.cout % 8 == 0) gex.deferred = &part_r;
       ADP_TRY(conv_gather(dt, at(ws, O.g_t), params[l].convT_w, tc ? w16(params[l].convT_w_bf16, L.wb_convT) : nullptr, at(ws, L.g_r),
                           L.cout, L.t_c1 ? at(ws, L.g_q) : nullptr, L.t_c1, B, O.hout, O.hout, L.t_cout, s, &gex,
                           deep_level(O.hout)));
@@ -633,7 +639,10 @@ extern "C" int adp_unet_backward_stages(const adp_unet_desc* d, const float* x, 
                              thin_tc_supported(B, 2, L.hin, L.hin);
       if (!fuse_act0) {
       ProfScope eprof(PROF_ELEM, s, (double)rows * L.cout * p.esz * (l == D - 1 ? 3.0 : 4.0));   // x, gA[, gB] -> dx
-      if (l == D - 1) {
+      if (l == D - 1 && part_r) {
+        ADP_TRY(finish_act(dt, part_r, rows * L.cout, at(ws, L.e), 0.f, nullptr, at(ws, L.g_e), s));
+        part_r = nullptr;
+      } else if (l == D - 1) {
         ADP_TRY(act_bn_bwd_apply(dt, at(ws, L.e), rows, L.cout, nullptr, nullptr, nullptr, nullptr, at(ws, L.g_r), 0.f,
                                  nullptr, 0.f, nullptr, 0, at(ws, L.g_e), nullptr, nullptr, s));
       } else if (L.bn_down) {

@@ -815,14 +815,18 @@ def test_d1_forward_band_kernel_inside_the_network(mode):
         assert float((a - b).norm() / b.norm()) <= 2e-2
 
 
-def _step_grads(case, mode, opts):
-    """One forward + backward of build_case(case) under the given library options; (y, {name: grad})."""
+def _step_grads(case, mode, opts, stages_per_group=0):
+    """One forward + backward of build_case(case) under the given library options; (y, {name: grad}).
+    stages_per_group > 0: the backward pass runs as several adp_unet_backward_stages calls (the data-parallel overlap)."""
     lib = _lib.load()
     prev = {k: lib.adp_set_option(k, v) for k, v in opts.items()}
     assert all(0 <= v <= 3 for v in prev.values()), prev
     try:
         _, net, x, _ = build_case(case, "bf16")
         net.train(mode == "train")
+        if stages_per_group:
+            from audio_depth_estimation_b200.training import default_stage_groups
+            net.stage_groups = default_stage_groups(net.num_downs, stages_per_group)
         y = net(x)
         y.backward(torch.ones_like(y) * 1e-3)
         torch.cuda.synchronize()
@@ -837,16 +841,20 @@ def test_deferred_split_sums_match_the_finishing_launch(mode):
     """"defer_finish": the split-K sums of the small levels are handed un-finished to bn_small_fwd / bn_small_bwd, which
     round them exactly as finish_partial_kernel would (the bf16 gradient tensor in between is never written, the skip
     half of a decoder gradient is finished on the way) and re-zero the scratch the engine now clears once per step --
-    against a finishing launch per split layer.  B = 8: five levels split K, the 4x4 and smaller levels run the
-    single-launch BatchNorm."""
+    against a finishing launch per split layer.  B = 8: the 16x16 and smaller levels split K and run the single-launch
+    BatchNorm; the innermost level (no BatchNorm) goes through finish_act."""
     case = ("unet_256", 64, 8, 256, False, 30.0, 970, True, True)
     y1, g1 = _step_grads(case, mode, {b"defer_finish": 3})
     y0, g0 = _step_grads(case, mode, {b"defer_finish": 0})
     y2, g2 = _step_grads(case, mode, {b"defer_finish": 3})     # (again: the scratch must have been left clean)
+    # the backward pass cut into calls of 2 / 3 stages: sums are only handed over to a consumer inside the same call
+    # (2: the innermost hand-over crosses a call boundary and falls back to the finishing launch; 3: it does not)
+    y3, g3 = _step_grads(case, mode, {b"defer_finish": 3}, stages_per_group=2)
+    y4, g4 = _step_grads(case, mode, {b"defer_finish": 3}, stages_per_group=3)
     assert np.isfinite(y1).all() and np.abs(y1).max() > 0
     # (train mode: batch statistics come from fp64 atomics in arrival order, split-K sums from fp32 atomics: single bf16
     # flips from run to run, also between two runs of the SAME configuration)
-    for ya, ga in ((y1, g1), (y2, g2)):
+    for ya, ga in ((y1, g1), (y2, g2), (y3, g3), (y4, g4)):
         assert rel_to_max(ya, y0) <= (1.5e-2 if mode == "train" else 8e-3), rel_to_max(ya, y0)
         for n in g0:
             a, b = ga[n], g0[n]
