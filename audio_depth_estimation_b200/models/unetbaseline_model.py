@@ -442,7 +442,10 @@ class UnetGenerator(nn.Module):
         if dy.dtype != torch.float32:
             dy = dy.float()
         params, grads = self._level_array(False, self._fwd_mirror), self._level_array(True)
-        groups = self.stage_groups or [(0, 2 * self.num_downs)]
+        # stage groups exist for whoever listens to grad_ready_hook (the gradient reducer overlaps its collective with the
+        # remaining stages); without a listener one call runs them all -- split-K sums are then handed from every layer to
+        # its consumer (the library only does that inside one call)
+        groups = (self.stage_groups if self.grad_ready_hook is not None else None) or [(0, 2 * self.num_downs)]
         with torch.cuda.device(x.device):
             for gi, (b, e) in enumerate(groups):
                 _lib.check(lib.adp_unet_backward_stages(ctypes.byref(desc), x.data_ptr(), y.data_ptr(), dy.data_ptr(),

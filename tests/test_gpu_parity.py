@@ -827,6 +827,7 @@ def _step_grads(case, mode, opts, stages_per_group=0):
         if stages_per_group:
             from audio_depth_estimation_b200.training import default_stage_groups
             net.stage_groups = default_stage_groups(net.num_downs, stages_per_group)
+            net.grad_ready_hook = lambda gi: None          # (a listener: the backward pass keeps the group boundaries)
         y = net(x)
         y.backward(torch.ones_like(y) * 1e-3)
         torch.cuda.synchronize()
