@@ -2,7 +2,7 @@
 // accumulation in tensor memory).  Replaces cuDNN's kernels behind nn.Conv2d(k4,s2,p1) and
 // nn.ConvTranspose2d(k4,s2,p1) (models/unetbaseline_model.py:187,:196,:209,:218).
 //
-// Kernel 1 (tc_igemm_kernel) serves the "gather" (F1) and "parity" (F2) families of
+// Kernel 1 (tc_igemm_persist_kernel) serves the "gather" (F1) and "parity" (F2) families of
 // adp_conv_simt.cu as   D[128 pixels x BLOCK_N channels] = sum_kblocks A[128 x 64] * W[BLOCK_N x 64]^T :
 //   * A tiles are fetched by TMA straight from the NHWC activation tensor.  No im2col, no padded or
 //     space-to-depth copy: the stride-2 4x4 window is expressed through a 5-D view of the tensor
@@ -16,7 +16,9 @@
 //     on mbarriers; a STAGES-deep smem ring overlaps TMA with MMA.
 //   * the epilogue (4 warps = 128 TMEM lanes) reads the accumulator with tcgen05.ld and writes bf16
 //     NHWC rows (strided by parity for F2, split into two tensors for a concat gradient), or
-//     accumulates fp32 partial sums when the K range is split across CTAs (deep, small-M layers).
+//     accumulates fp32 partial sums when the K range is split across CTAs (deep, small-M layers); those are
+//     finished (rounded to bf16, cleared) by finish_partial_kernel or, inside the U-Net engine, by the
+//     BatchNorm / activation kernel that consumes the layer's output (ConvExtras::deferred).
 #include <stdlib.h>
 #include "adp_tc.cuh"
 

@@ -355,7 +355,7 @@ int adp_profile_read(double* ms, double* work, long long* calls);
 int adp_profile_read_n(int n, double* ms, double* work, long long* calls);
 
 /* Run-time form of the ADP_TC_* tuning variables: "tc_halo" (parity kernels load the tile's input window once per
- * channel chunk), "tc_cluster", "tc_max_bn", "side_stream" (U-Net weight gradients run on a library-owned side stream
+ * channel chunk), "tc_max_bn", "side_stream" (U-Net weight gradients run on a library-owned side stream
  * next to the data-gradient chain), "tc_stats", "tc_alt", "tc_skip_pad_taps", "center", "thin_fused", "d1_fused",
  * "defer_finish" (bit 0 forward, bit 1 backward: split-K sums of the small levels are finished by the single-launch
  * BatchNorm kernel that consumes them instead of a finishing launch).  Returns the previous value, -1 for an unknown
