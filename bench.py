@@ -349,8 +349,9 @@ def run_ours(args):
         finish()
         return
     traffic = None
-    tpath = os.path.join(REPO, "profiles", "r1_tc_dram_per_step.json")
-    if os.path.exists(tpath) and B == 64 and args.precision == "bf16":
+    tpath = next((q for q in (os.path.join(REPO, "profiles", n) for n in ("r2_tc_dram_per_step.json", "r1_tc_dram_per_step.json"))
+                  if os.path.exists(q)), "")
+    if tpath and B == 64 and args.precision == "bf16":
         traffic = json.load(open(tpath))["dram_bytes_per_launch"]      # ncu capture of this workload, per launch
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
@@ -401,7 +402,7 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (gather + parity + wgrad families, all 14 layers x 3 passes)",
                      "achieved": achieved, "peak": pk["tc_burst"], "unit": "TFLOP/s",
                      "frac": (achieved / pk["tc_burst"]) if achieved else None, "traffic": traffic,
-                     "traffic_note": "mean DRAM bytes per tcgen05 conv launch (ncu, profiles/r1_tc_dram_per_step.json)",
+                     "traffic_note": "mean DRAM bytes per tcgen05 conv launch (ncu, profiles/%s)" % os.path.basename(tpath),
                      "peak_source": pk["source"] + ": bf16_tflops (burst) -- the timed region lasts %.2f s at full boost; "
                                     "against the sustained figure (%.0f) the fraction is %.3f" % (
                                         ms_eager * 1e-3, pk["tc_sustained"], (achieved / pk["tc_sustained"]) if achieved else 0.0),

@@ -10,7 +10,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_dram_per_step_tool_reproduces_the_committed_json(tmp_path):
     out = tmp_path / "dram.json"
     subprocess.run([sys.executable, os.path.join(REPO, "tools", "dram_per_step.py"),
-                    os.path.join(REPO, "profiles", "r1_tc_dram_launches.csv"), str(out)], check=True, capture_output=True)
+                    os.path.join(REPO, "profiles", "r1_tc_dram_launches.csv"), str(out), "--r1"], check=True, capture_output=True)
     got = json.load(open(out))
     ref = json.load(open(os.path.join(REPO, "profiles", "r1_tc_dram_per_step.json")))
     assert got["launches"] == ref["launches"] == 42           # gather + parity + wgrad of E2-E8 / D8-D2, three passes each

@@ -2,9 +2,13 @@
 training step into profiles/<name>.json (what bench.py reports as roofline.traffic).
 
     ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-        -k regex:tc_ -s 192 -c 48 --csv --log-file gpurun_out/tc_dram.csv \
+        -k regex:tc_ -c 800 --csv --log-file gpurun_out/tc_dram.csv \
         python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph
-    python tools/dram_per_step.py gpurun_out/tc_dram.csv profiles/r1_tc_dram_per_step.json
+    python tools/dram_per_step.py gpurun_out/tc_dram.csv profiles/r2_tc_dram_per_step.json
+
+The capture may hold several steps: the LAST complete one (from an STFT GEMM launch to the launch before the next) is used.
+Template arguments: tc_igemm_persist_kernel<BLOCK_N, EG, ATT, HALO, ALT> (round 1 captures: <BLOCK_N, CLUSTER, EG, ATT, HALO>,
+pass --r1 for those).
 """
 import csv
 import io
@@ -12,7 +16,7 @@ import json
 import sys
 
 
-def main(src, dst):
+def main(src, dst, r1=False):
     txt = open(src).read().splitlines()
     start = [k for k, line in enumerate(txt) if line.startswith('"ID"')][0]
     rows = list(csv.DictReader(io.StringIO("\n".join(txt[start:]))))
@@ -27,6 +31,12 @@ def main(src, dst):
         else:
             e["us"] = v * {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "nsecond": 1e-3, "ms": 1e3, "msecond": 1e3}[unit]
     launches = list(by_id.values())
+    eg_pos = 2 if r1 else 1
+    stft_at = [i for i, e in enumerate(launches)
+               if (lambda m: bool(m) and m.group(1).split(",")[eg_pos].strip().endswith("2"))(
+                   __import__("re").search(r"tc_igemm_persist_kernel<([^>]*)>", e["kernel"]))]
+    if len(stft_at) >= 2:          # several steps captured: keep the last complete one
+        launches = launches[stft_at[-2]:stft_at[-1]]
 
     def family(e):
         k = e["kernel"]
@@ -51,7 +61,7 @@ def main(src, dst):
 
     def is_stft(e):
         a = targs(e["kernel"])
-        return bool(a) and len(a) >= 3 and a[2] == 2
+        return bool(a) and len(a) >= 3 and a[eg_pos] == 2
 
     def is_thin(e):
         a = targs(e["kernel"])
@@ -73,4 +83,4 @@ def main(src, dst):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], "--r1" in sys.argv)
