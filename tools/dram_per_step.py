@@ -68,7 +68,8 @@ def main(src, dst, r1=False):
         return "gemm_tn" in e["kernel"] or is_stft(e) or (bool(a) and a[0] == 16)
     thin = [i for i, e in enumerate(per) if is_thin(e)]
     # the E1 pointwise GEMM is the launch right after the STFT GEMM, the last-layer dgrad the one right after gemm_tn<64>
-    for i, e in enumerate(per[:-1]):
+    # (round 1 only: since round 2 the thin layers run in adp_thin_tc.cu's own kernels, which the tc_ filter does not capture)
+    for i, e in enumerate(per[:-1] if r1 else []):
         if is_stft(e) or "gemm_tn_kernel<64>" in e["kernel"] or "gemm_tn_kernel<(int)64>" in e["kernel"]:
             thin.append(i + 1)
     conv = [i for i in range(len(per)) if i not in thin]
