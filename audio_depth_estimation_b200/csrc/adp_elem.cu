@@ -934,6 +934,8 @@ bool bn_small_ok(int dtype, long long rows, int C, int tensors) {
   // and the split-K finish folded in, 4096 rows -- the 8x8 levels at B = 64 -- is 30 us per step ahead of three launches)
   static const int max_rows = getenv("ADP_BN_SMALL_ROWS") ? atoi(getenv("ADP_BN_SMALL_ROWS")) : 4096;
   const size_t per_row = dtype == ADP_F32 ? 32 : 16;
+  // (above 1024 rows only with >= 64 blocks: a 4096-row slab per block is a long serial walk, it needs the width)
+  if (rows > 1024 && C < 512) return false;
   return on && C % 8 == 0 && rows >= 1 && rows <= max_rows && (size_t)rows * per_row * tensors <= 200 * 1024;
 }
 
