@@ -1,9 +1,30 @@
-"""Mirror of dataloader/utils_dataset.py:10-28: get_transform(cfg, convert, depth_norm).
+"""Mirror of dataloader/utils_dataset.py:10-49: get_transform(cfg, convert, depth_norm) and MinMaxNorm.
 
 The returned callable applies Resize((S,S)) with torchvision's tensor semantics (antialiased
-bilinear) through adp_resize_aa; it expects CUDA fp32 tensors [..., H, W].
+bilinear) through adp_resize_aa; it expects CUDA fp32 tensors [..., H, W].  depth_norm=True appends the
+reference's MinMaxNorm(0, max_depth) (:23-27, :31-49; used by the sibling sparse-depth dataset, not by the V1 / V2 audio
+path, whose depth normalisation lives in __getitem__).
 """
+import torch
+
 from .. import feature
+
+
+class MinMaxNorm(torch.nn.Module):
+    """(x - min) / (max - min); `min` / `max` are floats, or 2-tuples applied per channel of a [2, ...] tensor
+    (reference :31-49, same assertion and the same channel rule)."""
+
+    def __init__(self, min, max):
+        super().__init__()
+        assert isinstance(min, (float, tuple)) and isinstance(max, (float, tuple))
+        self.min = torch.tensor(min)
+        self.max = torch.tensor(max)
+
+    def forward(self, tensor):
+        lo, hi = self.min.to(tensor.device), self.max.to(tensor.device)
+        if tensor.shape[0] == 2:
+            return torch.stack([(tensor[c] - lo[c]) / (hi[c] - lo[c]) for c in range(2)], dim=0)
+        return (tensor - lo) / (hi - lo)
 
 
 class Resize:
@@ -30,4 +51,6 @@ def get_transform(cfg, convert=False, depth_norm=False):
         raise NotImplementedError("convert=True (ToTensor on PIL images) is the image branch, outside the audio hot path")
     if "resize" in str(cfg.dataset.preprocess):
         steps.append(Resize((cfg.dataset.images_size, cfg.dataset.images_size)))
+    if depth_norm:
+        steps.append(MinMaxNorm(min=0.0, max=cfg.dataset.max_depth))
     return Compose(steps)

@@ -152,3 +152,21 @@ def test_v2_and_v1_spectrogram_getitem_on_gpu(v2_tree, tmp_path):
     ref1 = fo.feature_v1(np.stack((wl, wr)), 256)
     assert np.abs(x1.cpu().numpy() - ref1).max() <= 1e-4 * np.abs(ref1).max()
     assert np.allclose(g1.numpy(), 5.0 / 12.0)
+
+
+def test_get_transform_depth_norm_appends_the_reference_minmaxnorm():
+    """dataloader/utils_dataset.py:23-27, :31-49: get_transform(depth_norm=True) ends with MinMaxNorm(0, max_depth);
+    floats normalise the whole tensor, 2-tuples normalise the two channels of a [2, ...] tensor separately."""
+    import torch
+    from types import SimpleNamespace
+    from audio_depth_estimation_b200.dataloader.utils_dataset import MinMaxNorm, get_transform
+    cfg = SimpleNamespace(dataset=SimpleNamespace(preprocess="none", images_size=256, max_depth=12.0))
+    t = get_transform(cfg, convert=False, depth_norm=True)
+    x = torch.tensor([[[0.0, 3.0], [6.0, 12.0]]])
+    assert torch.equal(t(x), x / 12.0)
+    assert len(get_transform(cfg, convert=False, depth_norm=False).transforms) == 0
+    two = MinMaxNorm(min=(0.0, 1.0), max=(2.0, 5.0))
+    y = two(torch.tensor([[1.0, 2.0], [3.0, 5.0]]))
+    assert torch.equal(y, torch.tensor([[0.5, 1.0], [0.5, 1.0]]))
+    with pytest.raises(AssertionError):
+        MinMaxNorm(min=0, max=12)          # (ints are rejected, as in the reference)
