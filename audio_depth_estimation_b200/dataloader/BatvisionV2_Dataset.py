@@ -25,8 +25,6 @@ class BatvisionV2Dataset(Dataset):
         self.audio_format = cfg.dataset.audio_format
         self.use_image = use_image
         self.device = torch.device("cuda") if torch.cuda.is_available() else None
-        if use_image:
-            raise NotImplementedError("use_image=True (camera branch, reference :199-210) is outside the audio hot path")
         # (os.listdir order, as the reference :22-26 -- the row order of .instances follows it)
         locations = [d for d in os.listdir(self.root_dir)
                      if os.path.isdir(os.path.join(self.root_dir, d))
@@ -59,6 +57,8 @@ class BatvisionV2Dataset(Dataset):
     def __getitem__(self, idx):
         inst = self.instances.iloc[idx]
         gt_depth = self._depth(inst)
+        if self.use_image:      # camera branch (reference :87-90): the RGB frame instead of the echo, host-side only
+            return self._load_image(os.path.join(self.root_dir, inst["camera path"], inst["camera file name"])), gt_depth
         waveform, sr = load_audio(os.path.join(self.root_dir, inst["audio path"], inst["audio file name"]))
         n_fft, win_length, hop_length = 400, 200, 100
         if self.cfg.dataset.max_depth:
@@ -92,6 +92,16 @@ class BatvisionV2Dataset(Dataset):
             raise RuntimeError("BatvisionV2Dataset needs a CUDA device for the spectrogram transform "
                                "(no CPU fallback); use audio_format='waveform' in CPU worker processes")
         return waveform.to(self.device, dtype=torch.float32)
+
+    def _load_image(self, image_path):
+        """Reference :199-210: cv2.imread -> RGB -> cv2.resize (bilinear) to images_size -> float32 / 255 -> [3, S, S]."""
+        import cv2
+        image = cv2.imread(image_path)
+        if image is None:
+            raise RuntimeError("Could not load image file %s" % image_path)
+        image = cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
+        image = cv2.resize(image, (self.cfg.dataset.images_size, self.cfg.dataset.images_size))
+        return torch.from_numpy(image.astype(np.float32) / 255.0).permute(2, 0, 1)
 
     def _get_spectrogram(self, waveform, n_fft=400, power=1.0, win_length=400, hop_length=100):
         return feature.spectrogram(waveform, n_fft=n_fft, power=power, win_length=win_length, hop_length=hop_length)

@@ -170,3 +170,31 @@ def test_get_transform_depth_norm_appends_the_reference_minmaxnorm():
     assert torch.equal(y, torch.tensor([[0.5, 1.0], [0.5, 1.0]]))
     with pytest.raises(AssertionError):
         MinMaxNorm(min=0, max=12)          # (ints are rejected, as in the reference)
+
+
+def test_v2_dataset_camera_branch(v2_tree):
+    """use_image=True (BatvisionV2_Dataset.py:87-90, :199-210): the RGB camera frame, resized and scaled to [0, 1], takes the
+    place of the echo; the depth target is the same as on the audio path."""
+    cv2 = pytest.importorskip("cv2")
+    from audio_depth_estimation_b200.dataloader.BatvisionV2_Dataset import BatvisionV2Dataset
+    root, _ = v2_tree
+    rng = np.random.default_rng(7)
+    for loc in ("office_a", "hall_b"):
+        (root / loc / "camera").mkdir()
+        df = pd.read_csv(root / loc / "train.csv")
+        df["camera path"] = loc + "/camera"
+        df["camera file name"] = ["c%d.png" % i for i in range(len(df))]
+        for name in df["camera file name"]:
+            cv2.imwrite(str(root / loc / "camera" / name), rng.integers(0, 256, size=(72, 128, 3), dtype=np.uint8))
+        df.to_csv(root / loc / "train.csv", index=False)
+    ds = BatvisionV2Dataset(cfg_v2(root), "train.csv", use_image=True)
+    ref = BatvisionV2Dataset(cfg_v2(root), "train.csv")
+    img, gt = ds[1]
+    inst = ds.instances.iloc[1]
+    bgr = cv2.imread(os.path.join(str(root), inst["camera path"], inst["camera file name"]))
+    want = cv2.resize(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB), (64, 64)).astype(np.float32) / 255.0
+    assert img.shape == (3, 64, 64) and img.dtype == torch.float32
+    assert np.array_equal(img.numpy(), want.transpose(2, 0, 1))
+    assert torch.equal(gt, ref[1][1])
+    with pytest.raises(RuntimeError):
+        ds._load_image(str(root / "missing.png"))
