@@ -1,4 +1,4 @@
-"""Mirror of dataloader/utils_dataset.py:10-49: get_transform(cfg, convert, depth_norm) and MinMaxNorm.
+"""Mirror of dataloader/utils_dataset.py:10-49: get_transform(cfg, convert, depth_norm), ToTensor and MinMaxNorm.
 
 The returned callable applies Resize((S,S)) with torchvision's tensor semantics (antialiased
 bilinear) through adp_resize_aa; it expects CUDA fp32 tensors [..., H, W].  depth_norm=True appends the
@@ -27,6 +27,23 @@ class MinMaxNorm(torch.nn.Module):
         return (tensor - lo) / (hi - lo)
 
 
+class ToTensor:
+    """torchvision.transforms.ToTensor for what the reference feeds it (:14-16): a PIL image or an HWC / HW numpy array
+    becomes a CHW float32 tensor, uint8 input scaled by 1/255; other dtypes keep their values.  The tensor is moved to the
+    current CUDA device when there is one, because the Resize that follows runs there."""
+
+    def __call__(self, pic):
+        import numpy as np
+        arr = np.asarray(pic)
+        if arr.ndim == 2:
+            arr = arr[:, :, None]
+        if arr.ndim != 3:
+            raise ValueError("ToTensor expects an image with 2 or 3 dimensions, got shape %s" % (arr.shape,))
+        t = torch.from_numpy(np.ascontiguousarray(arr.transpose(2, 0, 1)))
+        t = t.to(torch.float32).div(255) if arr.dtype == np.uint8 else t
+        return t.cuda() if torch.cuda.is_available() else t
+
+
 class Resize:
     def __init__(self, size):
         self.size = size if isinstance(size, int) else size[0]
@@ -48,7 +65,7 @@ class Compose:
 def get_transform(cfg, convert=False, depth_norm=False):
     steps = []
     if convert:
-        raise NotImplementedError("convert=True (ToTensor on PIL images) is the image branch, outside the audio hot path")
+        steps.append(ToTensor())
     if "resize" in str(cfg.dataset.preprocess):
         steps.append(Resize((cfg.dataset.images_size, cfg.dataset.images_size)))
     if depth_norm:

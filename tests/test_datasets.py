@@ -198,3 +198,19 @@ def test_v2_dataset_camera_branch(v2_tree):
     assert torch.equal(gt, ref[1][1])
     with pytest.raises(RuntimeError):
         ds._load_image(str(root / "missing.png"))
+
+
+def test_get_transform_convert_is_totensor():
+    """dataloader/utils_dataset.py:14-16: convert=True starts the chain with ToTensor (HWC uint8 -> CHW float in [0, 1];
+    float arrays keep their values; a 2-D array gains a channel axis)."""
+    from audio_depth_estimation_b200.dataloader.utils_dataset import get_transform
+    cfg = SimpleNamespace(dataset=SimpleNamespace(preprocess="none", images_size=64, max_depth=12.0))
+    t = get_transform(cfg, convert=True)
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, size=(5, 7, 3), dtype=np.uint8)
+    out = t(img).cpu()
+    assert out.shape == (3, 5, 7) and out.dtype == torch.float32
+    assert np.array_equal(out.numpy(), img.transpose(2, 0, 1).astype(np.float32) / 255.0)
+    depth = rng.uniform(0, 12, size=(5, 7)).astype(np.float32)
+    out = get_transform(cfg, convert=True, depth_norm=True)(depth).cpu()
+    assert out.shape == (1, 5, 7) and np.allclose(out.numpy()[0], depth / 12.0, rtol=1e-6)
