@@ -100,6 +100,7 @@ def test_config_loader_keys():
     assert c.dataset.max_depth == 30.0 and c.dataset.images_size == 256 and c.dataset.depth_norm is False
     c1 = load_config("batvisionv1", "test")
     assert c1.dataset.depth_norm is True and c1.dataset.max_depth == 12.0 and c1.mode.batch_size == 1
+    assert c1.mode.stat_dir == "./eval/" and c1.mode.num_threads == 4 and c1.mode.eval_on == "test"     # conf/mode/test.yaml as shipped by the reference
     assert c.model.generator == "unet_256"
 
 
