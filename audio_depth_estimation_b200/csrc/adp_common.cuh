@@ -345,7 +345,7 @@ struct ConvExtras {
   void* y_act0; void* y_act1;
   int* fold_done;
   // gather / parity, split-K launch on a scratch the engine keeps clean: leave the fp32 partial sums [pixels][N0+N1]
-  // un-finished for the consumer (bn_small_fwd / bn_small_bwd round and clear them: one launch less per layer);
+  // un-finished for the consumer (bn_small_fwd / bn_small_bwd / finish_act round and clear them: one launch less per layer);
   // *deferred = the sums then, else untouched
   float** deferred;
 };
@@ -402,7 +402,8 @@ struct GemmEpilogue {
 int tc_gemm_rows(const void* a0, int K0, const void* a1, int K1, const void* bm, int b_kn, void* c16_0, int N0, void* c16_1,
                  int N1, float* c32, long long M, cudaStream_t s, const GemmEpilogue* epi = nullptr);
 // fp32 scratch used to split the K range of deep, small-M layers across CTAs (NULL: never split)
-// clean: the caller has zeroed it on the launching stream; split launches then skip their memset and re-zero what they used
+// clean: the caller has zeroed it on the launching stream; split launches then skip their memset, and whoever finishes the
+// sums (finish_partial_kernel or the deferred consumer) re-zeroes what was used
 void tc_set_scratch(void* ptr, size_t bytes, bool clean = false);
 // switches ("tc_halo", "tc_max_bn", "tc_stats"): returns the previous value, -1 for an unknown name
 int tc_set_option(const char* name, int value);

@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) tc_igemm_persist_kernel(cons
 }
 
 // fp32 partial sums [pixels][N] -> bf16 outputs (split at N0); rezero: the sums are cleared as they are read, so a scratch
-// that was zero before the convolution is zero again afterwards (the engine clears it once per pass instead of per layer)
+// that was zero before the convolution is zero again afterwards (the engine clears it once per step instead of per layer)
 __global__ void __launch_bounds__(256)
 finish_partial_kernel(float* __restrict__ partial, long long pixels, int N, int N0, int N1, bf16* __restrict__ y0,
                       bf16* __restrict__ y1, int rezero) {
